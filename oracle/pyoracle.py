@@ -1,0 +1,326 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the two CPU oracles.
+
+* ``RefLib``      : the UNMODIFIED reference sources compiled by gcc for one compile-time
+                    geometry (oracle/_ref/libref_<geom>.so, see oracle/build_ref.sh).
+* ``Restatement`` : our plain-C restatement (oracle/staggered_oracle.c), run-time geometry.
+
+numpy layouts equal the reference ABI (struct_c_def.h:16-42):
+  vec3_soa   -> complex128[3, sizeh]        su3_soa[8] -> complex128[8, 3, 3, sizeh]
+  double_soa[8] -> float64[8, sizeh]        vec3_soa[N] -> complex128[N, 3, sizeh]
+(complex64 / float32 for the ``_f`` twins).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = os.environ.get("STAPLE_REFERENCE", "/root/reference")
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ----------------------------------------------------------------------------- inputs
+def random_su3_conf(sizeh, seed, dtype=np.complex128):
+    """i.i.d. Haar-random SU(3) for every link: complex[8,3,3,sizeh] (row 2 = conj(r0 x r1))."""
+    rng = np.random.default_rng(seed)
+    n = 8 * sizeh
+    z = rng.standard_normal((n, 3, 3)) + 1j * rng.standard_normal((n, 3, 3))
+    q, r = np.linalg.qr(z)
+    d = np.diagonal(r, axis1=1, axis2=2)
+    q = q * (d / np.abs(d))[:, None, :]
+    det = np.linalg.det(q)
+    q = q / (det ** (1.0 / 3.0))[:, None, None]
+    q[:, 2, :] = np.conj(np.cross(q[:, 0, :], q[:, 1, :]))
+    u = q.reshape(8, sizeh, 3, 3).transpose(0, 2, 3, 1)
+    return np.ascontiguousarray(u).astype(dtype)
+
+
+def gaussian_vec(sizeh, seed, n=None, dtype=np.complex128):
+    rng = np.random.default_rng(seed)
+    shape = (3, sizeh) if n is None else (n, 3, sizeh)
+    v = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2.0)
+    return np.ascontiguousarray(v).astype(dtype)
+
+
+# ----------------------------------------------------------------------------- reference build
+def ref_lib_path(n0, n1, n2, n3, nr=1):
+    return os.path.join(HERE, "_ref", "libref_%dx%dx%dx%d_r%d.so" % (n0, n1, n2, n3, nr))
+
+
+def build_ref(n0, n1, n2, n3, nr=1):
+    """Compile the reference for one geometry if /root/reference is present; returns path or None."""
+    path = ref_lib_path(n0, n1, n2, n3, nr)
+    if os.path.isdir(os.path.join(REFERENCE, "src")):
+        subprocess.run([os.path.join(HERE, "build_ref.sh")] + [str(x) for x in (n0, n1, n2, n3, nr)],
+                       check=True, stdout=subprocess.DEVNULL)
+    return path if os.path.exists(path) else None
+
+
+def have_ref(n0, n1, n2, n3, nr=1):
+    return os.path.exists(ref_lib_path(n0, n1, n2, n3, nr)) or os.path.isdir(os.path.join(REFERENCE, "src"))
+
+
+class RefLib:
+    """The reference's own functions for one (LOC_N0..3, NRANKS_D3) geometry."""
+
+    def __init__(self, n0, n1, n2, n3, nr=1, rank=0):
+        path = build_ref(n0, n1, n2, n3, nr)
+        if path is None:
+            raise FileNotFoundError("no reference build for this geometry: " + ref_lib_path(n0, n1, n2, n3, nr))
+        self.lib = C.CDLL(path)
+        o = (C.c_int * 12)()
+        self.lib.ref_geometry(o)
+        self.loc_n = tuple(o[0:4]); self.nranks = o[4]; self.nd = tuple(o[5:9])
+        self.sizeh = o[9]; self.d3_halo = o[10]; self.gl_sizeh = o[11]
+        self.vol3h = self.nd[0] * self.nd[1] * self.nd[2] // 2
+        L = self.lib
+        L.ref_ferm_param_new.restype = C.c_void_p
+        L.ref_ferm_param_new.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
+        L.ref_approx_new.restype = C.c_void_p
+        L.ref_approx_new.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.l2norm2_global.restype = C.c_double
+        L.l2norm2_global_f.restype = C.c_double
+        L.real_scal_prod_global.restype = C.c_double
+        L.real_scal_prod_global_f.restype = C.c_double
+        L.ker_find_max_eigenvalue_openacc.restype = C.c_double
+        self.set_rank(rank)
+        self.set_inverter_tricks(0, 0, 0.1, 10000)
+
+    def set_rank(self, rank):
+        if self.lib.ref_setup(C.c_int(rank)) != 0:
+            raise RuntimeError("reference set_geom_glv failed")
+        self.rank = rank
+
+    def set_inverter_tricks(self, sp_accel, mixed, delta, restart):
+        self.lib.ref_set_inverter_tricks(C.c_int(sp_accel), C.c_int(mixed), C.c_double(delta), C.c_int(restart))
+
+    # --- inputs
+    def phases(self, eb=(0, 0, 0, 0, 0, 0), im_chem_pot=0.0, charge=0.0):
+        ph = np.zeros((8, self.sizeh), np.float64)
+        self.lib.ref_phases(ptr(ph), *[C.c_double(x) for x in eb], C.c_double(im_chem_pot), C.c_double(charge))
+        return ph
+
+    def phases_f(self, eb=(0, 0, 0, 0, 0, 0), im_chem_pot=0.0, charge=0.0):
+        ph = np.zeros((8, self.sizeh), np.float32)
+        self.lib.ref_phases_f(ptr(ph), *[C.c_double(x) for x in eb], C.c_double(im_chem_pot), C.c_double(charge))
+        return ph
+
+    def ferm_param(self, mass, ph, ph_f=None):
+        return C.c_void_p(self.lib.ref_ferm_param_new(C.c_double(mass), ptr(ph), ptr(ph_f)))
+
+    def approx(self, a0, a, b):
+        a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+        return C.c_void_p(self.lib.ref_approx_new(C.c_int(len(b)), C.c_double(a0), ptr(a), ptr(b)))
+
+    def _sfx(self, a):
+        return "_f" if a.dtype in (np.complex64, np.float32) else ""
+
+    # --- operator
+    def dslash(self, name, u, inp, ph, out=None):
+        """name in acc_Deo, acc_Doe, acc_Deo_unsafe, acc_Doe_bulk, acc_Deo_d3p, ..."""
+        out = np.zeros_like(inp) if out is None else out
+        getattr(self.lib, name + self._sfx(inp))(ptr(u), ptr(out), ptr(inp), ptr(ph))
+        return out
+
+    def mdagm(self, u, inp, ph, mass, shift=None, ph_f=None):
+        out = np.zeros_like(inp); tmp = np.zeros_like(inp)
+        sfx = self._sfx(inp)
+        pars = self.ferm_param(mass, ph if sfx == "" else None, ph if sfx else None)
+        if shift is None:
+            getattr(self.lib, "fermion_matrix_multiplication" + sfx)(ptr(u), ptr(out), ptr(inp), ptr(tmp), pars)
+        else:
+            getattr(self.lib, "fermion_matrix_multiplication_shifted" + sfx)(
+                ptr(u), ptr(out), ptr(inp), ptr(tmp), pars, C.c_double(shift))
+        return out
+
+    # --- solvers
+    def multishift_invert(self, u, ph, mass, approx_a0_a_b, inp, residuo, max_cg):
+        a0, a, b = approx_a0_a_b
+        n = len(b); sfx = self._sfx(inp)
+        out = np.zeros((n,) + inp.shape, inp.dtype); ps = np.zeros_like(out)
+        r, h, s, p = (np.zeros_like(inp) for _ in range(4))
+        pars = self.ferm_param(mass, ph if sfx == "" else None, ph if sfx else None)
+        cg = C.c_int(0)
+        ok = getattr(self.lib, "multishift_invert" + sfx)(
+            ptr(u), pars, self.approx(a0, a, b), ptr(out), ptr(inp), C.c_double(residuo),
+            ptr(r), ptr(h), ptr(s), ptr(p), ptr(ps), C.c_int(max_cg), C.byref(cg))
+        return out, cg.value, ok
+
+    def recombine(self, shifted, inp, approx_a0_a_b):
+        a0, a, b = approx_a0_a_b
+        out = np.zeros_like(inp)
+        getattr(self.lib, "recombine_shifted_vec3_to_vec3" + self._sfx(inp))(
+            ptr(shifted), ptr(inp), ptr(out), self.approx(a0, a, b))
+        return out
+
+    def cg(self, u, ph, mass, inp, res, max_cg, shift, guess=None):
+        sfx = self._sfx(inp)
+        sol = np.zeros_like(inp) if guess is None else guess.copy()
+        r, h, s, p = (np.zeros_like(inp) for _ in range(4))
+        pars = self.ferm_param(mass, ph if sfx == "" else None, ph if sfx else None)
+        cg = C.c_int(0)
+        ok = getattr(self.lib, "ker_invert_openacc" + sfx)(
+            ptr(u), pars, ptr(sol), ptr(inp), C.c_double(res), ptr(r), ptr(h), ptr(s), ptr(p),
+            C.c_int(max_cg), C.c_double(shift), C.byref(cg))
+        return sol, cg.value, ok
+
+    def mixed_cg(self, u, u_f, ph, ph_f, mass, inp, res, max_cg, shift, guess=None):
+        sol = np.zeros_like(inp) if guess is None else guess.copy()
+        d = [np.zeros_like(inp) for _ in range(4)]
+        f = [np.zeros(inp.shape, np.complex64) for _ in range(5)]
+        st = np.zeros((1,) + inp.shape, inp.dtype); st_f = np.zeros((1,) + inp.shape, np.complex64)
+        self.lib.ref_ip_dp(ptr(u), ptr(st), C.c_int(1), *[ptr(x) for x in d])
+        self.lib.ref_ip_sp(ptr(u_f), ptr(st_f), C.c_int(1), *[ptr(x) for x in f])
+        pars = self.ferm_param(mass, ph, ph_f)
+        cg = C.c_int(0)
+        ok = self.lib.ref_inverter_mixed_precision(pars, ptr(sol), ptr(inp), C.c_double(res), C.c_int(max_cg),
+                                                   C.c_double(shift), C.byref(cg))
+        return sol, cg.value, ok
+
+    def max_eigenvalue(self, u, ph, mass, start):
+        p = start.copy(); r = np.zeros_like(p); h = np.zeros_like(p)
+        pars = self.ferm_param(mass, ph)
+        return self.lib.ker_find_max_eigenvalue_openacc(ptr(u), pars, ptr(r), ptr(h), ptr(p))
+
+    # --- reductions
+    def l2norm2(self, a):
+        return getattr(self.lib, "l2norm2_global" + self._sfx(a))(ptr(a))
+
+    def real_scal_prod(self, a, b):
+        return getattr(self.lib, "real_scal_prod_global" + self._sfx(a))(ptr(a), ptr(b))
+
+
+# ----------------------------------------------------------------------------- restatement
+class SoGeom(C.Structure):
+    _fields_ = [("loc_n", C.c_int * 4), ("nranks_d3", C.c_int), ("halo_width", C.c_int),
+                ("d3_halo", C.c_int), ("d3_fhalo", C.c_int), ("nd", C.c_int * 4),
+                ("vol3h", C.c_long), ("sizeh", C.c_long), ("r0_lo", C.c_long), ("r0_hi", C.c_long),
+                ("r1_lo", C.c_long), ("r1_hi", C.c_long), ("gl_n", C.c_int * 4)]
+
+
+def build_restatement():
+    path = os.path.join(HERE, "libstaggered_oracle.so")
+    subprocess.run(["make", "-s", "-C", HERE], check=True, stdout=subprocess.DEVNULL)
+    return path
+
+
+class Restatement:
+    """Plain-C restatement of the path (oracle/staggered_oracle.c) for one run-time geometry."""
+    OPS = dict(in1xfactor_plus_in2=0, scale=1, add_factor_x_in2=2, in1xmass2_minus_in2_minus_in3=3,
+               in1xmass_minus_in2=4, in1_minus_in2=5, assign=6, zero=7, fact1_minus_in2=8,
+               in1_minus_in2_allxfact=9)
+
+    def __init__(self, n0, n1, n2, n3, nr=1, halo_width=2):
+        self.lib = C.CDLL(build_restatement())
+        self.g = SoGeom()
+        self.lib.so_geom_init(C.byref(self.g), n0, n1, n2, n3, nr, halo_width)
+        self.sizeh = self.g.sizeh; self.vol3h = self.g.vol3h; self.nd = tuple(self.g.nd)
+        self.loc_n = (n0, n1, n2, n3); self.nranks = nr; self.d3_halo = self.g.d3_halo
+        L = self.lib
+        for s in ("", "_f"):
+            getattr(L, "so_l2norm2" + s).restype = C.c_double
+            getattr(L, "so_real_scal_prod" + s).restype = C.c_double
+        L.so_find_max_eigenvalue.restype = C.c_double
+        L.so_snum.restype = C.c_long
+        L.so_lnh_to_gl_snum.restype = C.c_long
+
+    def _sfx(self, a):
+        return "_f" if a.dtype in (np.complex64, np.float32) else ""
+
+    def gp(self):
+        return C.byref(self.g)
+
+    def phases(self, rank=0, eb=(0, 0, 0, 0, 0, 0), im_chem_pot=0.0, charge=0.0, single=False):
+        ph = np.zeros((8, self.sizeh), np.float32 if single else np.float64)
+        e = (C.c_double * 6)(*eb)
+        fn = self.lib.so_calc_u1_phases_f if single else self.lib.so_calc_u1_phases
+        fn(self.gp(), C.c_int(rank), ptr(ph), e, C.c_double(im_chem_pot), C.c_double(charge))
+        return ph
+
+    def dslash(self, which, u, inp, ph, d3lo=None, d3hi=None, out=None):
+        """which: 'deo' | 'doe'."""
+        out = np.zeros_like(inp) if out is None else out
+        d3lo = self.d3_halo if d3lo is None else d3lo
+        d3hi = self.d3_halo + self.loc_n[3] if d3hi is None else d3hi
+        getattr(self.lib, "so_" + which + self._sfx(inp))(self.gp(), ptr(u), ptr(out), ptr(inp), ptr(ph),
+                                                         C.c_int(d3lo), C.c_int(d3hi))
+        return out
+
+    def mdagm(self, u, inp, ph, mass, shift=0.0):
+        out = np.zeros_like(inp); tmp = np.zeros_like(inp)
+        getattr(self.lib, "so_fermion_matrix_multiplication_shifted" + self._sfx(inp))(
+            self.gp(), ptr(u), ptr(out), ptr(inp), ptr(tmp), ptr(ph), C.c_double(mass), C.c_double(shift))
+        return out
+
+    def axpy_like(self, op, out, a=None, b=None, c=None, f1=0.0):
+        getattr(self.lib, "so_axpy_like" + self._sfx(out))(
+            self.gp(), C.c_int(self.OPS[op]), ptr(out), ptr(a), ptr(b), ptr(c), C.c_double(f1), C.c_double(0))
+        return out
+
+    def l2norm2(self, a):
+        return getattr(self.lib, "so_l2norm2" + self._sfx(a))(self.gp(), ptr(a))
+
+    def real_scal_prod(self, a, b):
+        return getattr(self.lib, "so_real_scal_prod" + self._sfx(a))(self.gp(), ptr(a), ptr(b))
+
+    def multishift_invert(self, u, ph, mass, shifts, inp, residuo, max_cg):
+        shifts = np.ascontiguousarray(shifts, np.float64); n = len(shifts)
+        out = np.zeros((n,) + inp.shape, inp.dtype); ps = np.zeros_like(out)
+        r, h, s, p = (np.zeros_like(inp) for _ in range(4))
+        cg = C.c_int(0); rel = np.zeros(n)
+        ok = getattr(self.lib, "so_multishift_invert" + self._sfx(inp))(
+            self.gp(), ptr(u), ptr(ph), C.c_double(mass), C.c_int(n), ptr(shifts), ptr(out), ptr(inp),
+            C.c_double(residuo), ptr(r), ptr(h), ptr(s), ptr(p), ptr(ps), C.c_int(max_cg), C.byref(cg), ptr(rel))
+        return out, cg.value, ok, rel
+
+    def recombine(self, shifted, inp, a0, a):
+        a = np.ascontiguousarray(a, np.float64); out = np.zeros_like(inp)
+        getattr(self.lib, "so_recombine" + self._sfx(inp))(self.gp(), ptr(shifted), ptr(inp), ptr(out),
+                                                          C.c_int(len(a)), C.c_double(a0), ptr(a))
+        return out
+
+    def cg(self, u, ph, mass, inp, res, max_cg, shift, restarting_every=10000, guess=None):
+        sol = np.zeros_like(inp) if guess is None else guess.copy()
+        r, h, s, p = (np.zeros_like(inp) for _ in range(4))
+        cg = C.c_int(0)
+        ok = getattr(self.lib, "so_cg" + self._sfx(inp))(
+            self.gp(), ptr(u), ptr(ph), C.c_double(mass), ptr(sol), ptr(inp), C.c_double(res), ptr(r), ptr(h),
+            ptr(s), ptr(p), C.c_int(max_cg), C.c_double(shift), C.c_int(restarting_every), C.byref(cg))
+        return sol, cg.value, ok
+
+    def mixed_cg(self, u, u_f, ph, ph_f, mass, inp, res, max_cg, shift, mixed_delta=0.1, guess=None):
+        sol = np.zeros_like(inp) if guess is None else guess.copy()
+        d = [np.zeros_like(inp) for _ in range(3)]
+        f = [np.zeros(inp.shape, np.complex64) for _ in range(5)]
+        cg = C.c_int(0); mt = C.c_int(0)
+        ok = self.lib.so_inverter_mixed_precision(
+            self.gp(), ptr(u), ptr(u_f), ptr(ph), ptr(ph_f), C.c_double(mass), ptr(sol), ptr(inp),
+            C.c_double(res), C.c_int(max_cg), C.c_double(shift), C.c_double(mixed_delta),
+            *[ptr(x) for x in d], *[ptr(x) for x in f], C.byref(cg), C.byref(mt))
+        return sol, cg.value, ok, mt.value
+
+    def max_eigenvalue(self, u, ph, mass, start):
+        p = start.copy(); r = np.zeros_like(p); h = np.zeros_like(p)
+        return self.lib.so_find_max_eigenvalue(self.gp(), ptr(u), ptr(ph), C.c_double(mass), ptr(r), ptr(h), ptr(p), None)
+
+    # multi-rank helpers (global <-> rank-local boxes)
+    def scatter_vec(self, rank, gl):
+        lnh = np.zeros((3, self.sizeh), np.complex128)
+        self.lib.so_scatter_vec(self.gp(), C.c_int(rank), ptr(gl), ptr(lnh)); return lnh
+
+    def gather_vec(self, rank, gl, lnh):
+        self.lib.so_gather_vec(self.gp(), C.c_int(rank), ptr(gl), ptr(lnh))
+
+    def scatter_conf(self, rank, gl):
+        lnh = np.zeros((8, 3, 3, self.sizeh), np.complex128)
+        self.lib.so_scatter_conf(self.gp(), C.c_int(rank), ptr(gl), ptr(lnh)); return lnh
+
+    def exchange_halo(self, vecs, thickness=1):
+        """vecs: list (one per rank) of complex128[ncomp, sizeh] arrays, exchanged in place."""
+        ncomp = vecs[0].reshape(-1, self.sizeh).shape[0]
+        arr = (C.c_void_p * len(vecs))(*[v.ctypes.data for v in vecs])
+        self.lib.so_exchange_halo(self.gp(), arr, C.c_int(ncomp), C.c_int(thickness))

@@ -1,0 +1,242 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+ *
+ * Glue compiled TOGETHER WITH the unmodified OpenStaPLE hot-path sources (from
+ * /root/reference, see oracle/build_ref.sh) into oracle/_ref/libref_<geom>.so.
+ * It only (1) defines the few globals that the reference's main() programs
+ * normally define, (2) offers small constructors for the reference's structs so
+ * that the Python tests can call the reference functions (acc_Deo, acc_Doe,
+ * fermion_matrix_multiplication, multishift_invert, ...) directly via ctypes,
+ * and (3) provides a single-process "mailbox" MPI so that the reference's own
+ * halo-exchange code (src/Mpi/communications.c:34-332) can be executed rank by
+ * rank inside one process.  No arithmetic of the path is restated here.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "mpi.h"
+#include "OpenAcc/struct_c_def.h"
+#include "OpenAcc/sp_struct_c_def.h"
+#include "OpenAcc/geometry.h"
+#include "Mpi/multidev.h"
+#include "Include/fermion_parameters.h"
+#include "Include/inverter_tricks.h"
+#include "OpenAcc/backfield.h"
+#include "OpenAcc/sp_backfield.h"
+#include "Mpi/communications.h"
+#include "OpenAcc/inverter_package.h"
+#include "OpenAcc/inverter_wrappers.h"
+#include "OpenAcc/inverter_mixedp.h"
+#include "RationalApprox/rationalapprox.h"
+
+int verbosity_lv = 0;
+vec3_soa_f *aux1_f = NULL;                 /* alloc_vars globals used by inverter_wrappers.c:60-71 */
+vec3_soa_f *ferm_shiftmulti_acc_f = NULL;
+
+void ref_geometry(int *o)
+{
+	o[0] = LOC_N0; o[1] = LOC_N1; o[2] = LOC_N2; o[3] = LOC_N3;
+	o[4] = NRANKS_D3;
+	o[5] = nd0; o[6] = nd1; o[7] = nd2; o[8] = nd3;
+	o[9] = sizeh; o[10] = D3_HALO; o[11] = GL_SIZEH;
+}
+
+
+/* index helpers straight from the reference's header-only geometry (geometry_multidev.h:209-262) */
+int ref_snum_acc(int d0, int d1, int d2, int d3) { return snum_acc(d0, d1, d2, d3); }
+int ref_lnh_to_gl_snum(int d0, int d1, int d2, int d3, int rank)
+{ return lnh_to_gl_snum(d0, d1, d2, d3, xyzt_rank(rank)); }
+/* loop bounds exactly as spelled in fermionic_utilities.c:41 (reductions) and :188 (updates) */
+void ref_ranges(long *o)
+{
+#if NRANKS_D3 > 1
+	o[0] = (LNH_SIZEH-LOC_SIZEH)/2; o[1] = (LNH_SIZEH+LOC_SIZEH)/2;
+#else
+	o[0] = 0; o[1] = sizeh;
+#endif
+	o[2] = LNH_VOL3/2*(D3_HALO-D3_FERMION_HALO); o[3] = LNH_SIZEH-LNH_VOL3/2*(D3_HALO-D3_FERMION_HALO);
+}
+
+/* Select which rank of the D3 ring this process currently "is". */
+int ref_setup(int rank)
+{
+	geom_par.gnx = GL_N0; geom_par.gny = GL_N1; geom_par.gnz = GL_N2; geom_par.gnt = GL_N3;
+	geom_par.xmap = 0; geom_par.ymap = 1; geom_par.zmap = 2; geom_par.tmap = 3;
+	devinfo.myrank = rank; devinfo.nranks = NRANKS_D3;
+	devinfo.myrank_world = rank; devinfo.nranks_world = NRANKS_D3;
+	devinfo.replica_idx = 0; devinfo.num_replicas = 1;
+	int res = set_geom_glv(&geom_par);
+#ifdef MULTIDEVICE
+	devinfo.mpi_comm = 0;
+	devinfo.async_comm_fermion = 0; devinfo.async_comm_gauge = 0;
+	devinfo.proc_per_node = NRANKS_D3;
+	devinfo.namelen = 0; devinfo.processor_name[0] = 0;
+	init_multidev1D(&devinfo);
+#endif
+	return res;
+}
+
+void ref_set_async_fermion_comms(int on)
+{
+#ifdef MULTIDEVICE
+	devinfo.async_comm_fermion = on;
+#endif
+}
+
+void ref_set_verbosity(int v) { verbosity_lv = v; }
+
+ferm_param *ref_ferm_param_new(double mass, double_soa *phases, float_soa *phases_f)
+{
+	ferm_param *p = (ferm_param *) calloc(1, sizeof(ferm_param));
+	p->ferm_mass = mass; p->phases = phases; p->phases_f = phases_f;
+	p->degeneracy = 1; p->number_of_ps = 1; strcpy(p->name, "oracle");
+	return p;
+}
+
+RationalApprox *ref_approx_new(int order, double a0, const double *a, const double *b)
+{
+	RationalApprox *r = (RationalApprox *) calloc(1, sizeof(RationalApprox));
+	r->approx_order = order; r->RA_a0 = a0;
+	for (int i = 0; i < order; i++) { r->RA_a[i] = a[i]; r->RA_b[i] = b[i]; }
+	r->exponent_num = -1; r->exponent_den = 4; r->lambda_min = 0; r->lambda_max = 1;
+	return r;
+}
+
+int ref_approx_read(RationalApprox *r, char *filename)
+{
+	return rationalapprox_read_custom_nomefile(r, filename);
+}
+
+void ref_approx_get(const RationalApprox *r, int *order, double *a0, double *a, double *b,
+										int *num, int *den, double *lmin, double *lmax)
+{
+	*order = r->approx_order; *a0 = r->RA_a0; *num = r->exponent_num; *den = r->exponent_den;
+	*lmin = r->lambda_min; *lmax = r->lambda_max;
+	for (int i = 0; i < r->approx_order; i++) { a[i] = r->RA_a[i]; b[i] = r->RA_b[i]; }
+}
+
+void ref_set_inverter_tricks(int singlePInvAccelMultiInv, int useMixedPrecision,
+														 double mixedPrecisionDelta, int restartingEvery)
+{
+	inverter_tricks.singlePInvAccelMultiInv = singlePInvAccelMultiInv;
+	inverter_tricks.useMixedPrecision = useMixedPrecision;
+	inverter_tricks.mixedPrecisionDelta = mixedPrecisionDelta;
+	inverter_tricks.restartingEvery = restartingEvery;
+}
+
+void ref_set_sp_globals(vec3_soa_f *aux1, vec3_soa_f *shiftmulti)
+{
+	aux1_f = aux1; ferm_shiftmulti_acc_f = shiftmulti;
+}
+
+void ref_phases(double_soa *ph, double ex, double ey, double ez, double bx, double by, double bz,
+								double im_chem_pot, double charge)
+{
+	bf_param b = { ex, ey, ez, bx, by, bz };
+	calc_u1_phases(ph, b, im_chem_pot, charge);
+}
+
+void ref_phases_f(float_soa *ph, double ex, double ey, double ez, double bx, double by, double bz,
+									double im_chem_pot, double charge)
+{
+	bf_param b = { ex, ey, ez, bx, by, bz };
+	calc_u1_phases_f(ph, b, (float) im_chem_pot, (float) charge);
+}
+
+/* inverter_package travels by value in the reference API (inverter_package.h:12-29). */
+static inverter_package the_ip;
+void ref_ip_dp(su3_soa *u, vec3_soa *shift_temp, int nshift, vec3_soa *r, vec3_soa *h,
+							 vec3_soa *s, vec3_soa *p)
+{ setup_inverter_package_dp(&the_ip, u, shift_temp, nshift, r, h, s, p); }
+void ref_ip_sp(su3_soa_f *u, vec3_soa_f *shift_temp, int nshift, vec3_soa_f *r, vec3_soa_f *h,
+							 vec3_soa_f *s, vec3_soa_f *p, vec3_soa_f *out)
+{ setup_inverter_package_sp(&the_ip, u, shift_temp, nshift, r, h, s, p, out); }
+int ref_inverter_multishift_wrapper(ferm_param *pars, RationalApprox *approx, vec3_soa *out,
+																		const vec3_soa *in, double res, int max_cg, int importance)
+{ return inverter_multishift_wrapper(the_ip, pars, approx, out, in, res, max_cg, importance); }
+int ref_inverter_wrapper(ferm_param *pars, vec3_soa *out, const vec3_soa *in, double res,
+												 int max_cg, double shift, int importance)
+{ return inverter_wrapper(the_ip, pars, out, in, res, max_cg, shift, importance); }
+int ref_inverter_mixed_precision(ferm_param *pars, vec3_soa *solution, const vec3_soa *in,
+																 double res, int max_cg, double shift, int *cg_return)
+{ return inverter_mixed_precision(the_ip, pars, solution, in, res, max_cg, shift, cg_return); }
+
+#ifdef MULTIDEVICE
+/* ---- single-process mailbox MPI ------------------------------------------------
+ * Sends are copied into a mailbox keyed by (src,dst,tag); receives are served from
+ * it if the matching message is already there, otherwise they are left pending
+ * (nonblocking) or skipped (blocking).  Running the reference's exchange routine
+ * twice for every rank therefore completes all transfers with the reference's own
+ * offsets, counts, tags and neighbour ranks. */
+#define MB_MAX 4096
+typedef struct { int src, dst, tag; size_t bytes; void *data; } mb_msg;
+static mb_msg mb[MB_MAX]; static int mb_n = 0;
+typedef struct { int src, tag; size_t bytes; void *dst; int live; } mb_pend;
+static mb_pend pend[MB_MAX]; static int pend_n = 0;
+static long mb_missing = 0;
+
+void ref_mailbox_clear(void)
+{
+	for (int i = 0; i < mb_n; i++) free(mb[i].data);
+	mb_n = 0; pend_n = 0; mb_missing = 0;
+}
+long ref_mailbox_missing(void) { long m = mb_missing; mb_missing = 0; return m; }
+
+static size_t dtsize(MPI_Datatype t) { return (size_t) t; }
+static void mb_post(const void *buf, size_t bytes, int dst, int tag)
+{
+	for (int i = 0; i < mb_n; i++)
+		if (mb[i].src == devinfo.myrank && mb[i].dst == dst && mb[i].tag == tag) {
+			if (mb[i].bytes != bytes) { mb[i].data = realloc(mb[i].data, bytes); mb[i].bytes = bytes; }
+			memcpy(mb[i].data, buf, bytes); return;
+		}
+	if (mb_n == MB_MAX) { printf("oracle mailbox full\n"); exit(1); }
+	mb[mb_n].src = devinfo.myrank; mb[mb_n].dst = dst; mb[mb_n].tag = tag; mb[mb_n].bytes = bytes;
+	mb[mb_n].data = malloc(bytes); memcpy(mb[mb_n].data, buf, bytes); mb_n++;
+}
+static int mb_fetch(void *buf, size_t bytes, int src, int tag)
+{
+	for (int i = 0; i < mb_n; i++)
+		if (mb[i].src == src && mb[i].dst == devinfo.myrank && mb[i].tag == tag) {
+			if (mb[i].bytes != bytes) { printf("oracle mailbox size mismatch\n"); exit(1); }
+			memcpy(buf, mb[i].data, bytes); return 1;
+		}
+	mb_missing++; return 0;
+}
+int MPI_Init(int *a, char ***b) { return 0; }
+int MPI_Finalize(void) { return 0; }
+int MPI_Abort(MPI_Comm c, int e) { exit(e); }
+int MPI_Barrier(MPI_Comm c) { return 0; }
+int MPI_Comm_rank(MPI_Comm c, int *r) { *r = devinfo.myrank; return 0; }
+int MPI_Comm_size(MPI_Comm c, int *n) { *n = NRANKS_D3; return 0; }
+int MPI_Comm_split(MPI_Comm c, int a, int b, MPI_Comm *o) { *o = 0; return 0; }
+int MPI_Get_processor_name(char *n, int *l) { n[0] = 0; *l = 0; return 0; }
+int MPI_Bcast(void *b, int n, MPI_Datatype t, int r, MPI_Comm c) { return 0; }
+int MPI_Allreduce(const void *s, void *r, int n, MPI_Datatype t, MPI_Op o, MPI_Comm c)
+{ memcpy(r, s, n * dtsize(t)); return 0; }   /* local contribution only; harness sums over ranks */
+int MPI_Sendrecv(const void *sb, int sn, MPI_Datatype st, int dst, int stag, void *rb, int rn,
+								 MPI_Datatype rt, int src, int rtag, MPI_Comm c, MPI_Status *s)
+{ mb_post(sb, sn * dtsize(st), dst, stag); mb_fetch(rb, rn * dtsize(rt), src, rtag); return 0; }
+int MPI_Send(const void *b, int n, MPI_Datatype t, int dst, int tag, MPI_Comm c)
+{ mb_post(b, n * dtsize(t), dst, tag); return 0; }
+int MPI_Recv(void *b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status *s)
+{ mb_fetch(b, n * dtsize(t), src, tag); return 0; }
+int MPI_Isend(const void *b, int n, MPI_Datatype t, int dst, int tag, MPI_Comm c, MPI_Request *rq)
+{ mb_post(b, n * dtsize(t), dst, tag); *rq = -1; return 0; }
+int MPI_Irecv(void *b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Request *rq)
+{
+	if (pend_n == MB_MAX) pend_n = 0;
+	pend[pend_n].src = src; pend[pend_n].tag = tag; pend[pend_n].bytes = n * dtsize(t);
+	pend[pend_n].dst = b; pend[pend_n].live = 1; *rq = pend_n++; return 0;
+}
+int MPI_Wait(MPI_Request *rq, MPI_Status *s)
+{
+	if (*rq >= 0 && pend[*rq].live) {
+		mb_fetch(pend[*rq].dst, pend[*rq].bytes, pend[*rq].src, pend[*rq].tag); pend[*rq].live = 0;
+	}
+	return 0;
+}
+int MPI_Waitall(int n, MPI_Request *rq, MPI_Status *s)
+{ for (int i = 0; i < n; i++) MPI_Wait(&rq[i], s); return 0; }
+#else
+int MPI_Abort(MPI_Comm c, int e) { exit(e); }
+#endif
