@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the staggered fermion-solver hot path (BASELINE.json):
+Deo/Doe GFLOP/s (570 flop/site) and HBM GB/s against the roofline, plus M^+M and multishift CG.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lattice 32x32x32x32]
+
+One "step" = one acc_Doe followed by one acc_Deo on the SAME gauge field (the stock deo_doe_test
+loop, src/tests_and_benchmarks/deo_doe_test.c:236-269), on synthetic Haar-random SU(3) links and a
+Gaussian source.  N=1 workload: BASELINE configs[1], 32^4 FP64.  N>1: weak scaling -- every GPU owns
+a 32^3 x 32 slab of a 32^3 x (32 N) lattice (the reference's D3 "salamino"), with the halo exchange of
+acc_Deo/acc_Doe inside the step.  `value` is timed with inputs resident in HBM; `e2e` is the same step
+driven through the C ABI with HOST buffers (pinned host memory made present, staple_acc_update_device
+of the source before and staple_acc_update_host of the result after, both inside the timed region; the
+gauge field stays resident, as it does across operator calls in the reference).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SITE = 570.0            # SURVEY 8d / BASELINE.json convention
+BYTES_PER_SITE_FP64 = 928.0      # 8 links x 96 B + 8 phases x 8 B + 48 B spinor in + 48 B out
+EB = (0.0,) * 6                  # throughput runs: zero background field (theta in {0, pi})
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lattice", default="32x32x32x32", help="per-GPU local lattice LOC_N0xLOC_N1xLOC_N2xLOC_N3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solver", action="store_true")
+    ap.add_argument("--shifts", type=int, default=15)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []; self.proc = None; self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def haar_su3_torch(torch, n, device, seed):
+    """n Haar-random SU(3) matrices on the GPU -> complex128[n,3,3] (rows orthonormal, det 1)."""
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    z = torch.complex(torch.randn((n, 3, 3), generator=g, device=device, dtype=torch.float64),
+                      torch.randn((n, 3, 3), generator=g, device=device, dtype=torch.float64))
+    q, r = torch.linalg.qr(z)
+    d = torch.diagonal(r, dim1=1, dim2=2)
+    q = q * (d / d.abs()).unsqueeze(1)
+    det = torch.linalg.det(q)
+    q = q / torch.pow(det, 1.0 / 3.0).reshape(-1, 1, 1)
+    return q
+
+
+def make_fields(torch, lat, seed):
+    """synthetic inputs in the reference layouts: u[8,3,3,sizeh], phases[8,sizeh], source[3,sizeh]."""
+    S = lat.sizeh
+    u = lat.new_conf()
+    chunk = 1 << 20
+    flat = u.view(8, 3, 3, S)
+    for k in range(8):
+        for lo in range(0, S, chunk):
+            hi = min(S, lo + chunk)
+            q = haar_su3_torch(torch, hi - lo, lat.device, seed * 1000 + k * 17 + lo // chunk)
+            flat[k, :, :, lo:hi] = q.permute(1, 2, 0)
+    g = torch.Generator(device=lat.device); g.manual_seed(seed + 99)
+    v = torch.complex(torch.randn((3, S), generator=g, device=lat.device, dtype=torch.float64),
+                      torch.randn((3, S), generator=g, device=lat.device, dtype=torch.float64)) / np.sqrt(2.0)
+    return u, v
+
+
+def staggered_phases(lat, rank):
+    """calc_u1_phases with zero EM field and zero chemical potential (backfield.c:20-187): staggered
+    eta_mu and the antiperiodic time boundary only, theta in {0, pi}.  Host-side input producer."""
+    nd0, nd1, nd2, nd3 = lat.nd
+    gl_t = lat.loc_n[3] * lat.nranks
+    d0, d1, d2, d3 = np.meshgrid(np.arange(nd0), np.arange(nd1), np.arange(nd2), np.arange(nd3), indexing="ij")
+    t = (d3 + rank * lat.loc_n[3] - lat.d3_halo) % gl_t
+    x, y, z = d0, d1, d2
+    idxh = (d0 + nd0 * (d1 + nd1 * (d2 + nd2 * d3))) // 2
+    par = (x + y + z + t) % 2
+    ph = np.zeros((8, lat.sizeh))
+    twopi = 2 * 3.14159265358979323846
+    args = [np.zeros_like(x, dtype=float), 0.5 * (x & 1), 0.5 * ((x + y) & 1), 0.5 * ((x + y + z) & 1) + 0.5 * (t == gl_t - 1)]
+    for mu in range(4):
+        a = args[mu].astype(float)
+        a = np.where(a > 0.5, a - 1.0, a)
+        ph[2 * mu + par, idxh] = a * twopi
+    return ph
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (gcc build of the unmodified sources,
+    oracle/_ref; single-threaded because OpenACC pragmas are ignored by gcc) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.pyoracle import RefLib, Restatement, gaussian_vec, random_su3_conf, ref_lib_path
+    loc = tuple(int(x) for x in args.lattice.split("x"))
+    kind = "reference"
+    try:
+        R = RefLib(*loc)
+        run = lambda u, a, b, ph: (R.dslash("acc_Doe", u, a, ph, out=b), R.dslash("acc_Deo", u, b, ph, out=a))
+        ph = R.phases()
+    except Exception:
+        kind = "port"
+        R = Restatement(*loc)
+        run = lambda u, a, b, ph: (R.dslash("doe", u, a, ph, out=b), R.dslash("deo", u, b, ph, out=a))
+        ph = R.phases(0)
+    u = random_su3_conf(R.sizeh, 1); a = gaussian_vec(R.sizeh, 2); b = np.zeros_like(a)
+    steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        run(u, a, b, ph)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run(u, a, b, ph)
+    dt = (time.perf_counter() - t0) / steps
+    gflops = 2 * FLOP_PER_SITE * R.sizeh / dt / 1e9
+    line = {"impl": "reference", "metric": "deo_doe_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "deo_doe %s FP64 (Doe+Deo per step)" % args.lattice},
+            "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": kind,
+                             "sample": "%d Doe+Deo pairs on the full %s lattice, 1 host thread" % (steps, args.lattice)},
+            "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline(args, loc, u_host, v_host, ph_host):
+    """rank 0, N=1: the reference (oracle/_ref) or, failing that, the oracle port on a bounded sample."""
+    from oracle.pyoracle import RefLib, Restatement
+    sizeh = v_host.shape[1]
+    try:
+        R = RefLib(*loc); kind = "reference"
+        f = lambda a, b: (R.dslash("acc_Doe", u_host, a, ph_host, out=b), R.dslash("acc_Deo", u_host, b, ph_host, out=a))
+    except Exception:
+        R = Restatement(*loc); kind = "port"
+        f = lambda a, b: (R.dslash("doe", u_host, a, ph_host, out=b), R.dslash("deo", u_host, b, ph_host, out=a))
+    a = v_host.copy(); b = np.zeros_like(a)
+    f(a, b)
+    n = 0; t0 = time.perf_counter()
+    while True:
+        f(a, b); n += 1
+        if time.perf_counter() - t0 > 10.0 or n >= 64:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 2 * FLOP_PER_SITE * sizeh / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
+            "sample": "%d Doe+Deo pairs on the full %s lattice (%.2f s each), 1 host thread; gcc -O3 build of the "
+                      "reference is single-threaded (OpenACC pragmas ignored)" % (n, "x".join(map(str, loc)), dt)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import openstaple_b200 as osb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    loc = tuple(int(x) for x in args.lattice.split("x"))
+    lat = osb.Lattice(loc, nranks_d3=world, halo_width=2, device=local_rank)
+    if world > 1:
+        lat.init_multidev(dist, async_comm_fermion=1)
+    dev = lat.device
+    u, v = make_fields(torch, lat, seed=1 + rank)
+    ph_host = staggered_phases(lat, rank)
+    ph = lat.to_device(ph_host)
+    if world > 1:
+        lat.communicate_su3_borders(u, 2)
+        lat.communicate_fermion_borders(v)
+    a, b = v.clone(), lat.new_vec()
+    interior = lat.vol3h * loc[3]
+    pars = lat.ferm_param(0.0507, ph)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def step():
+        lat.acc_Doe(u, b, a, ph)
+        lat.acc_Deo(u, a, b, ph)
+
+    def renorm():
+        # keep the ping-pong vector O(1) without touching the timed region
+        nrm = lat.l2norm2_global(a)
+        lat.multiply_fermion_x_doublefactor(a, 1.0 / np.sqrt(nrm / (3 * interior * world)))
+        if world > 1:
+            lat.communicate_fermion_borders(a)
+
+    # ---------------- device-resident timing (value)
+    for _ in range(max(3, args.warmup)):
+        step()
+    renorm()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = lat.kernel_launches()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lat.kernel_launches() - l0
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    sites_per_step = 2 * interior * world                      # Doe + Deo outputs, all ranks
+    gflops = FLOP_PER_SITE * sites_per_step / (ms_step * 1e-3) / 1e9
+
+    # ---------------- dominant kernel alone (roofline): Deo launches back to back on this stream
+    renorm()
+    nk = max(20, args.steps // 2)
+    barrier()
+    e0.record()
+    for _ in range(nk):
+        lat.acc_Deo_unsafe(u, b, a, ph)
+    e1.record()
+    barrier()
+    ms_kernel = e0.elapsed_time(e1) / nk
+    peak, peak_src = peaks()
+    achieved = BYTES_PER_SITE_FP64 * interior / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "dslash_kernel<double,0,EPI_NONE> (acc_Deo_unsafe)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "bytes_per_launch": BYTES_PER_SITE_FP64 * interior, "us_per_launch": ms_kernel * 1e3,
+                "traffic": None}
+    tf = os.path.join(ROOT, "profiles", "dslash_traffic.json")
+    if os.path.exists(tf):
+        try:
+            t = json.load(open(tf))
+            if t.get("lattice") == args.lattice:
+                roofline["traffic"] = t.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---------------- M^+M (fused mass epilogue)
+    tmp, out = lat.new_vec(), lat.new_vec()
+    for _ in range(3):
+        lat.fermion_matrix_multiplication(u, out, a, tmp, pars)
+    barrier(); e0.record()
+    for _ in range(nk):
+        lat.fermion_matrix_multiplication(u, out, a, tmp, pars)
+    e1.record(); barrier()
+    ms_mdagm = max_over_ranks(e0.elapsed_time(e1) / nk)
+
+    # ---------------- end to end through the C ABI with host buffers
+    h_in = lat.host_array((3, lat.sizeh), np.complex128)
+    h_out = lat.host_array((3, lat.sizeh), np.complex128)
+    h_in.np[...] = a.cpu().numpy()
+    d_tmp = lat.new_vec()
+    vec_bytes = 48 * lat.sizeh
+
+    def e2e_step():
+        h_in.update_device()
+        lat.acc_Doe(u, d_tmp, h_in, ph)
+        lat.acc_Deo(u, h_out, d_tmp, ph)
+        h_out.update_host()
+
+    for _ in range(3):
+        e2e_step()
+    ne = max(10, args.steps // 4)
+    barrier(); t0 = time.perf_counter(); e0.record()
+    for _ in range(ne):
+        e2e_step()
+    e1.record(); barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / ne)
+    e2e = {"value": FLOP_PER_SITE * sites_per_step / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s",
+           "h2d_bytes_per_step": vec_bytes, "d2h_bytes_per_step": vec_bytes, "ms_per_step": ms_e2e,
+           "note": "source uploaded from and result downloaded to pinned host memory every step; gauge field resident"}
+
+    # ---------------- multishift CG (secondary metric: s/solve)
+    solver = None
+    if not args.no_solver:
+        n = args.shifts
+        shifts = np.geomspace(1e-4, 2.0, n)
+        approx = osb.RationalApprox.make(1.0, np.ones(n), shifts)
+        sol, ps = lat.new_vec(n), lat.new_vec(n)
+        r, h, s, p = (lat.new_vec() for _ in range(4))
+        src = v.clone()
+        if world > 1:
+            lat.communicate_fermion_borders(src)
+        lat.multishift_invert(u, pars, approx, sol, src, 1e-8, r, h, s, p, ps, 40)       # warm-up
+        barrier(); t0 = time.perf_counter()
+        st, cg = lat.multishift_invert(u, pars, approx, sol, src, 1e-8, r, h, s, p, ps, 20000)
+        barrier(); wall = time.perf_counter() - t0
+        it, act, loop_ms = lat.last_solve_stats()
+        fused_bytes = (2240.0 * it + 192.0 * act) * interior            # SURVEY 8d fused accounting, actual active shifts
+        solver = {"s_per_solve": wall, "iterations": cg, "status": st, "shifts": n, "residue": 1e-8,
+                  "ms_per_iteration": loop_ms / max(it, 1), "active_shift_iterations": act,
+                  "algorithmic_GBps": fused_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else None,
+                  "roofline_frac": fused_bytes / (loop_ms * 1e-3) / 1e9 / peak if loop_ms > 0 else None}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, loc, u.cpu().numpy(), v.cpu().numpy(), ph_host)
+
+    if rank == 0:
+        line = {"metric": "deo_doe_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "deo_doe %s per GPU, FP64, one acc_Doe + one acc_Deo per step, D3 slabs over %d GPU(s)"
+                                       % (args.lattice, world),
+                           "global_lattice": "%dx%dx%dx%d" % (loc[0], loc[1], loc[2], loc[3] * world),
+                           "l2_policy": "inputs larger than L2 (links 384 MiB read per application at 32^4 vs 126 MB L2)",
+                           "flop_per_site": FLOP_PER_SITE, "bytes_per_site": BYTES_PER_SITE_FP64},
+                "hbm_GBps": BYTES_PER_SITE_FP64 * sites_per_step / world / (ms_step * 1e-3) / 1e9,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "mdagm": {"ms": ms_mdagm, "algorithmic_GBps": 1904.0 * interior / (ms_mdagm * 1e-3) / 1e9,
+                          "gflops": 1140.0 * interior * world / (ms_mdagm * 1e-3) / 1e9},
+                "multishift": solver}
+        print(json.dumps(line))
+    h_in.free(); h_out.free()
+    if world > 1:
+        lat.shutdown_multidev()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

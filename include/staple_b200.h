@@ -1,0 +1,285 @@
+/* staple_b200.h -- C ABI of libstaple_b200.so
+ *
+ * B200-native (CUDA sm_100a) replacement for OpenStaPLE's fermion-solver hot path:
+ *   src/OpenAcc/fermion_matrix.[ch]          even/odd staggered Dirac operator
+ *   src/OpenAcc/fermionic_utilities.[ch]     BLAS-1 updates and reductions
+ *   src/OpenAcc/inverter_multishift_full.*   CG-M (multishift CG)
+ *   src/OpenAcc/inverter_full.*              restarted CG
+ *   src/OpenAcc/inverter_mixedp.*            FP32 inner / FP64 outer CG
+ *   src/OpenAcc/inverter_wrappers.*, inverter_package.*, float_double_conv.*
+ *   src/Mpi/communications.c:34-332, multidev.c   D3-slab halo layer
+ *
+ * Every entry point below keeps the NAME, ARGUMENT ORDER, ARGUMENT MEANING and RETURN
+ * CONVENTION of the reference function cited next to it ("ref:" = path:line under the
+ * OpenStaPLE source tree).  Lattice arrays are passed as plain pointers to the
+ * reference's SoA layouts (struct_c_def.h:16-42):
+ *
+ *   vec3_soa   : complex c0[sizeh], c1[sizeh], c2[sizeh]           (48*sizeh bytes FP64)
+ *   su3_soa    : vec3_soa r0, r1, r2  (r2 stored, never read)      (144*sizeh bytes)
+ *   double_soa : double d[sizeh]
+ *   u[8], backfield[8] : index k = 2*dir + parity ; arrays of vec3_soa are contiguous
+ *   idxh = snum_acc(d0,d1,d2,d3) = (d0 + nd0*(d1 + nd1*(d2 + nd2*d3)))/2      (geometry_multidev.h:219)
+ *
+ * The reference fixes the geometry at compile time (geom_defines.txt -> -DLOC_N0.. macros).
+ * This library takes the same numbers once at run time (staple_init_geometry) so that a
+ * single .so serves every lattice; the struct tags are declared incomplete here, and are
+ * layout-compatible with the reference's complete types of the same name when both headers
+ * are visible.
+ *
+ * Pointer semantics (ref: OpenACC present table, alloc_vars.c:94-144).  An array argument
+ * may be (a) a DEVICE pointer (cudaMalloc / torch tensor) -- used as is; or (b) a HOST
+ * pointer previously made "present" with staple_acc_enter_data()/staple_posix_memalign()
+ * -- translated to its device mirror, which the caller synchronises with
+ * staple_acc_update_device()/staple_acc_update_host() exactly where the reference has
+ * `#pragma acc update device/host`.  Anything else aborts with a message (no CPU fallback).
+ */
+#ifndef STAPLE_B200_H_
+#define STAPLE_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ types (layout = reference) */
+typedef struct vec3_soa_t vec3_soa;         /* ref: OpenAcc/struct_c_def.h:16-20 */
+typedef struct su3_soa_t su3_soa;           /* ref: OpenAcc/struct_c_def.h:35-42 */
+typedef struct double_soa_t double_soa;     /* ref: OpenAcc/struct_c_def.h:25-27 */
+typedef struct vec3_soa_f_t vec3_soa_f;     /* generated sp_struct_c_def.h */
+typedef struct su3_soa_f_t su3_soa_f;
+typedef struct float_soa_t float_soa;
+
+#ifndef MAX_APPROX_ORDER
+#define MAX_APPROX_ORDER 25                 /* ref: RationalApprox/rationalapprox.h:8 */
+#endif
+#ifndef RATIONAL_APPROX_H_
+typedef struct RationalApprox_t {           /* ref: RationalApprox/rationalapprox.h:15-26 */
+	int exponent_num;
+	int exponent_den;
+	int approx_order;
+	double lambda_min;
+	double lambda_max;
+	int gmp_remez_precision;
+	double error;
+	double RA_a0;
+	double RA_a[MAX_APPROX_ORDER];
+	double RA_b[MAX_APPROX_ORDER];
+} RationalApprox;
+#endif
+
+#ifndef FERMION_PARAMETERS_H
+typedef struct ferm_param_t {               /* ref: Include/fermion_parameters.h:9-41 */
+	double ferm_mass;
+	int degeneracy;
+	int number_of_ps;
+	char name[30];
+	double ferm_charge;
+	double ferm_im_chem_pot;
+	int index_of_the_first_ps;
+	int index_of_the_first_shift;
+	double_soa *phases;        /* read by the path */
+	double_soa *mag_re;
+	double_soa *mag_im;
+	int printed_bf_dbg_info;
+	float_soa *phases_f;       /* read by the _f path */
+	RationalApprox approx_fi_mother, approx_md_mother, approx_li_mother;
+	RationalApprox approx_fi, approx_md, approx_li;
+} ferm_param;
+#endif
+
+#ifndef INVERTER_PACKAGE_H_
+typedef struct inverter_package_t {         /* ref: OpenAcc/inverter_package.h:12-29 (passed BY VALUE) */
+	const su3_soa *u;
+	const su3_soa_f *u_f;
+	vec3_soa *ferm_shift_temp;
+	vec3_soa_f *ferm_shift_temp_f;
+	int nshifts;
+	vec3_soa *loc_r, *loc_h, *loc_s, *loc_p;
+	vec3_soa_f *loc_r_f, *loc_h_f, *loc_s_f, *loc_p_f;
+	vec3_soa_f *out_f;
+} inverter_package;
+#endif
+
+#ifndef INVERTER_TRICKS_H_
+typedef struct inv_tricks_t {               /* ref: Include/inverter_tricks.h:4-11 */
+	int singlePInvAccelMultiInv;
+	int useMixedPrecision;
+	double mixedPrecisionDelta;
+	int restartingEvery;
+} inv_tricks;
+extern inv_tricks inverter_tricks;          /* weak in the library; the host's definition wins */
+#endif
+
+/* complex return values: {re, im} pairs, ABI-identical to C99 `double complex` */
+typedef struct { double re, im; } staple_dcomplex;
+
+#ifndef INVERTER_SUCCESS
+#define INVERTER_SUCCESS 1                  /* ref: OpenAcc/inverter_full.h:12-13 */
+#define INVERTER_FAILURE 0
+#endif
+#ifndef CONVERGENCE_CRITICAL
+#define CONVERGENCE_CRITICAL 1              /* ref: OpenAcc/inverter_wrappers.h:11-12 */
+#define CONVERGENCE_NONCRITICAL 0
+#endif
+
+extern int verbosity_lv;                    /* ref: Include/common_defines.h:88 (weak in the library) */
+extern int multishift_invert_iterations;    /* ref: OpenAcc/inverter_wrappers.c:43 */
+
+/* ------------------------------------------------------------------ library set-up (new; replaces compile-time macros) */
+/* ref: geom_defines.txt / configure.ac:70-132 -> LOC_N0..3, NRANKS_D3; geometry_multidev.h:6-12 HALO_WIDTH
+ * (2 for ACTION_TYPE TLSM, 1 for WILSON).  Returns 0 on success.  Selects the CUDA device
+ * `device` (ref: deviceinit.c / main.c:231) ; pass -1 to keep the current device. */
+int staple_init_geometry(int loc_n0, int loc_n1, int loc_n2, int loc_n3, int nranks_d3,
+												 int halo_width, int device);
+void staple_shutdown(void);
+/* geometry queries: sizeh, nd[4], reduction range R0 and update range R1 (fermionic_utilities.c:41,188) */
+long staple_sizeh(void);
+void staple_geometry(int nd[4], long ranges[4]);
+/* Use an existing CUDA stream (e.g. torch's current stream) for all work; NULL = library stream. */
+void staple_set_stream(void *cuda_stream);
+void *staple_get_stream(void);
+void staple_synchronize(void);
+/* number of CUDA kernels launched by this library since start (bench.py "gpu_launches") */
+unsigned long long staple_kernel_launches(void);
+const char *staple_version(void);
+
+/* ------------------------------------------------------------------ memory boundary */
+/* ref: Include/memory_wrapper.c:14-31 posix_memalign_wrapper + alloc_vars.c `#pragma acc enter data create`:
+ * pinned host allocation with a device mirror. */
+int staple_posix_memalign(void **memptr, size_t alignment, size_t size);
+void staple_free(void *memptr);                                   /* ref: memory_wrapper.c:33-57 free_wrapper */
+void staple_acc_enter_data(const void *host, size_t bytes);       /* #pragma acc enter data create(...) */
+void staple_acc_exit_data(const void *host);                      /* #pragma acc exit data delete(...)  */
+void staple_acc_update_device(const void *host, size_t bytes);    /* #pragma acc update device(...)     */
+void staple_acc_update_host(void *host, size_t bytes);            /* #pragma acc update host(...)       */
+void *staple_acc_deviceptr(const void *host);                     /* acc_deviceptr()                    */
+
+/* ------------------------------------------------------------------ rank / halo layer */
+/* ref: Mpi/multidev.c:20-108 pre_init_multidev1D + init_multidev1D.  MPI is replaced by NCCL over
+ * NVLink: rank 0 creates an id (128 bytes) with staple_nccl_unique_id(), the host program
+ * distributes it (MPI_Bcast / torch.distributed.broadcast / file), every rank calls
+ * staple_init_multidev1D().  async_comm_fermion mirrors devinfo.async_comm_fermion. */
+int staple_nccl_unique_id(void *id128);
+int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_comm_fermion);
+void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
+int staple_myrank(void);
+
+void communicate_fermion_borders(vec3_soa *lnh_fermion);          /* ref: Mpi/communications.c:158-167 */
+void communicate_fermion_borders_hostonly(vec3_soa *lnh_fermion); /* ref: :171-182 (same exchange, device resident) */
+void communicate_su3_borders(su3_soa *lnh_conf, int thickness);   /* ref: :306-318 */
+void communicate_su3_borders_hostonly(su3_soa *lnh_conf, int thickness); /* ref: :319-332 */
+void communicate_fermion_borders_f(vec3_soa_f *lnh_fermion);      /* generated Mpi/sp_communications.c */
+void communicate_su3_borders_f(su3_soa_f *lnh_conf, int thickness);
+/* ref: :257-271 / :273-303 take MPI_Request arrays; here the requests are CUDA events owned by the
+ * library: *_async starts the exchange on the comm stream, staple_wait_borders() joins it. */
+void communicate_fermion_borders_async(vec3_soa *lnh_fermion, void *unused_send_req, void *unused_recv_req);
+void communicate_su3_borders_async(su3_soa *lnh_conf, int thickness, void *unused_send_req, void *unused_recv_req);
+void staple_wait_borders(void);
+
+/* ------------------------------------------------------------------ Dirac operator  (ref: OpenAcc/fermion_matrix.h:20-106) */
+#define STAPLE_DSLASH_DECL(name) \
+	void name(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *backfield); \
+	void name##_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *backfield);
+STAPLE_DSLASH_DECL(acc_Deo)          /* ref: fermion_matrix.c:159-212 */
+STAPLE_DSLASH_DECL(acc_Doe)          /* ref: :214-268 */
+STAPLE_DSLASH_DECL(acc_Deo_unsafe)   /* ref: :47-99  */
+STAPLE_DSLASH_DECL(acc_Doe_unsafe)   /* ref: :101-157 */
+STAPLE_DSLASH_DECL(acc_Deo_bulk)     /* ref: :271-325 */
+STAPLE_DSLASH_DECL(acc_Doe_bulk)     /* ref: :327-382 */
+STAPLE_DSLASH_DECL(acc_Deo_d3p)      /* ref: :496-550 */
+STAPLE_DSLASH_DECL(acc_Doe_d3p)      /* ref: :552-607 */
+STAPLE_DSLASH_DECL(acc_Deo_d3m)      /* ref: :609-662 */
+STAPLE_DSLASH_DECL(acc_Doe_d3m)      /* ref: :664-718 */
+void acc_Deo_d3c(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *backfield, int off3, int thick3);   /* ref: :386-439 */
+void acc_Doe_d3c(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *backfield, int off3, int thick3);   /* ref: :441-494 */
+void acc_Deo_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *backfield, int off3, int thick3);
+void acc_Doe_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *backfield, int off3, int thick3);
+
+/* out = (m^2 [+shift]) in - Deo Doe in ; temp1 = odd-site scratch.  ref: fermion_matrix.c:723-746 */
+void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars);
+void fermion_matrix_multiplication_shifted(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars, double shift);
+void fermion_matrix_multiplication_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars);
+void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars, double shift);
+
+/* ------------------------------------------------------------------ BLAS-1  (ref: OpenAcc/fermionic_utilities.h:38-123) */
+#define STAPLE_BLAS_DECL(V, S) \
+	staple_dcomplex scal_prod_global##S(const V *in_vect1, const V *in_vect2);            /* ref: fermionic_utilities.c:85-100,126-146 */ \
+	double real_scal_prod_global##S(const V *in_vect1, const V *in_vect2);                /* ref: :101-110,147-161 */ \
+	double l2norm2_global##S(const V *in_vect1);                                          /* ref: :111-120,162-175 */ \
+	void combine_in1xfactor_plus_in2##S(const V *in_vect1, const double factor, const V *in_vect2, V *out);       /* ref: :180-193 */ \
+	void multiply_fermion_x_doublefactor##S(V *in1, const double factor);                 /* ref: :196-207 */ \
+	void combine_add_factor_x_in2_to_in1##S(V *in1, const V *in2, double factor);         /* ref: :209-220 */ \
+	void combine_in1xferm_mass2_minus_in2_minus_in3##S(const V *in_vect1, double ferm_mass, const V *in_vect2, const V *in_vect3, V *out); /* ref: :225-238 */ \
+	void combine_inside_loop##S(V *vect_out, V *vect_r, const V *vect_s, const V *vect_p, const double omega);   /* ref: :241-259 */ \
+	void combine_in1xferm_mass_minus_in2##S(const V *in_vect1, double ferm_mass2, V *in_vect2);                  /* ref: :261-272 */ \
+	void combine_in1_minus_in2##S(const V *in_vect1, const V *in_vect2, V *out);          /* ref: :274-285 */ \
+	void assign_in_to_out##S(const V *in_vect1, V *out);                                  /* ref: :287-299 */ \
+	void set_vec3_soa_to_zero##S(V *fermion);                                             /* ref: :302-314 */ \
+	void multiple_combine_in1_minus_in2x_factor_back_into_in1##S(V *out, const V *in, const int maxiter, const int *flag, const double *omegas); /* ref: :315-340 */ \
+	void multiple1_combine_in1_x_fact1_plus_in2_x_fact2_back_into_in1##S(V *in1, int maxiter, const int *flag, const double *gammas, const V *in2, const double *zeta_iii); /* ref: :342-378 */ \
+	void combine_in1_x_fact1_minus_in2_back_into_in2##S(const V *in1, double fact1, V *in2);                     /* ref: :379-400 */ \
+	void combine_in1_minus_in2_allxfact##S(const V *in1, const V *in2, double fact, V *out);                     /* ref: :401-415 */ \
+	void calc_new_trialsol_for_inversion_in_force##S(int halfLen, V *inout, int nPrecCalculations);              /* ref: :417-455 */
+STAPLE_BLAS_DECL(vec3_soa, )
+STAPLE_BLAS_DECL(vec3_soa_f, _f)
+
+/* ------------------------------------------------------------------ precision conversion (ref: OpenAcc/float_double_conv.c:9-150) */
+void convert_float_to_double_vec3_soa(const vec3_soa_f *f_var, vec3_soa *d_var);
+void convert_double_to_float_vec3_soa(const vec3_soa *d_var, vec3_soa_f *f_var);
+void convert_float_to_double_su3_soa(const su3_soa_f *f_var, su3_soa *d_var);   /* one su3_soa; call 8x for a conf */
+void convert_double_to_float_su3_soa(const su3_soa *d_var, su3_soa_f *f_var);
+void convert_float_to_double_real_soa(const float_soa *f_var, double_soa *d_var);
+void convert_double_to_float_real_soa(const double_soa *d_var, float_soa *f_var);
+
+/* ------------------------------------------------------------------ solvers */
+/* CG-M for (M^+M + RA_b[i]) out[i] = in.  ref: OpenAcc/inverter_multishift_full.c:23-252 */
+int multishift_invert(const su3_soa *u, ferm_param *pars, RationalApprox *approx, vec3_soa *out,
+											const vec3_soa *in, double residuo, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_s,
+											vec3_soa *loc_p, vec3_soa *shiftferm, const int max_cg, int *cg_return);
+int multishift_invert_f(const su3_soa_f *u, ferm_param *pars, RationalApprox *approx, vec3_soa_f *out,
+												const vec3_soa_f *in, double residuo, vec3_soa_f *loc_r, vec3_soa_f *loc_h,
+												vec3_soa_f *loc_s, vec3_soa_f *loc_p, vec3_soa_f *shiftferm, const int max_cg, int *cg_return);
+/* out = RA_a0 in + sum_i RA_a[i] in_shifted[i].  ref: inverter_multishift_full.c:254-282 */
+void recombine_shifted_vec3_to_vec3(const vec3_soa *in_shifted, const vec3_soa *in, vec3_soa *out, const RationalApprox *approx);
+void recombine_shifted_vec3_to_vec3_f(const vec3_soa_f *in_shifted, const vec3_soa_f *in, vec3_soa_f *out, const RationalApprox *approx);
+/* restarted CG on (M^+M + shift).  ref: OpenAcc/inverter_full.c:19-132 */
+int ker_invert_openacc(const su3_soa *u, ferm_param *pars, vec3_soa *solution, const vec3_soa *in, double res,
+											 vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_s, vec3_soa *loc_p, const int max_cg,
+											 double shift, int *cg_return);
+int ker_invert_openacc_f(const su3_soa_f *u, ferm_param *pars, vec3_soa_f *solution, const vec3_soa_f *in, double res,
+												 vec3_soa_f *loc_r, vec3_soa_f *loc_h, vec3_soa_f *loc_s, vec3_soa_f *loc_p,
+												 const int max_cg, double shift, int *cg_return);
+/* FP32 inner CG with FP64 reliable updates.  ref: OpenAcc/inverter_mixedp.c:24-181 */
+void combine_add_in2_into_in1_mixed_precision(vec3_soa *in1, const vec3_soa_f *in2);
+int inverter_mixed_precision(inverter_package ip, ferm_param *pars, vec3_soa *solution, const vec3_soa *in,
+														 double res, const int max_cg, double shift, int *cg_return);
+/* ref: OpenAcc/inverter_package.c:18-72 */
+void setup_inverter_package_dp(inverter_package *ip, su3_soa *u, vec3_soa *ferm_shift_temp, int nshifts,
+															 vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_s, vec3_soa *loc_p);
+void setup_inverter_package_sp(inverter_package *ip, su3_soa_f *u_f, vec3_soa_f *ferm_shift_temp_f, int nshifts,
+															 vec3_soa_f *loc_r_f, vec3_soa_f *loc_h_f, vec3_soa_f *loc_s_f, vec3_soa_f *loc_p_f,
+															 vec3_soa_f *out_f);
+/* ref: OpenAcc/inverter_wrappers.c:24-159.  The reference's FP32-accelerated branch uses the globals
+ * ferm_shiftmulti_acc_f and aux1_f (alloc_vars); supply them with staple_set_sp_globals(). */
+void convergence_messages(int conv_importance, int inverter_status);
+int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalApprox *approx, vec3_soa *out,
+																const vec3_soa *in, double res, int max_cg, int convergence_importance);
+int inverter_wrapper(inverter_package ip, ferm_param *pars, vec3_soa *out, const vec3_soa *in, double res,
+										 int max_cg, double shift, int convergence_importance);
+void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f);
+
+/* "next" row N1.  ref: OpenAcc/find_min_max.c:21-117 */
+double ker_find_max_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p);
+void find_min_max_eigenvalue_soloopenacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h,
+																				 vec3_soa *loc_p1, vec3_soa *loc_p2, double *minmax);
+
+/* ------------------------------------------------------------------ introspection for benches/tests */
+/* statistics of the last multishift_invert[_f] call: iterations, sum over iterations of active
+ * shifts (for the algorithmic-bytes roofline figure), device time of the loop in ms. */
+void staple_last_solve_stats(int *iterations, long long *active_shift_iterations, double *loop_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAPLE_B200_H_ */

@@ -1,0 +1,445 @@
+// Context, geometry, memory boundary and the D3 rank/halo layer of libstaple_b200.so.
+//   geometry        <- geometry.h:12-29, Mpi/geometry_multidev.h:6-148 (compile-time macros there)
+//   memory boundary <- Include/memory_wrapper.c:14-57 + alloc_vars.c `#pragma acc enter data create`
+//   rank layer      <- Mpi/multidev.c:20-108, Mpi/communications.c:34-332 (MPI there, NCCL/NVLink here)
+#include "staple_internal.cuh"
+#include <dlfcn.h>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+// ---- globals the path reads; weak so that the host program's own definitions win at link time
+extern "C" {
+__attribute__((weak)) int verbosity_lv = 0;                                // common_defines.h:88
+__attribute__((weak)) inv_tricks inverter_tricks = { 0, 0, 0.1, 10000 };   // inverter_tricks.h:4-11
+int multishift_invert_iterations = 0;                                     // inverter_wrappers.c:43
+}
+
+namespace staple {
+
+static Ctx g_ctx;
+Ctx &ctx() { return g_ctx; }
+
+void require_init(const char *fn)
+{
+	if (!g_ctx.inited) {
+		fprintf(stderr, "libstaple_b200: %s called before staple_init_geometry()\n", fn);
+		exit(1);
+	}
+}
+void count_launch(int n) { g_ctx.launches += n; }
+
+// ------------------------------------------------------------------ present table
+struct Entry { size_t bytes; char *dptr; bool owned_host; };
+static std::map<uintptr_t, Entry> g_present;   // keyed by host base address
+static std::mutex g_present_mu;
+// small cache of pointers already classified as device memory
+struct DevRange { uintptr_t p; };
+static uintptr_t g_devcache[64];
+
+void *resolve_raw(const void *p, const char *what)
+{
+	if (p == nullptr) return nullptr;
+	uintptr_t a = (uintptr_t) p;
+	if (!g_present.empty()) {
+		auto it = g_present.upper_bound(a);
+		if (it != g_present.begin()) {
+			--it;
+			if (a < it->first + it->second.bytes) return it->second.dptr + (a - it->first);
+		}
+	}
+	unsigned h = (unsigned) ((a >> 8) * 2654435761u) & 63u;
+	if (g_devcache[h] == a) return const_cast<void *>(p);
+	cudaPointerAttributes at;
+	cudaError_t e = cudaPointerGetAttributes(&at, p);
+	if (e == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+		g_devcache[h] = a;
+		return const_cast<void *>(p);
+	}
+	cudaGetLastError();
+	fprintf(stderr,
+					"libstaple_b200: FATAL: argument '%s' (%p) is not present on the device.\n"
+					"  Pass a device pointer, or make the host array present with staple_posix_memalign()/\n"
+					"  staple_acc_enter_data() (OpenACC `enter data create`).  There is no CPU fallback.\n",
+					what, p);
+	exit(1);
+}
+
+// ------------------------------------------------------------------ NCCL (resolved at run time)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclChar = 0, ncclDouble = 8 };   // nccl.h ncclDataType_t: ncclInt8=0 ... ncclFloat64=8
+enum { ncclSum = 0 };
+
+struct Comm {
+	void *lib = nullptr;
+	ncclComm_t comm = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static Comm *load_nccl()
+{
+	static Comm c;
+	if (c.lib) return &c;
+	// prefer the copy already mapped into the process (torch's bundled libnccl.so.2)
+	const char *names[] = { "libnccl.so.2", "libnccl.so", nullptr };
+	for (int i = 0; names[i] && !c.lib; i++) c.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+	if (!c.lib) {
+		fprintf(stderr, "libstaple_b200: FATAL: cannot load libnccl.so.2 (%s)\n", dlerror());
+		exit(1);
+	}
+#define LOADSYM(field, name)                                                      \
+	*(void **) (&c.field) = dlsym(c.lib, name);                                     \
+	if (!c.field) { fprintf(stderr, "libstaple_b200: FATAL: NCCL symbol %s missing\n", name); exit(1); }
+	LOADSYM(GetUniqueId, "ncclGetUniqueId")
+	LOADSYM(CommInitRank, "ncclCommInitRank")
+	LOADSYM(CommDestroy, "ncclCommDestroy")
+	LOADSYM(Send, "ncclSend")
+	LOADSYM(Recv, "ncclRecv")
+	LOADSYM(AllReduce, "ncclAllReduce")
+	LOADSYM(GroupStart, "ncclGroupStart")
+	LOADSYM(GroupEnd, "ncclGroupEnd")
+	LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+	return &c;
+}
+
+#define STAPLE_NCCL_CHECK(c, x)                                                                       \
+	do {                                                                                                \
+		ncclResult_t r_ = (x);                                                                            \
+		if (r_ != 0) {                                                                                    \
+			fprintf(stderr, "libstaple_b200: NCCL error %s at %s:%d\n", (c)->GetErrorString(r_), __FILE__,  \
+							__LINE__);                                                                              \
+			exit(1);                                                                                        \
+		}                                                                                                 \
+	} while (0)
+
+void allreduce_results(int slot, int ndoubles, cudaStream_t s)
+{
+	Ctx &c = ctx();
+	if (c.nranks <= 1) return;
+	double *p = result(slot);
+	STAPLE_NCCL_CHECK(c.comm, c.comm->AllReduce(p, p, (size_t) ndoubles, ncclDouble, ncclSum, c.comm->comm, s));
+}
+
+// communications.c:34-104: for each of `narrays` arrays (stride_elems apart) send the first interior
+// `thickness` slices to rank L (received there in the top halo) and the last interior slices to rank R
+// (received in the bottom halo).  Offsets follow the reference literally:
+//   offset_size = vol3h*HALO_WIDTH ; slab = vol3h*thickness
+//   send [offset_size, +slab) -> L      recv [sizeh-offset_size, +slab) <- R
+//   send [sizeh-offset_size-slab, +slab) -> R   recv [offset_size-slab, +slab) <- L
+void exchange_slices(void *base, size_t elem_bytes, long stride_elems, int narrays, int thickness,
+										 cudaStream_t s)
+{
+	Ctx &c = ctx();
+	if (c.nranks <= 1) return;
+	const Geom &g = c.g;
+	const size_t slab = (size_t) g.vol3h * thickness * elem_bytes;
+	const size_t off = (size_t) g.vol3h * g.halo_width * elem_bytes;
+	const size_t total = (size_t) g.sizeh * elem_bytes;
+	Comm *n = c.comm;
+	STAPLE_NCCL_CHECK(n, n->GroupStart());
+	for (int a = 0; a < narrays; a++) {
+		char *p = (char *) base + (size_t) a * stride_elems * elem_bytes;
+		STAPLE_NCCL_CHECK(n, n->Send(p + off, slab, ncclChar, c.rank_L, n->comm, s));
+		STAPLE_NCCL_CHECK(n, n->Recv(p + total - off, slab, ncclChar, c.rank_R, n->comm, s));
+		STAPLE_NCCL_CHECK(n, n->Send(p + total - off - slab, slab, ncclChar, c.rank_R, n->comm, s));
+		STAPLE_NCCL_CHECK(n, n->Recv(p + off - slab, slab, ncclChar, c.rank_L, n->comm, s));
+	}
+	STAPLE_NCCL_CHECK(n, n->GroupEnd());
+}
+
+void fetch_results(int slot, int ndoubles, double *host_out)
+{
+	Ctx &c = ctx();
+	allreduce_results(slot, ndoubles, c.stream);
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(c.h_results + 2 * slot, result(slot), sizeof(double) * ndoubles,
+																		cudaMemcpyDeviceToHost, c.stream));
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+	for (int i = 0; i < ndoubles; i++) host_out[i] = c.h_results[2 * slot + i];
+}
+
+}   // namespace staple
+
+using namespace staple;
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *staple_version(void) { return "staple_b200 0.1 (sm_100a)"; }
+
+int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo_width, int device)
+{
+	Ctx &c = ctx();
+	if (n0 < 2 || n1 < 1 || n2 < 1 || n3 < 2 || (n0 & 1) || nranks_d3 < 1 || halo_width < 1 || halo_width > 2) {
+		fprintf(stderr, "libstaple_b200: invalid geometry %dx%dx%dx%d ranks %d halo %d (LOC_N0 must be even)\n",
+						n0, n1, n2, n3, nranks_d3, halo_width);
+		return 1;
+	}
+	if (nranks_d3 > 1 && ((n3 & 1) || (halo_width & 1))) {
+		// the reference flips parities in this case (io.c:595-597); not supported here
+		fprintf(stderr, "libstaple_b200: multi-rank needs even LOC_N3 and even HALO_WIDTH (TLSM)\n");
+		return 1;
+	}
+	if (device >= 0) STAPLE_CUDA_CHECK(cudaSetDevice(device));
+	STAPLE_CUDA_CHECK(cudaGetDevice(&c.device));
+	Geom &g = c.g;
+	g.nranks = nranks_d3; g.halo_width = halo_width;
+	g.d3_halo = nranks_d3 > 1 ? halo_width : 0;
+	g.d3_fhalo = nranks_d3 > 1 ? 1 : 0;
+	g.nd0 = n0; g.nd0h = n0 / 2; g.nd1 = n1; g.nd2 = n2; g.loc_n3 = n3; g.nd3 = n3 + 2 * g.d3_halo;
+	g.vol3h = (long) n0 * n1 * n2 / 2;
+	g.sizeh = g.vol3h * g.nd3;
+	const long loc_sizeh = g.vol3h * n3;
+	g.r0_lo = nranks_d3 > 1 ? (g.sizeh - loc_sizeh) / 2 : 0;
+	g.r0_hi = nranks_d3 > 1 ? (g.sizeh + loc_sizeh) / 2 : g.sizeh;
+	g.r1_lo = g.vol3h * (g.d3_halo - g.d3_fhalo);
+	g.r1_hi = g.sizeh - g.r1_lo;
+	if (!c.own_stream) {
+		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.s_p, cudaStreamNonBlocking));
+		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.s_m, cudaStreamNonBlocking));
+		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.s_comm, cudaStreamNonBlocking));
+		cudaEvent_t *evs[] = { &c.ev_fork, &c.ev_p, &c.ev_m, &c.ev_comm, &c.ev_misc };
+		for (auto e : evs) STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		STAPLE_CUDA_CHECK(cudaMalloc(&c.d_tickets, sizeof(unsigned int) * kResultSlots));
+		STAPLE_CUDA_CHECK(cudaMemset(c.d_tickets, 0, sizeof(unsigned int) * kResultSlots));
+		STAPLE_CUDA_CHECK(cudaMalloc(&c.d_results, sizeof(double) * 2 * kResultSlots));
+		STAPLE_CUDA_CHECK(cudaMemset(c.d_results, 0, sizeof(double) * 2 * kResultSlots));
+		STAPLE_CUDA_CHECK(cudaHostAlloc(&c.h_results, sizeof(double) * 2 * kResultSlots, cudaHostAllocDefault));
+		c.stream = c.own_stream;
+	}
+	{	// one partial per 128-site CTA of the largest fused-reduction launch
+		const long need = g.sizeh / 128 + 4096;
+		if (need > c.max_partials) {
+			if (c.d_partials) STAPLE_CUDA_CHECK(cudaFree(c.d_partials));
+			c.max_partials = need;
+			STAPLE_CUDA_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kResultSlots * 2 * c.max_partials));
+		}
+	}
+	if (nranks_d3 == 1) { c.myrank = 0; c.nranks = 1; c.rank_L = c.rank_R = 0; }
+	c.inited = true;
+	return 0;
+}
+
+void staple_shutdown(void)
+{
+	Ctx &c = ctx();
+	if (!c.inited) return;
+	cudaDeviceSynchronize();
+	c.inited = false;
+}
+
+long staple_sizeh(void) { require_init("staple_sizeh"); return ctx().g.sizeh; }
+
+void staple_geometry(int nd[4], long ranges[4])
+{
+	require_init("staple_geometry");
+	const Geom &g = ctx().g;
+	nd[0] = g.nd0; nd[1] = g.nd1; nd[2] = g.nd2; nd[3] = g.nd3;
+	ranges[0] = g.r0_lo; ranges[1] = g.r0_hi; ranges[2] = g.r1_lo; ranges[3] = g.r1_hi;
+}
+
+void staple_set_stream(void *s)
+{
+	require_init("staple_set_stream");
+	ctx().stream = s ? (cudaStream_t) s : ctx().own_stream;
+}
+void *staple_get_stream(void) { return (void *) ctx().stream; }
+void staple_synchronize(void) { STAPLE_CUDA_CHECK(cudaStreamSynchronize(ctx().stream)); }
+unsigned long long staple_kernel_launches(void) { return ctx().launches; }
+
+// ------------------------------------------------------------------ memory boundary
+void staple_acc_enter_data(const void *host, size_t bytes)
+{
+	std::lock_guard<std::mutex> lk(g_present_mu);
+	uintptr_t a = (uintptr_t) host;
+	auto it = g_present.find(a);
+	if (it != g_present.end()) {
+		if (it->second.bytes >= bytes) return;
+		cudaFree(it->second.dptr);
+		g_present.erase(it);
+	}
+	Entry e; e.bytes = bytes; e.owned_host = false;
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &e.dptr, bytes));
+	g_present[a] = e;
+}
+
+void staple_acc_exit_data(const void *host)
+{
+	std::lock_guard<std::mutex> lk(g_present_mu);
+	auto it = g_present.find((uintptr_t) host);
+	if (it == g_present.end()) return;
+	cudaFree(it->second.dptr);
+	g_present.erase(it);
+}
+
+void *staple_acc_deviceptr(const void *host) { return resolve_raw(host, "staple_acc_deviceptr"); }
+
+void staple_acc_update_device(const void *host, size_t bytes)
+{
+	void *d = resolve_raw(host, "staple_acc_update_device");
+	if (d == host) return;
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx().stream));
+}
+
+void staple_acc_update_host(void *host, size_t bytes)
+{
+	void *d = resolve_raw(host, "staple_acc_update_host");
+	if (d == host) return;
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+}
+
+int staple_posix_memalign(void **memptr, size_t alignment, size_t size)
+{
+	(void) alignment;   // cudaHostAlloc returns page-aligned memory (>= the reference's ALIGN 128)
+	void *h = nullptr;
+	if (cudaHostAlloc(&h, size, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return 12; /* ENOMEM */ }
+	staple_acc_enter_data(h, size);
+	{
+		std::lock_guard<std::mutex> lk(g_present_mu);
+		g_present[(uintptr_t) h].owned_host = true;
+	}
+	*memptr = h;
+	return 0;
+}
+
+void staple_free(void *memptr)
+{
+	if (!memptr) return;
+	bool owned = false;
+	{
+		std::lock_guard<std::mutex> lk(g_present_mu);
+		auto it = g_present.find((uintptr_t) memptr);
+		if (it != g_present.end()) owned = it->second.owned_host;
+	}
+	staple_acc_exit_data(memptr);
+	if (owned) cudaFreeHost(memptr);
+}
+
+// ------------------------------------------------------------------ rank layer
+int staple_nccl_unique_id(void *id128)
+{
+	Comm *n = load_nccl();
+	ncclUniqueId id;
+	STAPLE_NCCL_CHECK(n, n->GetUniqueId(&id));
+	memcpy(id128, &id, sizeof(id));
+	return 0;
+}
+
+int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_comm_fermion)
+{
+	require_init("staple_init_multidev1D");
+	Ctx &c = ctx();
+	if (nranks != c.g.nranks) {
+		// multidev.c:40-44
+		fprintf(stderr, "MPI%02d - NRANKS_D3 is different from nranks: no salamino? Exiting now\n", myrank);
+		fprintf(stderr, "MPI%02d - NRANKS_D3 = %d, nranks = %d\n", myrank, c.g.nranks, nranks);
+		exit(1);
+	}
+	c.myrank = myrank; c.nranks = nranks;
+	c.rank_L = (myrank + (nranks - 1)) % nranks;   // multidev.c:60-61 (SALAMINO ring)
+	c.rank_R = (myrank + 1) % nranks;
+	c.async_comm_fermion = async_comm_fermion;
+	if (nranks > 1) {
+		Comm *n = load_nccl();
+		ncclUniqueId id;
+		memcpy(&id, id128, sizeof(id));
+		STAPLE_NCCL_CHECK(n, n->CommInitRank(&n->comm, nranks, id, myrank));
+		c.comm = n;
+	}
+	return 0;
+}
+
+void shutdown_multidev(void)
+{
+	Ctx &c = ctx();
+	if (c.comm && c.comm->comm) {
+		cudaDeviceSynchronize();
+		c.comm->CommDestroy(c.comm->comm);
+		c.comm->comm = nullptr;
+	}
+	c.comm = nullptr;
+}
+
+int staple_myrank(void) { return ctx().myrank; }
+
+// fermion borders: 3 colour arrays, thickness FERMION_HALO = 1 (communications.c:158-167)
+static void fermion_borders(void *v, size_t elem_bytes, cudaStream_t s)
+{
+	exchange_slices(v, elem_bytes, ctx().g.sizeh, 3, 1, s);
+}
+// gauge borders: 8 link arrays x rows r0,r1 x 3 columns (communications.c:306-318); r2 is not sent
+static void su3_borders(void *u, size_t elem_bytes, int thickness, cudaStream_t s)
+{
+	const long n = ctx().g.sizeh;
+	for (int k = 0; k < 8; k++)
+		exchange_slices((char *) u + (size_t) k * 9 * n * elem_bytes, elem_bytes, n, 6, thickness, s);
+}
+
+void communicate_fermion_borders(vec3_soa *f)
+{
+	require_init("communicate_fermion_borders");
+	fermion_borders(dev(f, "lnh_fermion"), 16, ctx().stream);
+}
+void communicate_fermion_borders_hostonly(vec3_soa *f) { communicate_fermion_borders(f); }
+void communicate_fermion_borders_f(vec3_soa_f *f)
+{
+	require_init("communicate_fermion_borders_f");
+	fermion_borders(dev(f, "lnh_fermion"), 8, ctx().stream);
+}
+void communicate_su3_borders(su3_soa *u, int thickness)
+{
+	require_init("communicate_su3_borders");
+	su3_borders(dev(u, "lnh_conf"), 16, thickness, ctx().stream);
+}
+void communicate_su3_borders_hostonly(su3_soa *u, int thickness) { communicate_su3_borders(u, thickness); }
+void communicate_su3_borders_f(su3_soa_f *u, int thickness)
+{
+	require_init("communicate_su3_borders_f");
+	su3_borders(dev(u, "lnh_conf"), 8, thickness, ctx().stream);
+}
+
+static void fork_comm()
+{
+	Ctx &c = ctx();
+	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_fork, 0));
+}
+void communicate_fermion_borders_async(vec3_soa *f, void *, void *)
+{
+	require_init("communicate_fermion_borders_async");
+	fork_comm();
+	fermion_borders(dev(f, "lnh_fermion"), 16, ctx().s_comm);
+	STAPLE_CUDA_CHECK(cudaEventRecord(ctx().ev_comm, ctx().s_comm));
+}
+void communicate_su3_borders_async(su3_soa *u, int thickness, void *, void *)
+{
+	require_init("communicate_su3_borders_async");
+	fork_comm();
+	su3_borders(dev(u, "lnh_conf"), 16, thickness, ctx().s_comm);
+	STAPLE_CUDA_CHECK(cudaEventRecord(ctx().ev_comm, ctx().s_comm));
+}
+void staple_wait_borders(void)
+{
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(ctx().stream, ctx().ev_comm, 0));
+}
+
+void staple_last_solve_stats(int *iterations, long long *active, double *loop_ms)
+{
+	if (iterations) *iterations = ctx().last_iterations;
+	if (active) *active = ctx().last_active;
+	if (loop_ms) *loop_ms = ctx().last_loop_ms;
+}
+
+}   // extern "C"

@@ -1,0 +1,143 @@
+// Internal declarations shared by the translation units of libstaple_b200.so.
+// The public boundary is include/staple_b200.h; nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include "../../include/staple_b200.h"
+
+#define STAPLE_CUDA_CHECK(x)                                                                     \
+	do {                                                                                           \
+		cudaError_t e_ = (x);                                                                        \
+		if (e_ != cudaSuccess) {                                                                     \
+			fprintf(stderr, "libstaple_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_),   \
+							__FILE__, __LINE__, #x);                                                           \
+			exit(1);                                                                                   \
+		}                                                                                            \
+	} while (0)
+
+namespace staple {
+
+// Run-time copy of the reference's compile-time geometry (geometry.h:12-29, geometry_multidev.h:6-148).
+struct Geom {
+	int nd0h, nd0, nd1, nd2, nd3;   // local+halo box, nd0h = nd0/2
+	int loc_n3;                     // LOC_N3
+	int nranks;                     // NRANKS_D3
+	int halo_width;                 // HALO_WIDTH
+	int d3_halo, d3_fhalo;          // D3_HALO, D3_FERMION_HALO
+	long vol3h;                     // nd0*nd1*nd2/2 : half-sites per d3 slice
+	long sizeh;                     // vol3h*nd3
+	long r0_lo, r0_hi;              // reduction range  (fermionic_utilities.c:41)
+	long r1_lo, r1_hi;              // update range     (fermionic_utilities.c:188)
+};
+
+constexpr int kResultSlots = 16;        // device scalars produced by reductions
+
+struct Comm;   // NCCL state, staple_core.cu
+
+struct Ctx {
+	bool inited = false;
+	Geom g{};
+	int device = 0;
+	cudaStream_t own_stream = nullptr;   // created by the library
+	cudaStream_t stream = nullptr;       // stream all entry points enqueue on
+	cudaStream_t s_p = nullptr, s_m = nullptr, s_comm = nullptr;   // OpenACC queues 2,3 + comm
+	cudaEvent_t ev_fork = nullptr, ev_p = nullptr, ev_m = nullptr, ev_comm = nullptr, ev_misc = nullptr;
+	double *d_partials = nullptr;        // [kResultSlots][2][max_partials] per-block partial sums
+	long max_partials = 0;
+	unsigned int *d_tickets = nullptr;   // [kResultSlots]
+	double *d_results = nullptr;         // [kResultSlots][2]
+	double *h_results = nullptr;         // pinned mirror
+	unsigned long long launches = 0;
+	// rank layer (multidev.h:10-41)
+	int myrank = 0, nranks = 1, rank_L = 0, rank_R = 0, async_comm_fermion = 0;
+	Comm *comm = nullptr;
+	// last multishift statistics
+	int last_iterations = 0;
+	long long last_active = 0;
+	double last_loop_ms = 0;
+};
+
+Ctx &ctx();
+void require_init(const char *fn);
+
+// host->device pointer translation (OpenACC "present" semantics); aborts if not present
+void *resolve_raw(const void *p, const char *what);
+template <typename T>
+inline T *dev(const T *p, const char *what) { return static_cast<T *>(resolve_raw(p, what)); }
+
+inline double *partials(int slot) { return ctx().d_partials + (size_t) slot * 2 * ctx().max_partials; }
+inline unsigned int *ticket(int slot) { return ctx().d_tickets + slot; }
+inline double *result(int slot) { return ctx().d_results + 2 * slot; }
+
+// rank layer
+void allreduce_results(int slot, int ndoubles, cudaStream_t s);   // in-stream sum over ranks of d_results[slot]
+void exchange_slices(void *base, size_t elem_bytes, long stride_elems, int narrays, int thickness,
+										 cudaStream_t s);                              // communications.c:34-104 on device memory
+
+// ---- precision traits -------------------------------------------------------------------
+template <typename T> struct Prec;
+template <> struct Prec<double> { using cplx = double2; };
+template <> struct Prec<float> { using cplx = float2; };
+template <typename T> using cplx_t = typename Prec<T>::cplx;
+
+// operator launch description (fermion_matrix.c:47-157, :271-718)
+template <typename T>
+struct DslashArgs {
+	const cplx_t<T> *u;       // u[8] : k*9*sizeh + (3r+c)*sizeh + idxh
+	cplx_t<T> *out;
+	const cplx_t<T> *in;
+	const T *ph;              // backfield[8] : k*sizeh + idxh
+	const cplx_t<T> *in0;     // epilogue operand (M^+M) or null
+	double m2;                // mass^2 + shift for the fused epilogue
+	double *partials;         // fused Re(in0 . out) reduction (or null)
+	unsigned int *ticket;
+	double *result;
+	unsigned int ticket_target;   // total blocks contributing to this reduction
+	unsigned int partial_offset;  // first partial index of this launch
+	const int *skip;          // device flag: nonzero -> kernel is a no-op (solver overrun)
+	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites)
+	int nd0h, nd1, nd2, nd3;
+	long vol3h, sizeh;
+};
+
+enum Epilogue { EPI_NONE = 0, EPI_MASS = 1, EPI_MASS_DOT = 2 };
+
+// launches on stream s the operator for output parity `par` over d3 in [d3lo, d3hi)
+template <typename T>
+void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
+									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
+									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s);
+unsigned int dslash_blocks(int d3lo, int d3hi);
+
+// full operator with halo handling (acc_Deo/acc_Doe, fermion_matrix.c:159-268); epilogue as above.
+template <typename T>
+void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
+									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip);
+// out = (mass^2+shift) in - Deo Doe in; optionally leaves Re(in.out) (local, not yet all-reduced) in result(dot_slot)
+template <typename T>
+void apply_mdagm(const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, cplx_t<T> *tmp, const T *ph,
+								 double m2, int dot_slot, const int *skip);
+
+// BLAS-1 (device pointers)
+enum BlasOp {
+	OP_IN1XFACTOR_PLUS_IN2, OP_SCALE, OP_ADD_FACTOR_X_IN2, OP_IN1XMASS2_MINUS_IN2_MINUS_IN3,
+	OP_IN1XMASS_MINUS_IN2, OP_IN1_MINUS_IN2, OP_ASSIGN, OP_ZERO, OP_FACT1_MINUS_IN2, OP_IN1_MINUS_IN2_ALLXFACT,
+	OP_INSIDE_LOOP
+};
+template <typename T>
+void blas(BlasOp op, cplx_t<T> *out, const cplx_t<T> *a, const cplx_t<T> *b, const cplx_t<T> *c, double f1,
+					cplx_t<T> *out2 = nullptr);
+enum RedOp { RED_L2NORM2, RED_REAL_DOT, RED_CPLX_DOT };
+// enqueue local reduction into result(slot) (no all-reduce, no host sync)
+template <typename T>
+void reduce_local(RedOp op, const cplx_t<T> *a, const cplx_t<T> *b, int slot);
+// full reduction: local + all-reduce + copy to host + sync; returns {re, im}
+template <typename T>
+staple_dcomplex reduce_global(RedOp op, const cplx_t<T> *a, const cplx_t<T> *b);
+void fetch_results(int slot, int ndoubles, double *host_out);   // all-reduce + D2H + sync
+
+void count_launch(int n = 1);
+
+}   // namespace staple

@@ -1,0 +1,667 @@
+// Hand-written sm_100a kernels of the staggered hot path and their C entry points:
+//   Dirac operator  <- OpenAcc/fermion_matrix.c:47-746 + OpenAcc/matvecmul.h:88-172
+//   BLAS-1          <- OpenAcc/fermionic_utilities.c:32-455
+//   conversions     <- OpenAcc/float_double_conv.c:9-150
+// One thread per output half-lattice site; every SoA stream (6 link entries x 8 links, 8 phases,
+// 3 colours of 8 neighbour spinors) is read with 128-bit (FP64) / 64-bit (FP32) loads that are
+// contiguous across the warp because idxh is the fastest index of every array.
+#include "staple_internal.cuh"
+
+namespace staple {
+
+constexpr int kBlock = 128;      // dslash CTA size
+constexpr int kBlasBlock = 256;
+
+// ------------------------------------------------------------------ small complex helpers
+template <typename T> __device__ __forceinline__ cplx_t<T> mk(T x, T y);
+template <> __device__ __forceinline__ double2 mk<double>(double x, double y) { return make_double2(x, y); }
+template <> __device__ __forceinline__ float2 mk<float>(float x, float y) { return make_float2(x, y); }
+
+// streaming (read-once) loads for links/phases, cached read-only loads for spinors
+template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ V ld_cached(const V *p) { return __ldg(p); }
+
+template <typename C> __device__ __forceinline__ C cmul(C a, C b)   // a*b
+{ C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+template <typename C> __device__ __forceinline__ void cfma(C &acc, C a, C b)   // acc += a*b
+{ acc.x += a.x * b.x; acc.x -= a.y * b.y; acc.y += a.x * b.y; acc.y += a.y * b.x; }
+template <typename C> __device__ __forceinline__ void cfma_ca(C &acc, C a, C b)   // acc += conj(a)*b
+{ acc.x += a.x * b.x; acc.x += a.y * b.y; acc.y += a.x * b.y; acc.y -= a.y * b.x; }
+template <typename C> __device__ __forceinline__ C cross(C a, C b, C c, C d)   // a*b - c*d
+{ C r; r.x = a.x * b.x - a.y * b.y - (c.x * d.x - c.y * d.y); r.y = a.x * b.y + a.y * b.x - (c.x * d.y + c.y * d.x); return r; }
+
+__device__ __forceinline__ void sincos_t(double th, double *s, double *c) { sincos(th, s, c); }
+__device__ __forceinline__ void sincos_t(float th, float *s, float *c) { sincosf(th, s, c); }
+
+// One hop: acc += U(im) e^{i th(im)} v(iv)            (DAG=false, matvecmul.h:88-126)
+//          acc -= U(im)^+ e^{-i th(im)} v(iv)         (DAG=true,  matvecmul.h:129-172)
+// uk -> u[k].r0.c0, phk -> backfield[k].d ; third row rebuilt as conj(r0 x r1).
+template <typename T, bool DAG>
+__device__ __forceinline__ void hop(cplx_t<T> acc[3], const cplx_t<T> *__restrict__ uk, const T *__restrict__ phk,
+																		long im, const cplx_t<T> *__restrict__ in, long iv, long n)
+{
+	using C = cplx_t<T>;
+	const T th = ld_stream(phk + im);
+	const C m00 = ld_stream(uk + im), m01 = ld_stream(uk + n + im), m02 = ld_stream(uk + 2 * n + im);
+	const C m10 = ld_stream(uk + 3 * n + im), m11 = ld_stream(uk + 4 * n + im), m12 = ld_stream(uk + 5 * n + im);
+	const C v0 = ld_cached(in + iv), v1 = ld_cached(in + n + iv), v2 = ld_cached(in + 2 * n + iv);
+	T s, c;
+	sincos_t(th, &s, &c);
+	// x = r0 x r1 (unconjugated); third row of U is conj(x)
+	const C x0 = cross(m01, m12, m02, m11);
+	const C x1 = cross(m02, m10, m00, m12);
+	const C x2 = cross(m00, m11, m01, m10);
+	if (!DAG) {
+		const C p = mk<T>(c, s);
+		const C w0 = cmul(v0, p), w1 = cmul(v1, p), w2 = cmul(v2, p);
+		cfma(acc[0], m00, w0); cfma(acc[0], m01, w1); cfma(acc[0], m02, w2);
+		cfma(acc[1], m10, w0); cfma(acc[1], m11, w1); cfma(acc[1], m12, w2);
+		cfma_ca(acc[2], x0, w0); cfma_ca(acc[2], x1, w1); cfma_ca(acc[2], x2, w2);
+	} else {
+		const C p = mk<T>(-c, s);   // -conj(phase): the backward hops enter with a minus sign
+		const C w0 = cmul(v0, p), w1 = cmul(v1, p), w2 = cmul(v2, p);
+		cfma_ca(acc[0], m00, w0); cfma_ca(acc[0], m10, w1); cfma(acc[0], x0, w2);
+		cfma_ca(acc[1], m01, w0); cfma_ca(acc[1], m11, w1); cfma(acc[1], x1, w2);
+		cfma_ca(acc[2], m02, w0); cfma_ca(acc[2], m12, w1); cfma(acc[2], x2, w2);
+	}
+}
+
+// ------------------------------------------------------------------ deterministic grid reduction
+// Block sums go to partials[index]; the last block to arrive (ticket) adds all of them in a fixed
+// order, so the result does not depend on block scheduling.  NV = number of values (1 or 2).
+template <int NV>
+__device__ __forceinline__ void block_sum(double v[NV], double *sm)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+	}
+	__syncthreads();   // sm may still be in use by a previous call
+	if (lane == 0)
+		for (int k = 0; k < NV; k++) sm[k * 32 + warp] = v[k];
+	__syncthreads();
+	if (warp == 0) {
+#pragma unroll
+		for (int k = 0; k < NV; k++) {
+			double x = lane < nwarp ? sm[k * 32 + lane] : 0.0;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+			v[k] = x;
+		}
+	}
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials, long pstride, unsigned int *ticket,
+																									double *result, unsigned int target, unsigned int index)
+{
+	__shared__ double sm[NV * 32];
+	__shared__ bool last;
+	block_sum<NV>(v, sm);
+	if (threadIdx.x == 0) {
+		for (int k = 0; k < NV; k++) partials[k * pstride + index] = v[k];
+		__threadfence();
+		const unsigned int t = atomicAdd(ticket, 1u);
+		last = (t == target - 1);
+	}
+	__syncthreads();
+	if (last) {
+		__threadfence();
+		double s[NV];
+		for (int k = 0; k < NV; k++) {
+			s[k] = 0.0;
+			for (unsigned int i = threadIdx.x; i < target; i += blockDim.x) s[k] += __ldcg(partials + k * pstride + i);
+		}
+		block_sum<NV>(s, sm);
+		if (threadIdx.x == 0) {
+			for (int k = 0; k < NV; k++) result[k] = s[k];
+			*ticket = 0u;
+		}
+	}
+}
+
+// ------------------------------------------------------------------ Dirac operator kernel
+template <typename T, int PAR, int EPI>
+__global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArgs<T> a)
+{
+	using C = cplx_t<T>;
+	if (a.skip != nullptr && *a.skip != 0) return;
+	const long t = (long) blockIdx.x * kBlock + threadIdx.x;
+	double dot = 0.0;
+	if (t < a.nsites) {
+		const long idx = a.site_lo + t;
+		const long n = a.sizeh;
+		const int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
+		const int hd0 = (int) (idx % nd0h);
+		long q = idx / nd0h;
+		const int d1 = (int) (q % nd1); q /= nd1;
+		const int d2 = (int) (q % nd2);
+		const int d3 = (int) (q / nd2);
+		// d0 = 2*hd0 + rp  (fermion_matrix.c:64, :120)
+		const int rp = (d1 + d2 + d3 + PAR) & 1;
+		const long s1 = nd0h, s2 = (long) nd0h * nd1, s3 = a.vol3h;
+		const long i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
+		const long i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
+		const long i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
+		const long i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
+		const long i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
+		const long i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
+		const long i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
+		const long i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
+
+		C acc[3];
+		acc[0] = mk<T>(0, 0); acc[1] = mk<T>(0, 0); acc[2] = mk<T>(0, 0);
+		const long un = 9 * n;
+		// backward hops: link and phase of the OTHER parity at the neighbour index (:74-77, :130-133)
+		hop<T, true>(acc, a.u + (1 - PAR) * un, a.ph + (1 - PAR) * n, i0m, a.in, i0m, n);
+		hop<T, true>(acc, a.u + (3 - PAR) * un, a.ph + (3 - PAR) * n, i1m, a.in, i1m, n);
+		hop<T, true>(acc, a.u + (5 - PAR) * un, a.ph + (5 - PAR) * n, i2m, a.in, i2m, n);
+		hop<T, true>(acc, a.u + (7 - PAR) * un, a.ph + (7 - PAR) * n, i3m, a.in, i3m, n);
+		// forward hops: link and phase of this parity at the own index (:86-89, :144-147)
+		hop<T, false>(acc, a.u + (0 + PAR) * un, a.ph + (0 + PAR) * n, idx, a.in, i0p, n);
+		hop<T, false>(acc, a.u + (2 + PAR) * un, a.ph + (2 + PAR) * n, idx, a.in, i1p, n);
+		hop<T, false>(acc, a.u + (4 + PAR) * un, a.ph + (4 + PAR) * n, idx, a.in, i2p, n);
+		hop<T, false>(acc, a.u + (6 + PAR) * un, a.ph + (6 + PAR) * n, idx, a.in, i3p, n);
+
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			C o = mk<T>(acc[c].x * (T) 0.5, acc[c].y * (T) 0.5);   // :94-96
+			if (EPI != EPI_NONE) {
+				// fused combine_in1xferm_mass_minus_in2 (fermionic_utilities.c:261-272): double factor
+				const C x = ld_cached(a.in0 + c * n + idx);
+				o = mk<T>((T) ((double) x.x * a.m2 - (double) o.x), (T) ((double) x.y * a.m2 - (double) o.y));
+				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
+			}
+			a.out[c * n + idx] = o;
+		}
+	}
+	if (EPI == EPI_MASS_DOT) {
+		double v[1] = { dot };
+		grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
+	}
+}
+
+unsigned int dslash_blocks(int d3lo, int d3hi)
+{
+	const long nsites = (long) (d3hi - d3lo) * ctx().g.vol3h;
+	return (unsigned int) ((nsites + kBlock - 1) / kBlock);
+}
+
+template <typename T>
+void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
+									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
+									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s)
+{
+	const Geom &g = ctx().g;
+	if (d3hi <= d3lo) return;
+	DslashArgs<T> a;
+	a.u = u; a.out = out; a.in = in; a.ph = ph; a.in0 = in0; a.m2 = m2;
+	a.partials = dot_slot >= 0 ? partials(dot_slot) : nullptr;
+	a.ticket = dot_slot >= 0 ? ticket(dot_slot) : nullptr;
+	a.result = dot_slot >= 0 ? result(dot_slot) : nullptr;
+	a.ticket_target = ticket_target; a.partial_offset = partial_offset; a.skip = skip;
+	a.site_lo = (long) d3lo * g.vol3h; a.nsites = (long) (d3hi - d3lo) * g.vol3h;
+	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;
+	const unsigned int grid = dslash_blocks(d3lo, d3hi);
+#define STAPLE_LAUNCH(P, E) dslash_kernel<T, P, E><<<grid, kBlock, 0, s>>>(a)
+	if (par == 0) {
+		if (epi == EPI_NONE) STAPLE_LAUNCH(0, EPI_NONE);
+		else if (epi == EPI_MASS) STAPLE_LAUNCH(0, EPI_MASS);
+		else STAPLE_LAUNCH(0, EPI_MASS_DOT);
+	} else {
+		if (epi == EPI_NONE) STAPLE_LAUNCH(1, EPI_NONE);
+		else if (epi == EPI_MASS) STAPLE_LAUNCH(1, EPI_MASS);
+		else STAPLE_LAUNCH(1, EPI_MASS_DOT);
+	}
+#undef STAPLE_LAUNCH
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
+}
+
+// acc_Deo / acc_Doe (fermion_matrix.c:159-268): operator on the local interior followed by the exchange
+// of the first/last interior slice of `out` into the neighbours' halos.
+//   single rank      : one launch over all d3
+//   async_comm       : d3p (queue 2), d3m (queue 3), bulk (queue 1) ; halo exchange after the two
+//                      surface slices, overlapped with the bulk; join (:165-183)
+//   otherwise        : one launch, then blocking exchange (:194-205)
+template <typename T>
+void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
+									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip)
+{
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	const int lo = g.d3_halo, hi = g.d3_halo + g.loc_n3;
+	if (c.nranks <= 1) {
+		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, dslash_blocks(lo, hi), 0, skip, c.stream);
+		return;
+	}
+	if (!c.async_comm_fermion) {
+		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, dslash_blocks(lo, hi), 0, skip, c.stream);
+		exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.stream);
+		return;
+	}
+	const unsigned int bs = dslash_blocks(0, 1), bb = dslash_blocks(lo + 1, hi - 1);
+	const unsigned int target = 2 * bs + bb;
+	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_p, c.ev_fork, 0));
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_m, c.ev_fork, 0));
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p);        // d3p
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m);       // d3m
+	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, c.s_p));
+	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, c.s_m));
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo + 1, hi - 1, dot_slot, target, 2 * bs, skip, c.stream);   // bulk
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_p, 0));
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_m, 0));
+	exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.s_comm);
+	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_comm, c.s_comm));
+	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
+}
+
+// fermion_matrix_multiplication[_shifted] (fermion_matrix.c:723-746) with the mass term (and, for the
+// solvers, Re(in . out)) fused into the Deo epilogue.
+template <typename T>
+void apply_mdagm(const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, cplx_t<T> *tmp, const T *ph,
+								 double m2, int dot_slot, const int *skip)
+{
+	apply_dslash<T>(1, EPI_NONE, u, tmp, in, ph, nullptr, 0.0, -1, skip);
+	apply_dslash<T>(0, dot_slot >= 0 ? EPI_MASS_DOT : EPI_MASS, u, out, tmp, ph, in, m2, dot_slot, skip);
+}
+
+template void apply_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,
+																	 const double2 *, double, int, const int *);
+template void apply_dslash<float>(int, int, const float2 *, float2 *, const float2 *, const float *,
+																	const float2 *, double, int, const int *);
+template void apply_mdagm<double>(const double2 *, double2 *, const double2 *, double2 *, const double *,
+																	double, int, const int *);
+template void apply_mdagm<float>(const float2 *, float2 *, const float2 *, float2 *, const float *, double,
+																 int, const int *);
+template void launch_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,
+																		const double2 *, double, int, int, int, unsigned int, unsigned int, const int *,
+																		cudaStream_t);
+template void launch_dslash<float>(int, int, const float2 *, float2 *, const float2 *, const float *,
+																	 const float2 *, double, int, int, int, unsigned int, unsigned int, const int *,
+																	 cudaStream_t);
+
+// ------------------------------------------------------------------ BLAS-1 element-wise kernels
+// All arithmetic in double with double factors, stored back in T: this is what the reference's FP32
+// twin does too (float complex * double promotes; double_to_single_transformer.py leaves
+// fermionic_utilities.c out of filesALLDtoF).  Operands may alias element-wise (the reference calls
+// combine_in1xfactor_plus_in2(p, g, r, p)), hence no __restrict__.
+template <typename T, int OP>
+__global__ void __launch_bounds__(kBlasBlock) blas_kernel(cplx_t<T> *out, const cplx_t<T> *a, const cplx_t<T> *b,
+																													const cplx_t<T> *c, double f1, cplx_t<T> *out2, long lo,
+																													long cnt, long n)
+{
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+#pragma unroll
+	for (int col = 0; col < 3; col++) {
+		const long j = col * n + lo + t;
+		double rx = 0, ry = 0;
+		if (OP == OP_IN1XFACTOR_PLUS_IN2) { rx = a[j].x * f1 + b[j].x; ry = a[j].y * f1 + b[j].y; }
+		else if (OP == OP_SCALE) { rx = f1 * out[j].x; ry = f1 * out[j].y; }
+		else if (OP == OP_ADD_FACTOR_X_IN2) { rx = out[j].x + f1 * a[j].x; ry = out[j].y + f1 * a[j].y; }
+		else if (OP == OP_IN1XMASS2_MINUS_IN2_MINUS_IN3) {
+			rx = a[j].x * f1 - b[j].x - c[j].x; ry = a[j].y * f1 - b[j].y - c[j].y;
+		}
+		else if (OP == OP_IN1XMASS_MINUS_IN2) { rx = a[j].x * f1 - out[j].x; ry = a[j].y * f1 - out[j].y; }
+		else if (OP == OP_IN1_MINUS_IN2) { rx = (double) a[j].x - b[j].x; ry = (double) a[j].y - b[j].y; }
+		else if (OP == OP_ASSIGN) { rx = a[j].x; ry = a[j].y; }
+		else if (OP == OP_ZERO) { rx = 0; ry = 0; }
+		else if (OP == OP_FACT1_MINUS_IN2) { rx = f1 * a[j].x - out[j].x; ry = f1 * a[j].y - out[j].y; }
+		else if (OP == OP_IN1_MINUS_IN2_ALLXFACT) {
+			rx = f1 * ((double) a[j].x - b[j].x); ry = f1 * ((double) a[j].y - b[j].y);
+		}
+		else if (OP == OP_INSIDE_LOOP) {   // out += omega*p ; r -= omega*s  (out2 = r, a = s, b = p)
+			rx = out[j].x + b[j].x * f1; ry = out[j].y + b[j].y * f1;
+			out2[j] = mk<T>((T) (out2[j].x - a[j].x * f1), (T) (out2[j].y - a[j].y * f1));
+		}
+		out[j] = mk<T>((T) rx, (T) ry);
+	}
+}
+
+template <typename T>
+void blas(BlasOp op, cplx_t<T> *out, const cplx_t<T> *a, const cplx_t<T> *b, const cplx_t<T> *c, double f1,
+					cplx_t<T> *out2)
+{
+	Ctx &cx = ctx();
+	const Geom &g = cx.g;
+	long lo = g.r1_lo, cnt = g.r1_hi - g.r1_lo;
+	if (op == OP_ZERO) { lo = 0; cnt = g.sizeh; }   // set_vec3_soa_to_zero covers all sizeh (:309)
+	const unsigned int grid = (unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock);
+#define STAPLE_BLAS(O) case O: blas_kernel<T, O><<<grid, kBlasBlock, 0, cx.stream>>>(out, a, b, c, f1, out2, lo, cnt, g.sizeh); break;
+	switch (op) {
+		STAPLE_BLAS(OP_IN1XFACTOR_PLUS_IN2) STAPLE_BLAS(OP_SCALE) STAPLE_BLAS(OP_ADD_FACTOR_X_IN2)
+		STAPLE_BLAS(OP_IN1XMASS2_MINUS_IN2_MINUS_IN3) STAPLE_BLAS(OP_IN1XMASS_MINUS_IN2) STAPLE_BLAS(OP_IN1_MINUS_IN2)
+		STAPLE_BLAS(OP_ASSIGN) STAPLE_BLAS(OP_ZERO) STAPLE_BLAS(OP_FACT1_MINUS_IN2) STAPLE_BLAS(OP_IN1_MINUS_IN2_ALLXFACT)
+		STAPLE_BLAS(OP_INSIDE_LOOP)
+	}
+#undef STAPLE_BLAS
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
+}
+template void blas<double>(BlasOp, double2 *, const double2 *, const double2 *, const double2 *, double, double2 *);
+template void blas<float>(BlasOp, float2 *, const float2 *, const float2 *, const float2 *, double, float2 *);
+
+// multi-vector updates of the reference API (fermionic_utilities.c:315-378): small host arrays by value
+struct MultiArgs { int flag[MAX_APPROX_ORDER]; double f1[MAX_APPROX_ORDER]; double f2[MAX_APPROX_ORDER]; int maxiter; };
+
+template <typename T, int WHICH>   // 0: out[ia] -= f1*in[ia]   1: in1[ia] = f1*in1[ia] + f2*in2
+__global__ void __launch_bounds__(kBlasBlock) multi_kernel(cplx_t<T> *x, const cplx_t<T> *y, MultiArgs m, long lo,
+																													 long cnt, long n)
+{
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+	for (int col = 0; col < 3; col++) {
+		const long j = col * n + lo + t;
+		cplx_t<T> r2 = mk<T>(0, 0);
+		if (WHICH == 1) r2 = y[j];
+		for (int ia = 0; ia < m.maxiter; ia++) {
+			if (m.flag[ia] != 1) continue;
+			const long k = (long) ia * 3 * n + j;
+			if (WHICH == 0) x[k] = mk<T>((T) (x[k].x - m.f1[ia] * y[k].x), (T) (x[k].y - m.f1[ia] * y[k].y));
+			else x[k] = mk<T>((T) (m.f1[ia] * x[k].x + m.f2[ia] * r2.x), (T) (m.f1[ia] * x[k].y + m.f2[ia] * r2.y));
+		}
+	}
+}
+
+// calc_new_trialsol_for_inversion_in_force (fermionic_utilities.c:417-455)
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) trialsol_kernel(cplx_t<T> *v, int halfLen, int odd, long lo, long cnt, long n)
+{
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+	for (int iv = 0; iv < halfLen; iv++)
+		for (int col = 0; col < 3; col++) {
+			const long a = (long) iv * 3 * n + col * n + lo + t, b = (long) (iv + halfLen) * 3 * n + col * n + lo + t;
+			if (odd) v[b] = mk<T>((T) (2 * v[a].x - v[b].x), (T) (2 * v[a].y - v[b].y));
+			else v[a] = mk<T>((T) (2 * v[b].x - v[a].x), (T) (2 * v[b].y - v[a].y));
+		}
+}
+
+// ------------------------------------------------------------------ reductions (fermionic_utilities.c:32-175)
+template <typename T, int OP>
+__global__ void __launch_bounds__(kBlasBlock) reduce_kernel(const cplx_t<T> *a, const cplx_t<T> *b, long lo, long cnt,
+																														 long n, double *partials, long pstride, unsigned int *ticket,
+																														 double *result)
+{
+	double v[2] = { 0.0, 0.0 };
+	for (long t = (long) blockIdx.x * kBlasBlock + threadIdx.x; t < cnt; t += (long) gridDim.x * kBlasBlock) {
+		const long i = lo + t;
+		double sr = 0, si = 0;
+#pragma unroll
+		for (int col = 0; col < 3; col++) {
+			const cplx_t<T> x = a[col * n + i];
+			if (OP == RED_L2NORM2) sr += (double) x.x * x.x + (double) x.y * x.y;
+			else {
+				const cplx_t<T> y = b[col * n + i];
+				sr += (double) x.x * y.x + (double) x.y * y.y;
+				if (OP == RED_CPLX_DOT) si += (double) x.x * y.y - (double) x.y * y.x;
+			}
+		}
+		v[0] += sr; v[1] += si;
+	}
+	grid_sum_finalize<2>(v, partials, pstride, ticket, result, gridDim.x, blockIdx.x);
+}
+
+template <typename T>
+void reduce_local(RedOp op, const cplx_t<T> *a, const cplx_t<T> *b, int slot)
+{
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	const long lo = g.r0_lo, cnt = g.r0_hi - g.r0_lo;
+	long want = (cnt + kBlasBlock - 1) / kBlasBlock;
+	const unsigned int grid = (unsigned int) (want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+	double *p = partials(slot);
+#define STAPLE_RED(O) reduce_kernel<T, O><<<grid, kBlasBlock, 0, c.stream>>>(a, b, lo, cnt, g.sizeh, p, c.max_partials, ticket(slot), result(slot))
+	if (op == RED_L2NORM2) STAPLE_RED(RED_L2NORM2);
+	else if (op == RED_REAL_DOT) STAPLE_RED(RED_REAL_DOT);
+	else STAPLE_RED(RED_CPLX_DOT);
+#undef STAPLE_RED
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
+}
+template void reduce_local<double>(RedOp, const double2 *, const double2 *, int);
+template void reduce_local<float>(RedOp, const float2 *, const float2 *, int);
+
+template <typename T>
+staple_dcomplex reduce_global(RedOp op, const cplx_t<T> *a, const cplx_t<T> *b)
+{
+	reduce_local<T>(op, a, b, 0);
+	double h[2];
+	fetch_results(0, 2, h);
+	staple_dcomplex r = { h[0], h[1] };
+	return r;
+}
+template staple_dcomplex reduce_global<double>(RedOp, const double2 *, const double2 *);
+template staple_dcomplex reduce_global<float>(RedOp, const float2 *, const float2 *);
+
+// ------------------------------------------------------------------ conversions / recombine
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kBlasBlock) convert_kernel(const TI *in, TO *out, long cnt)
+{
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t < cnt) out[t] = (TO) in[t];
+}
+template <typename TI, typename TO>
+static void convert(const TI *in, TO *out, long cnt)
+{
+	convert_kernel<TI, TO><<<(unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(in, out, cnt);
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
+}
+
+// combine_add_in2_into_in1_mixed_precision (inverter_mixedp.c:24-34)
+__global__ void __launch_bounds__(kBlasBlock) add_mixed_kernel(double2 *x, const float2 *y, long lo, long cnt, long n)
+{
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+	for (int col = 0; col < 3; col++) {
+		const long j = col * n + lo + t;
+		x[j] = make_double2(x[j].x + (double) y[j].x, x[j].y + (double) y[j].y);
+	}
+}
+
+// recombine_shifted_vec3_to_vec3 (inverter_multishift_full.c:254-282): all sizeh, rounding to T after
+// every accumulation step exactly as the reference's in-memory accumulation does.
+struct RecombArgs { double a0; double a[MAX_APPROX_ORDER]; int order; };
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) recombine_kernel(const cplx_t<T> *sh, const cplx_t<T> *in, cplx_t<T> *out,
+																															 RecombArgs r, long n3)
+{
+	const long j = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (j >= n3) return;
+	cplx_t<T> o = mk<T>((T) (in[j].x * r.a0), (T) (in[j].y * r.a0));
+	for (int i = 0; i < r.order; i++) {
+		const cplx_t<T> s = sh[(long) i * n3 + j];
+		o = mk<T>((T) (o.x + r.a[i] * s.x), (T) (o.y + r.a[i] * s.y));
+	}
+	out[j] = o;
+}
+
+}   // namespace staple
+
+using namespace staple;
+
+// ====================================================================== C ABI
+#define DD(p) ((double2 *) dev(p, #p))
+#define DF(p) ((float2 *) dev(p, #p))
+#define CDD(p) ((const double2 *) dev(p, #p))
+#define CDF(p) ((const float2 *) dev(p, #p))
+
+extern "C" {
+
+// ---- operator variants.  `unsafe`: whole local interior, no exchange; bulk/d3p/d3m/d3c: d3 sub-ranges
+#define STAPLE_DSLASH_DEF(NAME, PAR, LO, HI, STREAM, FULL)                                                        \
+	void NAME(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *backfield)                     \
+	{                                                                                                               \
+		require_init(#NAME);                                                                                          \
+		Ctx &c = ctx(); const Geom &g = c.g; (void) g;                                                                \
+		if (FULL) apply_dslash<double>(PAR, EPI_NONE, CDD(u), DD(out), CDD(in), (const double *) dev(backfield, "backfield"), nullptr, 0.0, -1, nullptr); \
+		else launch_dslash<double>(PAR, EPI_NONE, CDD(u), DD(out), CDD(in), (const double *) dev(backfield, "backfield"), nullptr, 0.0, LO, HI, -1, 0, 0, nullptr, STREAM); \
+	}                                                                                                               \
+	void NAME##_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *backfield)            \
+	{                                                                                                               \
+		require_init(#NAME "_f");                                                                                     \
+		Ctx &c = ctx(); const Geom &g = c.g; (void) g;                                                                \
+		if (FULL) apply_dslash<float>(PAR, EPI_NONE, CDF(u), DF(out), CDF(in), (const float *) dev(backfield, "backfield"), nullptr, 0.0, -1, nullptr); \
+		else launch_dslash<float>(PAR, EPI_NONE, CDF(u), DF(out), CDF(in), (const float *) dev(backfield, "backfield"), nullptr, 0.0, LO, HI, -1, 0, 0, nullptr, STREAM); \
+	}
+STAPLE_DSLASH_DEF(acc_Deo, 0, 0, 0, c.stream, true)
+STAPLE_DSLASH_DEF(acc_Doe, 1, 0, 0, c.stream, true)
+STAPLE_DSLASH_DEF(acc_Deo_unsafe, 0, g.d3_halo, g.d3_halo + g.loc_n3, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Doe_unsafe, 1, g.d3_halo, g.d3_halo + g.loc_n3, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Deo_bulk, 0, g.d3_halo + 1, g.d3_halo + 1 + g.loc_n3 - 2, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Doe_bulk, 1, g.d3_halo + 1, g.d3_halo + 1 + g.loc_n3 - 2, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Deo_d3p, 0, g.nd3 - g.d3_halo - 1, g.nd3 - g.d3_halo, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Doe_d3p, 1, g.nd3 - g.d3_halo - 1, g.nd3 - g.d3_halo, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Deo_d3m, 0, g.d3_halo, g.d3_halo + 1, c.stream, false)
+STAPLE_DSLASH_DEF(acc_Doe_d3m, 1, g.d3_halo, g.d3_halo + 1, c.stream, false)
+
+void acc_Deo_d3c(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *bf, int off3, int thick3)
+{
+	require_init("acc_Deo_d3c");
+	launch_dslash<double>(0, EPI_NONE, CDD(u), DD(out), CDD(in), (const double *) dev(bf, "backfield"), nullptr, 0.0, off3, off3 + thick3, -1, 0, 0, nullptr, ctx().stream);
+}
+void acc_Doe_d3c(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *bf, int off3, int thick3)
+{
+	require_init("acc_Doe_d3c");
+	launch_dslash<double>(1, EPI_NONE, CDD(u), DD(out), CDD(in), (const double *) dev(bf, "backfield"), nullptr, 0.0, off3, off3 + thick3, -1, 0, 0, nullptr, ctx().stream);
+}
+void acc_Deo_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *bf, int off3, int thick3)
+{
+	require_init("acc_Deo_d3c_f");
+	launch_dslash<float>(0, EPI_NONE, CDF(u), DF(out), CDF(in), (const float *) dev(bf, "backfield"), nullptr, 0.0, off3, off3 + thick3, -1, 0, 0, nullptr, ctx().stream);
+}
+void acc_Doe_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *bf, int off3, int thick3)
+{
+	require_init("acc_Doe_d3c_f");
+	launch_dslash<float>(1, EPI_NONE, CDF(u), DF(out), CDF(in), (const float *) dev(bf, "backfield"), nullptr, 0.0, off3, off3 + thick3, -1, 0, 0, nullptr, ctx().stream);
+}
+
+void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars)
+{
+	require_init("fermion_matrix_multiplication");
+	apply_mdagm<double>(CDD(u), DD(out), CDD(in), DD(temp1), (const double *) dev(pars->phases, "pars->phases"),
+											pars->ferm_mass * pars->ferm_mass, -1, nullptr);
+}
+void fermion_matrix_multiplication_shifted(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1,
+																					 ferm_param *pars, double shift)
+{
+	require_init("fermion_matrix_multiplication_shifted");
+	apply_mdagm<double>(CDD(u), DD(out), CDD(in), DD(temp1), (const double *) dev(pars->phases, "pars->phases"),
+											pars->ferm_mass * pars->ferm_mass + shift, -1, nullptr);
+}
+void fermion_matrix_multiplication_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars)
+{
+	require_init("fermion_matrix_multiplication_f");
+	apply_mdagm<float>(CDF(u), DF(out), CDF(in), DF(temp1), (const float *) dev(pars->phases_f, "pars->phases_f"),
+										 pars->ferm_mass * pars->ferm_mass, -1, nullptr);
+}
+void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1,
+																						 ferm_param *pars, double shift)
+{
+	require_init("fermion_matrix_multiplication_shifted_f");
+	apply_mdagm<float>(CDF(u), DF(out), CDF(in), DF(temp1), (const float *) dev(pars->phases_f, "pars->phases_f"),
+										 pars->ferm_mass * pars->ferm_mass + shift, -1, nullptr);
+}
+
+// ---- BLAS-1
+#define STAPLE_BLAS_DEF(V, S, T, D, CD)                                                                              \
+	staple_dcomplex scal_prod_global##S(const V *a, const V *b) { require_init("scal_prod_global"); return reduce_global<T>(RED_CPLX_DOT, CD(a), CD(b)); } \
+	double real_scal_prod_global##S(const V *a, const V *b) { require_init("real_scal_prod_global"); return reduce_global<T>(RED_REAL_DOT, CD(a), CD(b)).re; } \
+	double l2norm2_global##S(const V *a) { require_init("l2norm2_global"); return reduce_global<T>(RED_L2NORM2, CD(a), nullptr).re; } \
+	void combine_in1xfactor_plus_in2##S(const V *in_vect1, const double factor, const V *in_vect2, V *out)             \
+	{ require_init("combine_in1xfactor_plus_in2"); blas<T>(OP_IN1XFACTOR_PLUS_IN2, D(out), CD(in_vect1), CD(in_vect2), nullptr, factor); } \
+	void multiply_fermion_x_doublefactor##S(V *in1, const double factor)                                               \
+	{ require_init("multiply_fermion_x_doublefactor"); blas<T>(OP_SCALE, D(in1), nullptr, nullptr, nullptr, factor); } \
+	void combine_add_factor_x_in2_to_in1##S(V *in1, const V *in2, double factor)                                       \
+	{ require_init("combine_add_factor_x_in2_to_in1"); blas<T>(OP_ADD_FACTOR_X_IN2, D(in1), CD(in2), nullptr, nullptr, factor); } \
+	void combine_in1xferm_mass2_minus_in2_minus_in3##S(const V *in_vect1, double ferm_mass, const V *in_vect2, const V *in_vect3, V *out) \
+	{ require_init("combine_in1xferm_mass2_minus_in2_minus_in3"); blas<T>(OP_IN1XMASS2_MINUS_IN2_MINUS_IN3, D(out), CD(in_vect1), CD(in_vect2), CD(in_vect3), ferm_mass); } \
+	void combine_inside_loop##S(V *vect_out, V *vect_r, const V *vect_s, const V *vect_p, const double omega)          \
+	{ require_init("combine_inside_loop"); blas<T>(OP_INSIDE_LOOP, D(vect_out), CD(vect_s), CD(vect_p), nullptr, omega, D(vect_r)); } \
+	void combine_in1xferm_mass_minus_in2##S(const V *in_vect1, double ferm_mass2, V *in_vect2)                         \
+	{ require_init("combine_in1xferm_mass_minus_in2"); blas<T>(OP_IN1XMASS_MINUS_IN2, D(in_vect2), CD(in_vect1), nullptr, nullptr, ferm_mass2); } \
+	void combine_in1_minus_in2##S(const V *in_vect1, const V *in_vect2, V *out)                                        \
+	{ require_init("combine_in1_minus_in2"); blas<T>(OP_IN1_MINUS_IN2, D(out), CD(in_vect1), CD(in_vect2), nullptr, 0.0); } \
+	void assign_in_to_out##S(const V *in_vect1, V *out)                                                                \
+	{ require_init("assign_in_to_out"); blas<T>(OP_ASSIGN, D(out), CD(in_vect1), nullptr, nullptr, 0.0); }            \
+	void set_vec3_soa_to_zero##S(V *fermion)                                                                           \
+	{ require_init("set_vec3_soa_to_zero"); blas<T>(OP_ZERO, D(fermion), nullptr, nullptr, nullptr, 0.0); }           \
+	void combine_in1_x_fact1_minus_in2_back_into_in2##S(const V *in1, double fact1, V *in2)                            \
+	{ require_init("combine_in1_x_fact1_minus_in2_back_into_in2"); blas<T>(OP_FACT1_MINUS_IN2, D(in2), CD(in1), nullptr, nullptr, fact1); } \
+	void combine_in1_minus_in2_allxfact##S(const V *in1, const V *in2, double fact, V *out)                            \
+	{ require_init("combine_in1_minus_in2_allxfact"); blas<T>(OP_IN1_MINUS_IN2_ALLXFACT, D(out), CD(in1), CD(in2), nullptr, fact); } \
+	void multiple_combine_in1_minus_in2x_factor_back_into_in1##S(V *out, const V *in, const int maxiter, const int *flag, const double *omegas) \
+	{                                                                                                                  \
+		require_init("multiple_combine_in1_minus_in2x_factor_back_into_in1");                                           \
+		const Geom &g = ctx().g; MultiArgs m; m.maxiter = maxiter;                                                      \
+		for (int i = 0; i < maxiter; i++) { m.flag[i] = flag[i]; m.f1[i] = omegas[i]; m.f2[i] = 0; }                    \
+		const long cnt = g.r1_hi - g.r1_lo;                                                                             \
+		multi_kernel<T, 0><<<(unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(D(out), CD(in), m, g.r1_lo, cnt, g.sizeh); \
+		STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();                                                          \
+	}                                                                                                                  \
+	void multiple1_combine_in1_x_fact1_plus_in2_x_fact2_back_into_in1##S(V *in1, int maxiter, const int *flag, const double *gammas, const V *in2, const double *zeta_iii) \
+	{                                                                                                                  \
+		require_init("multiple1_combine_in1_x_fact1_plus_in2_x_fact2_back_into_in1");                                   \
+		const Geom &g = ctx().g; MultiArgs m; m.maxiter = maxiter;                                                      \
+		for (int i = 0; i < maxiter; i++) { m.flag[i] = flag[i]; m.f1[i] = gammas[i]; m.f2[i] = zeta_iii[i]; }          \
+		const long cnt = g.r1_hi - g.r1_lo;                                                                             \
+		multi_kernel<T, 1><<<(unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(D(in1), CD(in2), m, g.r1_lo, cnt, g.sizeh); \
+		STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();                                                          \
+	}                                                                                                                  \
+	void calc_new_trialsol_for_inversion_in_force##S(int halfLen, V *inout, int nPrecCalculations)                     \
+	{                                                                                                                  \
+		require_init("calc_new_trialsol_for_inversion_in_force");                                                       \
+		const Geom &g = ctx().g; const long cnt = g.r1_hi - g.r1_lo;                                                    \
+		trialsol_kernel<T><<<(unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(D(inout), halfLen, nPrecCalculations % 2, g.r1_lo, cnt, g.sizeh); \
+		STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();                                                          \
+	}
+STAPLE_BLAS_DEF(vec3_soa, , double, DD, CDD)
+STAPLE_BLAS_DEF(vec3_soa_f, _f, float, DF, CDF)
+
+// ---- conversions (over all sizeh; su3: rows r0,r1,r2 of ONE su3_soa)
+void convert_float_to_double_vec3_soa(const vec3_soa_f *f, vec3_soa *d)
+{ require_init("convert_float_to_double_vec3_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 6 * ctx().g.sizeh); }
+void convert_double_to_float_vec3_soa(const vec3_soa *d, vec3_soa_f *f)
+{ require_init("convert_double_to_float_vec3_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 6 * ctx().g.sizeh); }
+void convert_float_to_double_su3_soa(const su3_soa_f *f, su3_soa *d)
+{ require_init("convert_float_to_double_su3_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 18 * ctx().g.sizeh); }
+void convert_double_to_float_su3_soa(const su3_soa *d, su3_soa_f *f)
+{ require_init("convert_double_to_float_su3_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 18 * ctx().g.sizeh); }
+void convert_float_to_double_real_soa(const float_soa *f, double_soa *d)
+{ require_init("convert_float_to_double_real_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), ctx().g.sizeh); }
+void convert_double_to_float_real_soa(const double_soa *d, float_soa *f)
+{ require_init("convert_double_to_float_real_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), ctx().g.sizeh); }
+
+void combine_add_in2_into_in1_mixed_precision(vec3_soa *in1, const vec3_soa_f *in2)
+{
+	require_init("combine_add_in2_into_in1_mixed_precision");
+	const Geom &g = ctx().g; const long cnt = g.r1_hi - g.r1_lo;
+	add_mixed_kernel<<<(unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(DD(in1), CDF(in2), g.r1_lo, cnt, g.sizeh);
+	STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();
+}
+
+void recombine_shifted_vec3_to_vec3(const vec3_soa *in_shifted, const vec3_soa *in, vec3_soa *out, const RationalApprox *approx)
+{
+	require_init("recombine_shifted_vec3_to_vec3");
+	RecombArgs r; r.a0 = approx->RA_a0; r.order = approx->approx_order;
+	for (int i = 0; i < r.order; i++) r.a[i] = approx->RA_a[i];
+	const long n3 = 3 * ctx().g.sizeh;
+	recombine_kernel<double><<<(unsigned int) ((n3 + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(CDD(in_shifted), CDD(in), DD(out), r, n3);
+	STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();
+}
+void recombine_shifted_vec3_to_vec3_f(const vec3_soa_f *in_shifted, const vec3_soa_f *in, vec3_soa_f *out, const RationalApprox *approx)
+{
+	require_init("recombine_shifted_vec3_to_vec3_f");
+	RecombArgs r; r.a0 = approx->RA_a0; r.order = approx->approx_order;
+	for (int i = 0; i < r.order; i++) r.a[i] = approx->RA_a[i];
+	const long n3 = 3 * ctx().g.sizeh;
+	recombine_kernel<float><<<(unsigned int) ((n3 + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, ctx().stream>>>(CDF(in_shifted), CDF(in), DF(out), r, n3);
+	STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();
+}
+
+}   // extern "C"

@@ -1,0 +1,657 @@
+// Solvers of the staggered hot path:
+//   multishift_invert[_f]        <- OpenAcc/inverter_multishift_full.c:23-252   (CG-M)
+//   ker_invert_openacc[_f]       <- OpenAcc/inverter_full.c:19-132              (restarted CG)
+//   inverter_mixed_precision     <- OpenAcc/inverter_mixedp.c:41-181
+//   wrappers / package           <- OpenAcc/inverter_wrappers.c:24-159, inverter_package.c:18-72
+//   power iteration              <- OpenAcc/find_min_max.c:21-117
+//
+// CG-M keeps ALL scalar recurrences (alpha, omega, zeta_i, gamma_i, convergence flags) in device
+// memory: the reduction kernels leave their sums in device slots, one-warp kernels advance the
+// recurrences, and the vector kernels read the coefficients from that control block.  The host only
+// enqueues iterations and polls a `done` flag every few iterations, so there is no host round trip
+// inside an iteration (the reference has >= 4 per iteration).  Kernels launched after convergence see
+// `done` and return immediately; the iteration count is the device-side counter, so it is exact.
+#include "staple_internal.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace staple {
+
+constexpr int kBlasBlock = 256;
+constexpr double kSafetyMargin = 0.95;   // inverter_multishift_full.c:18, inverter_full.c:17
+
+struct CgmCtl {
+	double alpha, delta, lambda, omega, omega_save, gammag, source_norm, residuo;
+	double zeta_i[MAX_APPROX_ORDER], zeta_ii[MAX_APPROX_ORDER], zeta_iii[MAX_APPROX_ORDER];
+	double omegas[MAX_APPROX_ORDER], gammas[MAX_APPROX_ORDER], shifts[MAX_APPROX_ORDER];
+	int flag[MAX_APPROX_ORDER];    // current flags (inverter_multishift_full.c:58)
+	int uflag[MAX_APPROX_ORDER];   // flags as they were when this iteration's updates were issued
+	int order, maxiter, umaxiter, cg, max_cg;
+	int done;        // set when maxiter==0 or cg==max_cg: later Dslash/update kernels are no-ops
+	int stop_u2;     // set one "iteration" later: silences the trailing shifted-vector update too
+	long long active_sum;
+};
+
+template <typename T> __device__ __forceinline__ cplx_t<T> mkc(double x, double y);
+template <> __device__ __forceinline__ double2 mkc<double>(double x, double y) { return make_double2(x, y); }
+template <> __device__ __forceinline__ float2 mkc<float>(double x, double y) { return make_float2((float) x, (float) y); }
+
+// setup (:65-104): delta=(r,r), source_norm=(in,in) arrive in result slots
+__global__ void cgm_init_kernel(CgmCtl *c, const double *delta_slot, const double *srcnorm_slot)
+{
+	if (threadIdx.x != 0) return;
+	c->delta = *delta_slot; c->source_norm = *srcnorm_slot;
+	c->omega = 1.0; c->gammag = 0.0; c->alpha = 0.0; c->lambda = 0.0; c->omega_save = 1.0;
+	for (int i = 0; i < c->order; i++) {
+		c->flag[i] = 1; c->uflag[i] = 1; c->zeta_i[i] = 1.0; c->zeta_ii[i] = 1.0; c->zeta_iii[i] = 1.0;
+		c->gammas[i] = 0.0; c->omegas[i] = 0.0;
+	}
+	c->maxiter = c->order; c->umaxiter = c->order; c->cg = 0; c->done = 0; c->stop_u2 = 0; c->active_sum = 0;
+}
+
+// after alpha = Re(p, s) (:122-137)
+__global__ void cgm_after_alpha_kernel(CgmCtl *c, const double *alpha_slot)
+{
+	if (c->done) { if (threadIdx.x == 0) c->stop_u2 = 1; return; }
+	const int i = threadIdx.x;
+	const double alpha = *alpha_slot;
+	const double omega_save = c->omega, delta = c->delta, gammag = c->gammag;
+	const int maxiter = c->maxiter, cg = c->cg;
+	const double omega = -delta / alpha;
+	if (i < maxiter && c->flag[i] == 1) {
+		const double zi = c->zeta_i[i], zii = c->zeta_ii[i];
+		const double ziii = (zi * zii * omega_save) /
+			(omega * gammag * (zi - zii) + zi * omega_save * (1.0 - c->shifts[i] * omega));
+		c->zeta_iii[i] = ziii;
+		c->omegas[i] = omega * ziii / zii;
+	}
+	__syncwarp();
+	if (i == 0) { c->alpha = alpha; c->omega_save = omega_save; c->omega = omega; c->cg = cg + 1; }
+}
+
+// after lambda = (r, r) (:143-171): gammas, convergence flags, zeta rotation, delta <- lambda
+__global__ void cgm_after_lambda_kernel(CgmCtl *c, const double *lambda_slot)
+{
+	if (c->done) return;
+	const int i = threadIdx.x;
+	const double lambda = *lambda_slot;
+	const double delta = c->delta, omega = c->omega, source_norm = c->source_norm, residuo = c->residuo;
+	const int order = c->order, old_maxiter = c->maxiter, cg = c->cg, max_cg = c->max_cg;
+	const double gammag = lambda / delta;
+	int active = 0, was = 0;
+	if (i < order) {
+		was = c->flag[i];
+		c->uflag[i] = was;
+		if (was == 1) {
+			const double zii = c->zeta_ii[i], ziii = c->zeta_iii[i];
+			c->gammas[i] = gammag * ziii * c->omegas[i] / (zii * omega);
+			const double fact = sqrt(delta * zii * zii / source_norm);
+			if (fact < residuo * kSafetyMargin) c->flag[i] = 0;
+			else active = 1;
+			c->zeta_i[i] = zii;
+			c->zeta_ii[i] = ziii;
+		}
+	}
+	const unsigned int wasm = __ballot_sync(0xffffffffu, was == 1);
+	const unsigned int act = __ballot_sync(0xffffffffu, active);
+	if (i == 0) {
+		c->umaxiter = old_maxiter;
+		const int maxiter = act ? 32 - __clz(act) : 0;   // highest still-active shift + 1
+		c->maxiter = maxiter;
+		c->lambda = lambda; c->gammag = gammag; c->delta = lambda;
+		c->active_sum += __popc(wasm);
+		if (maxiter == 0 || cg >= max_cg) c->done = 1;
+	}
+}
+
+// out_i -= omega_i ps_i (active i) ; r += omega s ; lambda partial = |r|^2 over the reduction range
+// (:139-142; multiple_combine_in1_minus_in2x_factor_back_into_in1 + combine_add_factor_x_in2_to_in1 + l2norm2)
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) cgm_update1_kernel(const CgmCtl *c, cplx_t<T> *out, const cplx_t<T> *ps,
+																																cplx_t<T> *r, const cplx_t<T> *s, long lo, long cnt, long n,
+																																long r0_lo, long r0_hi, double *partials,
+																																unsigned int *ticket, double *result);
+// p = r + gammag p ; ps_i = gamma_i ps_i + zeta_i^+ r  (:147-157)
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) cgm_update2_kernel(const CgmCtl *c, cplx_t<T> *ps, cplx_t<T> *p,
+																																const cplx_t<T> *r, long lo, long cnt, long n);
+
+__device__ __forceinline__ void block_sum1(double &v, double *sm)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if (lane == 0) sm[warp] = v;
+	__syncthreads();
+	if (warp == 0) {
+		double x = lane < nwarp ? sm[lane] : 0.0;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		v = x;
+	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) cgm_update1_kernel(const CgmCtl *c, cplx_t<T> *out, const cplx_t<T> *ps,
+																																cplx_t<T> *r, const cplx_t<T> *s, long lo, long cnt, long n,
+																																long r0_lo, long r0_hi, double *partials,
+																																unsigned int *ticket, double *result)
+{
+	if (c->done) return;
+	__shared__ double sm[32];
+	__shared__ bool last;
+	__shared__ double s_om[MAX_APPROX_ORDER];
+	__shared__ int s_fl[MAX_APPROX_ORDER];
+	const int maxiter = c->maxiter;
+	if (threadIdx.x < maxiter) { s_om[threadIdx.x] = c->omegas[threadIdx.x]; s_fl[threadIdx.x] = c->flag[threadIdx.x]; }
+	const double omega = c->omega;
+	__syncthreads();
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	double nrm = 0.0;
+	if (t < cnt) {
+		const long i = lo + t;
+#pragma unroll
+		for (int col = 0; col < 3; col++) {
+			const long j = col * n + i;
+			const cplx_t<T> rv = r[j], sv = s[j];
+			const cplx_t<T> rn = mkc<T>(rv.x + omega * sv.x, rv.y + omega * sv.y);
+			r[j] = rn;
+			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
+		}
+		for (int ia = 0; ia < maxiter; ia++) {
+			if (s_fl[ia] != 1) continue;
+			const double f = s_om[ia];
+			const long base = (long) ia * 3 * n;
+#pragma unroll
+			for (int col = 0; col < 3; col++) {
+				const long k = base + col * n + i;
+				const cplx_t<T> o = out[k], q = ps[k];
+				out[k] = mkc<T>(o.x - f * q.x, o.y - f * q.y);
+			}
+		}
+	}
+	block_sum1(nrm, sm);
+	if (threadIdx.x == 0) {
+		partials[blockIdx.x] = nrm;
+		__threadfence();
+		last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (last) {
+		__threadfence();
+		double acc = 0.0;
+		for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) acc += __ldcg(partials + k);
+		block_sum1(acc, sm);
+		if (threadIdx.x == 0) { result[0] = acc; *ticket = 0u; }
+	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) cgm_update2_kernel(const CgmCtl *c, cplx_t<T> *ps, cplx_t<T> *p,
+																																const cplx_t<T> *r, long lo, long cnt, long n)
+{
+	if (c->stop_u2) return;
+	__shared__ double s_g[MAX_APPROX_ORDER], s_z[MAX_APPROX_ORDER];
+	__shared__ int s_fl[MAX_APPROX_ORDER];
+	const int maxiter = c->umaxiter;
+	if (threadIdx.x < maxiter) {
+		s_g[threadIdx.x] = c->gammas[threadIdx.x]; s_z[threadIdx.x] = c->zeta_iii[threadIdx.x];
+		s_fl[threadIdx.x] = c->uflag[threadIdx.x];
+	}
+	const double gammag = c->gammag;
+	__syncthreads();
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+	const long i = lo + t;
+	cplx_t<T> rv[3];
+#pragma unroll
+	for (int col = 0; col < 3; col++) {
+		const long j = col * n + i;
+		rv[col] = r[j];
+		const cplx_t<T> pv = p[j];
+		p[j] = mkc<T>(pv.x * gammag + rv[col].x, pv.y * gammag + rv[col].y);
+	}
+	for (int ia = 0; ia < maxiter; ia++) {
+		if (s_fl[ia] != 1) continue;
+		const double g = s_g[ia], z = s_z[ia];
+		const long base = (long) ia * 3 * n;
+#pragma unroll
+		for (int col = 0; col < 3; col++) {
+			const long k = base + col * n + i;
+			const cplx_t<T> q = ps[k];
+			ps[k] = mkc<T>(g * q.x + z * rv[col].x, g * q.y + z * rv[col].y);
+		}
+	}
+}
+
+// ps_i = in for all i (the order assign_in_to_out calls of :89-95 in one pass)
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) broadcast_kernel(cplx_t<T> *dst, const cplx_t<T> *src, int order, long lo,
+																															 long cnt, long n)
+{
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+	for (int col = 0; col < 3; col++) {
+		const cplx_t<T> v = src[col * n + lo + t];
+		for (int ia = 0; ia < order; ia++) dst[(long) ia * 3 * n + col * n + lo + t] = v;
+	}
+}
+
+static CgmCtl *g_d_ctl = nullptr;
+static CgmCtl *g_h_ctl = nullptr;   // pinned, 2 snapshots
+static cudaEvent_t g_ev_snap[2] = { nullptr, nullptr }, g_ev_t0 = nullptr, g_ev_t1 = nullptr;
+
+static void ensure_ctl()
+{
+	if (g_d_ctl) return;
+	STAPLE_CUDA_CHECK(cudaMalloc(&g_d_ctl, sizeof(CgmCtl)));
+	STAPLE_CUDA_CHECK(cudaHostAlloc(&g_h_ctl, 2 * sizeof(CgmCtl), cudaHostAllocDefault));
+	for (int i = 0; i < 2; i++) STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_snap[i], cudaEventDisableTiming));
+	STAPLE_CUDA_CHECK(cudaEventCreate(&g_ev_t0));
+	STAPLE_CUDA_CHECK(cudaEventCreate(&g_ev_t1));
+}
+
+template <typename T> struct PhasesOf;
+template <> struct PhasesOf<double> { static const double *get(ferm_param *p) { return (const double *) dev(p->phases, "pars->phases"); } };
+template <> struct PhasesOf<float> { static const float *get(ferm_param *p) { return (const float *) dev(p->phases_f, "pars->phases_f"); } };
+
+enum { SLOT_TMP = 0, SLOT_DELTA = 1, SLOT_SRC = 2, SLOT_ALPHA = 3, SLOT_LAMBDA = 4 };
+
+template <typename T>
+static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox *approx, cplx_t<T> *out,
+													 const cplx_t<T> *in, double residuo, cplx_t<T> *loc_r, cplx_t<T> *loc_h, cplx_t<T> *loc_s,
+													 cplx_t<T> *loc_p, cplx_t<T> *shiftferm, const int max_cg, int *cg_return)
+{
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	ensure_ctl();
+	const int order = approx->approx_order;
+	if (order > MAX_APPROX_ORDER || order < 1) { fprintf(stderr, "multishift_invert: bad approx_order %d\n", order); exit(1); }
+	if (verbosity_lv > 3) printf("%s PRECISION VERSION OF MULTISHIFT INVERTER\n", sizeof(T) == 8 ? "DOUBLE" : "SINGLE");
+	const T *ph = PhasesOf<T>::get(pars);
+	const double m2 = pars->ferm_mass * pars->ferm_mass;
+	const long n = g.sizeh, lo = g.r1_lo, cnt = g.r1_hi - g.r1_lo;
+	const unsigned int grid = (unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock);
+	cudaStream_t st = c.stream;
+
+	// trial solution out = 0 (all sizeh, :67-70); r = p = in; delta = (r,r); source_norm = (in,in)
+	STAPLE_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(cplx_t<T>) * 3 * n * order, st));
+	blas<T>(OP_ASSIGN, loc_r, in, nullptr, nullptr, 0.0);
+	blas<T>(OP_ASSIGN, loc_p, loc_r, nullptr, nullptr, 0.0);
+	reduce_local<T>(RED_L2NORM2, loc_r, nullptr, SLOT_DELTA);
+	allreduce_results(SLOT_DELTA, 1, st);
+	reduce_local<T>(RED_L2NORM2, in, nullptr, SLOT_SRC);
+	allreduce_results(SLOT_SRC, 1, st);
+	broadcast_kernel<T><<<grid, kBlasBlock, 0, st>>>(shiftferm, in, order, lo, cnt, n);
+	count_launch();
+	CgmCtl *h = g_h_ctl;
+	memset(h, 0, sizeof(CgmCtl));
+	h->order = order; h->max_cg = max_cg; h->residuo = residuo;
+	for (int i = 0; i < order; i++) h->shifts[i] = approx->RA_b[i];
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(g_d_ctl, h, sizeof(CgmCtl), cudaMemcpyHostToDevice, st));
+	cgm_init_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_DELTA), result(SLOT_SRC));
+	count_launch();
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));   // h is reused for snapshots below
+
+	if (verbosity_lv > 0 && 0 == c.myrank) printf("STARTING CG-M:\n");
+	STAPLE_CUDA_CHECK(cudaEventRecord(g_ev_t0, st));
+	const int batch = 8;
+	int issued = 0, snap = 0, pending[2] = { 0, 0 };
+	bool finished = false;
+	while (!finished) {
+		for (int b = 0; b < batch; b++) {
+			// s = (M^+M) p, alpha = Re(p,s) fused in the Deo epilogue (:113-118)
+			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done);
+			allreduce_results(SLOT_ALPHA, 1, st);
+			cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA));
+			cgm_update1_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
+																												 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
+																												 result(SLOT_LAMBDA));
+			allreduce_results(SLOT_LAMBDA, 1, st);
+			cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA));
+			cgm_update2_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, shiftferm, loc_p, loc_r, lo, cnt, n);
+			count_launch(4);
+		}
+		issued += batch;
+		STAPLE_CUDA_CHECK(cudaGetLastError());
+		STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_ctl[snap], g_d_ctl, sizeof(CgmCtl), cudaMemcpyDeviceToHost, st));
+		STAPLE_CUDA_CHECK(cudaEventRecord(g_ev_snap[snap], st));
+		pending[snap] = 1;
+		const int other = snap ^ 1;
+		// look at the previous batch's snapshot while this one runs
+		if (pending[other]) {
+			STAPLE_CUDA_CHECK(cudaEventSynchronize(g_ev_snap[other]));
+			pending[other] = 0;
+			if (g_h_ctl[other].done) finished = true;
+		}
+		if (!finished && issued >= max_cg) {
+			STAPLE_CUDA_CHECK(cudaEventSynchronize(g_ev_snap[snap]));
+			pending[snap] = 0;
+			finished = true;   // max_cg reached: the device sets done itself at cg == max_cg
+		}
+		snap = other;
+	}
+	STAPLE_CUDA_CHECK(cudaEventRecord(g_ev_t1, st));
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_ctl[0], g_d_ctl, sizeof(CgmCtl), cudaMemcpyDeviceToHost, st));
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+	const int cg = g_h_ctl[0].cg;
+	const double source_norm = g_h_ctl[0].source_norm;
+	float ms = 0;
+	cudaEventElapsedTime(&ms, g_ev_t0, g_ev_t1);
+	c.last_iterations = cg; c.last_active = g_h_ctl[0].active_sum; c.last_loop_ms = ms;
+	multishift_invert_iterations += cg;
+
+	if (cg == max_cg && 0 == c.myrank) printf("WARNING: maximum number of iterations reached in invert\n");
+	if (verbosity_lv > 0 && 0 == c.myrank)
+		printf("Terminated multishift_invert ( target res = %1.1e,source_norm = %1.1e )\tCG count %d\n", residuo,
+					 source_norm, cg);
+
+	// post-loop verification of every shifted system (:211-229)
+	int check = 1;
+	if (verbosity_lv > 2 && 0 == c.myrank) printf("Relative Res:");
+	for (int i = 0; i < order; i++) {
+		blas<T>(OP_ASSIGN, loc_p, out + (long) i * 3 * n, nullptr, nullptr, 0.0);
+		apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2 + approx->RA_b[i], -1, nullptr);
+		blas<T>(OP_IN1_MINUS_IN2, loc_h, in, loc_s, nullptr, 0.0);
+		const double giustoono = reduce_global<T>(RED_L2NORM2, loc_h, nullptr).re / source_norm;
+		check *= (giustoono <= 1) ? 1 : 0;
+		if (verbosity_lv > 2 && 0 == c.myrank && residuo != 0) printf("\t%1.1e", sqrt(giustoono) / residuo);
+	}
+	if (verbosity_lv > 2 && 0 == c.myrank) printf("\n");
+	if (verbosity_lv > 0 && 0 == c.myrank)
+		printf("Inverter Multishift timings:\nTiming Loops    : %f / %d (%f per iteration)\n", ms * 1e-3, cg, ms * 1e-3 / (cg > 0 ? cg : 1));
+	*cg_return = cg;
+	return check == 1 ? INVERTER_SUCCESS : INVERTER_FAILURE;
+}
+
+// restarted CG (inverter_full.c:19-132).  Scalars are read back once per iteration here (two
+// reductions); the multishift solver above is the device-resident one.
+template <typename T>
+static int cg_impl(const cplx_t<T> *u, ferm_param *pars, cplx_t<T> *solution, const cplx_t<T> *in, double res,
+									 cplx_t<T> *loc_r, cplx_t<T> *loc_h, cplx_t<T> *loc_s, cplx_t<T> *loc_p, const int max_cg,
+									 double shift, int *cg_return)
+{
+	Ctx &c = ctx();
+	const T *ph = PhasesOf<T>::get(pars);
+	const double m2 = pars->ferm_mass * pars->ferm_mass + shift;
+	int cg = 0;
+	double delta, alpha, lambda = 0, omega, gammag;
+	const double source_norm = reduce_global<T>(RED_L2NORM2, in, nullptr).re;
+	do {
+		apply_mdagm<T>(u, loc_s, solution, loc_h, ph, m2, -1, nullptr);
+		blas<T>(OP_IN1_MINUS_IN2, loc_r, in, loc_s, nullptr, 0.0);
+		blas<T>(OP_ASSIGN, loc_p, loc_r, nullptr, nullptr, 0.0);
+		delta = reduce_global<T>(RED_L2NORM2, loc_r, nullptr).re;
+		if (verbosity_lv > 3 && 0 == c.myrank) printf("STARTING CG:\nCG\tR\n");
+		int cg_restarted = 0;
+		do {
+			cg++; cg_restarted++;
+			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, nullptr);
+			fetch_results(SLOT_ALPHA, 1, &alpha);
+			omega = delta / alpha;
+			blas<T>(OP_IN1XFACTOR_PLUS_IN2, solution, loc_p, solution, nullptr, omega);
+			blas<T>(OP_IN1XFACTOR_PLUS_IN2, loc_r, loc_s, loc_r, nullptr, -omega);
+			lambda = reduce_global<T>(RED_L2NORM2, loc_r, nullptr).re;
+			gammag = lambda / delta;
+			delta = lambda;
+			blas<T>(OP_IN1XFACTOR_PLUS_IN2, loc_p, loc_p, loc_r, nullptr, gammag);
+			if (verbosity_lv > 3 && cg % 100 == 0 && 0 == c.myrank) printf("%d\t%1.1e\n", cg, sqrt(lambda / source_norm) / res);
+		} while ((sqrt(lambda / source_norm) > res * kSafetyMargin) && cg_restarted < inverter_tricks.restartingEvery);
+	} while ((sqrt(lambda / source_norm) > res) && cg < max_cg);
+
+	apply_mdagm<T>(u, loc_s, solution, loc_h, ph, m2, -1, nullptr);
+	blas<T>(OP_IN1_MINUS_IN2, loc_h, in, loc_s, nullptr, 0.0);
+	const double current_res = reduce_global<T>(RED_L2NORM2, loc_h, nullptr).re / source_norm;
+	if (verbosity_lv > 1 && 0 == c.myrank) {
+		printf("Terminated invert after   %d    iterations", cg);
+		printf("[res/stop_res=  %e , stop_res=%e ]\n", sqrt(current_res) / res, res);
+	}
+	if (cg == max_cg && 0 == c.myrank) printf("WARNING: maximum number of iterations reached in invert\n");
+	*cg_return = cg;
+	return sqrt(current_res) <= res ? INVERTER_SUCCESS : INVERTER_FAILURE;
+}
+
+}   // namespace staple
+
+using namespace staple;
+
+#define DD(p) ((double2 *) dev(p, #p))
+#define DF(p) ((float2 *) dev(p, #p))
+#define CDD(p) ((const double2 *) dev(p, #p))
+#define CDF(p) ((const float2 *) dev(p, #p))
+
+static vec3_soa_f *g_aux1_f = nullptr, *g_ferm_shiftmulti_acc_f = nullptr;   // alloc_vars globals
+
+extern "C" {
+
+int multishift_invert(const su3_soa *u, ferm_param *pars, RationalApprox *approx, vec3_soa *out, const vec3_soa *in,
+											double residuo, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_s, vec3_soa *loc_p,
+											vec3_soa *shiftferm, const int max_cg, int *cg_return)
+{
+	require_init("multishift_invert");
+	return multishift_impl<double>(CDD(u), pars, approx, DD(out), CDD(in), residuo, DD(loc_r), DD(loc_h), DD(loc_s),
+																 DD(loc_p), DD(shiftferm), max_cg, cg_return);
+}
+int multishift_invert_f(const su3_soa_f *u, ferm_param *pars, RationalApprox *approx, vec3_soa_f *out,
+												const vec3_soa_f *in, double residuo, vec3_soa_f *loc_r, vec3_soa_f *loc_h, vec3_soa_f *loc_s,
+												vec3_soa_f *loc_p, vec3_soa_f *shiftferm, const int max_cg, int *cg_return)
+{
+	require_init("multishift_invert_f");
+	return multishift_impl<float>(CDF(u), pars, approx, DF(out), CDF(in), residuo, DF(loc_r), DF(loc_h), DF(loc_s),
+																DF(loc_p), DF(shiftferm), max_cg, cg_return);
+}
+
+int ker_invert_openacc(const su3_soa *u, ferm_param *pars, vec3_soa *solution, const vec3_soa *in, double res,
+											 vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_s, vec3_soa *loc_p, const int max_cg, double shift,
+											 int *cg_return)
+{
+	require_init("ker_invert_openacc");
+	return cg_impl<double>(CDD(u), pars, DD(solution), CDD(in), res, DD(loc_r), DD(loc_h), DD(loc_s), DD(loc_p), max_cg,
+												 shift, cg_return);
+}
+int ker_invert_openacc_f(const su3_soa_f *u, ferm_param *pars, vec3_soa_f *solution, const vec3_soa_f *in, double res,
+												 vec3_soa_f *loc_r, vec3_soa_f *loc_h, vec3_soa_f *loc_s, vec3_soa_f *loc_p, const int max_cg,
+												 double shift, int *cg_return)
+{
+	require_init("ker_invert_openacc_f");
+	return cg_impl<float>(CDF(u), pars, DF(solution), CDF(in), res, DF(loc_r), DF(loc_h), DF(loc_s), DF(loc_p), max_cg,
+												shift, cg_return);
+}
+
+// inverter_mixedp.c:41-181 -- FP32 CG with FP64 "magic touch" reliable updates, SAFETY_MARGIN 0.9
+int inverter_mixed_precision(inverter_package ip, ferm_param *pars, vec3_soa *solution_h, const vec3_soa *in_h, double res,
+														 const int max_cg, double shift, int *cg_return)
+{
+	require_init("inverter_mixed_precision");
+	Ctx &c = ctx();
+	const double2 *u = CDD(ip.u); const float2 *u_f = CDF(ip.u_f);
+	double2 *solution = DD(solution_h); const double2 *in = CDD(in_h);
+	double2 *d_r = DD(ip.loc_r), *d_h = DD(ip.loc_h), *d_s = DD(ip.loc_s);
+	float2 *loc_r = DF(ip.loc_r_f), *loc_h = DF(ip.loc_h_f), *loc_s = DF(ip.loc_s_f), *loc_p = DF(ip.loc_p_f), *out = DF(ip.out_f);
+	const double *ph = (const double *) dev(pars->phases, "pars->phases");
+	const float *ph_f = (const float *) dev(pars->phases_f, "pars->phases_f");
+	const double m2 = pars->ferm_mass * pars->ferm_mass + shift;
+	const long n = c.g.sizeh;
+	int cg = 0, magicTouchCount = 0;
+	double delta, alpha, lambda, omega, gammag, lastMaxResNorm = 0;
+	const double source_norm = reduce_global<double>(RED_L2NORM2, in, nullptr).re;
+
+	apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, nullptr);
+	blas<double>(OP_IN1_MINUS_IN2, d_r, in, d_s, nullptr, 0.0);
+	convert_double_to_float_vec3_soa((const vec3_soa *) d_r, (vec3_soa_f *) loc_r);
+	blas<float>(OP_ASSIGN, loc_p, loc_r, nullptr, nullptr, 0.0);
+	delta = reduce_global<float>(RED_L2NORM2, loc_r, nullptr).re;
+	blas<float>(OP_ZERO, out, nullptr, nullptr, nullptr, 0.0);
+	if (verbosity_lv > 3 && 0 == c.myrank) printf("STARTING CG:\nCG\tR - mixed precision\n");
+	do {
+		cg++;
+		apply_mdagm<float>(u_f, loc_s, loc_p, loc_h, ph_f, m2, SLOT_ALPHA, nullptr);
+		fetch_results(SLOT_ALPHA, 1, &alpha);
+		omega = delta / alpha;
+		blas<float>(OP_IN1XFACTOR_PLUS_IN2, out, loc_p, out, nullptr, omega);
+		if (lastMaxResNorm < delta) lastMaxResNorm = delta;
+		if (delta < inverter_tricks.mixedPrecisionDelta * lastMaxResNorm) {
+			combine_add_in2_into_in1_mixed_precision((vec3_soa *) solution, (const vec3_soa_f *) out);
+			apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, nullptr);
+			blas<double>(OP_IN1_MINUS_IN2, d_r, in, d_s, nullptr, 0.0);
+			convert_double_to_float_vec3_soa((const vec3_soa *) d_r, (vec3_soa_f *) loc_r);
+			blas<float>(OP_ZERO, out, nullptr, nullptr, nullptr, 0.0);
+			lastMaxResNorm = 0;
+			magicTouchCount++;
+		} else blas<float>(OP_IN1XFACTOR_PLUS_IN2, loc_r, loc_s, loc_r, nullptr, -omega);
+		lambda = reduce_global<float>(RED_L2NORM2, loc_r, nullptr).re;
+		gammag = lambda / delta;
+		delta = lambda;
+		blas<float>(OP_IN1XFACTOR_PLUS_IN2, loc_p, loc_p, loc_r, nullptr, gammag);
+	} while ((sqrt(lambda / source_norm) > res * 0.9) && cg < max_cg);
+	combine_add_in2_into_in1_mixed_precision((vec3_soa *) solution, (const vec3_soa_f *) out);
+
+	apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, nullptr);
+	blas<double>(OP_IN1_MINUS_IN2, d_h, in, d_s, nullptr, 0.0);
+	const double giustoono = reduce_global<double>(RED_L2NORM2, d_h, nullptr).re / source_norm;
+	if (verbosity_lv > 1 && 0 == c.myrank) {
+		printf("Terminated invert after   %d    iterations", cg);
+		printf("[res/stop_res=  %e , stop_res=%e ] (%d magic touches)\n", sqrt(giustoono) / res, res, magicTouchCount);
+	}
+	if (cg == max_cg && 0 == c.myrank) printf("WARNING: maximum number of iterations reached in invert\n");
+	(void) n;
+	*cg_return = cg;
+	return sqrt(giustoono) <= res ? INVERTER_SUCCESS : INVERTER_FAILURE;
+}
+
+// inverter_package.c:18-72 (including the aliasing check)
+static void check_aliases(void **p, int nptrs)
+{
+	for (int i = 0; i < nptrs; i++)
+		for (int j = i + 1; j < nptrs; j++)
+			if (p[i] == p[j] && 0 != p[i]) {
+				printf("BAD SETUP OF INVERTER PACKAGE! (%s:%d)\n", __FILE__, __LINE__);
+				printf("Pointer %p used twice (%d == %d).\n", p[i], i, j);
+				exit(1);
+			}
+}
+void setup_inverter_package_dp(inverter_package *ip, su3_soa *u, vec3_soa *ferm_shift_temp, int nshifts, vec3_soa *loc_r,
+															 vec3_soa *loc_h, vec3_soa *loc_s, vec3_soa *loc_p)
+{
+	ip->u = u; ip->ferm_shift_temp = ferm_shift_temp; ip->nshifts = nshifts;
+	ip->loc_r = loc_r; ip->loc_h = loc_h; ip->loc_s = loc_s; ip->loc_p = loc_p;
+	void *all[] = { loc_r, loc_h, loc_s, loc_p, ferm_shift_temp };
+	check_aliases(all, 5);
+}
+void setup_inverter_package_sp(inverter_package *ip, su3_soa_f *u_f, vec3_soa_f *ferm_shift_temp_f, int nshifts,
+															 vec3_soa_f *loc_r_f, vec3_soa_f *loc_h_f, vec3_soa_f *loc_s_f, vec3_soa_f *loc_p_f,
+															 vec3_soa_f *out_f)
+{
+	ip->u_f = u_f; ip->ferm_shift_temp_f = ferm_shift_temp_f; ip->nshifts = nshifts;
+	ip->loc_r_f = loc_r_f; ip->loc_h_f = loc_h_f; ip->loc_s_f = loc_s_f; ip->loc_p_f = loc_p_f; ip->out_f = out_f;
+	void *all[] = { loc_r_f, loc_h_f, loc_s_f, loc_p_f, ferm_shift_temp_f, out_f };
+	check_aliases(all, 6);
+}
+
+// inverter_wrappers.c:24-39
+void convergence_messages(int conv_importance, int inverter_status)
+{
+	if (INVERTER_FAILURE == inverter_status) {
+		if (CONVERGENCE_CRITICAL == conv_importance) {
+			if (0 == ctx().myrank)
+				printf("\n\n\t\tERROR : inverter failed to converge in a critical region of the code. Exiting now!!\n\n");
+			exit(1);
+		}
+		if (0 == ctx().myrank) printf("\n\t\tWARNING : inverter failed to converge.\n");
+	}
+}
+
+void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f)
+{
+	g_aux1_f = aux1_f; g_ferm_shiftmulti_acc_f = ferm_shiftmulti_acc_f;
+}
+
+// inverter_wrappers.c:117-159
+int inverter_wrapper(inverter_package ip, ferm_param *pars, vec3_soa *out, const vec3_soa *in, double res, int max_cg,
+										 double shift, int convergence_importance)
+{
+	int total_iterations = 0, cg_return = 0, temp_conv_check;
+	if (inverter_tricks.useMixedPrecision)
+		temp_conv_check = inverter_mixed_precision(ip, pars, out, in, res, max_cg, shift, &cg_return);
+	else
+		temp_conv_check = ker_invert_openacc(ip.u, pars, out, in, res, ip.loc_r, ip.loc_h, ip.loc_s, ip.loc_p, max_cg, shift,
+																				 &cg_return);
+	convergence_messages(convergence_importance, temp_conv_check);
+	total_iterations += cg_return;
+	return total_iterations;
+}
+
+// inverter_wrappers.c:45-115
+int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalApprox *approx, vec3_soa *out,
+																const vec3_soa *in, double res, int max_cg, int convergence_importance)
+{
+	require_init("inverter_multishift_wrapper");
+	int total_iterations = 0, cg_return = 0, temp_conv_check;
+	if (inverter_tricks.singlePInvAccelMultiInv) {
+		if (!g_aux1_f || !g_ferm_shiftmulti_acc_f) {
+			fprintf(stderr, "inverter_multishift_wrapper: singlePInvAccelMultiInv needs staple_set_sp_globals(aux1_f, ferm_shiftmulti_acc_f)\n");
+			exit(1);
+		}
+		convert_double_to_float_vec3_soa(in, g_aux1_f);
+		float singlePMultiInvTargetRes = 8e-7f * sqrtf((float) ctx().g.sizeh);
+		if (singlePMultiInvTargetRes < res) singlePMultiInvTargetRes = res;
+		if (0 == ctx().myrank && verbosity_lv > 3)
+			printf("Multishift inverter, single precision, target res %e\n", singlePMultiInvTargetRes);
+		temp_conv_check = multishift_invert_f(ip.u_f, pars, approx, g_ferm_shiftmulti_acc_f, g_aux1_f, singlePMultiInvTargetRes,
+																					ip.loc_r_f, ip.loc_h_f, ip.loc_s_f, ip.loc_p_f, ip.ferm_shift_temp_f, max_cg,
+																					&cg_return);
+		convergence_messages(convergence_importance, temp_conv_check);
+		total_iterations += cg_return;
+		const size_t vbytes_f = sizeof(float2) * 3 * ctx().g.sizeh, vbytes_d = sizeof(double2) * 3 * ctx().g.sizeh;
+		for (int ishift = 0; ishift < approx->approx_order; ishift++) {
+			const double bshift = approx->RA_b[ishift];
+			if (verbosity_lv > 0) printf("Shift %d, %f\n", ishift, bshift);
+			vec3_soa_f *src = (vec3_soa_f *) ((char *) g_ferm_shiftmulti_acc_f + ishift * vbytes_f);
+			vec3_soa *dst = (vec3_soa *) ((char *) out + ishift * vbytes_d);
+			convert_float_to_double_vec3_soa(src, dst);
+			// the reference adds the stale cg_return here (inverter_wrappers.c:91-95); the wrapper's own
+			// return value is the meaningful count, so that is what is accumulated
+			total_iterations += inverter_wrapper(ip, pars, dst, in, res, max_cg, bshift, convergence_importance);
+		}
+	} else {
+		if (0 == ctx().myrank && verbosity_lv > 3) printf("Multishift inverter, DOUBLE precision, target res %e\n", res);
+		temp_conv_check = multishift_invert(ip.u, pars, approx, out, in, res, ip.loc_r, ip.loc_h, ip.loc_s, ip.loc_p,
+																				ip.ferm_shift_temp, max_cg, &cg_return);
+		convergence_messages(convergence_importance, temp_conv_check);
+		total_iterations += cg_return;
+	}
+	return total_iterations;
+}
+
+// find_min_max.c:21-60
+double ker_find_max_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p)
+{
+	require_init("ker_find_max_eigenvalue_openacc");
+	int loop_count = 0;
+	double norm, inorm, old_norm;
+	norm = sqrt(l2norm2_global(loc_p));
+	do {
+		inorm = 1.0 / norm;
+		multiply_fermion_x_doublefactor(loc_p, inorm);
+		assign_in_to_out(loc_p, loc_r);
+		old_norm = norm;
+		fermion_matrix_multiplication(u, loc_p, loc_r, loc_h, pars);
+		norm = sqrt(l2norm2_global(loc_p));
+		old_norm = fabs(old_norm - norm);
+		old_norm /= norm;
+		loop_count++;
+	} while (old_norm > 1.0e-5);
+	return norm;
+}
+
+// find_min_max.c:100-117
+void find_min_max_eigenvalue_soloopenacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p1,
+																				 vec3_soa *loc_p2, double *minmax)
+{
+	(void) loc_p2;
+	minmax[0] = pars->ferm_mass * pars->ferm_mass;
+	minmax[1] = ker_find_max_eigenvalue_openacc(u, pars, loc_r, loc_h, loc_p1);
+}
+
+}   // extern "C"

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_r1():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ref_4x4x4x4_r1.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_r2():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ref_4x4x4x4_r2.npz")))
+
+
+def relerr(a, b):
+    """max |a-b| / max |b| -- the relative error used for every parity statement."""
+    a = np.asarray(a); b = np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

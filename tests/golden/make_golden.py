@@ -1,0 +1,102 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (gcc build of
+/root/reference, oracle/build_ref.sh) on seeded inputs.  Run in the dev container only:
+
+    python tests/golden/make_golden.py
+
+The fixtures pin the CPU restatement (oracle/staggered_oracle.c) and the CUDA path on the GPU
+box, where /root/reference does not exist.  Inputs are stored too, so nothing depends on the
+numpy RNG stream.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+from oracle.pyoracle import RefLib, gaussian_vec, ptr, random_su3_conf  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EB = (5.0, -5.0, 1.0, -5.0, 5.0, 3.0)      # tools/test background field: ex ey ez bx by bz
+MU, CHARGE = 1.0, 2.0                       # MuOverPiT 1, charge 2 (tools/test/fermion_parameters.set)
+MASS = 0.0507
+SHIFTS = np.array([2.0e-4, 3.0e-3, 4.0e-2, 0.5, 3.0])
+RA_A = np.array([0.11, 0.23, 0.37, 0.41, 0.53]); RA_A0 = 0.7
+
+
+def single_rank(n=(4, 4, 4, 4)):
+    R = RefLib(*n)
+    S = R.sizeh
+    d = {}
+    u = random_su3_conf(S, 11); v = gaussian_vec(S, 12); w = gaussian_vec(S, 13)
+    uf = u.astype(np.complex64); vf = v.astype(np.complex64); wf = w.astype(np.complex64)
+    d.update(u=u, v=v, w=w, mass=MASS, shifts=SHIFTS, ra_a=RA_A, ra_a0=RA_A0, eb=np.array(EB), mu=MU, charge=CHARGE,
+             loc_n=np.array(n))
+    for tag, args in (("p0", ((0,) * 6, 0.0, 0.0)), ("bf", (EB, MU, CHARGE))):
+        ph = R.phases(*args); phf = R.phases_f(*args)
+        d["ph_" + tag] = ph; d["phf_" + tag] = phf
+        d["deo_" + tag] = R.dslash("acc_Deo", u, v, ph)
+        d["doe_" + tag] = R.dslash("acc_Doe", u, v, ph)
+        d["mdagm_" + tag] = R.mdagm(u, v, ph, MASS)
+        d["mdagm_sh_" + tag] = R.mdagm(u, v, ph, MASS, shift=0.37)
+        d["deo_f_" + tag] = R.dslash("acc_Deo", uf, vf, phf)
+        d["doe_f_" + tag] = R.dslash("acc_Doe", uf, vf, phf)
+        d["mdagm_f_" + tag] = R.mdagm(uf, vf, phf, MASS)
+    ph = d["ph_bf"]; phf = d["phf_bf"]
+    d["l2norm2"] = R.l2norm2(v); d["real_scal_prod"] = R.real_scal_prod(v, w)
+    d["l2norm2_f"] = R.l2norm2(vf); d["real_scal_prod_f"] = R.real_scal_prod(vf, wf)
+    out, cg, ok = R.multishift_invert(u, ph, MASS, (RA_A0, RA_A, SHIFTS), v, 1e-9, 5000)
+    d["ms_out"] = out; d["ms_cg"] = cg; d["ms_ok"] = ok
+    d["ms_recombined"] = R.recombine(out, v, (RA_A0, RA_A, SHIFTS))
+    out, cg, ok = R.multishift_invert(uf, phf, MASS, (RA_A0, RA_A, SHIFTS), vf, 1e-4, 5000)
+    d["ms_f_out"] = out; d["ms_f_cg"] = cg; d["ms_f_ok"] = ok
+    sol, cg, ok = R.cg(u, ph, MASS, v, 1e-10, 5000, 0.01)
+    d["cg_sol"] = sol; d["cg_cg"] = cg; d["cg_ok"] = ok
+    R.set_inverter_tricks(0, 1, 0.1, 10000)
+    sol, cg, ok = R.mixed_cg(u, uf, ph, phf, MASS, v, 1e-10, 5000, 0.01)
+    d["mixed_sol"] = sol; d["mixed_cg"] = cg; d["mixed_ok"] = ok
+    d["max_eig"] = R.max_eigenvalue(u, ph, MASS, w)
+    np.savez_compressed(os.path.join(HERE, "ref_%dx%dx%dx%d_r1.npz" % n), **d)
+    print("single rank", n, "ms_cg", d["ms_cg"], d["ms_f_cg"], "cg", d["cg_cg"], "mixed", d["mixed_cg"])
+
+
+def multi_rank(loc=(4, 4, 4, 4), nr=2):
+    gl = (loc[0], loc[1], loc[2], loc[3] * nr)
+    G = RefLib(*gl)
+    R = RefLib(*loc, nr)
+    d = {}
+    u = random_su3_conf(G.sizeh, 21); v = gaussian_vec(G.sizeh, 22)
+    d.update(u=u, v=v, loc_n=np.array(loc), nranks=nr, eb=np.array(EB), mu=MU, charge=CHARGE, mass=MASS)
+    phg = G.phases(EB, MU, CHARGE)
+    d["doe_global"] = G.dslash("acc_Doe", u, v, phg)
+    d["mdagm_global"] = G.mdagm(u, v, phg, MASS)
+    d["l2norm2_global"] = G.l2norm2(v)
+    out, cg, ok = G.multishift_invert(u, phg, MASS, (RA_A0, RA_A, SHIFTS), v, 1e-9, 5000)
+    d["ms_out_global"] = out; d["ms_cg"] = cg
+    ro = (C.c_long * 4)(); R.lib.ref_ranges(ro); d["ranges"] = np.array(list(ro))
+    d["sizeh"] = R.sizeh; d["nd"] = np.array(R.nd)
+    loc_out = []
+    for r in range(nr):
+        R.set_rank(r)
+        d["gl_snum_r%d" % r] = np.array([R.lib.ref_lnh_to_gl_snum(0, 0, 0, d3, r) for d3 in range(R.nd[3])])
+        lu = np.zeros((8, 3, 3, R.sizeh), np.complex128); R.lib.send_lnh_subconf_to_buffer(ptr(u), ptr(lu), r)
+        lv = np.zeros((3, R.sizeh), np.complex128); R.lib.send_lnh_subfermion_to_buffer(ptr(v), ptr(lv), r)
+        ph = R.phases(EB, MU, CHARGE)
+        d["lnh_v_r%d" % r] = lv; d["lnh_ph_r%d" % r] = ph
+        o = R.dslash("acc_Doe_unsafe", lu, lv, ph)
+        d["doe_unsafe_r%d" % r] = o.copy()
+        d["l2norm2_loc_r%d" % r] = R.l2norm2(lv)       # mailbox Allreduce returns the local contribution
+        loc_out.append(o)
+    R.lib.ref_mailbox_clear()
+    for _ in range(2):
+        for r in range(nr):
+            R.set_rank(r); R.lib.communicate_fermion_borders(ptr(loc_out[r]))
+    for r in range(nr):
+        d["doe_exchanged_r%d" % r] = loc_out[r]
+    np.savez_compressed(os.path.join(HERE, "ref_%dx%dx%dx%d_r%d.npz" % (loc + (nr,))), **d)
+    print("multi rank", loc, nr, "ms_cg", cg)
+
+
+if __name__ == "__main__":
+    single_rank()
+    multi_rank()
