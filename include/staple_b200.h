@@ -136,6 +136,12 @@ void staple_shutdown(void);
 /* geometry queries: sizeh, nd[4], reduction range R0 and update range R1 (fermionic_utilities.c:41,188) */
 long staple_sizeh(void);
 void staple_geometry(int nd[4], long ranges[4]);
+/* Same numbers without a GPU or an initialised library (host-side sharding logic; ref:
+ * geometry_multidev.h:120-148, fermionic_utilities.c:41,188, communications.c:51-96):
+ * out[0..3]=nd0..3, [4]=sizeh, [5]=half-sites per d3 slice, [6,7]=R0, [8,9]=R1, fermion halo exchange in
+ * elements of one colour array: [10] send->L, [11] recv<-R, [12] send->R, [13] recv<-L, [14] slab length,
+ * [15]=D3_HALO.  Returns 0 on success, 1 for an unsupported geometry. */
+int staple_geometry_plan(const int loc_n[4], int nranks_d3, int halo_width, long out[16]);
 /* Use an existing CUDA stream (e.g. torch's current stream) for all work; NULL = library stream. */
 void staple_set_stream(void *cuda_stream);
 void *staple_get_stream(void);

@@ -117,6 +117,18 @@ def _sfx(x):
     return ""
 
 
+def geometry_plan(loc_n, nranks_d3=1, halo_width=2):
+    """Host-only sharding arithmetic of the D3 slab decomposition (staple_geometry_plan; needs no GPU):
+    local+halo box, sizeh, reduction/update ranges and the fermion halo offsets of
+    Mpi/communications.c:51-96, as a dict."""
+    L = load_library()
+    n = (C.c_int * 4)(*[int(x) for x in loc_n]); o = (C.c_long * 16)()
+    if L.staple_geometry_plan(n, int(nranks_d3), int(halo_width), o) != 0:
+        raise ValueError("unsupported geometry %r ranks %d halo %d" % (tuple(loc_n), nranks_d3, halo_width))
+    return dict(nd=tuple(o[0:4]), sizeh=o[4], vol3h=o[5], r0=(o[6], o[7]), r1=(o[8], o[9]),
+                send_L=o[10], recv_R=o[11], send_R=o[12], recv_L=o[13], slab=o[14], d3_halo=o[15])
+
+
 class HostArray:
     """Pinned host array made `present` on the device: staple_posix_memalign (the replacement of
     Include/memory_wrapper.c:14-31 + `#pragma acc enter data create`).  ``.np`` is a numpy view."""

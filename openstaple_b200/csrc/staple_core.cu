@@ -168,6 +168,31 @@ void fetch_results(int slot, int ndoubles, double *host_out)
 	for (int i = 0; i < ndoubles; i++) host_out[i] = c.h_results[2 * slot + i];
 }
 
+
+// geometry.h:12-29, Mpi/geometry_multidev.h:6-148 as run-time arithmetic (no CUDA calls: also used by
+// staple_geometry_plan, which must work on a host without a GPU)
+static bool geom_ok(int n0, int n1, int n2, int n3, int nranks_d3, int halo_width)
+{
+	if (n0 < 2 || n1 < 1 || n2 < 1 || n3 < 2 || (n0 & 1) || nranks_d3 < 1 || halo_width < 1 || halo_width > 2) return false;
+	// the reference flips parities for odd LOC_N3 / odd halo in multi-rank runs (io.c:595-597); not supported
+	if (nranks_d3 > 1 && ((n3 & 1) || (halo_width & 1))) return false;
+	return true;
+}
+static void fill_geom(Geom &g, int n0, int n1, int n2, int n3, int nranks_d3, int halo_width)
+{
+	g.nranks = nranks_d3; g.halo_width = halo_width;
+	g.d3_halo = nranks_d3 > 1 ? halo_width : 0;
+	g.d3_fhalo = nranks_d3 > 1 ? 1 : 0;
+	g.nd0 = n0; g.nd0h = n0 / 2; g.nd1 = n1; g.nd2 = n2; g.loc_n3 = n3; g.nd3 = n3 + 2 * g.d3_halo;
+	g.vol3h = (long) n0 * n1 * n2 / 2;
+	g.sizeh = g.vol3h * g.nd3;
+	const long loc_sizeh = g.vol3h * n3;
+	g.r0_lo = nranks_d3 > 1 ? (g.sizeh - loc_sizeh) / 2 : 0;
+	g.r0_hi = nranks_d3 > 1 ? (g.sizeh + loc_sizeh) / 2 : g.sizeh;
+	g.r1_lo = g.vol3h * (g.d3_halo - g.d3_fhalo);
+	g.r1_hi = g.sizeh - g.r1_lo;
+}
+
 }   // namespace staple
 
 using namespace staple;
@@ -180,30 +205,15 @@ const char *staple_version(void) { return "staple_b200 0.1 (sm_100a)"; }
 int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo_width, int device)
 {
 	Ctx &c = ctx();
-	if (n0 < 2 || n1 < 1 || n2 < 1 || n3 < 2 || (n0 & 1) || nranks_d3 < 1 || halo_width < 1 || halo_width > 2) {
-		fprintf(stderr, "libstaple_b200: invalid geometry %dx%dx%dx%d ranks %d halo %d (LOC_N0 must be even)\n",
-						n0, n1, n2, n3, nranks_d3, halo_width);
-		return 1;
-	}
-	if (nranks_d3 > 1 && ((n3 & 1) || (halo_width & 1))) {
-		// the reference flips parities in this case (io.c:595-597); not supported here
-		fprintf(stderr, "libstaple_b200: multi-rank needs even LOC_N3 and even HALO_WIDTH (TLSM)\n");
+	if (!geom_ok(n0, n1, n2, n3, nranks_d3, halo_width)) {
+		fprintf(stderr, "libstaple_b200: invalid geometry %dx%dx%dx%d ranks %d halo %d (LOC_N0 even; multi-rank needs even "
+						"LOC_N3 and HALO_WIDTH 2)\n", n0, n1, n2, n3, nranks_d3, halo_width);
 		return 1;
 	}
 	if (device >= 0) STAPLE_CUDA_CHECK(cudaSetDevice(device));
 	STAPLE_CUDA_CHECK(cudaGetDevice(&c.device));
 	Geom &g = c.g;
-	g.nranks = nranks_d3; g.halo_width = halo_width;
-	g.d3_halo = nranks_d3 > 1 ? halo_width : 0;
-	g.d3_fhalo = nranks_d3 > 1 ? 1 : 0;
-	g.nd0 = n0; g.nd0h = n0 / 2; g.nd1 = n1; g.nd2 = n2; g.loc_n3 = n3; g.nd3 = n3 + 2 * g.d3_halo;
-	g.vol3h = (long) n0 * n1 * n2 / 2;
-	g.sizeh = g.vol3h * g.nd3;
-	const long loc_sizeh = g.vol3h * n3;
-	g.r0_lo = nranks_d3 > 1 ? (g.sizeh - loc_sizeh) / 2 : 0;
-	g.r0_hi = nranks_d3 > 1 ? (g.sizeh + loc_sizeh) / 2 : g.sizeh;
-	g.r1_lo = g.vol3h * (g.d3_halo - g.d3_fhalo);
-	g.r1_hi = g.sizeh - g.r1_lo;
+	fill_geom(g, n0, n1, n2, n3, nranks_d3, halo_width);
 	if (!c.own_stream) {
 		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
 		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.s_p, cudaStreamNonBlocking));
@@ -228,6 +238,25 @@ int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo
 	}
 	if (nranks_d3 == 1) { c.myrank = 0; c.nranks = 1; c.rank_L = c.rank_R = 0; }
 	c.inited = true;
+	return 0;
+}
+
+// Pure host arithmetic (no GPU needed): everything a host program has to know to shard a lattice in D3
+// slabs the way the reference does.  out[0..3] = nd0..nd3, [4] = sizeh, [5] = vol3h (half-sites per d3
+// slice), [6..7] = reduction range R0, [8..9] = update range R1 (fermionic_utilities.c:41,188);
+// fermion halo exchange in ELEMENTS of each colour array, thickness 1 (communications.c:51-96):
+// [10] send-to-L offset, [11] recv-from-R offset, [12] send-to-R offset, [13] recv-from-L offset,
+// [14] slab length; [15] = D3_HALO.
+int staple_geometry_plan(const int loc_n[4], int nranks_d3, int halo_width, long out[16])
+{
+	if (!geom_ok(loc_n[0], loc_n[1], loc_n[2], loc_n[3], nranks_d3, halo_width)) return 1;
+	Geom g;
+	fill_geom(g, loc_n[0], loc_n[1], loc_n[2], loc_n[3], nranks_d3, halo_width);
+	out[0] = g.nd0; out[1] = g.nd1; out[2] = g.nd2; out[3] = g.nd3; out[4] = g.sizeh; out[5] = g.vol3h;
+	out[6] = g.r0_lo; out[7] = g.r0_hi; out[8] = g.r1_lo; out[9] = g.r1_hi;
+	const long off = g.vol3h * g.halo_width, slab = g.vol3h;
+	out[10] = off; out[11] = g.sizeh - off; out[12] = g.sizeh - off - slab; out[13] = off - slab; out[14] = slab;
+	out[15] = g.d3_halo;
 	return 0;
 }
 

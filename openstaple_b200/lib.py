@@ -36,6 +36,7 @@ def _declare(L):
     L.staple_init_geometry.argtypes = [i, i, i, i, i, i, i]; L.staple_init_geometry.restype = i
     L.staple_sizeh.restype = C.c_long
     L.staple_geometry.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_long)]
+    L.staple_geometry_plan.argtypes = [C.POINTER(C.c_int), i, i, C.POINTER(C.c_long)]; L.staple_geometry_plan.restype = i
     L.staple_set_stream.argtypes = [vp]
     L.staple_get_stream.restype = vp
     L.staple_kernel_launches.restype = C.c_ulonglong

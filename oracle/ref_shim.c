@@ -41,6 +41,22 @@ void ref_geometry(int *o)
 }
 
 
+/* sizeof/offsetof of every struct that crosses the C ABI, as the reference's own headers define them */
+#include <stddef.h>
+void ref_abi(long *o)
+{
+	o[0] = sizeof(vec3_soa); o[1] = sizeof(su3_soa); o[2] = sizeof(double_soa);
+	o[3] = sizeof(vec3_soa_f); o[4] = sizeof(su3_soa_f); o[5] = sizeof(float_soa);
+	o[6] = sizeof(ferm_param); o[7] = offsetof(ferm_param, ferm_mass); o[8] = offsetof(ferm_param, phases);
+	o[9] = offsetof(ferm_param, phases_f); o[10] = offsetof(ferm_param, approx_md);
+	o[11] = sizeof(RationalApprox); o[12] = offsetof(RationalApprox, approx_order);
+	o[13] = offsetof(RationalApprox, RA_a0); o[14] = offsetof(RationalApprox, RA_a); o[15] = offsetof(RationalApprox, RA_b);
+	o[16] = sizeof(inverter_package); o[17] = offsetof(inverter_package, nshifts);
+	o[18] = offsetof(inverter_package, loc_r); o[19] = offsetof(inverter_package, out_f);
+	o[20] = sizeof(inv_tricks); o[21] = offsetof(inv_tricks, mixedPrecisionDelta);
+	o[22] = offsetof(vec3_soa, c1); o[23] = offsetof(su3_soa, r1);
+}
+
 /* index helpers straight from the reference's header-only geometry (geometry_multidev.h:209-262) */
 int ref_snum_acc(int d0, int d1, int d2, int d3) { return snum_acc(d0, d1, d2, d3); }
 int ref_lnh_to_gl_snum(int d0, int d1, int d2, int d3, int rank)

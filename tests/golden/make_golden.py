@@ -97,6 +97,48 @@ def multi_rank(loc=(4, 4, 4, 4), nr=2):
     print("multi rank", loc, nr, "ms_cg", cg)
 
 
+class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
+    _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
+                ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
+                ("error", C.c_double), ("RA_a0", C.c_double), ("RA_a", C.c_double * 25), ("RA_b", C.c_double * 25)]
+
+
+def _ra_dict(tag, r):
+    return {tag + "_num": r.exponent_num, tag + "_den": r.exponent_den, tag + "_order": r.approx_order,
+            tag + "_lmin": r.lambda_min, tag + "_lmax": r.lambda_max, tag + "_prec": r.gmp_remez_precision,
+            tag + "_error": r.error, tag + "_a0": r.RA_a0, tag + "_a": np.array(r.RA_a[:r.approx_order]),
+            tag + "_b": np.array(r.RA_b[:r.approx_order])}
+
+
+def abi_and_approx():
+    """Struct layouts as the reference's headers define them (ref_abi), the shipped order-19 rational
+    approximations as the reference's own reader parses them (rationalapprox.c:83-117) and
+    rescale_rational_approximation (:145-194) applied to them."""
+    R = RefLib(4, 4, 4, 4)
+    o = (C.c_long * 24)(); R.lib.ref_abi(o)
+    d = {"abi": np.array(list(o)), "abi_sizeh": R.sizeh}
+    ref = os.environ.get("STAPLE_REFERENCE", "/root/reference")
+    files = {"m14": "saved_approxs/approx_-1_over_4_order_19_mloglm_6.4.REMEZ",
+             "p18": "saved_approxs/approx_1_over_8_order_19_mloglm_6.4.REMEZ",
+             "m14o9": "saved_approxs/approx_-1_over_4_order_9_mloglm_6.4.REMEZ"}
+    minmax = (C.c_double * 2)(0.0507 ** 2, 5.2)
+    for tag, f in files.items():
+        r = _RA(); assert C.sizeof(_RA) == o[11]
+        R.lib.ref_approx_read(C.byref(r), os.path.join(ref, f).encode())
+        d.update(_ra_dict(tag, r))
+        out = _RA()
+        R.lib.rescale_rational_approximation(C.byref(r), C.byref(out), minmax)
+        d.update(_ra_dict(tag + "_rescaled", out))
+    d["rescale_minmax"] = np.array(list(minmax))
+    np.savez_compressed(os.path.join(HERE, "ref_abi_approx.npz"), **d)
+    print("abi", list(o))
+
+
 if __name__ == "__main__":
-    single_rank()
-    multi_rank()
+    which = sys.argv[1:] or ["single", "multi", "abi"]
+    if "single" in which:
+        single_rank()
+    if "multi" in which:
+        multi_rank()
+    if "abi" in which:
+        abi_and_approx()

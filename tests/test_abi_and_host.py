@@ -1,0 +1,146 @@
+"""CPU tests of the drop-in boundary and the host-side logic (no compute call needs a GPU):
+  * libstaple_b200.so loads and exports every symbol include/staple_b200.h declares;
+  * the struct layouts that cross the boundary equal the reference's (sizeof/offsetof taken from the
+    reference's own headers by oracle/ref_shim.c:ref_abi, committed in tests/golden/ref_abi_approx.npz);
+  * .REMEZ reader and rescale_rational_approximation mirror (rationalapprox.c:83-117, :145-194);
+  * D3 slab sharding arithmetic (staple_geometry_plan) against the reference's ranges and halo offsets.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import openstaple_b200 as osb
+from openstaple_b200.api import FermParam, InverterPackage, InvTricks, RationalApprox
+from oracle.pyoracle import Restatement
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_abi_approx.npz")))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "staple_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set()
+    # plain prototypes
+    for m in re.finditer(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(\w+)\s*\(", txt, flags=re.M):
+        names.add(m.group(1))
+    names -= {"defined", "STAPLE_DSLASH_DECL", "STAPLE_BLAS_DECL", "name", "if", "sizeof"}
+    out = set(n for n in names if not n.isupper())
+    # macro-generated families
+    for m in re.finditer(r"^STAPLE_DSLASH_DECL\((\w+)\)", txt, flags=re.M):
+        out |= {m.group(1), m.group(1) + "_f"}
+    blas = re.search(r"#define STAPLE_BLAS_DECL\(V, S\)(.*?)\nSTAPLE_BLAS_DECL", txt, flags=re.S).group(1)
+    for m in re.finditer(r"(\w+)##S\(", blas):
+        out |= {m.group(1), m.group(1) + "_f"}
+    out -= {"name##_f", "name"}
+    return sorted(out)
+
+
+def test_library_exports_every_declared_symbol():
+    L = osb.load_library()
+    syms = declared_symbols()
+    assert len(syms) > 90, syms
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    for g in ("verbosity_lv", "multishift_invert_iterations"):
+        C.c_int.in_dll(L, g)
+    InvTricks.in_dll(L, "inverter_tricks")
+    assert b"sm_100a" in L.staple_version()
+    # the reference's own entry-point names are all there (fermion_matrix.h, fermionic_utilities.h, inverter_*.h)
+    for s in ("acc_Deo", "acc_Doe", "fermion_matrix_multiplication", "fermion_matrix_multiplication_shifted",
+              "multishift_invert", "multishift_invert_f", "recombine_shifted_vec3_to_vec3", "ker_invert_openacc",
+              "inverter_mixed_precision", "inverter_multishift_wrapper", "inverter_wrapper",
+              "scal_prod_global", "real_scal_prod_global", "l2norm2_global", "communicate_fermion_borders",
+              "communicate_su3_borders", "shutdown_multidev", "setup_inverter_package_dp", "setup_inverter_package_sp"):
+        assert s in syms
+
+
+def test_compute_without_init_fails_loudly():
+    """No CPU fallback: a compute entry point called without an initialised CUDA context aborts."""
+    import subprocess
+    import sys
+    code = ("import openstaple_b200 as o, numpy as np\n"
+            "L = o.load_library(); a = np.zeros(96)\n"
+            "L.l2norm2_global(a.ctypes.data)\nprint('SURVIVED')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "SURVIVED" not in r.stdout
+    assert "staple_init_geometry" in r.stderr
+
+
+def test_struct_layouts_match_reference(abi):
+    a = [int(x) for x in abi["abi"]]; S = int(abi["abi_sizeh"])
+    assert a[0] == 48 * S and a[1] == 144 * S and a[2] == 8 * S          # vec3_soa, su3_soa, double_soa
+    assert a[3] == 24 * S and a[4] == 72 * S and a[5] == 4 * S           # _f twins
+    assert a[22] == 16 * S and a[23] == 48 * S                           # c1 / r1 offsets (SoA strides used by the kernels)
+    assert C.sizeof(FermParam) == a[6]
+    assert (FermParam.ferm_mass.offset, FermParam.phases.offset, FermParam.phases_f.offset, FermParam.approx_md.offset) == tuple(a[7:11])
+    assert C.sizeof(RationalApprox) == a[11]
+    assert (RationalApprox.approx_order.offset, RationalApprox.RA_a0.offset, RationalApprox.RA_a.offset,
+            RationalApprox.RA_b.offset) == tuple(a[12:16])
+    assert C.sizeof(InverterPackage) == a[16]
+    assert (InverterPackage.nshifts.offset, InverterPackage.loc_r.offset, InverterPackage.out_f.offset) == tuple(a[17:20])
+    assert C.sizeof(InvTricks) == a[20] and InvTricks.mixedPrecisionDelta.offset == a[21]
+
+
+def write_remez(path, g, tag):
+    """the .REMEZ text layout the reference's reader expects (rationalapprox.c:96-106)."""
+    with open(path, "w") as f:
+        f.write("\nApproximation to f(x) = (x)^(%d/%d)\n" % (int(g[tag + "_num"]), int(g[tag + "_den"])))
+        f.write("Order: %d\nLambda Min: %.16e\nLambda Max: %.16e\n" % (int(g[tag + "_order"]), float(g[tag + "_lmin"]), float(g[tag + "_lmax"])))
+        f.write("GMP Remez Precision: %d\nError: %.16e\nRA_a0 = %.16e\n" % (int(g[tag + "_prec"]), float(g[tag + "_error"]), float(g[tag + "_a0"])))
+        for i, (x, y) in enumerate(zip(g[tag + "_a"], g[tag + "_b"])):
+            f.write("RA_a[%d] = %.16e, RA_b[%d] = %.16e\n" % (i, x, i, y))
+
+
+@pytest.mark.parametrize("tag", ["m14", "p18", "m14o9"])
+def test_remez_reader_and_rescale(abi, tag, tmp_path):
+    g = abi
+    p = str(tmp_path / "approx.REMEZ")
+    write_remez(p, g, tag)
+    r = RationalApprox.read(p)
+    assert (r.exponent_num, r.exponent_den, r.approx_order) == (int(g[tag + "_num"]), int(g[tag + "_den"]), int(g[tag + "_order"]))
+    assert r.lambda_min == float(g[tag + "_lmin"]) and r.RA_a0 == float(g[tag + "_a0"])
+    assert np.array_equal(np.array(r.RA_a[:r.approx_order]), g[tag + "_a"])
+    assert np.array_equal(np.array(r.RA_b[:r.approx_order]), g[tag + "_b"])
+    out = r.rescaled(tuple(g["rescale_minmax"]))
+    t = tag + "_rescaled"
+    assert abs(out.RA_a0 / float(g[t + "_a0"]) - 1) < 1e-15
+    assert np.allclose(np.array(out.RA_a[:r.approx_order]), g[t + "_a"], rtol=1e-15, atol=0)
+    assert np.allclose(np.array(out.RA_b[:r.approx_order]), g[t + "_b"], rtol=1e-15, atol=0)
+    assert abs(out.lambda_max / float(g[t + "_lmax"]) - 1) < 1e-15 and abs(out.lambda_min / float(g[t + "_lmin"]) - 1) < 1e-15
+
+
+@pytest.mark.parametrize("loc_n,nr", [((8, 8, 8, 8), 1), ((8, 8, 8, 8), 2), ((4, 4, 4, 4), 2), ((64, 64, 64, 16), 8),
+                                      ((64, 64, 64, 2), 8), ((48, 48, 48, 48), 2), ((32, 32, 32, 32), 1)])
+def test_geometry_plan_matches_oracle(loc_n, nr):
+    p = osb.geometry_plan(loc_n, nr)
+    S = Restatement(*loc_n, nr=nr)
+    assert p["nd"] == S.nd and p["sizeh"] == S.sizeh and p["vol3h"] == S.vol3h and p["d3_halo"] == S.d3_halo
+    assert p["r0"] == (S.g.r0_lo, S.g.r0_hi) and p["r1"] == (S.g.r1_lo, S.g.r1_hi)
+    if nr > 1:
+        # first/last interior slice -> neighbour's inner halo slice (communications.c:51-96)
+        v = p["vol3h"]; h = p["d3_halo"]
+        assert p["send_L"] == h * v and p["recv_L"] == (h - 1) * v
+        assert p["send_R"] == (h + loc_n[3] - 1) * v and p["recv_R"] == (h + loc_n[3]) * v and p["slab"] == v
+
+
+def test_geometry_plan_worked_example_and_rejections(golden_r2):
+    """8^3 x (2*8) -> nd3=12, sizeh=3072, R0=[512,2560), R1=[256,2816), halo offsets."""
+    p = osb.geometry_plan((8, 8, 8, 8), 2)
+    assert p == dict(nd=(8, 8, 8, 12), sizeh=3072, vol3h=256, r0=(512, 2560), r1=(256, 2816),
+                     send_L=512, recv_R=2560, send_R=2304, recv_L=256, slab=256, d3_halo=2)
+    g = golden_r2
+    q = osb.geometry_plan(tuple(int(x) for x in g["loc_n"]), int(g["nranks"]))
+    assert q["r0"] + q["r1"] == tuple(int(x) for x in g["ranges"]) and q["sizeh"] == int(g["sizeh"])
+    for bad in (((7, 8, 8, 8), 1), ((8, 8, 8, 7), 2), ((8, 8, 8, 1), 1), ((8, 0, 8, 8), 1)):
+        with pytest.raises(ValueError):
+            osb.geometry_plan(*bad)
+    with pytest.raises(ValueError):
+        osb.geometry_plan((8, 8, 8, 8), 2, halo_width=1)     # Wilson multi-rank flips parities (io.c:595-597)
