@@ -22,7 +22,7 @@ def load_library(build_if_missing=True):
     if not os.path.exists(path):
         raise RuntimeError("libstaple_b200.so is missing (run `python -m openstaple_b200.build`); "
                            "there is no CPU fallback for the hot path")
-    _LIB = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    _LIB = C.CDLL(path, mode=C.RTLD_LOCAL)   # never interpose on a host program (or the test oracle) by accident
     _declare(_LIB)
     return _LIB
 

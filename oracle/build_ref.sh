@@ -44,5 +44,7 @@ for f in $SRCS; do
 done
 gcc $CF -c "$HERE/ref_shim.c" -o "$OBJ/ref_shim.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
-gcc -shared -o "$OUT" "$OBJ"/*.o -lm
+# -Bsymbolic: calls between reference functions bind inside this .so even if the product library (which
+# exports the same names by design) is loaded in the same process
+gcc -shared -Wl,-Bsymbolic -o "$OUT" "$OBJ"/*.o -lm
 echo "built $OUT"
