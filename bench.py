@@ -92,29 +92,25 @@ class ClockSampler:
 
 
 def haar_su3_torch(torch, n, device, seed):
-    """n Haar-random SU(3) matrices on the GPU -> complex128[n,3,3] (rows orthonormal, det 1)."""
+    """n Haar-random SU(3) matrices on the GPU -> complex128[3,3,n] (row, col, site).  Gram-Schmidt of two
+    complex Gaussian 3-vectors gives Haar-distributed rows 0,1; row 2 = conj(r0 x r1) makes det = 1
+    (pure elementwise torch: batched torch.linalg.qr launches thousands of tiny kernels)."""
     g = torch.Generator(device=device); g.manual_seed(seed)
-    z = torch.complex(torch.randn((n, 3, 3), generator=g, device=device, dtype=torch.float64),
-                      torch.randn((n, 3, 3), generator=g, device=device, dtype=torch.float64))
-    q, r = torch.linalg.qr(z)
-    d = torch.diagonal(r, dim1=1, dim2=2)
-    q = q * (d / d.abs()).unsqueeze(1)
-    det = torch.linalg.det(q)
-    q = q / torch.pow(det, 1.0 / 3.0).reshape(-1, 1, 1)
-    return q
+    z = torch.complex(torch.randn((2, 3, n), generator=g, device=device, dtype=torch.float64),
+                      torch.randn((2, 3, n), generator=g, device=device, dtype=torch.float64))
+    r0 = z[0] / torch.linalg.vector_norm(z[0], dim=0, keepdim=True)
+    r1 = z[1] - (r0.conj() * z[1]).sum(0, keepdim=True) * r0
+    r1 = r1 / torch.linalg.vector_norm(r1, dim=0, keepdim=True)
+    r2 = torch.stack((r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0])).conj()
+    return torch.stack((r0, r1, r2))
 
 
 def make_fields(torch, lat, seed):
-    """synthetic inputs in the reference layouts: u[8,3,3,sizeh], phases[8,sizeh], source[3,sizeh]."""
+    """synthetic inputs in the reference layouts: u[8,3,3,sizeh], source[3,sizeh]."""
     S = lat.sizeh
     u = lat.new_conf()
-    chunk = 1 << 20
-    flat = u.view(8, 3, 3, S)
     for k in range(8):
-        for lo in range(0, S, chunk):
-            hi = min(S, lo + chunk)
-            q = haar_su3_torch(torch, hi - lo, lat.device, seed * 1000 + k * 17 + lo // chunk)
-            flat[k, :, :, lo:hi] = q.permute(1, 2, 0)
+        u[k] = haar_su3_torch(torch, S, lat.device, seed * 1000 + k * 17)
     g = torch.Generator(device=lat.device); g.manual_seed(seed + 99)
     v = torch.complex(torch.randn((3, S), generator=g, device=lat.device, dtype=torch.float64),
                       torch.randn((3, S), generator=g, device=lat.device, dtype=torch.float64)) / np.sqrt(2.0)
@@ -217,6 +213,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     loc = tuple(int(x) for x in args.lattice.split("x"))
+    torch.cuda.set_device(local_rank)
+    # everything (torch fills/copies, library kernels, timing events) on ONE non-default stream
+    torch.cuda.set_stream(torch.cuda.Stream(device=torch.device("cuda", local_rank)))
     lat = osb.Lattice(loc, nranks_d3=world, halo_width=2, device=local_rank)
     if world > 1:
         lat.init_multidev(dist, async_comm_fermion=1)

@@ -142,8 +142,12 @@ void staple_geometry(int nd[4], long ranges[4]);
  * elements of one colour array: [10] send->L, [11] recv<-R, [12] send->R, [13] recv<-L, [14] slab length,
  * [15]=D3_HALO.  Returns 0 on success, 1 for an unsupported geometry. */
 int staple_geometry_plan(const int loc_n[4], int nranks_d3, int halo_width, long out[16]);
-/* Use an existing CUDA stream (e.g. torch's current stream) for all work; NULL = library stream. */
+/* Stream all entry points enqueue on.  After staple_init_geometry it is a library-owned non-blocking
+ * stream; every host-visible result (reductions, solver returns, staple_acc_update_host) synchronises
+ * it.  staple_set_stream() switches to the caller's stream, used as is: NULL means CUDA's legacy default
+ * stream (e.g. torch's default stream).  staple_use_library_stream() switches back. */
 void staple_set_stream(void *cuda_stream);
+void staple_use_library_stream(void);
 void *staple_get_stream(void);
 void staple_synchronize(void);
 /* number of CUDA kernels launched by this library since start (bench.py "gpu_launches") */

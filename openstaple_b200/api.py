@@ -185,7 +185,12 @@ class Lattice:
 
     # ---- plumbing
     def use_torch_stream(self):
+        """enqueue on torch's CURRENT stream (handle 0 = the legacy default stream), so library kernels are
+        ordered with torch allocations, fills and copies of the same tensors."""
         self.L.staple_set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def use_library_stream(self):
+        self.L.staple_use_library_stream()
 
     def synchronize(self):
         self.L.staple_synchronize()

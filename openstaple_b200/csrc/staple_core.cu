@@ -176,6 +176,8 @@ static bool geom_ok(int n0, int n1, int n2, int n3, int nranks_d3, int halo_widt
 	if (n0 < 2 || n1 < 1 || n2 < 1 || n3 < 2 || (n0 & 1) || nranks_d3 < 1 || halo_width < 1 || halo_width > 2) return false;
 	// the reference flips parities for odd LOC_N3 / odd halo in multi-rank runs (io.c:595-597); not supported
 	if (nranks_d3 > 1 && ((n3 & 1) || (halo_width & 1))) return false;
+	// kernels use 32-bit site indices (the reference's own idxh is an int, geometry_multidev.h:219)
+	if ((double) n0 * n1 * n2 * (n3 + 4) / 2 >= 2147483648.0) return false;
 	return true;
 }
 static void fill_geom(Geom &g, int n0, int n1, int n2, int n3, int nranks_d3, int halo_width)
@@ -278,10 +280,18 @@ void staple_geometry(int nd[4], long ranges[4])
 	ranges[0] = g.r0_lo; ranges[1] = g.r0_hi; ranges[2] = g.r1_lo; ranges[3] = g.r1_hi;
 }
 
+// The handle is used as is: NULL is CUDA's legacy default stream (what a plain C host program and
+// torch's default stream use), not "the library stream" -- kernels must be ordered with the caller's
+// own copies and allocations on that stream.
 void staple_set_stream(void *s)
 {
 	require_init("staple_set_stream");
-	ctx().stream = s ? (cudaStream_t) s : ctx().own_stream;
+	ctx().stream = (cudaStream_t) s;
+}
+void staple_use_library_stream(void)
+{
+	require_init("staple_use_library_stream");
+	ctx().stream = ctx().own_stream;
 }
 void *staple_get_stream(void) { return (void *) ctx().stream; }
 void staple_synchronize(void) { STAPLE_CUDA_CHECK(cudaStreamSynchronize(ctx().stream)); }

@@ -30,15 +30,60 @@ template <typename C> __device__ __forceinline__ void cfma_ca(C &acc, C a, C b) 
 template <typename C> __device__ __forceinline__ C cross(C a, C b, C c, C d)   // a*b - c*d
 { C r; r.x = a.x * b.x - a.y * b.y - (c.x * d.x - c.y * d.y); r.y = a.x * b.y + a.y * b.x - (c.x * d.y + c.y * d.x); return r; }
 
-__device__ __forceinline__ void sincos_t(double th, double *s, double *c) { sincos(th, s, c); }
-__device__ __forceinline__ void sincos_t(float th, float *s, float *c) { sincosf(th, s, c); }
+// sin/cos of a link phase angle (matvecmul.h:96-97 `cos(arg)+I*sin(arg)`).  calc_u1_phases folds every
+// angle into (-pi, pi] (backfield.c:163-187), so a two-term Cody-Waite reduction by pi/2 (exact for
+// |k| <= 2 with FMA) plus the classic degree-13/14 minimax kernels on [-pi/4, pi/4] is enough: <= 1 ulp
+// from glibc's sin/cos over the whole range (checked on 2e7 samples), sin(fl(pi)) = 1.2246e-16 reproduced.
+// Unlike sincos() there is no Payne-Hanek slow-path CALL, so the operator stays one basic block and the
+// scheduler can overlap the next hop's loads with this hop's arithmetic.
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c)
+{
+	const double kd = rint(x * 0.63661977236758134308);
+	const int k = (int) kd;
+	double r = fma(-kd, 1.57079632679489655800e+00, x);
+	r = fma(-kd, 6.12323399573676603587e-17, r);
+	const double z = r * r;
+	double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+	ps = fma(z, ps, 2.75573137070700676789e-06);
+	ps = fma(z, ps, -1.98412698298579493134e-04);
+	ps = fma(z, ps, 8.33333333332248946124e-03);
+	const double ks = fma(z * r, fma(z, ps, -1.66666666666666324348e-01), r);
+	double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+	pc = fma(z, pc, -2.75573143513906633035e-07);
+	pc = fma(z, pc, 2.48015872894767294178e-05);
+	pc = fma(z, pc, -1.38888888888741095749e-03);
+	pc = fma(z, pc, 4.16666666666666019037e-02);
+	const double kc = 1.0 - fma(0.5, z, -(z * (z * pc)));
+	const double a = (k & 1) ? kc : ks, b = (k & 1) ? ks : kc;
+	*s = (k & 2) ? -a : a;
+	*c = ((k + 1) & 2) ? -b : b;
+}
+__device__ __forceinline__ void sincos_t(float x, float *s, float *c)
+{
+	const float kd = rintf(x * 0.63661977236758134308f);
+	const int k = (int) kd;
+	float r = fmaf(-kd, 1.5707963705062866f, x);
+	r = fmaf(-kd, -4.371139000186243e-08f, r);
+	const float z = r * r;
+	float ps = fmaf(z, 2.7183114939898219064e-6f, -1.98393348360966317347e-4f);
+	ps = fmaf(z, ps, 8.3333293858894631756e-3f);
+	ps = fmaf(z, ps, -0.166666666416265235595f);
+	const float ks = fmaf(z * r, ps, r);
+	float pc = fmaf(z, 2.43904487962774090654e-5f, -1.38867637746099294692e-3f);
+	pc = fmaf(z, pc, 4.16666233237390631894e-2f);
+	pc = fmaf(z, pc, -0.499999997251031003120f);
+	const float kc = fmaf(z, pc, 1.0f);
+	const float a = (k & 1) ? kc : ks, b = (k & 1) ? ks : kc;
+	*s = (k & 2) ? -a : a;
+	*c = ((k + 1) & 2) ? -b : b;
+}
 
 // One hop: acc += U(im) e^{i th(im)} v(iv)            (DAG=false, matvecmul.h:88-126)
 //          acc -= U(im)^+ e^{-i th(im)} v(iv)         (DAG=true,  matvecmul.h:129-172)
 // uk -> u[k].r0.c0, phk -> backfield[k].d ; third row rebuilt as conj(r0 x r1).
 template <typename T, bool DAG>
 __device__ __forceinline__ void hop(cplx_t<T> acc[3], const cplx_t<T> *__restrict__ uk, const T *__restrict__ phk,
-																		long im, const cplx_t<T> *__restrict__ in, long iv, long n)
+																		unsigned int im, const cplx_t<T> *__restrict__ in, unsigned int iv, long n)
 {
 	using C = cplx_t<T>;
 	const T th = ld_stream(phk + im);
@@ -128,28 +173,30 @@ __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArgs<T> a)
 {
 	using C = cplx_t<T>;
 	if (a.skip != nullptr && *a.skip != 0) return;
-	const long t = (long) blockIdx.x * kBlock + threadIdx.x;
+	// sizeh < 2^31 is checked at staple_init_geometry: site indices are 32-bit (no 64-bit divisions),
+	// only the array bases (k*9*sizeh) are 64-bit
+	const unsigned int t = blockIdx.x * kBlock + threadIdx.x;
 	double dot = 0.0;
-	if (t < a.nsites) {
-		const long idx = a.site_lo + t;
+	if (t < (unsigned int) a.nsites) {
+		const unsigned int idx = (unsigned int) a.site_lo + t;
 		const long n = a.sizeh;
-		const int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
-		const int hd0 = (int) (idx % nd0h);
-		long q = idx / nd0h;
-		const int d1 = (int) (q % nd1); q /= nd1;
-		const int d2 = (int) (q % nd2);
-		const int d3 = (int) (q / nd2);
+		const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
+		const unsigned int hd0 = idx % nd0h;
+		unsigned int q = idx / nd0h;
+		const unsigned int d1 = q % nd1; q /= nd1;
+		const unsigned int d2 = q % nd2;
+		const unsigned int d3 = q / nd2;
 		// d0 = 2*hd0 + rp  (fermion_matrix.c:64, :120)
-		const int rp = (d1 + d2 + d3 + PAR) & 1;
-		const long s1 = nd0h, s2 = (long) nd0h * nd1, s3 = a.vol3h;
-		const long i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
-		const long i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
-		const long i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
-		const long i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
-		const long i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
-		const long i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
-		const long i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
-		const long i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
+		const unsigned int rp = (d1 + d2 + d3 + PAR) & 1u;
+		const unsigned int s1 = nd0h, s2 = nd0h * nd1, s3 = (unsigned int) a.vol3h;
+		const unsigned int i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
+		const unsigned int i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
+		const unsigned int i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
+		const unsigned int i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
+		const unsigned int i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
+		const unsigned int i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
+		const unsigned int i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
+		const unsigned int i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
 
 		C acc[3];
 		acc[0] = mk<T>(0, 0); acc[1] = mk<T>(0, 0); acc[2] = mk<T>(0, 0);

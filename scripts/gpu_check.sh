@@ -1,16 +1,21 @@
 #!/usr/bin/env bash
-# Runs on the B200 box (under gpurun): parity tests, smoke, bench, ncu launch list + one full capture.
+# Runs on the B200 box (under gpurun): smoke, parity tests, bench, ncu launch list + one full capture.
+#   NCU=0 skips the profiler passes, REF=1 also runs the reference arm.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-cat gpurun_out/bench.json
-if [ "${NCU:-1}" = "1" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:dslash_kernel -s 10 -c 2 -f -o gpurun_out/prof_dslash \
-    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-solver > gpurun_out/ncu_full.log 2>&1
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+if [ "${REF:-0}" = "1" ]; then
+  timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
 fi
-tail -5 gpurun_out/smoke.log
+if [ "${NCU:-1}" = "1" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:staple:: -c 300 --csv \
+    --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:dslash_kernel -s 12 -c 2 -f -o gpurun_out/prof_dslash \
+    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-solver > gpurun_out/ncu_full.log 2>&1
+  tail -3 gpurun_out/ncu_full.log
+fi
+tail -3 gpurun_out/smoke.log
