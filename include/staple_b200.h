@@ -172,6 +172,10 @@ void *staple_acc_deviceptr(const void *host);                     /* acc_devicep
  * staple_init_multidev1D().  async_comm_fermion mirrors devinfo.async_comm_fermion. */
 int staple_nccl_unique_id(void *id128);
 int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_comm_fermion);
+/* Optional (collective, after staple_init_multidev1D): fermion halos through NVLink peer memory instead of
+ * ncclSend/Recv -- the surface kernels of acc_Deo/acc_Doe store their slice straight into the neighbour's
+ * staging area (CUDA IPC) and raise a flag; returns 1 if active, 0 if it fell back to NCCL. */
+int staple_enable_p2p(int on);
 void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
 int staple_myrank(void);
 

@@ -198,7 +198,7 @@ class Lattice:
     def kernel_launches(self):
         return int(self.L.staple_kernel_launches())
 
-    def init_multidev(self, dist, async_comm_fermion=1):
+    def init_multidev(self, dist, async_comm_fermion=1, p2p=0):
         """pre_init_multidev1D + init_multidev1D (Mpi/multidev.c:20-108) with torch.distributed as
         the out-of-band channel for the NCCL id."""
         rank, world = dist.get_rank(), dist.get_world_size()
@@ -214,6 +214,7 @@ class Lattice:
         raw = bytes(idt.numpy().tobytes())
         self.L.staple_init_multidev1D(rank, world, C.c_char_p(raw), int(async_comm_fermion))
         self.rank = rank
+        self.p2p = bool(self.L.staple_enable_p2p(int(p2p))) if world > 1 else False
 
     def shutdown_multidev(self):
         self.L.shutdown_multidev()

@@ -400,9 +400,77 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 	return 0;
 }
 
+// Peer-memory halo channel (collective: every rank calls it after staple_init_multidev1D).  Allocates the
+// staging area and flags, exports them with CUDA IPC, swaps the handles with the two ring neighbours over
+// the NCCL communicator (no MPI needed) and maps the neighbours' areas.  Returns 1 if the channel is active.
+int staple_enable_p2p(int on)
+{
+	require_init("staple_enable_p2p");
+	Ctx &c = ctx();
+	P2P &p = c.p2p;
+	if (!on || c.nranks <= 1) { p.on = false; return 0; }
+	if (p.stage_L) { p.on = true; return 1; }          // already mapped
+	if (!c.comm) { fprintf(stderr, "libstaple_b200: staple_enable_p2p before staple_init_multidev1D\n"); exit(1); }
+	const Geom &g = c.g;
+	p.slot_bytes = (size_t) 3 * g.vol3h * 16;
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.stage, 4 * p.slot_bytes));
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.flags, 2 * sizeof(unsigned long long)));
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 2 * sizeof(unsigned int)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.flags, 0, 2 * sizeof(unsigned long long)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 2 * sizeof(unsigned int)));
+	struct Handles { cudaIpcMemHandle_t stage, flags; } mine, fromL, fromR;
+	STAPLE_CUDA_CHECK(cudaIpcGetMemHandle(&mine.stage, p.stage));
+	STAPLE_CUDA_CHECK(cudaIpcGetMemHandle(&mine.flags, p.flags));
+	Handles *d = nullptr;      // [0] mine, [1] from L, [2] from R
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &d, 3 * sizeof(Handles)));
+	STAPLE_CUDA_CHECK(cudaMemcpy(d, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+	Comm *n = c.comm;
+	cudaStream_t st = c.s_comm;
+	STAPLE_NCCL_CHECK(n, n->GroupStart());
+	STAPLE_NCCL_CHECK(n, n->Send(d, sizeof(Handles), ncclChar, c.rank_L, n->comm, st));
+	STAPLE_NCCL_CHECK(n, n->Recv(d + 2, sizeof(Handles), ncclChar, c.rank_R, n->comm, st));
+	STAPLE_NCCL_CHECK(n, n->Send(d, sizeof(Handles), ncclChar, c.rank_R, n->comm, st));
+	STAPLE_NCCL_CHECK(n, n->Recv(d + 1, sizeof(Handles), ncclChar, c.rank_L, n->comm, st));
+	STAPLE_NCCL_CHECK(n, n->GroupEnd());
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+	STAPLE_CUDA_CHECK(cudaMemcpy(&fromL, d + 1, sizeof(Handles), cudaMemcpyDeviceToHost));
+	STAPLE_CUDA_CHECK(cudaMemcpy(&fromR, d + 2, sizeof(Handles), cudaMemcpyDeviceToHost));
+	STAPLE_CUDA_CHECK(cudaFree(d));
+	auto open = [](cudaIpcMemHandle_t h, void **out) {
+		cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; }
+		return e;
+	};
+	cudaError_t e1 = open(fromL.stage, (void **) &p.stage_L), e2 = open(fromL.flags, (void **) &p.flags_L);
+	cudaError_t e3 = cudaSuccess, e4 = cudaSuccess;
+	if (c.rank_R == c.rank_L) { p.stage_R = p.stage_L; p.flags_R = p.flags_L; }   // two ranks: same neighbour on both sides
+	else { e3 = open(fromR.stage, (void **) &p.stage_R); e4 = open(fromR.flags, (void **) &p.flags_R); }
+	if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+		fprintf(stderr, "MPI%02d - libstaple_b200: CUDA IPC mapping of the neighbours' halo staging failed (%s); "
+						"using NCCL send/recv for halos\n", c.myrank, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4));
+		p.stage_L = p.stage_R = nullptr; p.on = false;
+		return 0;
+	}
+	p.seq = 0;
+	p.on = true;
+	// nobody may push before everybody has zeroed flags and mapped: one tiny all-reduce as a barrier
+	allreduce_results(kResultSlots - 1, 1, st);
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+	return 1;
+}
+
 void shutdown_multidev(void)
 {
 	Ctx &c = ctx();
+	if (c.p2p.stage) {
+		cudaDeviceSynchronize();
+		if (c.comm && c.comm->comm) { allreduce_results(kResultSlots - 1, 1, c.s_comm); cudaStreamSynchronize(c.s_comm); }   // peers are done with our memory
+		if (c.p2p.stage_L) cudaIpcCloseMemHandle(c.p2p.stage_L);
+		if (c.p2p.flags_L) cudaIpcCloseMemHandle(c.p2p.flags_L);
+		if (c.p2p.stage_R && c.p2p.stage_R != c.p2p.stage_L) { cudaIpcCloseMemHandle(c.p2p.stage_R); cudaIpcCloseMemHandle(c.p2p.flags_R); }
+		cudaFree(c.p2p.stage); cudaFree(c.p2p.flags); cudaFree(c.p2p.tickets);
+		c.p2p = P2P();
+	}
 	if (c.comm && c.comm->comm) {
 		cudaDeviceSynchronize();
 		c.comm->CommDestroy(c.comm->comm);
@@ -416,7 +484,8 @@ int staple_myrank(void) { return ctx().myrank; }
 // fermion borders: 3 colour arrays, thickness FERMION_HALO = 1 (communications.c:158-167)
 static void fermion_borders(void *v, size_t elem_bytes, cudaStream_t s)
 {
-	exchange_slices(v, elem_bytes, ctx().g.sizeh, 3, 1, s);
+	if (ctx().nranks > 1 && ctx().p2p.on) p2p_exchange_fermion(v, elem_bytes, s);
+	else exchange_slices(v, elem_bytes, ctx().g.sizeh, 3, 1, s);
 }
 // gauge borders: 8 link arrays x rows r0,r1 x 3 columns (communications.c:306-318); r2 is not sent
 static void su3_borders(void *u, size_t elem_bytes, int thickness, cudaStream_t s)

@@ -36,6 +36,22 @@ constexpr int kResultSlots = 16;        // device scalars produced by reductions
 
 struct Comm;   // NCCL state, staple_core.cu
 
+// Peer-memory halo channel over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank
+// owns a staging area stage[2 parities][2 slots][3 colours x vol3h x 16 B] and two sequence flags;
+// slot 0 receives the data of this rank's LOWER fermion halo (written by rank L's top-face kernel),
+// slot 1 the UPPER halo (written by rank R's bottom-face kernel).  Exchange number `seq` uses parity
+// seq&1, which makes the channel write-after-read safe without any handshake.
+struct P2P {
+	bool on = false;
+	char *stage = nullptr;                    // local, cudaMalloc (IPC exported)
+	unsigned long long *flags = nullptr;      // local [2]
+	char *stage_L = nullptr, *stage_R = nullptr;                    // peer mappings
+	unsigned long long *flags_L = nullptr, *flags_R = nullptr;
+	unsigned int *tickets = nullptr;          // local [2]: last-block detection of the two face kernels
+	size_t slot_bytes = 0;                    // 3 * vol3h * 16
+	unsigned long long seq = 0;
+};
+
 struct Ctx {
 	bool inited = false;
 	Geom g{};
@@ -53,6 +69,7 @@ struct Ctx {
 	// rank layer (multidev.h:10-41)
 	int myrank = 0, nranks = 1, rank_L = 0, rank_R = 0, async_comm_fermion = 0;
 	Comm *comm = nullptr;
+	P2P p2p;
 	// last multishift statistics
 	int last_iterations = 0;
 	long long last_active = 0;
@@ -75,6 +92,10 @@ inline double *result(int slot) { return ctx().d_results + 2 * slot; }
 void allreduce_results(int slot, int ndoubles, cudaStream_t s);   // in-stream sum over ranks of d_results[slot]
 void exchange_slices(void *base, size_t elem_bytes, long stride_elems, int narrays, int thickness,
 										 cudaStream_t s);                              // communications.c:34-104 on device memory
+// peer-memory variant for one vector (3 colour arrays, thickness 1): push both faces + unpack both halos
+void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s);
+// unpack only (the faces were pushed by the surface kernels themselves); seq = exchange number
+void p2p_unpack(void *base, size_t elem_bytes, unsigned long long seq, cudaStream_t s, const int *skip);
 
 // ---- precision traits -------------------------------------------------------------------
 template <typename T> struct Prec;
@@ -97,6 +118,12 @@ struct DslashArgs {
 	unsigned int ticket_target;   // total blocks contributing to this reduction
 	unsigned int partial_offset;  // first partial index of this launch
 	const int *skip;          // device flag: nonzero -> kernel is a no-op (solver overrun)
+	// fused halo push (surface launches of exactly one d3 slice): the slice is ALSO stored into the
+	// neighbour's staging slot through its NVLink mapping, then the neighbour's flag is set to peer_seq
+	cplx_t<T> *peer;          // [3][vol3h] in the neighbour's memory, or null
+	unsigned long long *peer_flag;
+	unsigned long long peer_seq;
+	unsigned int *face_ticket;
 	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites)
 	int nd0h, nd1, nd2, nd3;
 	long vol3h, sizeh;
@@ -105,10 +132,12 @@ struct DslashArgs {
 enum Epilogue { EPI_NONE = 0, EPI_MASS = 1, EPI_MASS_DOT = 2 };
 
 // launches on stream s the operator for output parity `par` over d3 in [d3lo, d3hi)
+// face: 0 = no push, 1 = this launch is the TOP interior slice (-> rank R, slot 0), 2 = BOTTOM (-> rank L, slot 1)
 template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
-									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s);
+									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s,
+									 int face = 0, unsigned long long seq = 0);
 unsigned int dslash_blocks(int d3lo, int d3hi);
 
 // full operator with halo handling (acc_Deo/acc_Doe, fermion_matrix.c:159-268); epilogue as above.

@@ -154,10 +154,21 @@ __device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials
 	__syncthreads();
 	if (last) {
 		__threadfence();
+		// fixed summation order (thread t adds partials t, t+B, t+2B, ... in that order), but the loads are
+		// issued 8 at a time: a dependent-latency loop here costs ~0.4 us per trip on the kernel's tail
 		double s[NV];
 		for (int k = 0; k < NV; k++) {
 			s[k] = 0.0;
-			for (unsigned int i = threadIdx.x; i < target; i += blockDim.x) s[k] += __ldcg(partials + k * pstride + i);
+			for (unsigned int i0 = threadIdx.x; i0 < target; i0 += 8 * blockDim.x) {
+				double x[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					const unsigned int i = i0 + j * blockDim.x;
+					x[j] = i < target ? __ldcg(partials + k * pstride + i) : 0.0;
+				}
+#pragma unroll
+				for (int j = 0; j < 8; j++) s[k] += x[j];
+			}
 		}
 		block_sum<NV>(s, sm);
 		if (threadIdx.x == 0) {
@@ -165,6 +176,114 @@ __device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials
 			*ticket = 0u;
 		}
 	}
+}
+
+// ------------------------------------------------------------------ peer-memory halo channel (device side)
+// Producer: every thread has issued its peer stores; the last block to finish publishes `seq` in the
+// neighbour's flag with system-scope release semantics (fence.sys by all writers, ticket, fence.sys, store).
+__device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsigned long long seq, unsigned int *ticket)
+{
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned int t = atomicAdd(ticket, 1u);
+		if (t == gridDim.x - 1) {
+			__threadfence_system();
+			*ticket = 0u;
+			asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(seq) : "memory");
+		}
+	}
+}
+// Consumer: wait until the local flag has reached `seq` (written by the neighbour GPU over NVLink)
+__device__ __forceinline__ void face_wait(const unsigned long long *flag, unsigned long long seq)
+{
+	if (threadIdx.x == 0) {
+		unsigned long long v;
+		do {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+			if (v < seq) __nanosleep(200);
+		} while (v < seq);
+	}
+	__syncthreads();
+}
+
+// push one interior slice of a vector (3 colour arrays) into a neighbour's staging slot (standalone
+// communicate_fermion_borders; the operator's surface kernels do this themselves)
+template <typename C>
+__global__ void __launch_bounds__(256) p2p_push_kernel(const C *src, long n, long slice_lo, long vol3h, C *peer,
+																											 unsigned long long *peer_flag, unsigned long long seq,
+																											 unsigned int *ticket)
+{
+	for (long t = (long) blockIdx.x * 256 + threadIdx.x; t < 3 * vol3h; t += (long) gridDim.x * 256) {
+		const long c = t / vol3h, i = t - c * vol3h;
+		peer[t] = src[c * n + slice_lo + i];
+	}
+	face_signal(peer_flag, seq, ticket);
+}
+// copy both staging slots into the halo slices once the neighbours' data has landed
+template <typename C>
+__global__ void __launch_bounds__(256) p2p_unpack_kernel(C *dst, long n, long lower_lo, long upper_lo, long vol3h,
+																												 const C *slot0, const C *slot1, const unsigned long long *flags,
+																												 unsigned long long seq, const int *skip)
+{
+	if (skip != nullptr && *skip != 0) return;       // the producers skipped this exchange too (same flag on every rank)
+	const int half = gridDim.x / 2;
+	const int which = blockIdx.x >= half;            // first half of the grid: lower halo, second half: upper
+	face_wait(flags + which, seq);
+	const C *src = which ? slot1 : slot0;
+	const long lo = which ? upper_lo : lower_lo;
+	const int b = which ? blockIdx.x - half : blockIdx.x;
+	for (long t = (long) b * 256 + threadIdx.x; t < 3 * vol3h; t += (long) half * 256) {
+		const long c = t / vol3h, i = t - c * vol3h;
+		dst[c * n + lo + i] = __ldcg(src + t);
+	}
+}
+
+static inline char *p2p_slot(char *stage, unsigned long long seq, int slot)
+{
+	return stage + ((seq & 1ull) * 2 + slot) * ctx().p2p.slot_bytes;
+}
+
+void p2p_unpack(void *base, size_t elem_bytes, unsigned long long seq, cudaStream_t s, const int *skip)
+{
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	const long lower_lo = (long) (g.d3_halo - 1) * g.vol3h, upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
+	long want = (3 * g.vol3h + 255) / 256;
+	const int half = (int) (want < 148 ? want : 148);
+	if (elem_bytes == 16)
+		p2p_unpack_kernel<double2><<<2 * half, 256, 0, s>>>((double2 *) base, g.sizeh, lower_lo, upper_lo, g.vol3h,
+			(const double2 *) p2p_slot(c.p2p.stage, seq, 0), (const double2 *) p2p_slot(c.p2p.stage, seq, 1), c.p2p.flags, seq, skip);
+	else
+		p2p_unpack_kernel<float2><<<2 * half, 256, 0, s>>>((float2 *) base, g.sizeh, lower_lo, upper_lo, g.vol3h,
+			(const float2 *) p2p_slot(c.p2p.stage, seq, 0), (const float2 *) p2p_slot(c.p2p.stage, seq, 1), c.p2p.flags, seq, skip);
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
+}
+
+void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s)
+{
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	const unsigned long long seq = ++c.p2p.seq;
+	const long top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h, bot_lo = (long) g.d3_halo * g.vol3h;
+	long want = (3 * g.vol3h + 255) / 256;
+	const int grid = (int) (want < 148 ? want : 148);
+	// top interior slice -> rank R's lower halo (its slot 0); bottom interior slice -> rank L's upper halo (slot 1)
+	if (elem_bytes == 16) {
+		p2p_push_kernel<double2><<<grid, 256, 0, s>>>((const double2 *) base, g.sizeh, top_lo, g.vol3h,
+			(double2 *) p2p_slot(c.p2p.stage_R, seq, 0), c.p2p.flags_R + 0, seq, c.p2p.tickets + 0);
+		p2p_push_kernel<double2><<<grid, 256, 0, s>>>((const double2 *) base, g.sizeh, bot_lo, g.vol3h,
+			(double2 *) p2p_slot(c.p2p.stage_L, seq, 1), c.p2p.flags_L + 1, seq, c.p2p.tickets + 1);
+	} else {
+		p2p_push_kernel<float2><<<grid, 256, 0, s>>>((const float2 *) base, g.sizeh, top_lo, g.vol3h,
+			(float2 *) p2p_slot(c.p2p.stage_R, seq, 0), c.p2p.flags_R + 0, seq, c.p2p.tickets + 0);
+		p2p_push_kernel<float2><<<grid, 256, 0, s>>>((const float2 *) base, g.sizeh, bot_lo, g.vol3h,
+			(float2 *) p2p_slot(c.p2p.stage_L, seq, 1), c.p2p.flags_L + 1, seq, c.p2p.tickets + 1);
+	}
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch(2);
+	p2p_unpack(base, elem_bytes, seq, s, nullptr);
 }
 
 // ------------------------------------------------------------------ Dirac operator kernel
@@ -222,8 +341,10 @@ __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArgs<T> a)
 				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
 			}
 			a.out[c * n + idx] = o;
+			if (a.peer != nullptr) a.peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
+	if (a.peer != nullptr) face_signal(a.peer_flag, a.peer_seq, a.face_ticket);
 	if (EPI == EPI_MASS_DOT) {
 		double v[1] = { dot };
 		grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
@@ -239,11 +360,19 @@ unsigned int dslash_blocks(int d3lo, int d3hi)
 template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
-									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s)
+									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s,
+									 int face, unsigned long long seq)
 {
 	const Geom &g = ctx().g;
 	if (d3hi <= d3lo) return;
 	DslashArgs<T> a;
+	a.peer = nullptr; a.peer_flag = nullptr; a.peer_seq = 0; a.face_ticket = nullptr;
+	if (face != 0) {
+		P2P &p = ctx().p2p;
+		a.peer = (cplx_t<T> *) p2p_slot(face == 1 ? p.stage_R : p.stage_L, seq, face == 1 ? 0 : 1);
+		a.peer_flag = face == 1 ? p.flags_R + 0 : p.flags_L + 1;
+		a.peer_seq = seq; a.face_ticket = p.tickets + (face - 1);
+	}
 	a.u = u; a.out = out; a.in = in; a.ph = ph; a.in0 = in0; a.m2 = m2;
 	a.partials = dot_slot >= 0 ? partials(dot_slot) : nullptr;
 	a.ticket = dot_slot >= 0 ? ticket(dot_slot) : nullptr;
@@ -284,24 +413,31 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, dslash_blocks(lo, hi), 0, skip, c.stream);
 		return;
 	}
-	if (!c.async_comm_fermion) {
+	if (!c.async_comm_fermion && !c.p2p.on) {
 		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, dslash_blocks(lo, hi), 0, skip, c.stream);
 		exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.stream);
 		return;
 	}
 	const unsigned int bs = dslash_blocks(0, 1), bb = dslash_blocks(lo + 1, hi - 1);
 	const unsigned int target = 2 * bs + bb;
+	// peer-memory channel: the two surface kernels store their slice into the neighbours' staging slots
+	// themselves (compute + transfer in one kernel).  A solver's `skip` flag (set in the same iteration on
+	// every rank, because the all-reduced scalars are bit-identical) silences producers and consumer alike;
+	// sequence numbers keep counting on the host, flags only ever grow.
+	const bool p2p = c.p2p.on;
+	const unsigned long long seq = p2p ? ++c.p2p.seq : 0;
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_p, c.ev_fork, 0));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_m, c.ev_fork, 0));
-	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p);        // d3p
-	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m);       // d3m
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p, p2p ? 1 : 0, seq);    // d3p
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m, p2p ? 2 : 0, seq);   // d3m
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, c.s_p));
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, c.s_m));
 	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo + 1, hi - 1, dot_slot, target, 2 * bs, skip, c.stream);   // bulk
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_p, 0));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_m, 0));
-	exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.s_comm);
+	if (p2p) p2p_unpack(out, sizeof(cplx_t<T>), seq, c.s_comm, skip);
+	else exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.s_comm);
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_comm, c.s_comm));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
 }
@@ -326,10 +462,10 @@ template void apply_mdagm<float>(const float2 *, float2 *, const float2 *, float
 																 int, const int *);
 template void launch_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,
 																		const double2 *, double, int, int, int, unsigned int, unsigned int, const int *,
-																		cudaStream_t);
+																		cudaStream_t, int, unsigned long long);
 template void launch_dslash<float>(int, int, const float2 *, float2 *, const float2 *, const float *,
 																	 const float2 *, double, int, int, int, unsigned int, unsigned int, const int *,
-																	 cudaStream_t);
+																	 cudaStream_t, int, unsigned long long);
 
 // ------------------------------------------------------------------ BLAS-1 element-wise kernels
 // All arithmetic in double with double factors, stored back in T: this is what the reference's FP32

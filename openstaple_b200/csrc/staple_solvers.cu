@@ -24,11 +24,13 @@ struct CgmCtl {
 	double alpha, delta, lambda, omega, omega_save, gammag, source_norm, residuo;
 	double zeta_i[MAX_APPROX_ORDER], zeta_ii[MAX_APPROX_ORDER], zeta_iii[MAX_APPROX_ORDER];
 	double omegas[MAX_APPROX_ORDER], gammas[MAX_APPROX_ORDER], shifts[MAX_APPROX_ORDER];
+	// coefficients of the search-direction update ps_i = pgam_i ps_i + pzeta_i r that the reference performs at
+	// the end of an iteration (:152-157); here it is carried into the next iteration's single pass over ps_i
+	double pgam[MAX_APPROX_ORDER], pzeta[MAX_APPROX_ORDER];
 	int flag[MAX_APPROX_ORDER];    // current flags (inverter_multishift_full.c:58)
-	int uflag[MAX_APPROX_ORDER];   // flags as they were when this iteration's updates were issued
-	int order, maxiter, umaxiter, cg, max_cg;
-	int done;        // set when maxiter==0 or cg==max_cg: later Dslash/update kernels are no-ops
-	int stop_u2;     // set one "iteration" later: silences the trailing shifted-vector update too
+	int order, maxiter, cg, max_cg;
+	int pending;     // 1 once a ps_i update is waiting (every iteration but the first)
+	int done;        // set when maxiter==0 or cg==max_cg: every later kernel is a no-op
 	long long active_sum;
 };
 
@@ -43,16 +45,16 @@ __global__ void cgm_init_kernel(CgmCtl *c, const double *delta_slot, const doubl
 	c->delta = *delta_slot; c->source_norm = *srcnorm_slot;
 	c->omega = 1.0; c->gammag = 0.0; c->alpha = 0.0; c->lambda = 0.0; c->omega_save = 1.0;
 	for (int i = 0; i < c->order; i++) {
-		c->flag[i] = 1; c->uflag[i] = 1; c->zeta_i[i] = 1.0; c->zeta_ii[i] = 1.0; c->zeta_iii[i] = 1.0;
-		c->gammas[i] = 0.0; c->omegas[i] = 0.0;
+		c->flag[i] = 1; c->zeta_i[i] = 1.0; c->zeta_ii[i] = 1.0; c->zeta_iii[i] = 1.0;
+		c->gammas[i] = 0.0; c->omegas[i] = 0.0; c->pgam[i] = 1.0; c->pzeta[i] = 0.0;
 	}
-	c->maxiter = c->order; c->umaxiter = c->order; c->cg = 0; c->done = 0; c->stop_u2 = 0; c->active_sum = 0;
+	c->maxiter = c->order; c->cg = 0; c->done = 0; c->pending = 0; c->active_sum = 0;
 }
 
 // after alpha = Re(p, s) (:122-137)
 __global__ void cgm_after_alpha_kernel(CgmCtl *c, const double *alpha_slot)
 {
-	if (c->done) { if (threadIdx.x == 0) c->stop_u2 = 1; return; }
+	if (c->done) return;
 	const int i = threadIdx.x;
 	const double alpha = *alpha_slot;
 	const double omega_save = c->omega, delta = c->delta, gammag = c->gammag;
@@ -81,10 +83,10 @@ __global__ void cgm_after_lambda_kernel(CgmCtl *c, const double *lambda_slot)
 	int active = 0, was = 0;
 	if (i < order) {
 		was = c->flag[i];
-		c->uflag[i] = was;
 		if (was == 1) {
 			const double zii = c->zeta_ii[i], ziii = c->zeta_iii[i];
-			c->gammas[i] = gammag * ziii * c->omegas[i] / (zii * omega);
+			const double gi = gammag * ziii * c->omegas[i] / (zii * omega);
+			c->gammas[i] = gi; c->pgam[i] = gi; c->pzeta[i] = ziii;
 			const double fact = sqrt(delta * zii * zii / source_norm);
 			if (fact < residuo * kSafetyMargin) c->flag[i] = 0;
 			else active = 1;
@@ -95,26 +97,14 @@ __global__ void cgm_after_lambda_kernel(CgmCtl *c, const double *lambda_slot)
 	const unsigned int wasm = __ballot_sync(0xffffffffu, was == 1);
 	const unsigned int act = __ballot_sync(0xffffffffu, active);
 	if (i == 0) {
-		c->umaxiter = old_maxiter;
+		(void) old_maxiter;
 		const int maxiter = act ? 32 - __clz(act) : 0;   // highest still-active shift + 1
-		c->maxiter = maxiter;
+		c->maxiter = maxiter; c->pending = 1;
 		c->lambda = lambda; c->gammag = gammag; c->delta = lambda;
 		c->active_sum += __popc(wasm);
 		if (maxiter == 0 || cg >= max_cg) c->done = 1;
 	}
 }
-
-// out_i -= omega_i ps_i (active i) ; r += omega s ; lambda partial = |r|^2 over the reduction range
-// (:139-142; multiple_combine_in1_minus_in2x_factor_back_into_in1 + combine_add_factor_x_in2_to_in1 + l2norm2)
-template <typename T>
-__global__ void __launch_bounds__(kBlasBlock) cgm_update1_kernel(const CgmCtl *c, cplx_t<T> *out, const cplx_t<T> *ps,
-																																cplx_t<T> *r, const cplx_t<T> *s, long lo, long cnt, long n,
-																																long r0_lo, long r0_hi, double *partials,
-																																unsigned int *ticket, double *result);
-// p = r + gammag p ; ps_i = gamma_i ps_i + zeta_i^+ r  (:147-157)
-template <typename T>
-__global__ void __launch_bounds__(kBlasBlock) cgm_update2_kernel(const CgmCtl *c, cplx_t<T> *ps, cplx_t<T> *p,
-																																const cplx_t<T> *r, long lo, long cnt, long n);
 
 __device__ __forceinline__ void block_sum1(double &v, double *sm)
 {
@@ -132,41 +122,60 @@ __device__ __forceinline__ void block_sum1(double &v, double *sm)
 	}
 }
 
+// The ONE pass over the shifted vectors of an iteration (192 B per site and active shift in FP64):
+//   ps_i  <- pgam_i ps_i + pzeta_i r     the update the reference does at the end of the PREVIOUS iteration
+//                                        (:152-157, multiple1_combine_in1_x_fact1_plus_in2_x_fact2_back_into_in1)
+//   out_i <- out_i - omega_i ps_i        (:139,     multiple_combine_in1_minus_in2x_factor_back_into_in1)
+//   r     <- r + omega s ; lambda = |r|^2 over the reduction range   (:140-142)
+// Element for element the same arithmetic in the same order as the reference (ps_i is rounded to T before
+// it enters out_i, as it is when it goes through memory there); shifts that have converged are skipped:
+// their ps_i can no longer reach an output.
 template <typename T>
-__global__ void __launch_bounds__(kBlasBlock) cgm_update1_kernel(const CgmCtl *c, cplx_t<T> *out, const cplx_t<T> *ps,
-																																cplx_t<T> *r, const cplx_t<T> *s, long lo, long cnt, long n,
-																																long r0_lo, long r0_hi, double *partials,
-																																unsigned int *ticket, double *result)
+__global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, cplx_t<T> *out, cplx_t<T> *ps, cplx_t<T> *r,
+																																const cplx_t<T> *s, long lo, long cnt, long n, long r0_lo,
+																																long r0_hi, double *partials, unsigned int *ticket,
+																																double *result)
 {
 	if (c->done) return;
 	__shared__ double sm[32];
 	__shared__ bool last;
-	__shared__ double s_om[MAX_APPROX_ORDER];
+	__shared__ double s_om[MAX_APPROX_ORDER], s_g[MAX_APPROX_ORDER], s_z[MAX_APPROX_ORDER];
 	__shared__ int s_fl[MAX_APPROX_ORDER];
 	const int maxiter = c->maxiter;
-	if (threadIdx.x < maxiter) { s_om[threadIdx.x] = c->omegas[threadIdx.x]; s_fl[threadIdx.x] = c->flag[threadIdx.x]; }
+	if (threadIdx.x < maxiter) {
+		s_om[threadIdx.x] = c->omegas[threadIdx.x]; s_fl[threadIdx.x] = c->flag[threadIdx.x];
+		s_g[threadIdx.x] = c->pgam[threadIdx.x]; s_z[threadIdx.x] = c->pzeta[threadIdx.x];
+	}
 	const double omega = c->omega;
+	const int pending = c->pending;
 	__syncthreads();
 	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
 	double nrm = 0.0;
 	if (t < cnt) {
 		const long i = lo + t;
+		cplx_t<T> rv[3];
 #pragma unroll
 		for (int col = 0; col < 3; col++) {
 			const long j = col * n + i;
-			const cplx_t<T> rv = r[j], sv = s[j];
-			const cplx_t<T> rn = mkc<T>(rv.x + omega * sv.x, rv.y + omega * sv.y);
+			rv[col] = r[j];
+			const cplx_t<T> sv = s[j];
+			const cplx_t<T> rn = mkc<T>(rv[col].x + omega * sv.x, rv[col].y + omega * sv.y);
 			r[j] = rn;
 			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
 		}
 		for (int ia = 0; ia < maxiter; ia++) {
 			if (s_fl[ia] != 1) continue;
-			const double f = s_om[ia];
+			const double f = s_om[ia], g = s_g[ia], z = s_z[ia];
 			const long base = (long) ia * 3 * n;
 #pragma unroll
 			for (int col = 0; col < 3; col++) {
 				const long k = base + col * n + i;
-				const cplx_t<T> o = out[k], q = ps[k];
+				cplx_t<T> q = ps[k];
+				const cplx_t<T> o = out[k];
+				if (pending) {
+					q = mkc<T>(g * q.x + z * rv[col].x, g * q.y + z * rv[col].y);
+					ps[k] = q;
+				}
 				out[k] = mkc<T>(o.x - f * q.x, o.y - f * q.y);
 			}
 		}
@@ -181,47 +190,35 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_update1_kernel(const CgmCtl *c
 	if (last) {
 		__threadfence();
 		double acc = 0.0;
-		for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) acc += __ldcg(partials + k);
+		for (unsigned int k0 = threadIdx.x; k0 < gridDim.x; k0 += 8 * blockDim.x) {
+			double x[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const unsigned int k = k0 + j * blockDim.x;
+				x[j] = k < gridDim.x ? __ldcg(partials + k) : 0.0;
+			}
+#pragma unroll
+			for (int j = 0; j < 8; j++) acc += x[j];
+		}
 		block_sum1(acc, sm);
 		if (threadIdx.x == 0) { result[0] = acc; *ticket = 0u; }
 	}
 }
 
+// p = r + gammag p  (:147-148, combine_in1xfactor_plus_in2(loc_p, gammag, loc_r, loc_p)) with gammag on the device
 template <typename T>
-__global__ void __launch_bounds__(kBlasBlock) cgm_update2_kernel(const CgmCtl *c, cplx_t<T> *ps, cplx_t<T> *p,
-																																const cplx_t<T> *r, long lo, long cnt, long n)
+__global__ void __launch_bounds__(kBlasBlock) cgm_pupdate_kernel(const CgmCtl *c, cplx_t<T> *p, const cplx_t<T> *r, long lo,
+																																	long cnt, long n)
 {
-	if (c->stop_u2) return;
-	__shared__ double s_g[MAX_APPROX_ORDER], s_z[MAX_APPROX_ORDER];
-	__shared__ int s_fl[MAX_APPROX_ORDER];
-	const int maxiter = c->umaxiter;
-	if (threadIdx.x < maxiter) {
-		s_g[threadIdx.x] = c->gammas[threadIdx.x]; s_z[threadIdx.x] = c->zeta_iii[threadIdx.x];
-		s_fl[threadIdx.x] = c->uflag[threadIdx.x];
-	}
+	if (c->done) return;
 	const double gammag = c->gammag;
-	__syncthreads();
 	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
 	if (t >= cnt) return;
-	const long i = lo + t;
-	cplx_t<T> rv[3];
 #pragma unroll
 	for (int col = 0; col < 3; col++) {
-		const long j = col * n + i;
-		rv[col] = r[j];
-		const cplx_t<T> pv = p[j];
-		p[j] = mkc<T>(pv.x * gammag + rv[col].x, pv.y * gammag + rv[col].y);
-	}
-	for (int ia = 0; ia < maxiter; ia++) {
-		if (s_fl[ia] != 1) continue;
-		const double g = s_g[ia], z = s_z[ia];
-		const long base = (long) ia * 3 * n;
-#pragma unroll
-		for (int col = 0; col < 3; col++) {
-			const long k = base + col * n + i;
-			const cplx_t<T> q = ps[k];
-			ps[k] = mkc<T>(g * q.x + z * rv[col].x, g * q.y + z * rv[col].y);
-		}
+		const long j = col * n + lo + t;
+		const cplx_t<T> pv = p[j], rv = r[j];
+		p[j] = mkc<T>(pv.x * gammag + rv.x, pv.y * gammag + rv.y);
 	}
 }
 
@@ -305,12 +302,12 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done);
 			allreduce_results(SLOT_ALPHA, 1, st);
 			cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA));
-			cgm_update1_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
-																												 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
-																												 result(SLOT_LAMBDA));
+			cgm_fused_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
+																											 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
+																											 result(SLOT_LAMBDA));
 			allreduce_results(SLOT_LAMBDA, 1, st);
 			cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA));
-			cgm_update2_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, shiftferm, loc_p, loc_r, lo, cnt, n);
+			cgm_pupdate_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, lo, cnt, n);
 			count_launch(4);
 		}
 		issued += batch;

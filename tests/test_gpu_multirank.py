@@ -1,0 +1,132 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): one process per GPU, D3 slabs,
+NCCL / peer-memory halo exchange inside acc_Deo/acc_Doe, all-reduced CG scalars -- against the
+single-rank CPU oracle on the GLOBAL lattice and the reference's committed two-rank outputs.
+
+Run directly on a multi-GPU box:  python -m pytest tests/test_gpu_multirank.py -m gpu -x -q
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+EB = (5.0, -5.0, 1.0, -5.0, 5.0, 3.0)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _worker(rank, world, port, loc, mode, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        import openstaple_b200 as osb
+        from oracle.pyoracle import Restatement, gaussian_vec, random_su3_conf
+        torch.cuda.set_stream(torch.cuda.Stream(device=torch.device("cuda", rank)))
+        lat = osb.Lattice(loc, nranks_d3=world, device=rank)
+        lat.init_multidev(dist, async_comm_fermion=mode["async"], p2p=mode["p2p"])
+        S = Restatement(*loc, nr=world)
+        G = Restatement(loc[0], loc[1], loc[2], loc[3] * world)
+        u = random_su3_conf(G.sizeh, 3); v = gaussian_vec(G.sizeh, 4)
+        phg = G.phases(0, EB, 1.0, 2.0)
+        lu, lv, ph = S.scatter_conf(rank, u), S.scatter_vec(rank, v), S.phases(rank, EB, 1.0, 2.0)
+        errs = {}
+        # ---- link halos: scatter WITHOUT valid halos, then communicate_su3_borders must restore them
+        lu_nohalo = lu.copy()
+        h = S.d3_halo * S.vol3h
+        lu_nohalo[..., :h] = 0; lu_nohalo[..., S.sizeh - h:] = 0
+        du = lat.to_device(lu_nohalo)
+        lat.communicate_su3_borders(du, 2)
+        got = du.cpu().numpy()
+        errs["su3_borders_rows01"] = float(np.abs(got[:, :2] - lu[:, :2]).max())        # rows r0,r1 only are exchanged
+        du = lat.to_device(lu)
+        # ---- fermion halos
+        lv_nohalo = lv.copy(); lv_nohalo[:, :h] = 0; lv_nohalo[:, S.sizeh - h:] = 0
+        dv = lat.to_device(lv_nohalo)
+        lat.communicate_fermion_borders(dv)
+        r1lo, r1hi = S.g.r1_lo, S.g.r1_hi
+        errs["fermion_borders"] = float(np.abs(dv.cpu().numpy()[:, r1lo:r1hi] - lv[:, r1lo:r1hi]).max())
+        dv = lat.to_device(lv); dph = lat.to_device(ph)
+        # ---- operator with exchange: compare interior + 1 halo slice with the global oracle result
+        for name, which in (("acc_Doe", "doe"), ("acc_Deo", "deo")):
+            want = S.scatter_vec(rank, G.dslash(which, u, v, phg))
+            out = lat.new_vec()
+            for _ in range(3):          # repeated: exercises the double-buffered peer staging
+                getattr(lat, name)(du, out, dv, dph)
+            o = out.cpu().numpy()
+            errs[name] = _relerr(o[:, r1lo:r1hi], want[:, r1lo:r1hi])
+        # ---- M^+M and reductions
+        pars = lat.ferm_param(0.0507, dph)
+        out, tmp = lat.new_vec(), lat.new_vec()
+        lat.fermion_matrix_multiplication(du, out, dv, tmp, pars)
+        want = S.scatter_vec(rank, G.mdagm(u, v, phg, 0.0507))
+        errs["mdagm"] = _relerr(out.cpu().numpy()[:, r1lo:r1hi], want[:, r1lo:r1hi])
+        errs["l2norm2"] = abs(lat.l2norm2_global(dv) / G.l2norm2(v) - 1)
+        # ---- CG-M against the global oracle
+        shifts = np.array([1e-3, 1e-2, 0.1, 1.0])
+        wantx, cg_ref, ok, _ = G.multishift_invert(u, phg, 0.0507, shifts, v, 1e-8, 5000)
+        approx = osb.RationalApprox.make(1.0, np.ones(4), shifts)
+        sol, ps = lat.new_vec(4), lat.new_vec(4)
+        r, hh, s, p = (lat.new_vec() for _ in range(4))
+        st, cg = lat.multishift_invert(du, pars, approx, sol, dv, 1e-8, r, hh, s, p, ps, 5000)
+        got = sol.cpu().numpy()
+        r0lo, r0hi = S.g.r0_lo, S.g.r0_hi
+        e = 0.0
+        for i in range(4):
+            w = S.scatter_vec(rank, wantx[i])
+            e = max(e, _relerr(got[i][:, r0lo:r0hi], w[:, r0lo:r0hi]))
+        errs["cgm_sol"] = e
+        errs["cgm_iters"] = abs(cg - cg_ref) / cg_ref
+        errs["cgm_status"] = 0.0 if st == 1 else 1.0
+        lat.shutdown_multidev()
+        dist.destroy_process_group()
+        q.put((rank, errs, ""))
+    except Exception:      # pragma: no cover
+        import traceback
+        q.put((rank, {}, traceback.format_exc()))
+
+
+def _run(world, loc, mode):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue(); port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, loc, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    for rank, errs, tb in sorted(res):
+        assert tb == "", tb
+        assert errs["su3_borders_rows01"] == 0.0 and errs["fermion_borders"] == 0.0, (rank, errs)
+        for k in ("acc_Doe", "acc_Deo", "mdagm"):
+            assert errs[k] < 1e-13, (rank, k, errs)
+        assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0
+        assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)
+
+
+@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1))],
+                         ids=["sync-nccl", "async-nccl", "async-p2p"])
+@pytest.mark.parametrize("world,loc", [(2, (8, 8, 8, 8)), (2, (8, 4, 6, 2))])
+def test_two_gpus(world, loc, mode):
+    _run(world, loc, mode)
+
+
+@pytest.mark.parametrize("mode", [dict(**{"async": 1, "p2p": 1})], ids=["async-p2p"])
+def test_four_gpus(mode):
+    _run(4, (8, 8, 8, 4), mode)
