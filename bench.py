@@ -229,7 +229,7 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream(device=torch.device("cuda", local_rank)))
     lat = osb.Lattice(loc, nranks_d3=world, halo_width=2, device=local_rank)
     if world > 1:
-        lat.init_multidev(dist, async_comm_fermion=1)
+        lat.init_multidev(dist, async_comm_fermion=1, p2p=int(os.environ.get("STAPLE_P2P", "1")))
     dev = lat.device
     u, v = make_fields(torch, lat, seed=1 + rank)
     ph_host = staggered_phases(lat, rank)
@@ -378,6 +378,7 @@ def main():
                 "config": {"workload": "deo_doe %s per GPU, FP64, one acc_Doe + one acc_Deo per step, D3 slabs over %d GPU(s)"
                                        % (args.lattice, world),
                            "global_lattice": "%dx%dx%dx%d" % (loc[0], loc[1], loc[2], loc[3] * world),
+                           "halo": ("nvlink peer stores fused in the surface kernels" if getattr(lat, "p2p", False) else "nccl send/recv") if world > 1 else "none",
                            "l2_policy": "inputs larger than L2 (links 384 MiB read per application at 32^4 vs 126 MB L2)",
                            "flop_per_site": FLOP_PER_SITE, "bytes_per_site": BYTES_PER_SITE_FP64},
                 "hbm_GBps": BYTES_PER_SITE_FP64 * sites_per_step / world / (ms_step * 1e-3) / 1e9,
