@@ -9,7 +9,17 @@
 
 namespace staple {
 
-constexpr int kBlock = 128;      // dslash CTA size
+// tuning knobs (scripts/tune_dslash.py sweeps them; the defaults are the measured optimum, profiles/)
+#ifndef STAPLE_DSLASH_BLOCK
+#define STAPLE_DSLASH_BLOCK 128
+#endif
+#ifndef STAPLE_DSLASH_MINBLOCKS
+#define STAPLE_DSLASH_MINBLOCKS 1
+#endif
+#ifndef STAPLE_LINK_LOAD
+#define STAPLE_LINK_LOAD 0       // 0: ld.global.cs (evict-first streaming)  1: ld.global.nc  2: ld.global.lu  3: plain
+#endif
+constexpr int kBlock = STAPLE_DSLASH_BLOCK;      // dslash CTA size
 constexpr int kBlasBlock = 256;
 
 // ------------------------------------------------------------------ small complex helpers
@@ -18,7 +28,18 @@ template <> __device__ __forceinline__ double2 mk<double>(double x, double y) { 
 template <> __device__ __forceinline__ float2 mk<float>(float x, float y) { return make_float2(x, y); }
 
 // streaming (read-once) loads for links/phases, cached read-only loads for spinors
-template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ V ld_stream(const V *p)
+{
+#if STAPLE_LINK_LOAD == 0
+	return __ldcs(p);
+#elif STAPLE_LINK_LOAD == 1
+	return __ldg(p);
+#elif STAPLE_LINK_LOAD == 2
+	return __ldlu(p);
+#else
+	return *p;
+#endif
+}
 template <typename V> __device__ __forceinline__ V ld_cached(const V *p) { return __ldg(p); }
 
 template <typename C> __device__ __forceinline__ C cmul(C a, C b)   // a*b
@@ -288,7 +309,7 @@ void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s)
 
 // ------------------------------------------------------------------ Dirac operator kernel
 template <typename T, int PAR, int EPI>
-__global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArgs<T> a)
+__global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<T> a)
 {
 	using C = cplx_t<T>;
 	if (a.skip != nullptr && *a.skip != 0) return;

@@ -8,7 +8,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(HERE, "libstaple_b200.so")
+    # STAPLE_LIB selects a tuning variant of the SAME CUDA library (scripts/tune_dslash.py); never a fallback
+    return os.environ.get("STAPLE_LIB") or os.path.join(HERE, "libstaple_b200.so")
 
 
 def load_library(build_if_missing=True):
