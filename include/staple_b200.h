@@ -148,6 +148,8 @@ int staple_geometry_plan(const int loc_n[4], int nranks_d3, int halo_width, long
  * stream (e.g. torch's default stream).  staple_use_library_stream() switches back. */
 void staple_set_stream(void *cuda_stream);
 void staple_use_library_stream(void);
+/* CG-M replays its iteration batches as CUDA graphs on a single GPU (default on; 0 = direct launches). */
+void staple_set_use_graphs(int on);
 void *staple_get_stream(void);
 void staple_synchronize(void);
 /* number of CUDA kernels launched by this library since start (bench.py "gpu_launches") */
@@ -174,7 +176,9 @@ int staple_nccl_unique_id(void *id128);
 int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_comm_fermion);
 /* Optional (collective, after staple_init_multidev1D): fermion halos through NVLink peer memory instead of
  * ncclSend/Recv -- the surface kernels of acc_Deo/acc_Doe store their slice straight into the neighbour's
- * staging area (CUDA IPC) and raise a flag; returns 1 if active, 0 if it fell back to NCCL. */
+ * staging area (CUDA IPC) and raise a flag; returns 1 if active, 0 if it fell back to NCCL.
+ * on = 1: acc_Deo/acc_Doe are ONE kernel (face blocks first, then bulk) + one unpack kernel;
+ * on = 2: the reference's three-queue structure (d3p, d3m, bulk on separate streams) with peer stores. */
 int staple_enable_p2p(int on);
 void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
 int staple_myrank(void);

@@ -288,6 +288,7 @@ void staple_set_stream(void *s)
 	require_init("staple_set_stream");
 	ctx().stream = (cudaStream_t) s;
 }
+void staple_set_use_graphs(int on) { ctx().use_graphs = on != 0; }
 void staple_use_library_stream(void)
 {
 	require_init("staple_use_library_stream");
@@ -409,6 +410,7 @@ int staple_enable_p2p(int on)
 	Ctx &c = ctx();
 	P2P &p = c.p2p;
 	if (!on || c.nranks <= 1) { p.on = false; return 0; }
+	c.p2p_single_launch = (on != 2);                   // 2: keep the reference's d3p/d3m/bulk three-queue structure
 	if (p.stage_L) { p.on = true; return 1; }          // already mapped
 	if (!c.comm) { fprintf(stderr, "libstaple_b200: staple_enable_p2p before staple_init_multidev1D\n"); exit(1); }
 	const Geom &g = c.g;

@@ -70,6 +70,8 @@ struct Ctx {
 	int myrank = 0, nranks = 1, rank_L = 0, rank_R = 0, async_comm_fermion = 0;
 	Comm *comm = nullptr;
 	P2P p2p;
+	bool use_graphs = true;          // CG-M iteration batches as CUDA graphs (single GPU, non-default stream)
+	bool p2p_single_launch = true;   // acc_Deo/acc_Doe as one kernel + unpack (false: d3p/d3m/bulk on three streams)
 	// last multishift statistics
 	int last_iterations = 0;
 	long long last_active = 0;
@@ -124,6 +126,15 @@ struct DslashArgs {
 	unsigned long long *peer_flag;
 	unsigned long long peer_seq;
 	unsigned int *face_ticket;
+	// single-launch operator with fused halo push (fused != 0): blocks [0,fb) compute the TOP interior slice
+	// (-> rank R), blocks [fb,2fb) the BOTTOM one (-> rank L), the rest the bulk -- faces are scheduled first,
+	// so their NVLink stores overlap the bulk of the same kernel
+	int fused;
+	unsigned int face_blocks;
+	long top_lo, bot_lo;      // first idxh of the two surface slices; site_lo/nsites describe the bulk
+	cplx_t<T> *peer2;         // bottom face target (peer = top face target)
+	unsigned long long *peer_flag2;
+	unsigned int *face_ticket2;
 	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites)
 	int nd0h, nd1, nd2, nd3;
 	long vol3h, sizeh;

@@ -14,7 +14,7 @@ namespace staple {
 #define STAPLE_DSLASH_BLOCK 128
 #endif
 #ifndef STAPLE_DSLASH_MINBLOCKS
-#define STAPLE_DSLASH_MINBLOCKS 1
+#define STAPLE_DSLASH_MINBLOCKS 7       // 72 registers, 28 warps/SM: +8% over the unconstrained build (profiles/r01_tune_dslash_*.txt)
 #endif
 #ifndef STAPLE_LINK_LOAD
 #define STAPLE_LINK_LOAD 0       // 0: ld.global.cs (evict-first streaming)  1: ld.global.nc  2: ld.global.lu  3: plain
@@ -202,13 +202,14 @@ __device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials
 // ------------------------------------------------------------------ peer-memory halo channel (device side)
 // Producer: every thread has issued its peer stores; the last block to finish publishes `seq` in the
 // neighbour's flag with system-scope release semantics (fence.sys by all writers, ticket, fence.sys, store).
-__device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsigned long long seq, unsigned int *ticket)
+__device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsigned long long seq, unsigned int *ticket,
+																						unsigned int nblocks)
 {
 	__threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		const unsigned int t = atomicAdd(ticket, 1u);
-		if (t == gridDim.x - 1) {
+		if (t == nblocks - 1) {
 			__threadfence_system();
 			*ticket = 0u;
 			asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(seq) : "memory");
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(const C *src, long n, lon
 		const long c = t / vol3h, i = t - c * vol3h;
 		peer[t] = src[c * n + slice_lo + i];
 	}
-	face_signal(peer_flag, seq, ticket);
+	face_signal(peer_flag, seq, ticket, gridDim.x);
 }
 // copy both staging slots into the halo slices once the neighbours' data has landed
 template <typename C>
@@ -315,10 +316,25 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 	if (a.skip != nullptr && *a.skip != 0) return;
 	// sizeh < 2^31 is checked at staple_init_geometry: site indices are 32-bit (no 64-bit divisions),
 	// only the array bases (k*9*sizeh) are 64-bit
-	const unsigned int t = blockIdx.x * kBlock + threadIdx.x;
+	unsigned int t = blockIdx.x * kBlock + threadIdx.x;
+	unsigned int lo = (unsigned int) a.site_lo, ns = (unsigned int) a.nsites;
+	C *peer = a.peer;
+	unsigned long long *peer_flag = a.peer_flag;
+	unsigned int *face_ticket = a.face_ticket;
+	unsigned int face_nblocks = gridDim.x;
+	if (a.fused) {            // block-uniform segment selection: top face, bottom face, bulk
+		const unsigned int fb = a.face_blocks;
+		face_nblocks = fb;
+		if (blockIdx.x < fb) { lo = (unsigned int) a.top_lo; ns = (unsigned int) a.vol3h; }
+		else if (blockIdx.x < 2 * fb) {
+			t -= fb * kBlock; lo = (unsigned int) a.bot_lo; ns = (unsigned int) a.vol3h;
+			peer = a.peer2; peer_flag = a.peer_flag2; face_ticket = a.face_ticket2;
+		}
+		else { t -= 2 * fb * kBlock; peer = nullptr; }
+	}
 	double dot = 0.0;
-	if (t < (unsigned int) a.nsites) {
-		const unsigned int idx = (unsigned int) a.site_lo + t;
+	if (t < ns) {
+		const unsigned int idx = lo + t;
 		const long n = a.sizeh;
 		const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
 		const unsigned int hd0 = idx % nd0h;
@@ -362,10 +378,10 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
 			}
 			a.out[c * n + idx] = o;
-			if (a.peer != nullptr) a.peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
+			if (peer != nullptr) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
-	if (a.peer != nullptr) face_signal(a.peer_flag, a.peer_seq, a.face_ticket);
+	if (peer != nullptr) face_signal(peer_flag, a.peer_seq, face_ticket, face_nblocks);
 	if (EPI == EPI_MASS_DOT) {
 		double v[1] = { dot };
 		grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
@@ -388,7 +404,15 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	if (d3hi <= d3lo) return;
 	DslashArgs<T> a;
 	a.peer = nullptr; a.peer_flag = nullptr; a.peer_seq = 0; a.face_ticket = nullptr;
-	if (face != 0) {
+	a.fused = 0; a.face_blocks = 0; a.top_lo = a.bot_lo = 0; a.peer2 = nullptr; a.peer_flag2 = nullptr; a.face_ticket2 = nullptr;
+	if (face == 3) {         // whole local interior in one launch, both faces pushed
+		P2P &p = ctx().p2p;
+		a.fused = 1; a.face_blocks = dslash_blocks(0, 1);
+		a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
+		a.peer = (cplx_t<T> *) p2p_slot(p.stage_R, seq, 0); a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0;
+		a.peer2 = (cplx_t<T> *) p2p_slot(p.stage_L, seq, 1); a.peer_flag2 = p.flags_L + 1; a.face_ticket2 = p.tickets + 1;
+		a.peer_seq = seq;
+	} else if (face != 0) {
 		P2P &p = ctx().p2p;
 		a.peer = (cplx_t<T> *) p2p_slot(face == 1 ? p.stage_R : p.stage_L, seq, face == 1 ? 0 : 1);
 		a.peer_flag = face == 1 ? p.flags_R + 0 : p.flags_L + 1;
@@ -400,8 +424,9 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	a.result = dot_slot >= 0 ? result(dot_slot) : nullptr;
 	a.ticket_target = ticket_target; a.partial_offset = partial_offset; a.skip = skip;
 	a.site_lo = (long) d3lo * g.vol3h; a.nsites = (long) (d3hi - d3lo) * g.vol3h;
+	if (a.fused) { a.site_lo = (long) (d3lo + 1) * g.vol3h; a.nsites = (long) (d3hi - d3lo - 2) * g.vol3h; }   // bulk
 	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;
-	const unsigned int grid = dslash_blocks(d3lo, d3hi);
+	const unsigned int grid = a.fused ? 2 * a.face_blocks + dslash_blocks(d3lo + 1, d3hi - 1) : dslash_blocks(d3lo, d3hi);
 #define STAPLE_LAUNCH(P, E) dslash_kernel<T, P, E><<<grid, kBlock, 0, s>>>(a)
 	if (par == 0) {
 		if (epi == EPI_NONE) STAPLE_LAUNCH(0, EPI_NONE);
@@ -441,6 +466,15 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 	}
 	const unsigned int bs = dslash_blocks(0, 1), bb = dslash_blocks(lo + 1, hi - 1);
 	const unsigned int target = 2 * bs + bb;
+	if (c.p2p.on && c.p2p_single_launch) {
+		// ONE kernel: the face blocks (scheduled first) push their slice into the neighbours' staging slots
+		// over NVLink while the bulk blocks of the same launch run; then the unpack of what the neighbours
+		// pushed.  No stream fork/join, no events.
+		const unsigned long long seq1 = ++c.p2p.seq;
+		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3, seq1);
+		p2p_unpack(out, sizeof(cplx_t<T>), seq1, c.stream, skip);
+		return;
+	}
 	// peer-memory channel: the two surface kernels store their slice into the neighbours' staging slots
 	// themselves (compute + transfer in one kernel).  A solver's `skip` flag (set in the same iteration on
 	// every rank, because the all-reduced scalars are bit-identical) silences producers and consumer alike;

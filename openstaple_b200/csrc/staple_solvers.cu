@@ -296,7 +296,7 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	const int batch = 8;
 	int issued = 0, snap = 0, pending[2] = { 0, 0 };
 	bool finished = false;
-	while (!finished) {
+	auto enqueue_batch = [&]() {
 		for (int b = 0; b < batch; b++) {
 			// s = (M^+M) p, alpha = Re(p,s) fused in the Deo epilogue (:113-118)
 			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done);
@@ -310,6 +310,30 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 			cgm_pupdate_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, lo, cnt, n);
 			count_launch(4);
 		}
+	};
+	// Single GPU: a batch is a fixed sequence of launches on one stream whose every data dependence (flags,
+	// coefficients, `done`) lives in device memory, so it is captured ONCE into a CUDA graph and replayed --
+	// the iteration is launch-gap bound on small lattices.  (Multi-GPU batches carry per-exchange sequence
+	// numbers as kernel arguments and stay on direct launches; so does the legacy default stream, which
+	// cannot be captured.)
+	cudaGraphExec_t gexec = nullptr;
+	const unsigned long long launches_before = c.launches;
+	unsigned long long launches_per_batch = 0;
+	if (c.nranks == 1 && st != nullptr && c.use_graphs) {
+		cudaGraph_t graph = nullptr;
+		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+			enqueue_batch();
+			cudaError_t e = cudaStreamEndCapture(st, &graph);
+			launches_per_batch = c.launches - launches_before;
+			c.launches = launches_before;
+			if (e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+			if (graph) cudaGraphDestroy(graph);
+		}
+		cudaGetLastError();
+	}
+	while (!finished) {
+		if (gexec) { STAPLE_CUDA_CHECK(cudaGraphLaunch(gexec, st)); c.launches += launches_per_batch; }
+		else enqueue_batch();
 		issued += batch;
 		STAPLE_CUDA_CHECK(cudaGetLastError());
 		STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_ctl[snap], g_d_ctl, sizeof(CgmCtl), cudaMemcpyDeviceToHost, st));
@@ -332,6 +356,7 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	STAPLE_CUDA_CHECK(cudaEventRecord(g_ev_t1, st));
 	STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_ctl[0], g_d_ctl, sizeof(CgmCtl), cudaMemcpyDeviceToHost, st));
 	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (gexec) cudaGraphExecDestroy(gexec);
 	const int cg = g_h_ctl[0].cg;
 	const double source_norm = g_h_ctl[0].source_norm;
 	float ms = 0;

@@ -41,6 +41,7 @@ def _declare(L):
     L.staple_set_stream.argtypes = [vp]
     L.staple_get_stream.restype = vp
     L.staple_use_library_stream.argtypes = []
+    L.staple_set_use_graphs.argtypes = [i]
     L.staple_kernel_launches.restype = C.c_ulonglong
     L.staple_version.restype = C.c_char_p
     L.staple_posix_memalign.argtypes = [C.POINTER(vp), C.c_size_t, C.c_size_t]; L.staple_posix_memalign.restype = i

@@ -13,8 +13,10 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = [(b, m, l) for b, m, l in itertools.product((64, 128, 256), (1, 2), (0, 1, 3))
             if not (b == 256 and m == 2)]
-VARIANTS = [(128, 1, 0), (128, 1, 1), (128, 1, 2), (128, 1, 3), (64, 1, 0), (256, 1, 0), (128, 8, 0), (64, 16, 0),
-            (256, 4, 0), (128, 7, 0), (64, 12, 0), (96, 1, 0), (192, 1, 0), (128, 8, 3), (32, 1, 0)]
+VARIANTS = [(128, 1, 0), (128, 7, 0), (64, 14, 0), (64, 13, 0), (32, 28, 0), (128, 7, 2), (256, 3, 0), (192, 4, 0), (192, 5, 0),
+            (96, 9, 0), (96, 10, 0), (160, 5, 0), (160, 6, 0), (224, 4, 0), (64, 12, 0), (64, 15, 0)]
+if os.environ.get("STAPLE_TUNE_VARIANTS"):
+    VARIANTS = [tuple(int(x) for x in v.split(",")) for v in os.environ["STAPLE_TUNE_VARIANTS"].split(";")]
 
 
 def tag(v):
@@ -28,7 +30,9 @@ def build():
         flags = ["-DSTAPLE_DSLASH_BLOCK=%d" % v[0], "-DSTAPLE_DSLASH_MINBLOCKS=%d" % v[1], "-DSTAPLE_LINK_LOAD=%d" % v[2]]
         out = os.path.join(VDIR, "libstaple_%s.so" % tag(v))
         b(force=True, extra_flags=flags, out=out, tag="var_" + tag(v))
-        print("built", out)
+        r = subprocess.run("cuobjdump -res-usage %s | c++filt | grep -A1 'dslash_kernel<double, 0, 0>' | grep -o 'REG:[0-9]*\\|STACK:[0-9]*'" % out,
+                           shell=True, capture_output=True, text=True)
+        print("built", tag(v), " ".join(r.stdout.split()), flush=True)
 
 
 SNIPPET = r"""

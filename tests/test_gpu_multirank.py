@@ -120,8 +120,8 @@ def _run(world, loc, mode):
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)
 
 
-@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1))],
-                         ids=["sync-nccl", "async-nccl", "async-p2p"])
+@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1), (1, 2))],
+                         ids=["sync-nccl", "async-nccl", "p2p-single-launch", "p2p-three-queues"])
 @pytest.mark.parametrize("world,loc", [(2, (8, 8, 8, 8)), (2, (8, 4, 6, 2))])
 def test_two_gpus(world, loc, mode):
     _run(world, loc, mode)
