@@ -81,6 +81,7 @@ struct Comm {
 	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -106,6 +107,7 @@ static Comm *load_nccl()
 	LOADSYM(Send, "ncclSend")
 	LOADSYM(Recv, "ncclRecv")
 	LOADSYM(AllReduce, "ncclAllReduce")
+	LOADSYM(AllGather, "ncclAllGather")
 	LOADSYM(GroupStart, "ncclGroupStart")
 	LOADSYM(GroupEnd, "ncclGroupEnd")
 	LOADSYM(GetErrorString, "ncclGetErrorString")
@@ -128,6 +130,7 @@ void allreduce_results(int slot, int ndoubles, cudaStream_t s)
 	Ctx &c = ctx();
 	if (c.nranks <= 1) return;
 	double *p = result(slot);
+	if (c.p2p.on && c.p2p.d_redq != nullptr && ndoubles <= 2) { p2p_allreduce(p, ndoubles, s); return; }
 	STAPLE_NCCL_CHECK(c.comm, c.comm->AllReduce(p, p, (size_t) ndoubles, ncclDouble, ncclSum, c.comm->comm, s));
 }
 
@@ -401,9 +404,17 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 	return 0;
 }
 
-// Peer-memory halo channel (collective: every rank calls it after staple_init_multidev1D).  Allocates the
-// staging area and flags, exports them with CUDA IPC, swaps the handles with the two ring neighbours over
-// the NCCL communicator (no MPI needed) and maps the neighbours' areas.  Returns 1 if the channel is active.
+// Peer-memory channels (collective: every rank calls it after staple_init_multidev1D).  Allocates the mailbox
+// (halo staging + flags + reduction boxes), exports it with CUDA IPC, all-gathers the handles over the NCCL
+// communicator (no MPI needed) and maps every rank's mailbox.  Returns 1 if the channels are active.
+static void nccl_barrier(cudaStream_t st)
+{
+	Ctx &c = ctx();
+	double *p = result(kResultSlots - 1);
+	STAPLE_NCCL_CHECK(c.comm, c.comm->AllReduce(p, p, 1, ncclDouble, ncclSum, c.comm->comm, st));
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
 int staple_enable_p2p(int on)
 {
 	require_init("staple_enable_p2p");
@@ -413,64 +424,71 @@ int staple_enable_p2p(int on)
 	c.p2p_single_launch = (on != 2);                   // 2: keep the reference's d3p/d3m/bulk three-queue structure
 	if (p.stage_L) { p.on = true; return 1; }          // already mapped
 	if (!c.comm) { fprintf(stderr, "libstaple_b200: staple_enable_p2p before staple_init_multidev1D\n"); exit(1); }
+	if (c.nranks > kMaxRanks) { fprintf(stderr, "libstaple_b200: peer-memory channels support up to %d ranks\n", kMaxRanks); return 0; }
 	const Geom &g = c.g;
 	p.slot_bytes = (size_t) 3 * g.vol3h * 16;
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.stage, 4 * p.slot_bytes));
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.flags, 2 * sizeof(unsigned long long)));
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 2 * sizeof(unsigned int)));
-	STAPLE_CUDA_CHECK(cudaMemset(p.flags, 0, 2 * sizeof(unsigned long long)));
-	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 2 * sizeof(unsigned int)));
-	struct Handles { cudaIpcMemHandle_t stage, flags; } mine, fromL, fromR;
-	STAPLE_CUDA_CHECK(cudaIpcGetMemHandle(&mine.stage, p.stage));
-	STAPLE_CUDA_CHECK(cudaIpcGetMemHandle(&mine.flags, p.flags));
-	Handles *d = nullptr;      // [0] mine, [1] from L, [2] from R
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &d, 3 * sizeof(Handles)));
-	STAPLE_CUDA_CHECK(cudaMemcpy(d, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+	const size_t mb_bytes = kMailboxStage + 4 * p.slot_bytes;
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.mailbox, mb_bytes));
+	STAPLE_CUDA_CHECK(cudaMemset(p.mailbox, 0, kMailboxStage));
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 4 * sizeof(unsigned int)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 4 * sizeof(unsigned int)));
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.d_seq, 2 * sizeof(unsigned long long)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.d_seq, 0, 2 * sizeof(unsigned long long)));
+	p.d_redq = p.d_seq + 1;
+	cudaIpcMemHandle_t mine;
+	STAPLE_CUDA_CHECK(cudaIpcGetMemHandle(&mine, p.mailbox));
+	cudaIpcMemHandle_t *d = nullptr, all[kMaxRanks];
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &d, (size_t) (c.nranks + 1) * sizeof(mine)));
+	STAPLE_CUDA_CHECK(cudaMemcpy(d + c.nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice));
 	Comm *n = c.comm;
 	cudaStream_t st = c.s_comm;
-	STAPLE_NCCL_CHECK(n, n->GroupStart());
-	STAPLE_NCCL_CHECK(n, n->Send(d, sizeof(Handles), ncclChar, c.rank_L, n->comm, st));
-	STAPLE_NCCL_CHECK(n, n->Recv(d + 2, sizeof(Handles), ncclChar, c.rank_R, n->comm, st));
-	STAPLE_NCCL_CHECK(n, n->Send(d, sizeof(Handles), ncclChar, c.rank_R, n->comm, st));
-	STAPLE_NCCL_CHECK(n, n->Recv(d + 1, sizeof(Handles), ncclChar, c.rank_L, n->comm, st));
-	STAPLE_NCCL_CHECK(n, n->GroupEnd());
+	STAPLE_NCCL_CHECK(n, n->AllGather(d + c.nranks, d, sizeof(mine), ncclChar, n->comm, st));
 	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
-	STAPLE_CUDA_CHECK(cudaMemcpy(&fromL, d + 1, sizeof(Handles), cudaMemcpyDeviceToHost));
-	STAPLE_CUDA_CHECK(cudaMemcpy(&fromR, d + 2, sizeof(Handles), cudaMemcpyDeviceToHost));
+	STAPLE_CUDA_CHECK(cudaMemcpy(all, d, (size_t) c.nranks * sizeof(mine), cudaMemcpyDeviceToHost));
 	STAPLE_CUDA_CHECK(cudaFree(d));
-	auto open = [](cudaIpcMemHandle_t h, void **out) {
-		cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
-		if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; }
-		return e;
-	};
-	cudaError_t e1 = open(fromL.stage, (void **) &p.stage_L), e2 = open(fromL.flags, (void **) &p.flags_L);
-	cudaError_t e3 = cudaSuccess, e4 = cudaSuccess;
-	if (c.rank_R == c.rank_L) { p.stage_R = p.stage_L; p.flags_R = p.flags_L; }   // two ranks: same neighbour on both sides
-	else { e3 = open(fromR.stage, (void **) &p.stage_R); e4 = open(fromR.flags, (void **) &p.flags_R); }
-	if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
-		fprintf(stderr, "MPI%02d - libstaple_b200: CUDA IPC mapping of the neighbours' halo staging failed (%s); "
-						"using NCCL send/recv for halos\n", c.myrank, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4));
-		p.stage_L = p.stage_R = nullptr; p.on = false;
-		return 0;
+	bool ok = true;
+	cudaError_t err = cudaSuccess;
+	for (int r = 0; r < c.nranks; r++) {
+		if (r == c.myrank) { p.peer_mailbox[r] = p.mailbox; continue; }
+		void *ptr = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { cudaGetLastError(); ok = false; err = e; ptr = nullptr; }
+		p.peer_mailbox[r] = (char *) ptr;
 	}
-	p.seq = 0;
+	// every rank must agree (a partial set-up would deadlock the first exchange): sum of failure flags
+	{
+		double bad = ok ? 0.0 : 1.0, *slot = result(kResultSlots - 1);
+		STAPLE_CUDA_CHECK(cudaMemcpy(slot, &bad, sizeof(double), cudaMemcpyHostToDevice));
+		nccl_barrier(st);
+		STAPLE_CUDA_CHECK(cudaMemcpy(&bad, slot, sizeof(double), cudaMemcpyDeviceToHost));
+		if (bad != 0.0) {
+			if (!ok) fprintf(stderr, "MPI%02d - libstaple_b200: CUDA IPC mapping of a peer mailbox failed (%s); halos and "
+											 "reductions stay on NCCL\n", c.myrank, cudaGetErrorString(err));
+			for (int r = 0; r < c.nranks; r++)
+				if (r != c.myrank && p.peer_mailbox[r]) cudaIpcCloseMemHandle(p.peer_mailbox[r]);
+			cudaFree(p.mailbox); cudaFree(p.tickets); cudaFree(p.d_seq);
+			p = P2P();
+			return 0;
+		}
+	}
+	p.stage = p.mailbox + kMailboxStage;
+	p.flags = (unsigned long long *) (p.mailbox + kMailboxHaloFlags);
+	p.stage_L = p.peer_mailbox[c.rank_L] + kMailboxStage; p.stage_R = p.peer_mailbox[c.rank_R] + kMailboxStage;
+	p.flags_L = (unsigned long long *) (p.peer_mailbox[c.rank_L] + kMailboxHaloFlags);
+	p.flags_R = (unsigned long long *) (p.peer_mailbox[c.rank_R] + kMailboxHaloFlags);
 	p.on = true;
-	// nobody may push before everybody has zeroed flags and mapped: one tiny all-reduce as a barrier
-	allreduce_results(kResultSlots - 1, 1, st);
-	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
 	return 1;
 }
 
 void shutdown_multidev(void)
 {
 	Ctx &c = ctx();
-	if (c.p2p.stage) {
+	if (c.p2p.mailbox) {
 		cudaDeviceSynchronize();
-		if (c.comm && c.comm->comm) { allreduce_results(kResultSlots - 1, 1, c.s_comm); cudaStreamSynchronize(c.s_comm); }   // peers are done with our memory
-		if (c.p2p.stage_L) cudaIpcCloseMemHandle(c.p2p.stage_L);
-		if (c.p2p.flags_L) cudaIpcCloseMemHandle(c.p2p.flags_L);
-		if (c.p2p.stage_R && c.p2p.stage_R != c.p2p.stage_L) { cudaIpcCloseMemHandle(c.p2p.stage_R); cudaIpcCloseMemHandle(c.p2p.flags_R); }
-		cudaFree(c.p2p.stage); cudaFree(c.p2p.flags); cudaFree(c.p2p.tickets);
+		if (c.comm && c.comm->comm) nccl_barrier(c.s_comm);   // peers are done with our memory
+		for (int r = 0; r < c.nranks; r++)
+			if (r != c.myrank && c.p2p.peer_mailbox[r]) cudaIpcCloseMemHandle(c.p2p.peer_mailbox[r]);
+		cudaFree(c.p2p.mailbox); cudaFree(c.p2p.tickets); cudaFree(c.p2p.d_seq);
 		c.p2p = P2P();
 	}
 	if (c.comm && c.comm->comm) {

@@ -36,20 +36,37 @@ constexpr int kResultSlots = 16;        // device scalars produced by reductions
 
 struct Comm;   // NCCL state, staple_core.cu
 
-// Peer-memory halo channel over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank
-// owns a staging area stage[2 parities][2 slots][3 colours x vol3h x 16 B] and two sequence flags;
-// slot 0 receives the data of this rank's LOWER fermion halo (written by rank L's top-face kernel),
-// slot 1 the UPPER halo (written by rank R's bottom-face kernel).  Exchange number `seq` uses parity
-// seq&1, which makes the channel write-after-read safe without any handshake.
+// Peer-memory channels over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank owns ONE
+// shared "mailbox" allocation:
+//   halo flags[2] | reduction flags[2 parities][kMaxRanks] | reduction boxes[2][kMaxRanks][2 doubles] |
+//   halo staging stage[2 parities][2 slots][3 colours x vol3h x 16 B]
+// Halo slot 0 receives the data of this rank's LOWER fermion halo (written by rank L's top-face blocks),
+// slot 1 the UPPER halo (written by rank R's bottom-face blocks).  Exchange / reduction number s uses
+// parity s&1, which makes both channels write-after-read safe without a handshake.
+// The sequence numbers live in DEVICE memory (d_seq, d_redq) and are advanced by the consuming kernels,
+// so a captured CUDA graph of solver iterations replays correctly.
+constexpr int kMaxRanks = 16;
+constexpr size_t kMailboxHaloFlags = 0, kMailboxRedFlags = 64, kMailboxRedBox = 64 + 2 * kMaxRanks * 8,
+								 kMailboxStage = 1024;
 struct P2P {
 	bool on = false;
-	char *stage = nullptr;                    // local, cudaMalloc (IPC exported)
-	unsigned long long *flags = nullptr;      // local [2]
-	char *stage_L = nullptr, *stage_R = nullptr;                    // peer mappings
+	char *mailbox = nullptr;                  // local, cudaMalloc (IPC exported)
+	char *peer_mailbox[kMaxRanks] = {};       // every rank's mailbox as mapped here ([myrank] = local)
+	char *stage = nullptr;                    // = mailbox + kMailboxStage
+	unsigned long long *flags = nullptr;      // = mailbox + kMailboxHaloFlags
+	char *stage_L = nullptr, *stage_R = nullptr;
 	unsigned long long *flags_L = nullptr, *flags_R = nullptr;
-	unsigned int *tickets = nullptr;          // local [2]: last-block detection of the two face kernels
+	unsigned int *tickets = nullptr;          // local [4]: top face, bottom face, unpack
+	unsigned long long *d_seq = nullptr;      // local: number of completed halo exchanges
+	unsigned long long *d_redq = nullptr;     // local: number of completed reductions
 	size_t slot_bytes = 0;                    // 3 * vol3h * 16
-	unsigned long long seq = 0;
+};
+// by-value kernel argument of the peer-memory all-reduce
+struct RedView {
+	int nranks, myrank;
+	unsigned long long *q;
+	double *box[kMaxRanks];                   // reduction boxes of every rank (parity 0 base)
+	unsigned long long *flags[kMaxRanks];
 };
 
 struct Ctx {
@@ -96,8 +113,10 @@ void exchange_slices(void *base, size_t elem_bytes, long stride_elems, int narra
 										 cudaStream_t s);                              // communications.c:34-104 on device memory
 // peer-memory variant for one vector (3 colour arrays, thickness 1): push both faces + unpack both halos
 void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s);
-// unpack only (the faces were pushed by the surface kernels themselves); seq = exchange number
-void p2p_unpack(void *base, size_t elem_bytes, unsigned long long seq, cudaStream_t s, const int *skip);
+// unpack only (the faces were pushed by the surface kernels themselves); advances the exchange counter
+void p2p_unpack(void *base, size_t elem_bytes, cudaStream_t s, const int *skip);
+// in-place sum over ranks of `ndoubles` (1 or 2) doubles through the peer mailboxes, fixed rank order
+void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s);
 
 // ---- precision traits -------------------------------------------------------------------
 template <typename T> struct Prec;
@@ -122,9 +141,10 @@ struct DslashArgs {
 	const int *skip;          // device flag: nonzero -> kernel is a no-op (solver overrun)
 	// fused halo push (surface launches of exactly one d3 slice): the slice is ALSO stored into the
 	// neighbour's staging slot through its NVLink mapping, then the neighbour's flag is set to peer_seq
-	cplx_t<T> *peer;          // [3][vol3h] in the neighbour's memory, or null
+	cplx_t<T> *peer;          // [3][vol3h] in the neighbour's memory (parity-0 slot), or null
 	unsigned long long *peer_flag;
-	unsigned long long peer_seq;
+	const unsigned long long *seq_ptr;   // device counter of completed exchanges; this one is *seq_ptr + 1
+	long peer_parity_stride;             // elements between the parity-0 and parity-1 slot
 	unsigned int *face_ticket;
 	// single-launch operator with fused halo push (fused != 0): blocks [0,fb) compute the TOP interior slice
 	// (-> rank R), blocks [fb,2fb) the BOTTOM one (-> rank L), the rest the bulk -- faces are scheduled first,
@@ -148,7 +168,7 @@ template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
 									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s,
-									 int face = 0, unsigned long long seq = 0);
+									 int face = 0);
 unsigned int dslash_blocks(int d3lo, int d3hi);
 
 // full operator with halo handling (acc_Deo/acc_Doe, fermion_matrix.c:159-268); epilogue as above.

@@ -230,82 +230,135 @@ __device__ __forceinline__ void face_wait(const unsigned long long *flag, unsign
 }
 
 // push one interior slice of a vector (3 colour arrays) into a neighbour's staging slot (standalone
-// communicate_fermion_borders; the operator's surface kernels do this themselves)
+// communicate_fermion_borders; the operator's face blocks do this themselves)
 template <typename C>
 __global__ void __launch_bounds__(256) p2p_push_kernel(const C *src, long n, long slice_lo, long vol3h, C *peer,
-																											 unsigned long long *peer_flag, unsigned long long seq,
-																											 unsigned int *ticket)
+																											 long parity_stride, unsigned long long *peer_flag,
+																											 const unsigned long long *seq_ptr, unsigned int *ticket)
 {
+	const unsigned long long seq = *seq_ptr + 1;
+	peer += (seq & 1ull) * parity_stride;
 	for (long t = (long) blockIdx.x * 256 + threadIdx.x; t < 3 * vol3h; t += (long) gridDim.x * 256) {
 		const long c = t / vol3h, i = t - c * vol3h;
 		peer[t] = src[c * n + slice_lo + i];
 	}
 	face_signal(peer_flag, seq, ticket, gridDim.x);
 }
-// copy both staging slots into the halo slices once the neighbours' data has landed
+// copy both staging slots into the halo slices once the neighbours' data has landed; the last block to
+// finish advances the exchange counter
 template <typename C>
 __global__ void __launch_bounds__(256) p2p_unpack_kernel(C *dst, long n, long lower_lo, long upper_lo, long vol3h,
-																												 const C *slot0, const C *slot1, const unsigned long long *flags,
-																												 unsigned long long seq, const int *skip)
+																												 const C *slot0, const C *slot1, long parity_stride,
+																												 const unsigned long long *flags, unsigned long long *seq_ptr,
+																												 unsigned int *ticket, const int *skip)
 {
 	if (skip != nullptr && *skip != 0) return;       // the producers skipped this exchange too (same flag on every rank)
+	const unsigned long long seq = *seq_ptr + 1;
 	const int half = gridDim.x / 2;
 	const int which = blockIdx.x >= half;            // first half of the grid: lower halo, second half: upper
 	face_wait(flags + which, seq);
-	const C *src = which ? slot1 : slot0;
+	const C *src = (which ? slot1 : slot0) + (seq & 1ull) * parity_stride;
 	const long lo = which ? upper_lo : lower_lo;
 	const int b = which ? blockIdx.x - half : blockIdx.x;
 	for (long t = (long) b * 256 + threadIdx.x; t < 3 * vol3h; t += (long) half * 256) {
 		const long c = t / vol3h, i = t - c * vol3h;
 		dst[c * n + lo + i] = __ldcg(src + t);
 	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; *seq_ptr = seq; }
+	}
 }
 
-static inline char *p2p_slot(char *stage, unsigned long long seq, int slot)
-{
-	return stage + ((seq & 1ull) * 2 + slot) * ctx().p2p.slot_bytes;
-}
-
-void p2p_unpack(void *base, size_t elem_bytes, unsigned long long seq, cudaStream_t s, const int *skip)
+template <typename C>
+static void p2p_unpack_t(void *base, cudaStream_t s, const int *skip)
 {
 	Ctx &c = ctx();
 	const Geom &g = c.g;
+	P2P &p = c.p2p;
 	const long lower_lo = (long) (g.d3_halo - 1) * g.vol3h, upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
 	long want = (3 * g.vol3h + 255) / 256;
 	const int half = (int) (want < 148 ? want : 148);
-	if (elem_bytes == 16)
-		p2p_unpack_kernel<double2><<<2 * half, 256, 0, s>>>((double2 *) base, g.sizeh, lower_lo, upper_lo, g.vol3h,
-			(const double2 *) p2p_slot(c.p2p.stage, seq, 0), (const double2 *) p2p_slot(c.p2p.stage, seq, 1), c.p2p.flags, seq, skip);
-	else
-		p2p_unpack_kernel<float2><<<2 * half, 256, 0, s>>>((float2 *) base, g.sizeh, lower_lo, upper_lo, g.vol3h,
-			(const float2 *) p2p_slot(c.p2p.stage, seq, 0), (const float2 *) p2p_slot(c.p2p.stage, seq, 1), c.p2p.flags, seq, skip);
+	p2p_unpack_kernel<C><<<2 * half, 256, 0, s>>>((C *) base, g.sizeh, lower_lo, upper_lo, g.vol3h, (const C *) p.stage,
+		(const C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.flags, p.d_seq, p.tickets + 2, skip);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch();
 }
+void p2p_unpack(void *base, size_t elem_bytes, cudaStream_t s, const int *skip)
+{
+	if (elem_bytes == 16) p2p_unpack_t<double2>(base, s, skip);
+	else p2p_unpack_t<float2>(base, s, skip);
+}
 
-void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s)
+template <typename C>
+static void p2p_exchange_t(void *base, cudaStream_t s)
 {
 	Ctx &c = ctx();
 	const Geom &g = c.g;
-	const unsigned long long seq = ++c.p2p.seq;
+	P2P &p = c.p2p;
 	const long top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h, bot_lo = (long) g.d3_halo * g.vol3h;
 	long want = (3 * g.vol3h + 255) / 256;
 	const int grid = (int) (want < 148 ? want : 148);
+	const long ps = (long) (2 * p.slot_bytes / sizeof(C));
 	// top interior slice -> rank R's lower halo (its slot 0); bottom interior slice -> rank L's upper halo (slot 1)
-	if (elem_bytes == 16) {
-		p2p_push_kernel<double2><<<grid, 256, 0, s>>>((const double2 *) base, g.sizeh, top_lo, g.vol3h,
-			(double2 *) p2p_slot(c.p2p.stage_R, seq, 0), c.p2p.flags_R + 0, seq, c.p2p.tickets + 0);
-		p2p_push_kernel<double2><<<grid, 256, 0, s>>>((const double2 *) base, g.sizeh, bot_lo, g.vol3h,
-			(double2 *) p2p_slot(c.p2p.stage_L, seq, 1), c.p2p.flags_L + 1, seq, c.p2p.tickets + 1);
-	} else {
-		p2p_push_kernel<float2><<<grid, 256, 0, s>>>((const float2 *) base, g.sizeh, top_lo, g.vol3h,
-			(float2 *) p2p_slot(c.p2p.stage_R, seq, 0), c.p2p.flags_R + 0, seq, c.p2p.tickets + 0);
-		p2p_push_kernel<float2><<<grid, 256, 0, s>>>((const float2 *) base, g.sizeh, bot_lo, g.vol3h,
-			(float2 *) p2p_slot(c.p2p.stage_L, seq, 1), c.p2p.flags_L + 1, seq, c.p2p.tickets + 1);
-	}
+	p2p_push_kernel<C><<<grid, 256, 0, s>>>((const C *) base, g.sizeh, top_lo, g.vol3h, (C *) p.stage_R, ps, p.flags_R + 0,
+																					p.d_seq, p.tickets + 0);
+	p2p_push_kernel<C><<<grid, 256, 0, s>>>((const C *) base, g.sizeh, bot_lo, g.vol3h, (C *) (p.stage_L + p.slot_bytes), ps,
+																					p.flags_L + 1, p.d_seq, p.tickets + 1);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch(2);
-	p2p_unpack(base, elem_bytes, seq, s, nullptr);
+	p2p_unpack(base, sizeof(C), s, nullptr);
+}
+void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s)
+{
+	if (elem_bytes == 16) p2p_exchange_t<double2>(base, s);
+	else p2p_exchange_t<float2>(base, s);
+}
+
+// ---- all-reduce of one or two doubles through the mailboxes: every rank stores its value into every rank's
+// box (one warp, lane = destination rank), waits for all contributions to its own box and adds them in rank
+// order -- bit-identical results everywhere, ~one NVLink round trip instead of an NCCL launch
+__global__ void p2p_allreduce_kernel(double *vals, int nd, RedView v)
+{
+	const int lane = threadIdx.x;
+	const unsigned long long q = *v.q + 1;
+	const int par = (int) (q & 1ull);
+	if (lane < v.nranks) {
+		double *b = v.box[lane] + ((size_t) par * kMaxRanks + v.myrank) * 2;
+		b[0] = vals[0];
+		b[1] = nd > 1 ? vals[1] : 0.0;
+		__threadfence_system();
+		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(v.flags[lane] + par * kMaxRanks + v.myrank), "l"(q) : "memory");
+		const unsigned long long *f = v.flags[v.myrank] + par * kMaxRanks + lane;
+		unsigned long long got;
+		do {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
+		} while (got < q);
+	}
+	__syncwarp();
+	if (lane == 0) {
+		const double *mine = v.box[v.myrank] + (size_t) par * kMaxRanks * 2;
+		double s0 = 0.0, s1 = 0.0;
+		for (int r = 0; r < v.nranks; r++) { s0 += __ldcg(mine + 2 * r); s1 += __ldcg(mine + 2 * r + 1); }
+		vals[0] = s0;
+		if (nd > 1) vals[1] = s1;
+		*v.q = q;
+	}
+}
+void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
+{
+	Ctx &c = ctx();
+	P2P &p = c.p2p;
+	RedView v;
+	v.nranks = c.nranks; v.myrank = c.myrank; v.q = p.d_redq;
+	for (int r = 0; r < c.nranks; r++) {
+		v.box[r] = (double *) (p.peer_mailbox[r] + kMailboxRedBox);
+		v.flags[r] = (unsigned long long *) (p.peer_mailbox[r] + kMailboxRedFlags);
+	}
+	p2p_allreduce_kernel<<<1, 32, 0, s>>>(vals, ndoubles, v);
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
 }
 
 // ------------------------------------------------------------------ Dirac operator kernel
@@ -319,6 +372,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 	unsigned int t = blockIdx.x * kBlock + threadIdx.x;
 	unsigned int lo = (unsigned int) a.site_lo, ns = (unsigned int) a.nsites;
 	C *peer = a.peer;
+	unsigned long long peer_seq = 0;
 	unsigned long long *peer_flag = a.peer_flag;
 	unsigned int *face_ticket = a.face_ticket;
 	unsigned int face_nblocks = gridDim.x;
@@ -331,6 +385,10 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 			peer = a.peer2; peer_flag = a.peer_flag2; face_ticket = a.face_ticket2;
 		}
 		else { t -= 2 * fb * kBlock; peer = nullptr; }
+	}
+	if (peer != nullptr) {
+		peer_seq = *a.seq_ptr + 1;                       // this exchange's number (advanced by the unpack kernel)
+		peer += (peer_seq & 1ull) * a.peer_parity_stride;
 	}
 	double dot = 0.0;
 	if (t < ns) {
@@ -381,7 +439,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 			if (peer != nullptr) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
-	if (peer != nullptr) face_signal(peer_flag, a.peer_seq, face_ticket, face_nblocks);
+	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks);
 	if (EPI == EPI_MASS_DOT) {
 		double v[1] = { dot };
 		grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
@@ -398,25 +456,25 @@ template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
 									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s,
-									 int face, unsigned long long seq)
+									 int face)
 {
 	const Geom &g = ctx().g;
 	if (d3hi <= d3lo) return;
 	DslashArgs<T> a;
-	a.peer = nullptr; a.peer_flag = nullptr; a.peer_seq = 0; a.face_ticket = nullptr;
+	a.peer = nullptr; a.peer_flag = nullptr; a.seq_ptr = nullptr; a.peer_parity_stride = 0; a.face_ticket = nullptr;
 	a.fused = 0; a.face_blocks = 0; a.top_lo = a.bot_lo = 0; a.peer2 = nullptr; a.peer_flag2 = nullptr; a.face_ticket2 = nullptr;
-	if (face == 3) {         // whole local interior in one launch, both faces pushed
+	if (face != 0) {
+		// top interior slice -> rank R's slot 0 (its lower halo); bottom interior slice -> rank L's slot 1
 		P2P &p = ctx().p2p;
-		a.fused = 1; a.face_blocks = dslash_blocks(0, 1);
-		a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
-		a.peer = (cplx_t<T> *) p2p_slot(p.stage_R, seq, 0); a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0;
-		a.peer2 = (cplx_t<T> *) p2p_slot(p.stage_L, seq, 1); a.peer_flag2 = p.flags_L + 1; a.face_ticket2 = p.tickets + 1;
-		a.peer_seq = seq;
-	} else if (face != 0) {
-		P2P &p = ctx().p2p;
-		a.peer = (cplx_t<T> *) p2p_slot(face == 1 ? p.stage_R : p.stage_L, seq, face == 1 ? 0 : 1);
-		a.peer_flag = face == 1 ? p.flags_R + 0 : p.flags_L + 1;
-		a.peer_seq = seq; a.face_ticket = p.tickets + (face - 1);
+		cplx_t<T> *top = (cplx_t<T> *) p.stage_R, *bot = (cplx_t<T> *) (p.stage_L + p.slot_bytes);
+		a.seq_ptr = p.d_seq; a.peer_parity_stride = (long) (2 * p.slot_bytes / sizeof(cplx_t<T>));
+		if (face == 3) {       // whole local interior in one launch, both faces pushed
+			a.fused = 1; a.face_blocks = dslash_blocks(0, 1);
+			a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
+			a.peer = top; a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0;
+			a.peer2 = bot; a.peer_flag2 = p.flags_L + 1; a.face_ticket2 = p.tickets + 1;
+		} else if (face == 1) { a.peer = top; a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0; }
+		else { a.peer = bot; a.peer_flag = p.flags_L + 1; a.face_ticket = p.tickets + 1; }
 	}
 	a.u = u; a.out = out; a.in = in; a.ph = ph; a.in0 = in0; a.m2 = m2;
 	a.partials = dot_slot >= 0 ? partials(dot_slot) : nullptr;
@@ -470,9 +528,8 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		// ONE kernel: the face blocks (scheduled first) push their slice into the neighbours' staging slots
 		// over NVLink while the bulk blocks of the same launch run; then the unpack of what the neighbours
 		// pushed.  No stream fork/join, no events.
-		const unsigned long long seq1 = ++c.p2p.seq;
-		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3, seq1);
-		p2p_unpack(out, sizeof(cplx_t<T>), seq1, c.stream, skip);
+		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3);
+		p2p_unpack(out, sizeof(cplx_t<T>), c.stream, skip);
 		return;
 	}
 	// peer-memory channel: the two surface kernels store their slice into the neighbours' staging slots
@@ -480,18 +537,17 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 	// every rank, because the all-reduced scalars are bit-identical) silences producers and consumer alike;
 	// sequence numbers keep counting on the host, flags only ever grow.
 	const bool p2p = c.p2p.on;
-	const unsigned long long seq = p2p ? ++c.p2p.seq : 0;
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_p, c.ev_fork, 0));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_m, c.ev_fork, 0));
-	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p, p2p ? 1 : 0, seq);    // d3p
-	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m, p2p ? 2 : 0, seq);   // d3m
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p, p2p ? 1 : 0);    // d3p
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m, p2p ? 2 : 0);   // d3m
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, c.s_p));
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, c.s_m));
 	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo + 1, hi - 1, dot_slot, target, 2 * bs, skip, c.stream);   // bulk
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_p, 0));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_comm, c.ev_m, 0));
-	if (p2p) p2p_unpack(out, sizeof(cplx_t<T>), seq, c.s_comm, skip);
+	if (p2p) p2p_unpack(out, sizeof(cplx_t<T>), c.s_comm, skip);
 	else exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.s_comm);
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_comm, c.s_comm));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
@@ -517,10 +573,10 @@ template void apply_mdagm<float>(const float2 *, float2 *, const float2 *, float
 																 int, const int *);
 template void launch_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,
 																		const double2 *, double, int, int, int, unsigned int, unsigned int, const int *,
-																		cudaStream_t, int, unsigned long long);
+																		cudaStream_t, int);
 template void launch_dslash<float>(int, int, const float2 *, float2 *, const float2 *, const float *,
 																	 const float2 *, double, int, int, int, unsigned int, unsigned int, const int *,
-																	 cudaStream_t, int, unsigned long long);
+																	 cudaStream_t, int);
 
 // ------------------------------------------------------------------ BLAS-1 element-wise kernels
 // All arithmetic in double with double factors, stored back in T: this is what the reference's FP32

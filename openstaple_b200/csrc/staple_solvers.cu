@@ -140,15 +140,18 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, 
 	__shared__ double sm[32];
 	__shared__ bool last;
 	__shared__ double s_om[MAX_APPROX_ORDER], s_g[MAX_APPROX_ORDER], s_z[MAX_APPROX_ORDER];
-	__shared__ int s_fl[MAX_APPROX_ORDER];
+	__shared__ int s_ix[MAX_APPROX_ORDER], s_nact;
 	const int maxiter = c->maxiter;
-	if (threadIdx.x < maxiter) {
-		s_om[threadIdx.x] = c->omegas[threadIdx.x]; s_fl[threadIdx.x] = c->flag[threadIdx.x];
-		s_g[threadIdx.x] = c->pgam[threadIdx.x]; s_z[threadIdx.x] = c->pzeta[threadIdx.x];
+	if (threadIdx.x == 0) {       // compact list of the still-active shifts: no divergence, unrollable loop
+		int k = 0;
+		for (int ia = 0; ia < maxiter; ia++)
+			if (c->flag[ia] == 1) { s_ix[k] = ia; s_om[k] = c->omegas[ia]; s_g[k] = c->pgam[ia]; s_z[k] = c->pzeta[ia]; k++; }
+		s_nact = k;
 	}
 	const double omega = c->omega;
 	const int pending = c->pending;
 	__syncthreads();
+	const int nact = s_nact;
 	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
 	double nrm = 0.0;
 	if (t < cnt) {
@@ -163,20 +166,43 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, 
 			r[j] = rn;
 			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
 		}
-		for (int ia = 0; ia < maxiter; ia++) {
-			if (s_fl[ia] != 1) continue;
-			const double f = s_om[ia], g = s_g[ia], z = s_z[ia];
-			const long base = (long) ia * 3 * n;
+		// two shifts per trip: 12 independent 16-byte loads in flight per thread before the first use
+		int k = 0;
+		for (; k + 2 <= nact; k += 2) {
+			cplx_t<T> q[2][3], o[2][3];
+#pragma unroll
+			for (int u2 = 0; u2 < 2; u2++) {
+				const long base = (long) s_ix[k + u2] * 3 * n + i;
+#pragma unroll
+				for (int col = 0; col < 3; col++) { q[u2][col] = ps[base + col * n]; o[u2][col] = out[base + col * n]; }
+			}
+#pragma unroll
+			for (int u2 = 0; u2 < 2; u2++) {
+				const long base = (long) s_ix[k + u2] * 3 * n + i;
+				const double f = s_om[k + u2], g = s_g[k + u2], z = s_z[k + u2];
+#pragma unroll
+				for (int col = 0; col < 3; col++) {
+					cplx_t<T> qq = q[u2][col];
+					if (pending) {
+						qq = mkc<T>(g * qq.x + z * rv[col].x, g * qq.y + z * rv[col].y);
+						ps[base + col * n] = qq;
+					}
+					out[base + col * n] = mkc<T>(o[u2][col].x - f * qq.x, o[u2][col].y - f * qq.y);
+				}
+			}
+		}
+		if (k < nact) {
+			const long base = (long) s_ix[k] * 3 * n + i;
+			const double f = s_om[k], g = s_g[k], z = s_z[k];
 #pragma unroll
 			for (int col = 0; col < 3; col++) {
-				const long k = base + col * n + i;
-				cplx_t<T> q = ps[k];
-				const cplx_t<T> o = out[k];
+				cplx_t<T> qq = ps[base + col * n];
+				const cplx_t<T> o = out[base + col * n];
 				if (pending) {
-					q = mkc<T>(g * q.x + z * rv[col].x, g * q.y + z * rv[col].y);
-					ps[k] = q;
+					qq = mkc<T>(g * qq.x + z * rv[col].x, g * qq.y + z * rv[col].y);
+					ps[base + col * n] = qq;
 				}
-				out[k] = mkc<T>(o.x - f * q.x, o.y - f * q.y);
+				out[base + col * n] = mkc<T>(o.x - f * qq.x, o.y - f * qq.y);
 			}
 		}
 	}
@@ -313,13 +339,14 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	};
 	// Single GPU: a batch is a fixed sequence of launches on one stream whose every data dependence (flags,
 	// coefficients, `done`) lives in device memory, so it is captured ONCE into a CUDA graph and replayed --
-	// the iteration is launch-gap bound on small lattices.  (Multi-GPU batches carry per-exchange sequence
-	// numbers as kernel arguments and stay on direct launches; so does the legacy default stream, which
-	// cannot be captured.)
+	// the iteration is launch-gap bound on small lattices.  Multi-GPU batches qualify too when halos and
+	// all-reduces go through the peer mailboxes (their sequence numbers are device-resident, and no NCCL call
+	// is left inside the iteration).  The legacy default stream cannot be captured: direct launches there.
 	cudaGraphExec_t gexec = nullptr;
 	const unsigned long long launches_before = c.launches;
 	unsigned long long launches_per_batch = 0;
-	if (c.nranks == 1 && st != nullptr && c.use_graphs) {
+	const bool capturable = c.nranks == 1 || (c.p2p.on && c.p2p_single_launch && c.p2p.d_redq != nullptr);
+	if (capturable && st != nullptr && c.use_graphs) {
 		cudaGraph_t graph = nullptr;
 		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
 			enqueue_batch();
