@@ -177,8 +177,9 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 /* Optional (collective, after staple_init_multidev1D): fermion halos through NVLink peer memory instead of
  * ncclSend/Recv -- the surface kernels of acc_Deo/acc_Doe store their slice straight into the neighbour's
  * staging area (CUDA IPC) and raise a flag; returns 1 if active, 0 if it fell back to NCCL.
- * on = 1: acc_Deo/acc_Doe are ONE kernel (face blocks first, then bulk) + one unpack kernel;
- * on = 2: the reference's three-queue structure (d3p, d3m, bulk on separate streams) with peer stores. */
+ * on = 1: acc_Deo/acc_Doe with their exchange are ONE kernel (face blocks first, bulk, unpack blocks last);
+ * on = 2: the reference's three-queue structure (d3p, d3m, bulk on separate streams) with peer stores;
+ * on = 3: one operator kernel + a separate unpack kernel.  Global sums use the same mailboxes. */
 int staple_enable_p2p(int on);
 void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
 int staple_myrank(void);

@@ -422,6 +422,7 @@ int staple_enable_p2p(int on)
 	P2P &p = c.p2p;
 	if (!on || c.nranks <= 1) { p.on = false; return 0; }
 	c.p2p_single_launch = (on != 2);                   // 2: keep the reference's d3p/d3m/bulk three-queue structure
+	c.p2p_unpack_in_kernel = (on != 3);                // 3: single operator launch + separate unpack kernel
 	if (p.stage_L) { p.on = true; return 1; }          // already mapped
 	if (!c.comm) { fprintf(stderr, "libstaple_b200: staple_enable_p2p before staple_init_multidev1D\n"); exit(1); }
 	if (c.nranks > kMaxRanks) { fprintf(stderr, "libstaple_b200: peer-memory channels support up to %d ranks\n", kMaxRanks); return 0; }

@@ -88,6 +88,7 @@ struct Ctx {
 	Comm *comm = nullptr;
 	P2P p2p;
 	bool use_graphs = true;          // CG-M iteration batches as CUDA graphs (single GPU, non-default stream)
+	bool p2p_unpack_in_kernel = true; // ... and the unpack blocks ride in the same launch
 	bool p2p_single_launch = true;   // acc_Deo/acc_Doe as one kernel + unpack (false: d3p/d3m/bulk on three streams)
 	// last multishift statistics
 	int last_iterations = 0;
@@ -117,6 +118,43 @@ void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s);
 void p2p_unpack(void *base, size_t elem_bytes, cudaStream_t s, const int *skip);
 // in-place sum over ranks of `ndoubles` (1 or 2) doubles through the peer mailboxes, fixed rank order
 void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s);
+RedView make_redview();
+inline RedView single_rank_redview() { RedView v; v.nranks = 1; v.myrank = 0; v.q = nullptr; return v; }
+
+#ifdef __CUDACC__
+// One warp: every rank stores its value into every rank's box (lane = destination rank), waits for all
+// contributions to its own box and adds them in rank order -- bit-identical results everywhere, about one
+// NVLink round trip, and usable as the prologue of a kernel that consumes the sum (no separate launch).
+__device__ __forceinline__ void p2p_allreduce_warp(double *vals, int nd, const RedView &v)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned long long q = *v.q + 1;
+	const int par = (int) (q & 1ull);
+	if (lane < v.nranks) {
+		double *b = v.box[lane] + ((size_t) par * kMaxRanks + v.myrank) * 2;
+		b[0] = vals[0];
+		b[1] = nd > 1 ? vals[1] : 0.0;
+		__threadfence_system();
+		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(v.flags[lane] + par * kMaxRanks + v.myrank), "l"(q) : "memory");
+		const unsigned long long *f = v.flags[v.myrank] + par * kMaxRanks + lane;
+		unsigned long long got;
+		do {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
+		} while (got < q);
+	}
+	__syncwarp();
+	if (lane == 0) {
+		const double *mine = v.box[v.myrank] + (size_t) par * kMaxRanks * 2;
+		double s0 = 0.0, s1 = 0.0;
+		for (int r = 0; r < v.nranks; r++) { s0 += __ldcg(mine + 2 * r); s1 += __ldcg(mine + 2 * r + 1); }
+		vals[0] = s0;
+		if (nd > 1) vals[1] = s1;
+		*v.q = q;
+		__threadfence();
+	}
+	__syncwarp();
+}
+#endif
 
 // ---- precision traits -------------------------------------------------------------------
 template <typename T> struct Prec;
@@ -155,6 +193,15 @@ struct DslashArgs {
 	cplx_t<T> *peer2;         // bottom face target (peer = top face target)
 	unsigned long long *peer_flag2;
 	unsigned int *face_ticket2;
+	// ... and, scheduled last, 2*unpack_blocks blocks that wait for the neighbours' flags and copy the two staged
+	// slices into the halo slices of `out`: a whole acc_Deo/acc_Doe with its exchange is ONE launch
+	unsigned int bulk_blocks, unpack_blocks;
+	const cplx_t<T> *unpack_src;       // local staging, parity-0 slot 0 (slot 1 follows after slot_elems)
+	long slot_elems;
+	const unsigned long long *local_flags;
+	unsigned long long *seq_rw;        // the exchange counter, advanced by the last unpack block
+	unsigned int *unpack_ticket;       // [0] ticket of the unpack blocks, [1] number of face groups that have signalled
+	long lower_lo, upper_lo;           // first idxh of the lower / upper halo slice
 	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites)
 	int nd0h, nd1, nd2, nd3;
 	long vol3h, sizeh;

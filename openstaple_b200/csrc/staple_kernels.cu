@@ -203,7 +203,7 @@ __device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials
 // Producer: every thread has issued its peer stores; the last block to finish publishes `seq` in the
 // neighbour's flag with system-scope release semantics (fence.sys by all writers, ticket, fence.sys, store).
 __device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsigned long long seq, unsigned int *ticket,
-																						unsigned int nblocks)
+																						unsigned int nblocks, unsigned int *groups_done = nullptr)
 {
 	__threadfence_system();
 	__syncthreads();
@@ -213,6 +213,7 @@ __device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsig
 			__threadfence_system();
 			*ticket = 0u;
 			asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(seq) : "memory");
+			if (groups_done != nullptr) atomicAdd(groups_done, 1u);   // this launch's face group no longer needs the old counter
 		}
 	}
 }
@@ -316,47 +317,25 @@ void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s)
 	else p2p_exchange_t<float2>(base, s);
 }
 
-// ---- all-reduce of one or two doubles through the mailboxes: every rank stores its value into every rank's
-// box (one warp, lane = destination rank), waits for all contributions to its own box and adds them in rank
-// order -- bit-identical results everywhere, ~one NVLink round trip instead of an NCCL launch
-__global__ void p2p_allreduce_kernel(double *vals, int nd, RedView v)
-{
-	const int lane = threadIdx.x;
-	const unsigned long long q = *v.q + 1;
-	const int par = (int) (q & 1ull);
-	if (lane < v.nranks) {
-		double *b = v.box[lane] + ((size_t) par * kMaxRanks + v.myrank) * 2;
-		b[0] = vals[0];
-		b[1] = nd > 1 ? vals[1] : 0.0;
-		__threadfence_system();
-		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(v.flags[lane] + par * kMaxRanks + v.myrank), "l"(q) : "memory");
-		const unsigned long long *f = v.flags[v.myrank] + par * kMaxRanks + lane;
-		unsigned long long got;
-		do {
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
-		} while (got < q);
-	}
-	__syncwarp();
-	if (lane == 0) {
-		const double *mine = v.box[v.myrank] + (size_t) par * kMaxRanks * 2;
-		double s0 = 0.0, s1 = 0.0;
-		for (int r = 0; r < v.nranks; r++) { s0 += __ldcg(mine + 2 * r); s1 += __ldcg(mine + 2 * r + 1); }
-		vals[0] = s0;
-		if (nd > 1) vals[1] = s1;
-		*v.q = q;
-	}
-}
-void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
+// ---- all-reduce of one or two doubles through the mailboxes (device side: staple_internal.cuh)
+__global__ void p2p_allreduce_kernel(double *vals, int nd, RedView v) { p2p_allreduce_warp(vals, nd, v); }
+
+RedView make_redview()
 {
 	Ctx &c = ctx();
 	P2P &p = c.p2p;
 	RedView v;
 	v.nranks = c.nranks; v.myrank = c.myrank; v.q = p.d_redq;
+	for (int r = 0; r < kMaxRanks; r++) { v.box[r] = nullptr; v.flags[r] = nullptr; }
 	for (int r = 0; r < c.nranks; r++) {
 		v.box[r] = (double *) (p.peer_mailbox[r] + kMailboxRedBox);
 		v.flags[r] = (unsigned long long *) (p.peer_mailbox[r] + kMailboxRedFlags);
 	}
-	p2p_allreduce_kernel<<<1, 32, 0, s>>>(vals, ndoubles, v);
+	return v;
+}
+void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
+{
+	p2p_allreduce_kernel<<<1, 32, 0, s>>>(vals, ndoubles, make_redview());
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch();
 }
@@ -384,7 +363,37 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 			t -= fb * kBlock; lo = (unsigned int) a.bot_lo; ns = (unsigned int) a.vol3h;
 			peer = a.peer2; peer_flag = a.peer_flag2; face_ticket = a.face_ticket2;
 		}
-		else { t -= 2 * fb * kBlock; peer = nullptr; }
+		else if (blockIdx.x < 2 * fb + a.bulk_blocks) { t -= 2 * fb * kBlock; peer = nullptr; }
+		else {
+			// ---- unpack blocks (scheduled after every face and bulk block of this launch)
+			const unsigned int ub = a.unpack_blocks, b = blockIdx.x - (2 * fb + a.bulk_blocks);
+			const unsigned int which = b >= ub;                  // 0: lower halo (slot 0, from rank L), 1: upper (slot 1, from R)
+			const unsigned long long seq = *a.seq_rw + 1;
+			face_wait(a.local_flags + which, seq);
+			const C *src = a.unpack_src + (seq & 1ull) * a.peer_parity_stride + which * a.slot_elems;
+			const unsigned int tt = (b - which * ub) * kBlock + threadIdx.x;
+			if (tt < (unsigned int) a.vol3h) {
+				const long dst = (which ? a.upper_lo : a.lower_lo) + tt;
+#pragma unroll
+				for (int c = 0; c < 3; c++) a.out[c * a.sizeh + dst] = __ldcg(src + c * a.vol3h + tt);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				__threadfence();
+				if (atomicAdd(a.unpack_ticket, 1u) == 2 * ub - 1) {
+					// last unpack block: both face groups of THIS launch have read the counter once they have signalled
+					while (atomicAdd(a.unpack_ticket + 1, 0u) < 2u) __nanosleep(100);
+					a.unpack_ticket[0] = 0u; a.unpack_ticket[1] = 0u;
+					__threadfence();
+					*a.seq_rw = seq;
+				}
+			}
+			if (EPI == EPI_MASS_DOT) {       // contributes a zero partial so that the ticket count stays gridDim.x
+				double v[1] = { 0.0 };
+				grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
+			}
+			return;
+		}
 	}
 	if (peer != nullptr) {
 		peer_seq = *a.seq_ptr + 1;                       // this exchange's number (advanced by the unpack kernel)
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 			if (peer != nullptr) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
-	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks);
+	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks, a.fused == 2 ? a.unpack_ticket + 1 : nullptr);
 	if (EPI == EPI_MASS_DOT) {
 		double v[1] = { dot };
 		grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
@@ -463,13 +472,22 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	DslashArgs<T> a;
 	a.peer = nullptr; a.peer_flag = nullptr; a.seq_ptr = nullptr; a.peer_parity_stride = 0; a.face_ticket = nullptr;
 	a.fused = 0; a.face_blocks = 0; a.top_lo = a.bot_lo = 0; a.peer2 = nullptr; a.peer_flag2 = nullptr; a.face_ticket2 = nullptr;
+	a.bulk_blocks = 0; a.unpack_blocks = 0; a.unpack_src = nullptr; a.slot_elems = 0; a.local_flags = nullptr; a.seq_rw = nullptr;
+	a.unpack_ticket = nullptr; a.lower_lo = a.upper_lo = 0;
 	if (face != 0) {
 		// top interior slice -> rank R's slot 0 (its lower halo); bottom interior slice -> rank L's slot 1
 		P2P &p = ctx().p2p;
 		cplx_t<T> *top = (cplx_t<T> *) p.stage_R, *bot = (cplx_t<T> *) (p.stage_L + p.slot_bytes);
 		a.seq_ptr = p.d_seq; a.peer_parity_stride = (long) (2 * p.slot_bytes / sizeof(cplx_t<T>));
-		if (face == 3) {       // whole local interior in one launch, both faces pushed
-			a.fused = 1; a.face_blocks = dslash_blocks(0, 1);
+		if (face == 3 || face == 4) {       // whole local interior in one launch, both faces pushed (4: and halos unpacked)
+			a.fused = face == 4 ? 2 : 1; a.face_blocks = dslash_blocks(0, 1);
+			a.bulk_blocks = dslash_blocks(d3lo + 1, d3hi - 1);
+			if (face == 4) {
+				a.unpack_blocks = a.face_blocks;
+				a.unpack_src = (const cplx_t<T> *) p.stage; a.slot_elems = (long) (p.slot_bytes / sizeof(cplx_t<T>));
+				a.local_flags = p.flags; a.seq_rw = p.d_seq; a.unpack_ticket = p.tickets + 2;
+				a.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; a.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
+			}
 			a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
 			a.peer = top; a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0;
 			a.peer2 = bot; a.peer_flag2 = p.flags_L + 1; a.face_ticket2 = p.tickets + 1;
@@ -484,7 +502,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	a.site_lo = (long) d3lo * g.vol3h; a.nsites = (long) (d3hi - d3lo) * g.vol3h;
 	if (a.fused) { a.site_lo = (long) (d3lo + 1) * g.vol3h; a.nsites = (long) (d3hi - d3lo - 2) * g.vol3h; }   // bulk
 	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;
-	const unsigned int grid = a.fused ? 2 * a.face_blocks + dslash_blocks(d3lo + 1, d3hi - 1) : dslash_blocks(d3lo, d3hi);
+	const unsigned int grid = a.fused ? 2 * a.face_blocks + a.bulk_blocks + 2 * a.unpack_blocks : dslash_blocks(d3lo, d3hi);
 #define STAPLE_LAUNCH(P, E) dslash_kernel<T, P, E><<<grid, kBlock, 0, s>>>(a)
 	if (par == 0) {
 		if (epi == EPI_NONE) STAPLE_LAUNCH(0, EPI_NONE);
@@ -528,8 +546,12 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		// ONE kernel: the face blocks (scheduled first) push their slice into the neighbours' staging slots
 		// over NVLink while the bulk blocks of the same launch run; then the unpack of what the neighbours
 		// pushed.  No stream fork/join, no events.
-		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3);
-		p2p_unpack(out, sizeof(cplx_t<T>), c.stream, skip);
+		if (c.p2p_unpack_in_kernel)
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * bs, 0, skip, c.stream, 4);
+		else {
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3);
+			p2p_unpack(out, sizeof(cplx_t<T>), c.stream, skip);
+		}
 		return;
 	}
 	// peer-memory channel: the two surface kernels store their slice into the neighbours' staging slots

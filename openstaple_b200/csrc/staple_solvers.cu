@@ -52,11 +52,12 @@ __global__ void cgm_init_kernel(CgmCtl *c, const double *delta_slot, const doubl
 }
 
 // after alpha = Re(p, s) (:122-137)
-__global__ void cgm_after_alpha_kernel(CgmCtl *c, const double *alpha_slot)
+__global__ void cgm_after_alpha_kernel(CgmCtl *c, double *alpha_slot, RedView red)
 {
 	if (c->done) return;
+	if (red.nranks > 1) p2p_allreduce_warp(alpha_slot, 1, red);   // sum over ranks fused into the consumer
 	const int i = threadIdx.x;
-	const double alpha = *alpha_slot;
+	const double alpha = *(volatile double *) alpha_slot;
 	const double omega_save = c->omega, delta = c->delta, gammag = c->gammag;
 	const int maxiter = c->maxiter, cg = c->cg;
 	const double omega = -delta / alpha;
@@ -72,11 +73,12 @@ __global__ void cgm_after_alpha_kernel(CgmCtl *c, const double *alpha_slot)
 }
 
 // after lambda = (r, r) (:143-171): gammas, convergence flags, zeta rotation, delta <- lambda
-__global__ void cgm_after_lambda_kernel(CgmCtl *c, const double *lambda_slot)
+__global__ void cgm_after_lambda_kernel(CgmCtl *c, double *lambda_slot, RedView red)
 {
 	if (c->done) return;
+	if (red.nranks > 1) p2p_allreduce_warp(lambda_slot, 1, red);
 	const int i = threadIdx.x;
-	const double lambda = *lambda_slot;
+	const double lambda = *(volatile double *) lambda_slot;
 	const double delta = c->delta, omega = c->omega, source_norm = c->source_norm, residuo = c->residuo;
 	const int order = c->order, old_maxiter = c->maxiter, cg = c->cg, max_cg = c->max_cg;
 	const double gammag = lambda / delta;
@@ -322,17 +324,21 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	const int batch = 8;
 	int issued = 0, snap = 0, pending[2] = { 0, 0 };
 	bool finished = false;
+	// multi-GPU with the peer mailboxes: the all-reduce of alpha / lambda is the prologue of the one-warp kernel
+	// that advances the recurrences (K12-14 + C4 of the reference fused), no NCCL call inside the iteration
+	const bool fuse_red = c.nranks > 1 && c.p2p.on && c.p2p.d_redq != nullptr;
+	const RedView red = fuse_red ? make_redview() : single_rank_redview();
 	auto enqueue_batch = [&]() {
 		for (int b = 0; b < batch; b++) {
 			// s = (M^+M) p, alpha = Re(p,s) fused in the Deo epilogue (:113-118)
 			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done);
-			allreduce_results(SLOT_ALPHA, 1, st);
-			cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA));
+			if (!fuse_red) allreduce_results(SLOT_ALPHA, 1, st);
+			cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA), red);
 			cgm_fused_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
 																											 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
 																											 result(SLOT_LAMBDA));
-			allreduce_results(SLOT_LAMBDA, 1, st);
-			cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA));
+			if (!fuse_red) allreduce_results(SLOT_LAMBDA, 1, st);
+			cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA), red);
 			cgm_pupdate_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, lo, cnt, n);
 			count_launch(4);
 		}

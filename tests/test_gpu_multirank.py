@@ -120,13 +120,18 @@ def _run(world, loc, mode):
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)
 
 
-@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1), (1, 2))],
-                         ids=["sync-nccl", "async-nccl", "p2p-single-launch", "p2p-three-queues"])
+@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3))],
+                         ids=["sync-nccl", "async-nccl", "p2p-one-launch", "p2p-three-queues", "p2p-launch+unpack"])
 @pytest.mark.parametrize("world,loc", [(2, (8, 8, 8, 8)), (2, (8, 4, 6, 2))])
 def test_two_gpus(world, loc, mode):
     _run(world, loc, mode)
 
 
-@pytest.mark.parametrize("mode", [dict(**{"async": 1, "p2p": 1})], ids=["async-p2p"])
+@pytest.mark.parametrize("mode", [dict(**{"async": 1, "p2p": 1}), dict(**{"async": 1, "p2p": 0})], ids=["p2p", "nccl"])
 def test_four_gpus(mode):
     _run(4, (8, 8, 8, 4), mode)
+
+
+def test_eight_gpus_all_surface():
+    """LOC_N3 = 2: no bulk at all, every site is on a face (the 64^3 x 16 strong-scaling end point)."""
+    _run(8, (8, 8, 8, 2), {"async": 1, "p2p": 1})
