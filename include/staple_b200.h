@@ -150,6 +150,9 @@ void staple_set_stream(void *cuda_stream);
 void staple_use_library_stream(void);
 /* CG-M replays its iteration batches as CUDA graphs on a single GPU (default on; 0 = direct launches). */
 void staple_set_use_graphs(int on);
+/* CG-M: run the scalar recurrences (ref: inverter_multishift_full.c:122-137, :143-171) in the tail of the kernel whose
+ * grid reduction produces alpha / lambda (default on; 0 = one-warp kernels of their own, for A/B comparisons). */
+void staple_set_cgm_fuse_tail(int on);
 void *staple_get_stream(void);
 void staple_synchronize(void);
 /* number of CUDA kernels launched by this library since start (bench.py "gpu_launches") */
@@ -166,6 +169,16 @@ void staple_acc_exit_data(const void *host);                      /* #pragma acc
 void staple_acc_update_device(const void *host, size_t bytes);    /* #pragma acc update device(...)     */
 void staple_acc_update_host(void *host, size_t bytes);            /* #pragma acc update host(...)       */
 void *staple_acc_deviceptr(const void *host);                     /* acc_deviceptr()                    */
+/* The host-buffer round trip of the stock operator test in ONE call (ref: tests_and_benchmarks/deo_doe_test.c:
+ * `#pragma acc update device(in)`; acc_Doe(u,tmp,in); acc_Deo(u,out,tmp); `#pragma acc update host(out)`),
+ * software-pipelined over d3 chunks of `chunk_slices` slices (0 = library default): chunk uploads on a copy
+ * stream, acc_Doe_d3c / acc_Deo_d3c launches as soon as the +-1 neighbour chunks they read have landed, chunk
+ * downloads on a second copy stream -- PCIe runs in both directions while the operator computes.  `in` and `out`
+ * are present host arrays (staple_posix_memalign), `tmp` an odd-site scratch vector; returns after `out` is valid
+ * on the host.  Results are bit-identical to the unpipelined sequence.  Single rank only (with NRANKS_D3 > 1 the
+ * plain sequence incl. the halo exchanges is executed). */
+void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *tmp,
+																 const double_soa *backfield, int chunk_slices);
 
 /* ------------------------------------------------------------------ rank / halo layer */
 /* ref: Mpi/multidev.c:20-108 pre_init_multidev1D + init_multidev1D.  MPI is replaced by NCCL over

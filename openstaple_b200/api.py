@@ -270,6 +270,11 @@ class Lattice:
     def acc_Doe_d3c(self, u, out, inp, backfield, off3, thick3):
         getattr(self.L, "acc_Doe_d3c" + _sfx(inp))(_addr(u), _addr(out), _addr(inp), _addr(backfield), off3, thick3)
 
+    def acc_Doe_Deo_streamed(self, u, out, inp, tmp, backfield, chunk_slices=0):
+        """deo_doe_test.c's `update device(in); acc_Doe; acc_Deo; update host(out)` round trip on HostArrays,
+        pipelined over d3 chunks (staple_acc_Doe_Deo_streamed); returns with `out` valid on the host."""
+        self.L.staple_acc_Doe_Deo_streamed(_addr(u), _addr(out), _addr(inp), _addr(tmp), _addr(backfield), int(chunk_slices))
+
     def fermion_matrix_multiplication(self, u, out, inp, temp1, pars, single=None):
         s = _sfx(inp) if single is None else ("_f" if single else "")
         getattr(self.L, "fermion_matrix_multiplication" + s)(_addr(u), _addr(out), _addr(inp), _addr(temp1), C.addressof(pars))

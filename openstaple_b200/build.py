@@ -22,16 +22,22 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=(), out=None, tag="obj"):
-    """extra_flags/out/tag: tuning variants (scripts/tune_dslash.py) built next to the default library."""
+def build(force=False, verbose=False, extra_flags=(), out=None, tag="obj", only=None):
+    """extra_flags/out/tag: tuning variants (scripts/tune_*.py) built next to the default library; `only` lists the
+    sources the extra flags affect -- the other objects are taken from the default build (build/obj)."""
     lib = out or LIB
     if not force and not extra_flags and not _stale():
         return lib
     objdir = os.path.join(HERE, "..", "build", tag)
     os.makedirs(objdir, exist_ok=True)
+    default_objdir = os.path.join(HERE, "..", "build", "obj")
 
     def cc(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if only is not None and src not in only:
+            dflt = os.path.join(default_objdir, src.replace(".cu", ".o"))
+            if os.path.exists(dflt) and os.path.getmtime(dflt) >= os.path.getmtime(os.path.join(CSRC, src)):
+                return dflt
         cmd = [NVCC] + FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -292,6 +292,7 @@ void staple_set_stream(void *s)
 	ctx().stream = (cudaStream_t) s;
 }
 void staple_set_use_graphs(int on) { ctx().use_graphs = on != 0; }
+void staple_set_cgm_fuse_tail(int on) { ctx().cgm_fuse_tail = on != 0; }
 void staple_use_library_stream(void)
 {
 	require_init("staple_use_library_stream");

@@ -35,6 +35,7 @@ struct Geom {
 constexpr int kResultSlots = 16;        // device scalars produced by reductions
 
 struct Comm;   // NCCL state, staple_core.cu
+struct CgmCtl; // CG-M control block, below
 
 // Peer-memory channels over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank owns ONE
 // shared "mailbox" allocation:
@@ -90,6 +91,10 @@ struct Ctx {
 	bool use_graphs = true;          // CG-M iteration batches as CUDA graphs (single GPU, non-default stream)
 	bool p2p_unpack_in_kernel = true; // ... and the unpack blocks ride in the same launch
 	bool p2p_single_launch = true;   // acc_Deo/acc_Doe as one kernel + unpack (false: d3p/d3m/bulk on three streams)
+	// set by the CG-M solver around its iteration batches: fuse the after-alpha recurrences into the Deo tail
+	CgmCtl *cgm_hook = nullptr;
+	bool cgm_fuse_tail = true;       // false: one-warp kernels of their own (staple_set_cgm_fuse_tail, A/B tests)
+	RedView cgm_hook_red{};
 	// last multishift statistics
 	int last_iterations = 0;
 	long long last_active = 0;
@@ -156,6 +161,81 @@ __device__ __forceinline__ void p2p_allreduce_warp(double *vals, int nd, const R
 }
 #endif
 
+// ---- CG-M control block (inverter_multishift_full.c:53-58 host arrays, here device resident)
+constexpr double kSafetyMargin = 0.95;   // inverter_multishift_full.c:18, inverter_full.c:17
+struct CgmCtl {
+	double alpha, delta, lambda, omega, omega_save, gammag, source_norm, residuo;
+	double zeta_i[MAX_APPROX_ORDER], zeta_ii[MAX_APPROX_ORDER], zeta_iii[MAX_APPROX_ORDER];
+	double omegas[MAX_APPROX_ORDER], gammas[MAX_APPROX_ORDER], shifts[MAX_APPROX_ORDER];
+	// coefficients of the search-direction update ps_i = pgam_i ps_i + pzeta_i r that the reference performs at
+	// the end of an iteration (:152-157); here it is carried into the next iteration's single pass over ps_i
+	double pgam[MAX_APPROX_ORDER], pzeta[MAX_APPROX_ORDER];
+	int flag[MAX_APPROX_ORDER];    // current flags (inverter_multishift_full.c:58)
+	int order, maxiter, cg, max_cg;
+	int pending;     // 1 once a ps_i update is waiting (every iteration but the first)
+	int done;        // set when maxiter==0 or cg==max_cg: every later kernel is a no-op
+	long long active_sum;
+};
+
+#ifdef __CUDACC__
+// The scalar recurrences of one CG-M iteration, executed by ONE full warp (lane = shift index).  They run either
+// as one-warp kernels of their own or -- fused -- as the tail of the kernel whose grid reduction produced the
+// scalar (the last block to arrive, once the sum is final).  Multi-rank: the sum over ranks through the peer
+// mailboxes is the first thing the warp does.
+// after alpha = Re(p, s)  (inverter_multishift_full.c:122-137)
+__device__ __forceinline__ void cgm_after_alpha_warp(CgmCtl *c, double *alpha_slot, const RedView &red)
+{
+	if (red.nranks > 1) p2p_allreduce_warp(alpha_slot, 1, red);
+	const int i = threadIdx.x & 31;
+	const double alpha = *(volatile double *) alpha_slot;
+	const double omega_save = c->omega, delta = c->delta, gammag = c->gammag;
+	const int maxiter = c->maxiter, cg = c->cg;
+	const double omega = -delta / alpha;
+	if (i < maxiter && c->flag[i] == 1) {
+		const double zi = c->zeta_i[i], zii = c->zeta_ii[i];
+		const double ziii = (zi * zii * omega_save) /
+			(omega * gammag * (zi - zii) + zi * omega_save * (1.0 - c->shifts[i] * omega));
+		c->zeta_iii[i] = ziii;
+		c->omegas[i] = omega * ziii / zii;
+	}
+	__syncwarp();
+	if (i == 0) { c->alpha = alpha; c->omega_save = omega_save; c->omega = omega; c->cg = cg + 1; }
+}
+// after lambda = (r, r)  (:143-171): gammas, convergence flags, zeta rotation, delta <- lambda
+__device__ __forceinline__ void cgm_after_lambda_warp(CgmCtl *c, double *lambda_slot, const RedView &red)
+{
+	if (red.nranks > 1) p2p_allreduce_warp(lambda_slot, 1, red);
+	const int i = threadIdx.x & 31;
+	const double lambda = *(volatile double *) lambda_slot;
+	const double delta = c->delta, omega = c->omega, source_norm = c->source_norm, residuo = c->residuo;
+	const int order = c->order, cg = c->cg, max_cg = c->max_cg;
+	const double gammag = lambda / delta;
+	int active = 0, was = 0;
+	if (i < order) {
+		was = c->flag[i];
+		if (was == 1) {
+			const double zii = c->zeta_ii[i], ziii = c->zeta_iii[i];
+			const double gi = gammag * ziii * c->omegas[i] / (zii * omega);
+			c->gammas[i] = gi; c->pgam[i] = gi; c->pzeta[i] = ziii;
+			const double fact = sqrt(delta * zii * zii / source_norm);
+			if (fact < residuo * kSafetyMargin) c->flag[i] = 0;
+			else active = 1;
+			c->zeta_i[i] = zii;
+			c->zeta_ii[i] = ziii;
+		}
+	}
+	const unsigned int wasm = __ballot_sync(0xffffffffu, was == 1);
+	const unsigned int act = __ballot_sync(0xffffffffu, active);
+	if (i == 0) {
+		const int maxiter = act ? 32 - __clz(act) : 0;   // highest still-active shift + 1
+		c->maxiter = maxiter; c->pending = 1;
+		c->lambda = lambda; c->gammag = gammag; c->delta = lambda;
+		c->active_sum += __popc(wasm);
+		if (maxiter == 0 || cg >= max_cg) c->done = 1;
+	}
+}
+#endif
+
 // ---- precision traits -------------------------------------------------------------------
 template <typename T> struct Prec;
 template <> struct Prec<double> { using cplx = double2; };
@@ -177,6 +257,8 @@ struct DslashArgs {
 	unsigned int ticket_target;   // total blocks contributing to this reduction
 	unsigned int partial_offset;  // first partial index of this launch
 	const int *skip;          // device flag: nonzero -> kernel is a no-op (solver overrun)
+	CgmCtl *cgm;              // EPI_MASS_DOT only: the block that completes the alpha sum also advances the CG-M recurrences
+	RedView cgm_red;
 	// fused halo push (surface launches of exactly one d3 slice): the slice is ALSO stored into the
 	// neighbour's staging slot through its NVLink mapping, then the neighbour's flag is set to peer_seq
 	cplx_t<T> *peer;          // [3][vol3h] in the neighbour's memory (parity-0 slot), or null

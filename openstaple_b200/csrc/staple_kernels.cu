@@ -159,8 +159,10 @@ __device__ __forceinline__ void block_sum(double v[NV], double *sm)
 	}
 }
 
+// Returns true (block-uniform) in the block that completed the sum; result[] is then final and, after the
+// __syncthreads() the caller issues, visible to every thread of that block.
 template <int NV>
-__device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials, long pstride, unsigned int *ticket,
+__device__ __forceinline__ bool grid_sum_finalize(double v[NV], double *partials, long pstride, unsigned int *ticket,
 																									double *result, unsigned int target, unsigned int index)
 {
 	__shared__ double sm[NV * 32];
@@ -197,6 +199,7 @@ __device__ __forceinline__ void grid_sum_finalize(double v[NV], double *partials
 			*ticket = 0u;
 		}
 	}
+	return last;
 }
 
 // ------------------------------------------------------------------ peer-memory halo channel (device side)
@@ -341,6 +344,19 @@ void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------ Dirac operator kernel
+// Fused Re(in0 . out): block partial -> deterministic grid sum; inside a CG-M solve the block that completes the
+// sum (alpha) also runs the recurrences that consume it, so no one-warp kernel sits between M^+M and the update
+template <typename T>
+__device__ __forceinline__ void dslash_finish_dot(const DslashArgs<T> &a, double dot)
+{
+	double v[1] = { dot };
+	const bool last = grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
+	if (last && a.cgm != nullptr) {
+		__syncthreads();
+		if (threadIdx.x < 32) cgm_after_alpha_warp(a.cgm, a.result, a.cgm_red);
+	}
+}
+
 template <typename T, int PAR, int EPI>
 __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<T> a)
 {
@@ -388,10 +404,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 					*a.seq_rw = seq;
 				}
 			}
-			if (EPI == EPI_MASS_DOT) {       // contributes a zero partial so that the ticket count stays gridDim.x
-				double v[1] = { 0.0 };
-				grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
-			}
+			if (EPI == EPI_MASS_DOT) dslash_finish_dot(a, 0.0);   // a zero partial, so that the ticket count stays gridDim.x
 			return;
 		}
 	}
@@ -449,10 +462,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 		}
 	}
 	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks, a.fused == 2 ? a.unpack_ticket + 1 : nullptr);
-	if (EPI == EPI_MASS_DOT) {
-		double v[1] = { dot };
-		grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
-	}
+	if (EPI == EPI_MASS_DOT) dslash_finish_dot(a, dot);
 }
 
 unsigned int dslash_blocks(int d3lo, int d3hi)
@@ -499,6 +509,8 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	a.ticket = dot_slot >= 0 ? ticket(dot_slot) : nullptr;
 	a.result = dot_slot >= 0 ? result(dot_slot) : nullptr;
 	a.ticket_target = ticket_target; a.partial_offset = partial_offset; a.skip = skip;
+	a.cgm = (epi == EPI_MASS_DOT) ? ctx().cgm_hook : nullptr;
+	a.cgm_red = ctx().cgm_hook_red;
 	a.site_lo = (long) d3lo * g.vol3h; a.nsites = (long) (d3hi - d3lo) * g.vol3h;
 	if (a.fused) { a.site_lo = (long) (d3lo + 1) * g.vol3h; a.nsites = (long) (d3hi - d3lo - 2) * g.vol3h; }   // bulk
 	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;
@@ -855,6 +867,122 @@ void acc_Doe_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, co
 {
 	require_init("acc_Doe_d3c_f");
 	launch_dslash<float>(1, EPI_NONE, CDF(u), DF(out), CDF(in), (const float *) dev(bf, "backfield"), nullptr, 0.0, off3, off3 + thick3, -1, 0, 0, nullptr, ctx().stream);
+}
+
+// deo_doe_test.c's host round trip (update device; acc_Doe; acc_Deo; update host) pipelined over d3 chunks.
+// Chunk k of Doe reads `in` chunks k-1,k,k+1 (periodic), chunk k of Deo reads the Doe output of k-1,k,k+1: both
+// are issued on the compute stream as soon as the last chunk they depend on has been uploaded / computed, and
+// every finished Deo chunk is downloaded on its own copy stream.  Same kernels, same per-site arithmetic as the
+// whole-lattice launch => bit-identical results.
+void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_soa *in_h, vec3_soa *tmp,
+																 const double_soa *backfield, int chunk_slices)
+{
+	require_init("staple_acc_Doe_Deo_streamed");
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	const double2 *d_u = CDD(u); const double *d_ph = (const double *) dev(backfield, "backfield");
+	double2 *d_in = (double2 *) dev(in_h, "in"), *d_out = DD(out_h), *d_tmp = DD(tmp);
+	const bool in_host = (const void *) d_in != (const void *) in_h, out_host = (void *) d_out != (void *) out_h;
+	const size_t vbytes = sizeof(double2) * 3 * g.sizeh;
+	if (c.nranks > 1 || !in_host || !out_host) {
+		if (in_host) staple_acc_update_device(in_h, vbytes);
+		apply_dslash<double>(1, EPI_NONE, d_u, d_tmp, d_in, d_ph, nullptr, 0.0, -1, nullptr);
+		apply_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, -1, nullptr);
+		if (out_host) staple_acc_update_host(out_h, vbytes);
+		else STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+		return;
+	}
+	constexpr int kMaxChunks = 128;
+	static cudaEvent_t ev_up[kMaxChunks], ev_deo[kMaxChunks];
+	static bool have_events = false;
+	if (!have_events) {
+		for (int k = 0; k < kMaxChunks; k++) {
+			STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(&ev_up[k], cudaEventDisableTiming));
+			STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(&ev_deo[k], cudaEventDisableTiming));
+		}
+		have_events = true;
+	}
+	int cs = chunk_slices > 0 ? chunk_slices : (g.nd3 >= 32 ? g.nd3 / 32 : 1);
+	if (cs > g.nd3) cs = g.nd3;
+	while (g.nd3 % cs != 0 || g.nd3 / cs > kMaxChunks) cs++;   // cs = nd3 always qualifies
+	const int nc = g.nd3 / cs;
+	const size_t pitch = sizeof(double2) * g.sizeh, width = sizeof(double2) * g.vol3h * cs;
+	cudaStream_t s_up = c.s_p, s_dn = c.s_m, st = c.stream;
+	auto enqueue = [&]() {
+		// the copy streams may not touch `in`/`out` on the device before earlier work of the compute stream is done
+		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, st));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_up, c.ev_fork, 0));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, c.ev_fork, 0));
+		bool doe_done[kMaxChunks] = {}, deo_done[kMaxChunks] = {};
+		auto deps_ok = [&](const bool *have, int k, int upto) {   // chunks k-1,k,k+1 (mod nc) all present
+			for (int d = -1; d <= 1; d++) {
+				const int j = (k + d + nc) % nc;
+				if (have ? !have[j] : j > upto) return false;
+			}
+			return true;
+		};
+		for (int j = 0; j < nc; j++) {
+			const size_t off = (size_t) j * cs * g.vol3h;
+			STAPLE_CUDA_CHECK(cudaMemcpy2DAsync(d_in + off, pitch, (const double2 *) in_h + off, pitch, width, 3,
+																					cudaMemcpyHostToDevice, s_up));
+			STAPLE_CUDA_CHECK(cudaEventRecord(ev_up[j], s_up));
+			bool waited = false;
+			for (int k = 0; k < nc; k++) {
+				if (doe_done[k] || !deps_ok(nullptr, k, j)) continue;
+				if (!waited) { STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, ev_up[j], 0)); waited = true; }
+				launch_dslash<double>(1, EPI_NONE, d_u, d_tmp, d_in, d_ph, nullptr, 0.0, k * cs, (k + 1) * cs, -1, 0, 0, nullptr, st);
+				doe_done[k] = true;
+			}
+			for (int k = 0; k < nc; k++) {
+				if (deo_done[k] || !deps_ok(doe_done, k, 0)) continue;
+				launch_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, k * cs, (k + 1) * cs, -1, 0, 0, nullptr, st);
+				deo_done[k] = true;
+				STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[k], st));
+				STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[k], 0));
+				const size_t o2 = (size_t) k * cs * g.vol3h;
+				STAPLE_CUDA_CHECK(cudaMemcpy2DAsync((double2 *) out_h + o2, pitch, d_out + o2, pitch, width, 3,
+																						cudaMemcpyDeviceToHost, s_dn));
+			}
+		}
+		// join: everything (last download included) is ordered before whatever follows on the compute stream
+		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, s_up));
+		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, s_dn));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_p, 0));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_m, 0));
+	};
+	// The schedule is ~8 API calls per chunk: on the host that costs more than the PCIe time it hides.  It only
+	// depends on the pointers and the chunking, so it is captured ONCE into a CUDA graph (three streams, copy
+	// nodes included) and replayed with a single launch.  The legacy default stream cannot be captured: direct
+	// issue there.
+	struct Cached { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
+	static Cached cache[4] = {};
+	static int cache_next = 0;
+	Cached *hit = nullptr;
+	if (st != nullptr && c.use_graphs) {
+		for (auto &e : cache)
+			if (e.exec && e.u == u && e.out == out_h && e.in == in_h && e.tmp == tmp && e.ph == backfield && e.d_in == d_in && e.d_out == d_out && e.cs == cs && e.sizeh == g.sizeh) hit = &e;
+		if (!hit) {
+			const unsigned long long before = c.launches;
+			cudaGraph_t graph = nullptr;
+			cudaGraphExec_t exec = nullptr;
+			if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+				enqueue();
+				if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph != nullptr &&
+						cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+					Cached &e = cache[cache_next]; cache_next = (cache_next + 1) % 4;
+					if (e.exec) cudaGraphExecDestroy(e.exec);
+					e = Cached{ u, out_h, in_h, tmp, backfield, d_in, d_out, cs, g.sizeh, exec, c.launches - before };
+					hit = &e;
+				}
+				if (graph) cudaGraphDestroy(graph);
+			}
+			cudaGetLastError();
+			c.launches = before;
+		}
+	}
+	if (hit) { STAPLE_CUDA_CHECK(cudaGraphLaunch(hit->exec, st)); c.launches += hit->launches; }
+	else enqueue();
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars)

@@ -18,22 +18,6 @@
 namespace staple {
 
 constexpr int kBlasBlock = 256;
-constexpr double kSafetyMargin = 0.95;   // inverter_multishift_full.c:18, inverter_full.c:17
-
-struct CgmCtl {
-	double alpha, delta, lambda, omega, omega_save, gammag, source_norm, residuo;
-	double zeta_i[MAX_APPROX_ORDER], zeta_ii[MAX_APPROX_ORDER], zeta_iii[MAX_APPROX_ORDER];
-	double omegas[MAX_APPROX_ORDER], gammas[MAX_APPROX_ORDER], shifts[MAX_APPROX_ORDER];
-	// coefficients of the search-direction update ps_i = pgam_i ps_i + pzeta_i r that the reference performs at
-	// the end of an iteration (:152-157); here it is carried into the next iteration's single pass over ps_i
-	double pgam[MAX_APPROX_ORDER], pzeta[MAX_APPROX_ORDER];
-	int flag[MAX_APPROX_ORDER];    // current flags (inverter_multishift_full.c:58)
-	int order, maxiter, cg, max_cg;
-	int pending;     // 1 once a ps_i update is waiting (every iteration but the first)
-	int done;        // set when maxiter==0 or cg==max_cg: every later kernel is a no-op
-	long long active_sum;
-};
-
 template <typename T> __device__ __forceinline__ cplx_t<T> mkc(double x, double y);
 template <> __device__ __forceinline__ double2 mkc<double>(double x, double y) { return make_double2(x, y); }
 template <> __device__ __forceinline__ float2 mkc<float>(double x, double y) { return make_float2((float) x, (float) y); }
@@ -51,61 +35,17 @@ __global__ void cgm_init_kernel(CgmCtl *c, const double *delta_slot, const doubl
 	c->maxiter = c->order; c->cg = 0; c->done = 0; c->pending = 0; c->active_sum = 0;
 }
 
-// after alpha = Re(p, s) (:122-137)
+// standalone one-warp forms of the recurrences (NCCL all-reduce path, where the sum over ranks is a library call
+// between the reduction kernel and its consumer)
 __global__ void cgm_after_alpha_kernel(CgmCtl *c, double *alpha_slot, RedView red)
 {
 	if (c->done) return;
-	if (red.nranks > 1) p2p_allreduce_warp(alpha_slot, 1, red);   // sum over ranks fused into the consumer
-	const int i = threadIdx.x;
-	const double alpha = *(volatile double *) alpha_slot;
-	const double omega_save = c->omega, delta = c->delta, gammag = c->gammag;
-	const int maxiter = c->maxiter, cg = c->cg;
-	const double omega = -delta / alpha;
-	if (i < maxiter && c->flag[i] == 1) {
-		const double zi = c->zeta_i[i], zii = c->zeta_ii[i];
-		const double ziii = (zi * zii * omega_save) /
-			(omega * gammag * (zi - zii) + zi * omega_save * (1.0 - c->shifts[i] * omega));
-		c->zeta_iii[i] = ziii;
-		c->omegas[i] = omega * ziii / zii;
-	}
-	__syncwarp();
-	if (i == 0) { c->alpha = alpha; c->omega_save = omega_save; c->omega = omega; c->cg = cg + 1; }
+	cgm_after_alpha_warp(c, alpha_slot, red);
 }
-
-// after lambda = (r, r) (:143-171): gammas, convergence flags, zeta rotation, delta <- lambda
 __global__ void cgm_after_lambda_kernel(CgmCtl *c, double *lambda_slot, RedView red)
 {
 	if (c->done) return;
-	if (red.nranks > 1) p2p_allreduce_warp(lambda_slot, 1, red);
-	const int i = threadIdx.x;
-	const double lambda = *(volatile double *) lambda_slot;
-	const double delta = c->delta, omega = c->omega, source_norm = c->source_norm, residuo = c->residuo;
-	const int order = c->order, old_maxiter = c->maxiter, cg = c->cg, max_cg = c->max_cg;
-	const double gammag = lambda / delta;
-	int active = 0, was = 0;
-	if (i < order) {
-		was = c->flag[i];
-		if (was == 1) {
-			const double zii = c->zeta_ii[i], ziii = c->zeta_iii[i];
-			const double gi = gammag * ziii * c->omegas[i] / (zii * omega);
-			c->gammas[i] = gi; c->pgam[i] = gi; c->pzeta[i] = ziii;
-			const double fact = sqrt(delta * zii * zii / source_norm);
-			if (fact < residuo * kSafetyMargin) c->flag[i] = 0;
-			else active = 1;
-			c->zeta_i[i] = zii;
-			c->zeta_ii[i] = ziii;
-		}
-	}
-	const unsigned int wasm = __ballot_sync(0xffffffffu, was == 1);
-	const unsigned int act = __ballot_sync(0xffffffffu, active);
-	if (i == 0) {
-		(void) old_maxiter;
-		const int maxiter = act ? 32 - __clz(act) : 0;   // highest still-active shift + 1
-		c->maxiter = maxiter; c->pending = 1;
-		c->lambda = lambda; c->gammag = gammag; c->delta = lambda;
-		c->active_sum += __popc(wasm);
-		if (maxiter == 0 || cg >= max_cg) c->done = 1;
-	}
+	cgm_after_lambda_warp(c, lambda_slot, red);
 }
 
 __device__ __forceinline__ void block_sum1(double &v, double *sm)
@@ -132,11 +72,72 @@ __device__ __forceinline__ void block_sum1(double &v, double *sm)
 // Element for element the same arithmetic in the same order as the reference (ps_i is rounded to T before
 // it enters out_i, as it is when it goes through memory there); shifts that have converged are skipped:
 // their ps_i can no longer reach an output.
+// tuning knobs of the shifted-vector pass (scripts/tune_cgm.py sweeps them on the GPU)
+#ifndef STAPLE_CGM_BLOCK
+#define STAPLE_CGM_BLOCK 256
+#endif
+#ifndef STAPLE_CGM_MINBLOCKS
+#define STAPLE_CGM_MINBLOCKS 1
+#endif
+#ifndef STAPLE_CGM_UNROLL
+#define STAPLE_CGM_UNROLL 2      // shifts per trip: 6*UNROLL independent 16-byte loads in flight per thread
+#endif
+#ifndef STAPLE_CGM_STREAM
+#define STAPLE_CGM_STREAM 0      // 1: out_i / ps_i with evict-first loads and stores (they are touched once per iteration)
+#endif
+constexpr int kCgmBlock = STAPLE_CGM_BLOCK;
+
+template <typename V> __device__ __forceinline__ V cgm_ld(const V *p)
+{
+#if STAPLE_CGM_STREAM
+	return __ldcs(p);
+#else
+	return *p;
+#endif
+}
+template <typename V> __device__ __forceinline__ void cgm_st(V *p, V v)
+{
+#if STAPLE_CGM_STREAM
+	__stcs(p, v);
+#else
+	*p = v;
+#endif
+}
+
+// U shifts of one site: all loads first, then the arithmetic of inverter_multishift_full.c:139,152-157
+template <typename T, int U>
+__device__ __forceinline__ void cgm_shift_group(cplx_t<T> *out, cplx_t<T> *ps, const cplx_t<T> rv[3], long i, long n,
+																								const int *s_ix, const double *s_om, const double *s_g, const double *s_z,
+																								int k, int pending)
+{
+	cplx_t<T> q[U][3], o[U][3];
+#pragma unroll
+	for (int u2 = 0; u2 < U; u2++) {
+		const long base = (long) s_ix[k + u2] * 3 * n + i;
+#pragma unroll
+		for (int col = 0; col < 3; col++) { q[u2][col] = cgm_ld(ps + base + col * n); o[u2][col] = cgm_ld(out + base + col * n); }
+	}
+#pragma unroll
+	for (int u2 = 0; u2 < U; u2++) {
+		const long base = (long) s_ix[k + u2] * 3 * n + i;
+		const double f = s_om[k + u2], g = s_g[k + u2], z = s_z[k + u2];
+#pragma unroll
+		for (int col = 0; col < 3; col++) {
+			cplx_t<T> qq = q[u2][col];
+			if (pending) {
+				qq = mkc<T>(g * qq.x + z * rv[col].x, g * qq.y + z * rv[col].y);
+				cgm_st(ps + base + col * n, qq);
+			}
+			cgm_st(out + base + col * n, mkc<T>(o[u2][col].x - f * qq.x, o[u2][col].y - f * qq.y));
+		}
+	}
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, cplx_t<T> *out, cplx_t<T> *ps, cplx_t<T> *r,
+__global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_kernel(CgmCtl *c, cplx_t<T> *out, cplx_t<T> *ps, cplx_t<T> *r,
 																																const cplx_t<T> *s, long lo, long cnt, long n, long r0_lo,
 																																long r0_hi, double *partials, unsigned int *ticket,
-																																double *result)
+																																double *result, int fuse_tail, RedView red)
 {
 	if (c->done) return;
 	__shared__ double sm[32];
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, 
 	const int pending = c->pending;
 	__syncthreads();
 	const int nact = s_nact;
-	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	const long t = (long) blockIdx.x * kCgmBlock + threadIdx.x;
 	double nrm = 0.0;
 	if (t < cnt) {
 		const long i = lo + t;
@@ -168,45 +169,10 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, 
 			r[j] = rn;
 			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
 		}
-		// two shifts per trip: 12 independent 16-byte loads in flight per thread before the first use
 		int k = 0;
-		for (; k + 2 <= nact; k += 2) {
-			cplx_t<T> q[2][3], o[2][3];
-#pragma unroll
-			for (int u2 = 0; u2 < 2; u2++) {
-				const long base = (long) s_ix[k + u2] * 3 * n + i;
-#pragma unroll
-				for (int col = 0; col < 3; col++) { q[u2][col] = ps[base + col * n]; o[u2][col] = out[base + col * n]; }
-			}
-#pragma unroll
-			for (int u2 = 0; u2 < 2; u2++) {
-				const long base = (long) s_ix[k + u2] * 3 * n + i;
-				const double f = s_om[k + u2], g = s_g[k + u2], z = s_z[k + u2];
-#pragma unroll
-				for (int col = 0; col < 3; col++) {
-					cplx_t<T> qq = q[u2][col];
-					if (pending) {
-						qq = mkc<T>(g * qq.x + z * rv[col].x, g * qq.y + z * rv[col].y);
-						ps[base + col * n] = qq;
-					}
-					out[base + col * n] = mkc<T>(o[u2][col].x - f * qq.x, o[u2][col].y - f * qq.y);
-				}
-			}
-		}
-		if (k < nact) {
-			const long base = (long) s_ix[k] * 3 * n + i;
-			const double f = s_om[k], g = s_g[k], z = s_z[k];
-#pragma unroll
-			for (int col = 0; col < 3; col++) {
-				cplx_t<T> qq = ps[base + col * n];
-				const cplx_t<T> o = out[base + col * n];
-				if (pending) {
-					qq = mkc<T>(g * qq.x + z * rv[col].x, g * qq.y + z * rv[col].y);
-					ps[base + col * n] = qq;
-				}
-				out[base + col * n] = mkc<T>(o.x - f * qq.x, o.y - f * qq.y);
-			}
-		}
+		for (; k + STAPLE_CGM_UNROLL <= nact; k += STAPLE_CGM_UNROLL)
+			cgm_shift_group<T, STAPLE_CGM_UNROLL>(out, ps, rv, i, n, s_ix, s_om, s_g, s_z, k, pending);
+		for (; k < nact; k++) cgm_shift_group<T, 1>(out, ps, rv, i, n, s_ix, s_om, s_g, s_z, k, pending);
 	}
 	block_sum1(nrm, sm);
 	if (threadIdx.x == 0) {
@@ -230,6 +196,12 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_fused_kernel(const CgmCtl *c, 
 		}
 		block_sum1(acc, sm);
 		if (threadIdx.x == 0) { result[0] = acc; *ticket = 0u; }
+		// every other block has finished (and read the control block at its start): lambda is final, advance the
+		// recurrences here instead of in a one-warp kernel of their own
+		if (fuse_tail) {
+			__syncthreads();
+			if (threadIdx.x < 32) cgm_after_lambda_warp(c, result, red);
+		}
 	}
 }
 
@@ -298,6 +270,7 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	const double m2 = pars->ferm_mass * pars->ferm_mass;
 	const long n = g.sizeh, lo = g.r1_lo, cnt = g.r1_hi - g.r1_lo;
 	const unsigned int grid = (unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock);
+	const unsigned int grid_f = (unsigned int) ((cnt + kCgmBlock - 1) / kCgmBlock);
 	cudaStream_t st = c.stream;
 
 	// trial solution out = 0 (all sizeh, :67-70); r = p = in; delta = (r,r); source_norm = (in,in)
@@ -328,20 +301,32 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	// that advances the recurrences (K12-14 + C4 of the reference fused), no NCCL call inside the iteration
 	const bool fuse_red = c.nranks > 1 && c.p2p.on && c.p2p.d_redq != nullptr;
 	const RedView red = fuse_red ? make_redview() : single_rank_redview();
+	// single rank, or sums over ranks through the peer mailboxes: the recurrences ride in the tail of the kernel
+	// whose grid reduction feeds them (Deo -> alpha, shifted pass -> lambda): 4 launches per iteration.  With NCCL
+	// all-reduces the sum is a library call between producer and consumer: 6 launches + 2 collectives.
+	const bool fuse_tail = (c.nranks == 1 || fuse_red) && c.cgm_fuse_tail;
 	auto enqueue_batch = [&]() {
+		if (fuse_tail) { c.cgm_hook = g_d_ctl; c.cgm_hook_red = red; }
 		for (int b = 0; b < batch; b++) {
 			// s = (M^+M) p, alpha = Re(p,s) fused in the Deo epilogue (:113-118)
 			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done);
-			if (!fuse_red) allreduce_results(SLOT_ALPHA, 1, st);
-			cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA), red);
-			cgm_fused_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
+			if (!fuse_tail) {
+				if (!fuse_red) allreduce_results(SLOT_ALPHA, 1, st);
+				cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA), red);
+				count_launch();
+			}
+			cgm_fused_kernel<T><<<grid_f, kCgmBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
 																											 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
-																											 result(SLOT_LAMBDA));
-			if (!fuse_red) allreduce_results(SLOT_LAMBDA, 1, st);
-			cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA), red);
+																											 result(SLOT_LAMBDA), fuse_tail ? 1 : 0, red);
+			if (!fuse_tail) {
+				if (!fuse_red) allreduce_results(SLOT_LAMBDA, 1, st);
+				cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA), red);
+				count_launch();
+			}
 			cgm_pupdate_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, lo, cnt, n);
-			count_launch(4);
+			count_launch(2);
 		}
+		c.cgm_hook = nullptr;
 	};
 	// Single GPU: a batch is a fixed sequence of launches on one stream whose every data dependence (flags,
 	// coefficients, `done`) lives in device memory, so it is captured ONCE into a CUDA graph and replayed --

@@ -42,6 +42,7 @@ def _declare(L):
     L.staple_get_stream.restype = vp
     L.staple_use_library_stream.argtypes = []
     L.staple_set_use_graphs.argtypes = [i]
+    L.staple_set_cgm_fuse_tail.argtypes = [i]
     L.staple_kernel_launches.restype = C.c_ulonglong
     L.staple_version.restype = C.c_char_p
     L.staple_posix_memalign.argtypes = [C.POINTER(vp), C.c_size_t, C.c_size_t]; L.staple_posix_memalign.restype = i
@@ -50,6 +51,7 @@ def _declare(L):
         getattr(L, f).argtypes = [vp, C.c_size_t]
     L.staple_acc_exit_data.argtypes = [vp]
     L.staple_acc_deviceptr.argtypes = [vp]; L.staple_acc_deviceptr.restype = vp
+    L.staple_acc_Doe_Deo_streamed.argtypes = [vp, vp, vp, vp, vp, i]; L.staple_acc_Doe_Deo_streamed.restype = None
     L.staple_nccl_unique_id.argtypes = [vp]; L.staple_nccl_unique_id.restype = i
     L.staple_init_multidev1D.argtypes = [i, i, vp, i]; L.staple_init_multidev1D.restype = i
     L.staple_myrank.restype = i

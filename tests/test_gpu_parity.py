@@ -335,6 +335,42 @@ def test_host_pointer_boundary(osb):
         a.free()
 
 
+@pytest.mark.parametrize("on_stream", [False, True], ids=["legacy-stream-direct", "own-stream-graph"])
+@pytest.mark.parametrize("loc_n,chunk", [((8, 8, 8, 8), 0), ((8, 8, 8, 8), 1), ((8, 8, 8, 8), 2), ((8, 8, 8, 8), 8),
+                                         ((8, 4, 6, 10), 5), ((4, 4, 4, 2), 1), ((8, 8, 8, 48), 0), ((8, 8, 8, 12), 3)])
+def test_streamed_host_round_trip(osb, loc_n, chunk, on_stream):
+    """staple_acc_Doe_Deo_streamed (update device / acc_Doe / acc_Deo / update host pipelined over d3 chunks)
+    is BIT-identical to the plain sequence and matches the oracle; repeated calls reuse the buffers (and, on a
+    capturable stream, the cached CUDA graph of the schedule) safely."""
+    import contextlib
+    import torch
+    ctx = torch.cuda.stream(torch.cuda.Stream()) if on_stream else contextlib.nullcontext()
+    with ctx:
+        c = make_case(osb, loc_n)
+        lat, S = c["lat"], c["S"]
+        hin = lat.host_array((3, lat.sizeh), np.complex128)
+        hout = lat.host_array((3, lat.sizeh), np.complex128)
+        tmp, plain = lat.new_vec(), lat.new_vec()
+        for rep, src in enumerate((c["v"], c["w"], c["v"])):
+            hin.np[...] = src
+            hout.np[...] = 0
+            lat.acc_Doe_Deo_streamed(c["d_u"], hout, hin, tmp, c["d_ph"], chunk)
+            d_src = lat.to_device(src)
+            lat.acc_Doe(c["d_u"], tmp, d_src, c["d_ph"])
+            lat.acc_Deo(c["d_u"], plain, tmp, c["d_ph"])
+            assert np.array_equal(hout.np, plain.cpu().numpy()), rep
+            ref = S.dslash("deo", c["u"], S.dslash("doe", c["u"], src, c["ph"]), c["ph"])
+            assert relerr(hout.np, ref) < TOL64
+        # device pointers fall through to the plain sequence
+        dout = lat.new_vec()
+        lat.acc_Doe_Deo_streamed(c["d_u"], dout, c["d_v"], tmp, c["d_ph"], chunk)
+        lat.acc_Doe(c["d_u"], tmp, c["d_v"], c["d_ph"]); lat.acc_Deo(c["d_u"], plain, tmp, c["d_ph"])
+        assert np.array_equal(dout.cpu().numpy(), plain.cpu().numpy())
+        hin.free(); hout.free()
+        torch.cuda.synchronize()
+    lat.use_torch_stream()
+
+
 def test_not_present_pointer_aborts():
     """A plain host pointer is a fatal error (no silent CPU path), like an OpenACC `present` miss."""
     import subprocess, sys, os
@@ -438,3 +474,28 @@ def test_multishift_graph_replay_matches_direct_launches(osb):
         assert abs(res[0][0] - cg_ref) <= 0.02 * cg_ref
         assert relerr(res[0][1], want) < 1e-7
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_multishift_fused_tail_matches_separate_kernels(osb, single):
+    """The CG-M scalar recurrences run in the tail of the Deo kernel (alpha) and of the shifted pass (lambda);
+    with the one-warp kernels of their own instead, iteration count and solutions are bit-identical."""
+    c = make_case(osb, (8, 8, 8, 8))
+    lat = c["lat"]
+    shifts = np.array([1e-4, 1e-3, 1e-2, 0.1, 1.0, 5.0])
+    pars = lat.ferm_param(0.0507, c["d_ph"], c["d_phf"])
+    approx = osb.RationalApprox.make(1.0, np.ones(6), shifts)
+    u, v = (c["d_uf"], c["d_vf"]) if single else (c["d_u"], c["d_v"])
+    res = []
+    for fuse in (1, 0):
+        lat.L.staple_set_cgm_fuse_tail(fuse)
+        l0 = lat.kernel_launches()
+        out, ps = lat.new_vec(6, single=single), lat.new_vec(6, single=single)
+        r, h, s_, p = (lat.new_vec(single=single) for _ in range(4))
+        st, cg = lat.multishift_invert(u, pars, approx, out, v, 1e-5 if single else 1e-9, r, h, s_, p, ps, 10000)
+        assert st == osb.INVERTER_SUCCESS
+        res.append((cg, out.cpu().numpy(), lat.kernel_launches() - l0))
+    lat.L.staple_set_cgm_fuse_tail(1)
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1])
+    assert res[0][2] < res[1][2]          # 4 instead of 6 launches per iteration
