@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver", action="store_true")
     ap.add_argument("--shifts", type=int, default=15)
+    ap.add_argument("--stream-mode", type=int, default=0, help="0: copy-engine downloads, 1: Deo chunk kernels store to the pinned host buffer")
     ap.add_argument("--stream-chunk", type=int, default=0, help="d3 slices per chunk of the pipelined host round trip (0 = library default)")
     return ap.parse_args()
 
@@ -338,6 +339,8 @@ def main():
         # the same round trip as ONE C-ABI call, software-pipelined over d3 chunks (single rank; with D3 slabs
         # the library runs the plain sequence incl. the halo exchanges)
         lat.acc_Doe_Deo_streamed(u, h_out, h_in, d_tmp, ph, args.stream_chunk)
+
+    lat.L.staple_set_streamed_mode(args.stream_mode)
 
     def time_e2e(fn):
         for _ in range(3):

@@ -49,6 +49,8 @@ typedef struct double_soa_t double_soa;     /* ref: OpenAcc/struct_c_def.h:25-27
 typedef struct vec3_soa_f_t vec3_soa_f;     /* generated sp_struct_c_def.h */
 typedef struct su3_soa_f_t su3_soa_f;
 typedef struct float_soa_t float_soa;
+typedef struct tamat_soa_t tamat_soa;       /* ref: OpenAcc/struct_c_def.h:45-51  {c01,c02,c12 complex[sizeh]; ic00,ic11 double[sizeh]} */
+typedef struct tamat_soa_f_t tamat_soa_f;
 
 #ifndef MAX_APPROX_ORDER
 #define MAX_APPROX_ORDER 25                 /* ref: RationalApprox/rationalapprox.h:8 */
@@ -179,6 +181,9 @@ void *staple_acc_deviceptr(const void *host);                     /* acc_devicep
  * plain sequence incl. the halo exchanges is executed). */
 void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *tmp,
 																 const double_soa *backfield, int chunk_slices);
+/* how the result of the call above reaches the host: 0 (default) = chunk downloads by the copy engine, 1 = the Deo
+ * chunk kernels store it straight into the pinned host buffer (download fused into the operator epilogue). */
+void staple_set_streamed_mode(int mode);
 
 /* ------------------------------------------------------------------ rank / halo layer */
 /* ref: Mpi/multidev.c:20-108 pre_init_multidev1D + init_multidev1D.  MPI is replaced by NCCL over
@@ -305,6 +310,25 @@ void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f
 double ker_find_max_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p);
 void find_min_max_eigenvalue_soloopenacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h,
 																				 vec3_soa *loc_p1, vec3_soa *loc_p2, double *minmax);
+
+/* "next" row N2: fermion-force outer products, the step after every MD multishift solve.
+ * ref: OpenAcc/fermion_force_utilities.c:17-201, fermion_force_utilities.h:16-216; set_su3_soa_to_zero: su3_utilities.c.
+ * aux_u / auxmat / pseudo_ipdot are gl(3) fields in the su3_soa[8] layout (all three rows meaningful), ipdot is
+ * tamat_soa[8]; all loops cover the local interior d3 in [D3_HALO, nd3-D3_HALO) like the reference's.
+ * ker_openacc_compute_fermion_force: for every shift of tpars->approx_md, aux_u += RA_a[i] * outer products of
+ * in_shiftmulti[i] and acc_Doe(in_shiftmulti[i]); loc_s / loc_h are scratch (left as the reference leaves them). */
+#define STAPLE_FORCE_DECL(S, SU3, VEC3, TAMAT) \
+	void set_tamat_soa_to_zero##S(TAMAT *matrix);                                               /* ref: fermion_force_utilities.c:17-29 */ \
+	void set_su3_soa_to_zero##S(SU3 *matrix);                                                   /* ref: su3_utilities.c (all 8 links, all sizeh) */ \
+	void direct_product_of_fermions_into_auxmat##S(const VEC3 *loc_s, const VEC3 *loc_h, SU3 *aux_u, \
+																								 const RationalApprox *approx, int iter);     /* ref: :31-95 */ \
+	void multiply_conf_times_force_and_take_ta_nophase##S(const SU3 *u, const SU3 *auxmat, TAMAT *ipdot); /* ref: :97-121 */ \
+	void multiply_backfield_times_force##S(ferm_param *tpars, const SU3 *auxmat, SU3 *pseudo_ipdot);       /* ref: :123-153 */ \
+	void accumulate_gl3soa_into_gl3soa##S(const SU3 *auxmat, SU3 *pseudo_ipdot);                /* ref: :155-180 */ \
+	void ker_openacc_compute_fermion_force##S(const SU3 *u, SU3 *aux_u, const VEC3 *in_shiftmulti, VEC3 *loc_s, \
+																						VEC3 *loc_h, ferm_param *tpars);                  /* ref: :183-201 */
+STAPLE_FORCE_DECL(, su3_soa, vec3_soa, tamat_soa)
+STAPLE_FORCE_DECL(_f, su3_soa_f, vec3_soa_f, tamat_soa_f)
 
 /* ------------------------------------------------------------------ introspection for benches/tests */
 /* statistics of the last multishift_invert[_f] call: iterations, sum over iterations of active

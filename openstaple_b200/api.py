@@ -117,6 +117,16 @@ def _sfx(x):
     return ""
 
 
+def tamat_fields(ta):
+    """views of a tamat_soa[8] array [8, 8, sizeh] (numpy or torch): (c01, c02, c12) complex [8, sizeh], (ic00, ic11) real."""
+    n = ta.shape[-1]
+    if hasattr(ta, "numpy") and not isinstance(ta, np.ndarray):
+        ta = ta.cpu().numpy()
+    cdt = np.complex64 if ta.dtype == np.float32 else np.complex128
+    c = [np.ascontiguousarray(ta[:, 2 * j:2 * j + 2, :]).reshape(8, 2 * n).view(cdt) for j in range(3)]
+    return c[0], c[1], c[2], ta[:, 6, :], ta[:, 7, :]
+
+
 def geometry_plan(loc_n, nranks_d3=1, halo_width=2):
     """Host-only sharding arithmetic of the D3 slab decomposition (staple_geometry_plan; needs no GPU):
     local+halo box, sizeh, reduction/update ranges and the fermion halo offsets of
@@ -230,6 +240,12 @@ class Lattice:
     def new_conf(self, single=False):
         return self.torch.zeros((8, 3, 3, self.sizeh), dtype=self._cdt(single), device=self.device)
 
+    def new_tamat(self, single=False):
+        """tamat_soa[8] (struct_c_def.h:45-51) as reals: [8, 8, sizeh]; rows 0-5 = c01, c02, c12 (re/im interleaved
+        per element), rows 6, 7 = ic00, ic11.  See :func:`tamat_fields`."""
+        return self.torch.zeros((8, 8, self.sizeh), dtype=self.torch.float32 if single else self.torch.float64,
+                                device=self.device)
+
     def to_device(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
@@ -339,6 +355,28 @@ class Lattice:
 
     def calc_new_trialsol_for_inversion_in_force(self, halfLen, inout, nPrecCalculations):
         getattr(self.L, "calc_new_trialsol_for_inversion_in_force" + _sfx(inout))(halfLen, _addr(inout), nPrecCalculations)
+
+    # ---- fermion-force outer products (OpenAcc/fermion_force_utilities.h)
+    def set_tamat_soa_to_zero(self, matrix): getattr(self.L, "set_tamat_soa_to_zero" + _sfx(matrix))(_addr(matrix))
+    def set_su3_soa_to_zero(self, matrix): getattr(self.L, "set_su3_soa_to_zero" + _sfx(matrix))(_addr(matrix))
+
+    def direct_product_of_fermions_into_auxmat(self, loc_s, loc_h, aux_u, approx, it):
+        getattr(self.L, "direct_product_of_fermions_into_auxmat" + _sfx(loc_s))(
+            _addr(loc_s), _addr(loc_h), _addr(aux_u), C.addressof(approx), int(it))
+
+    def multiply_conf_times_force_and_take_ta_nophase(self, u, auxmat, ipdot):
+        getattr(self.L, "multiply_conf_times_force_and_take_ta_nophase" + _sfx(u))(_addr(u), _addr(auxmat), _addr(ipdot))
+
+    def multiply_backfield_times_force(self, tpars, auxmat, pseudo_ipdot):
+        getattr(self.L, "multiply_backfield_times_force" + _sfx(auxmat))(C.addressof(tpars), _addr(auxmat), _addr(pseudo_ipdot))
+
+    def accumulate_gl3soa_into_gl3soa(self, auxmat, pseudo_ipdot):
+        getattr(self.L, "accumulate_gl3soa_into_gl3soa" + _sfx(auxmat))(_addr(auxmat), _addr(pseudo_ipdot))
+
+    def ker_openacc_compute_fermion_force(self, u, aux_u, in_shiftmulti, loc_s, loc_h, tpars):
+        """tpars.approx_md holds the shifts' residues RA_a (fermion_force_utilities.c:195)."""
+        getattr(self.L, "ker_openacc_compute_fermion_force" + _sfx(u))(
+            _addr(u), _addr(aux_u), _addr(in_shiftmulti), _addr(loc_s), _addr(loc_h), C.addressof(tpars))
 
     # ---- conversions (OpenAcc/float_double_conv.c)
     def convert_double_to_float_vec3_soa(self, d, f): self.L.convert_double_to_float_vec3_soa(_addr(d), _addr(f))

@@ -93,6 +93,8 @@ struct Ctx {
 	bool p2p_single_launch = true;   // acc_Deo/acc_Doe as one kernel + unpack (false: d3p/d3m/bulk on three streams)
 	// set by the CG-M solver around its iteration batches: fuse the after-alpha recurrences into the Deo tail
 	CgmCtl *cgm_hook = nullptr;
+	void *out_host_hook = nullptr;   // staple_acc_Doe_Deo_streamed: the Deo chunk kernels also store their result in host memory
+	int streamed_mode = 0;           // 0: chunk downloads by the copy engine  1: stores over PCIe from the Deo kernels
 	bool cgm_fuse_tail = true;       // false: one-warp kernels of their own (staple_set_cgm_fuse_tail, A/B tests)
 	RedView cgm_hook_red{};
 	// last multishift statistics
@@ -247,6 +249,7 @@ template <typename T>
 struct DslashArgs {
 	const cplx_t<T> *u;       // u[8] : k*9*sizeh + (3r+c)*sizeh + idxh
 	cplx_t<T> *out;
+	cplx_t<T> *out_host;      // optional second copy of the result, stored straight into (mapped, pinned) HOST memory
 	const cplx_t<T> *in;
 	const T *ph;              // backfield[8] : k*sizeh + idxh
 	const cplx_t<T> *in0;     // epilogue operand (M^+M) or null

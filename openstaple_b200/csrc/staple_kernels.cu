@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
 			}
 			a.out[c * n + idx] = o;
+			if (a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
 			if (peer != nullptr) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
@@ -505,6 +506,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 		else { a.peer = bot; a.peer_flag = p.flags_L + 1; a.face_ticket = p.tickets + 1; }
 	}
 	a.u = u; a.out = out; a.in = in; a.ph = ph; a.in0 = in0; a.m2 = m2;
+	a.out_host = (cplx_t<T> *) ctx().out_host_hook;
 	a.partials = dot_slot >= 0 ? partials(dot_slot) : nullptr;
 	a.ticket = dot_slot >= 0 ? ticket(dot_slot) : nullptr;
 	a.result = dot_slot >= 0 ? result(dot_slot) : nullptr;
@@ -902,14 +904,33 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 		}
 		have_events = true;
 	}
-	int cs = chunk_slices > 0 ? chunk_slices : (g.nd3 >= 32 ? g.nd3 / 32 : 1);
+	// default: 16 chunks -- measured optimum on PCIe Gen5 (profiles/r01_streamed_trace.txt): smaller chunks lose copy
+	// efficiency (3 strided pieces per chunk and direction), bigger ones lengthen the 5-chunk pipeline head and tail
+	int cs = chunk_slices > 0 ? chunk_slices : (g.nd3 >= 16 ? g.nd3 / 16 : 1);
 	if (cs > g.nd3) cs = g.nd3;
 	while (g.nd3 % cs != 0 || g.nd3 / cs > kMaxChunks) cs++;   // cs = nd3 always qualifies
 	const int nc = g.nd3 / cs;
 	const size_t pitch = sizeof(double2) * g.sizeh, width = sizeof(double2) * g.vol3h * cs;
 	cudaStream_t s_up = c.s_p, s_dn = c.s_m, st = c.stream;
+	// mode 0 (default): chunk downloads by the copy engine after every Deo chunk.
+	// mode 1: the Deo chunk kernels store their result straight into the pinned host buffer (UVA: the host address is
+	// valid on the device) -- the download is fused into the operator's epilogue and runs on its own stream next to
+	// the Doe chunks.  Measured: SM stores over PCIe reach ~31 GB/s against ~45 GB/s for the copy engine, so this is
+	// an option, not the default.
+	const int mode = c.streamed_mode;
+	// STAPLE_STREAMED_TRACE=1: direct issue with timing events after every chunk upload / Deo chunk / chunk download;
+	// the timeline (ms since the call started) is printed on stderr.  Diagnostic only.
+	static const bool trace = getenv("STAPLE_STREAMED_TRACE") != nullptr;
+	static cudaEvent_t tev0, tev_up[kMaxChunks], tev_deo[kMaxChunks], tev_dn[kMaxChunks];
+	static bool have_tev = false;
+	if (trace && !have_tev) {
+		cudaEventCreate(&tev0);
+		for (int k = 0; k < kMaxChunks; k++) { cudaEventCreate(&tev_up[k]); cudaEventCreate(&tev_deo[k]); cudaEventCreate(&tev_dn[k]); }
+		have_tev = true;
+	}
 	auto enqueue = [&]() {
-		// the copy streams may not touch `in`/`out` on the device before earlier work of the compute stream is done
+		// the side streams may not touch `in`/`out` on the device before earlier work of the compute stream is done
+		if (trace) cudaEventRecord(tev0, st);
 		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, st));
 		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_up, c.ev_fork, 0));
 		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, c.ev_fork, 0));
@@ -926,6 +947,7 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 			STAPLE_CUDA_CHECK(cudaMemcpy2DAsync(d_in + off, pitch, (const double2 *) in_h + off, pitch, width, 3,
 																					cudaMemcpyHostToDevice, s_up));
 			STAPLE_CUDA_CHECK(cudaEventRecord(ev_up[j], s_up));
+			if (trace) cudaEventRecord(tev_up[j], s_up);
 			bool waited = false;
 			for (int k = 0; k < nc; k++) {
 				if (doe_done[k] || !deps_ok(nullptr, k, j)) continue;
@@ -933,18 +955,34 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 				launch_dslash<double>(1, EPI_NONE, d_u, d_tmp, d_in, d_ph, nullptr, 0.0, k * cs, (k + 1) * cs, -1, 0, 0, nullptr, st);
 				doe_done[k] = true;
 			}
+			bool doe_marked = false;
 			for (int k = 0; k < nc; k++) {
 				if (deo_done[k] || !deps_ok(doe_done, k, 0)) continue;
-				launch_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, k * cs, (k + 1) * cs, -1, 0, 0, nullptr, st);
-				deo_done[k] = true;
-				STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[k], st));
-				STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[k], 0));
 				const size_t o2 = (size_t) k * cs * g.vol3h;
-				STAPLE_CUDA_CHECK(cudaMemcpy2DAsync((double2 *) out_h + o2, pitch, d_out + o2, pitch, width, 3,
-																						cudaMemcpyDeviceToHost, s_dn));
+				if (mode == 1) {
+					// Deo chunks on the second stream, after every Doe chunk issued so far (in order on `st`)
+					if (!doe_marked) {
+						STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[j], st));
+						STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[j], 0));
+						doe_marked = true;
+					}
+					c.out_host_hook = out_h;
+					launch_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, k * cs, (k + 1) * cs, -1, 0, 0, nullptr, s_dn);
+					c.out_host_hook = nullptr;
+					if (trace) cudaEventRecord(tev_dn[k], s_dn);
+				} else {
+					launch_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, k * cs, (k + 1) * cs, -1, 0, 0, nullptr, st);
+					STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[k], st));
+					STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[k], 0));
+					if (trace) cudaEventRecord(tev_deo[k], st);
+					STAPLE_CUDA_CHECK(cudaMemcpy2DAsync((double2 *) out_h + o2, pitch, d_out + o2, pitch, width, 3,
+																							cudaMemcpyDeviceToHost, s_dn));
+					if (trace) cudaEventRecord(tev_dn[k], s_dn);
+				}
+				deo_done[k] = true;
 			}
 		}
-		// join: everything (last download included) is ordered before whatever follows on the compute stream
+		// join: everything (last download / host store included) is ordered before whatever follows on the compute stream
 		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, s_up));
 		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, s_dn));
 		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_p, 0));
@@ -954,13 +992,13 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	// depends on the pointers and the chunking, so it is captured ONCE into a CUDA graph (three streams, copy
 	// nodes included) and replayed with a single launch.  The legacy default stream cannot be captured: direct
 	// issue there.
-	struct Cached { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
+	struct Cached { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs, mode; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
 	static Cached cache[4] = {};
 	static int cache_next = 0;
 	Cached *hit = nullptr;
-	if (st != nullptr && c.use_graphs) {
+	if (st != nullptr && c.use_graphs && !trace) {
 		for (auto &e : cache)
-			if (e.exec && e.u == u && e.out == out_h && e.in == in_h && e.tmp == tmp && e.ph == backfield && e.d_in == d_in && e.d_out == d_out && e.cs == cs && e.sizeh == g.sizeh) hit = &e;
+			if (e.exec && e.u == u && e.out == out_h && e.in == in_h && e.tmp == tmp && e.ph == backfield && e.d_in == d_in && e.d_out == d_out && e.cs == cs && e.mode == mode && e.sizeh == g.sizeh) hit = &e;
 		if (!hit) {
 			const unsigned long long before = c.launches;
 			cudaGraph_t graph = nullptr;
@@ -971,7 +1009,7 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 						cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
 					Cached &e = cache[cache_next]; cache_next = (cache_next + 1) % 4;
 					if (e.exec) cudaGraphExecDestroy(e.exec);
-					e = Cached{ u, out_h, in_h, tmp, backfield, d_in, d_out, cs, g.sizeh, exec, c.launches - before };
+					e = Cached{ u, out_h, in_h, tmp, backfield, d_in, d_out, cs, mode, g.sizeh, exec, c.launches - before };
 					hit = &e;
 				}
 				if (graph) cudaGraphDestroy(graph);
@@ -983,6 +1021,16 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	if (hit) { STAPLE_CUDA_CHECK(cudaGraphLaunch(hit->exec, st)); c.launches += hit->launches; }
 	else enqueue();
 	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (trace) {
+		fprintf(stderr, "streamed trace: mode %d, %d chunks of %d slices\n chunk   upload_done   deo_done   download_done [ms]\n", mode, nc, cs);
+		for (int k = 0; k < nc; k++) {
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, tev0, tev_up[k]);
+			if (mode == 0) cudaEventElapsedTime(&b, tev0, tev_deo[k]);
+			cudaEventElapsedTime(&d, tev0, tev_dn[k]);
+			fprintf(stderr, " %3d   %9.4f   %9.4f   %9.4f\n", k, a, b, d);
+		}
+	}
 }
 
 void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars)

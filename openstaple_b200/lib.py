@@ -43,6 +43,7 @@ def _declare(L):
     L.staple_use_library_stream.argtypes = []
     L.staple_set_use_graphs.argtypes = [i]
     L.staple_set_cgm_fuse_tail.argtypes = [i]
+    L.staple_set_streamed_mode.argtypes = [i]
     L.staple_kernel_launches.restype = C.c_ulonglong
     L.staple_version.restype = C.c_char_p
     L.staple_posix_memalign.argtypes = [C.POINTER(vp), C.c_size_t, C.c_size_t]; L.staple_posix_memalign.restype = i
@@ -86,6 +87,13 @@ def _declare(L):
         getattr(L, "recombine_shifted_vec3_to_vec3" + s).argtypes = [vp, vp, vp, vp]
         getattr(L, "ker_invert_openacc" + s).argtypes = [vp, vp, vp, vp, d, vp, vp, vp, vp, i, d, C.POINTER(i)]
         getattr(L, "ker_invert_openacc" + s).restype = i
+        getattr(L, "set_tamat_soa_to_zero" + s).argtypes = [vp]
+        getattr(L, "set_su3_soa_to_zero" + s).argtypes = [vp]
+        getattr(L, "direct_product_of_fermions_into_auxmat" + s).argtypes = [vp, vp, vp, vp, i]
+        getattr(L, "multiply_conf_times_force_and_take_ta_nophase" + s).argtypes = [vp, vp, vp]
+        getattr(L, "multiply_backfield_times_force" + s).argtypes = [vp, vp, vp]
+        getattr(L, "accumulate_gl3soa_into_gl3soa" + s).argtypes = [vp, vp]
+        getattr(L, "ker_openacc_compute_fermion_force" + s).argtypes = [vp, vp, vp, vp, vp, vp]
         getattr(L, "communicate_fermion_borders" + s).argtypes = [vp]
         getattr(L, "communicate_su3_borders" + s).argtypes = [vp, i]
     for f in ("convert_float_to_double_vec3_soa", "convert_double_to_float_vec3_soa", "convert_float_to_double_su3_soa",

@@ -186,6 +186,32 @@ class RefLib:
         pars = self.ferm_param(mass, ph)
         return self.lib.ker_find_max_eigenvalue_openacc(ptr(u), pars, ptr(r), ptr(h), ptr(p))
 
+    # --- fermion-force outer products (fermion_force_utilities.c)
+    def compute_fermion_force(self, u, aux, shiftmulti, ph, ra_a):
+        """ker_openacc_compute_fermion_force: aux (gl3 field [8,3,3,sizeh]) accumulated in place; -> (loc_s, loc_h)."""
+        sfx = self._sfx(u)
+        ra_a = np.ascontiguousarray(ra_a, np.float64)
+        pars = self.ferm_param(0.1, ph if sfx == "" else None, ph if sfx else None)
+        self.lib.ref_ferm_param_set_md(pars, C.c_int(len(ra_a)), ptr(ra_a), ptr(np.zeros_like(ra_a)))
+        s = np.zeros_like(shiftmulti[0]); h = np.zeros_like(s)
+        getattr(self.lib, "ker_openacc_compute_fermion_force" + sfx)(ptr(u), ptr(aux), ptr(shiftmulti), ptr(s), ptr(h), pars)
+        return s, h
+
+    def direct_product(self, s, h, aux, a):
+        ap = self.approx(1.0, [a], [0.0])
+        getattr(self.lib, "direct_product_of_fermions_into_auxmat" + self._sfx(s))(ptr(s), ptr(h), ptr(aux), ap, C.c_int(0))
+
+    def multiply_backfield_times_force(self, ph, aux, pseudo):
+        sfx = self._sfx(aux)
+        pars = self.ferm_param(0.1, ph if sfx == "" else None, ph if sfx else None)
+        getattr(self.lib, "multiply_backfield_times_force" + sfx)(pars, ptr(aux), ptr(pseudo))
+
+    def accumulate_gl3(self, aux, pseudo):
+        getattr(self.lib, "accumulate_gl3soa_into_gl3soa" + self._sfx(aux))(ptr(aux), ptr(pseudo))
+
+    def take_ta(self, u, aux, ta):
+        getattr(self.lib, "multiply_conf_times_force_and_take_ta_nophase" + self._sfx(u))(ptr(u), ptr(aux), ptr(ta))
+
     # --- reductions
     def l2norm2(self, a):
         return getattr(self.lib, "l2norm2_global" + self._sfx(a))(ptr(a))
@@ -306,6 +332,28 @@ class Restatement:
     def max_eigenvalue(self, u, ph, mass, start):
         p = start.copy(); r = np.zeros_like(p); h = np.zeros_like(p)
         return self.lib.so_find_max_eigenvalue(self.gp(), ptr(u), ptr(ph), C.c_double(mass), ptr(r), ptr(h), ptr(p), None)
+
+    # fermion-force outer products (tamat_soa[8] as reals [8, 8, sizeh], see staggered_oracle_impl.h)
+    def compute_fermion_force(self, u, aux, shiftmulti, ph, ra_a):
+        ra_a = np.ascontiguousarray(ra_a, np.float64)
+        s = np.zeros_like(shiftmulti[0]); h = np.zeros_like(s)
+        getattr(self.lib, "so_compute_fermion_force" + self._sfx(u))(
+            self.gp(), ptr(u), ptr(aux), ptr(shiftmulti), ptr(s), ptr(h), ptr(ph), C.c_int(len(ra_a)), ptr(ra_a))
+        return s, h
+
+    def direct_product(self, s, h, aux, a):
+        getattr(self.lib, "so_direct_product_of_fermions_into_auxmat" + self._sfx(s))(
+            self.gp(), ptr(s), ptr(h), ptr(aux), C.c_double(a))
+
+    def multiply_backfield_times_force(self, ph, aux, pseudo):
+        getattr(self.lib, "so_multiply_backfield_times_force" + self._sfx(aux))(self.gp(), ptr(ph), ptr(aux), ptr(pseudo))
+
+    def accumulate_gl3(self, aux, pseudo):
+        getattr(self.lib, "so_accumulate_gl3soa_into_gl3soa" + self._sfx(aux))(self.gp(), ptr(aux), ptr(pseudo))
+
+    def take_ta(self, u, aux, ta):
+        getattr(self.lib, "so_multiply_conf_times_force_and_take_ta_nophase" + self._sfx(u))(
+            self.gp(), ptr(u), ptr(aux), ptr(ta))
 
     # multi-rank helpers (global <-> rank-local boxes)
     def scatter_vec(self, rank, gl):

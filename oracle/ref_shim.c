@@ -81,6 +81,7 @@ int ref_setup(int rank)
 	devinfo.myrank_world = rank; devinfo.nranks_world = NRANKS_D3;
 	devinfo.replica_idx = 0; devinfo.num_replicas = 1;
 	int res = set_geom_glv(&geom_par);
+	compute_nnp_and_nnm_openacc();      /* neighbour tables used by the fermion-force outer products */
 #ifdef MULTIDEVICE
 	devinfo.mpi_comm = 0;
 	devinfo.async_comm_fermion = 0; devinfo.async_comm_gauge = 0;
@@ -106,6 +107,13 @@ ferm_param *ref_ferm_param_new(double mass, double_soa *phases, float_soa *phase
 	p->ferm_mass = mass; p->phases = phases; p->phases_f = phases_f;
 	p->degeneracy = 1; p->number_of_ps = 1; strcpy(p->name, "oracle");
 	return p;
+}
+
+/* approx_md of a ferm_param (read by ker_openacc_compute_fermion_force, fermion_force_utilities.c:195) */
+void ref_ferm_param_set_md(ferm_param *p, int order, const double *a, const double *b)
+{
+	p->approx_md.approx_order = order;
+	for (int i = 0; i < order; i++) { p->approx_md.RA_a[i] = a[i]; p->approx_md.RA_b[i] = b[i]; }
 }
 
 RationalApprox *ref_approx_new(int order, double a0, const double *a, const double *b)

@@ -146,6 +146,8 @@ void so_exchange_halo(const so_geom *g, double complex **ranks, int ncomp_arrays
 #define RSIN sin
 #define CONJ conj
 #define HALF 0.5
+static inline double so_cimag(double complex z) { return cimag(z); }
+static inline float so_cimag_f(float complex z) { return cimagf(z); }
 #include "staggered_oracle_impl.h"
 #undef R
 #undef C

@@ -66,7 +66,13 @@ int so_multishift_invert##S(const so_geom *g, const C *u, const R *ph, double ma
 void so_recombine##S(const so_geom *g, const C *in_shifted, const C *in, C *out, int order, \
 		double a0, const double *a); \
 int so_cg##S(const so_geom *g, const C *u, const R *ph, double mass, C *solution, const C *in, \
-		double res, C *r, C *h, C *s, C *p, int max_cg, double shift, int restarting_every, int *cg_return);
+		double res, C *r, C *h, C *s, C *p, int max_cg, double shift, int restarting_every, int *cg_return); \
+void so_direct_product_of_fermions_into_auxmat##S(const so_geom *g, const C *s, const C *h, C *aux, double a); \
+void so_compute_fermion_force##S(const so_geom *g, const C *u, C *aux, const C *in_shiftmulti, C *s, C *h, \
+		const R *ph, int order, const double *ra_a); \
+void so_multiply_backfield_times_force##S(const so_geom *g, const R *ph, const C *aux, C *pseudo); \
+void so_accumulate_gl3soa_into_gl3soa##S(const so_geom *g, const C *aux, C *pseudo); \
+void so_multiply_conf_times_force_and_take_ta_nophase##S(const so_geom *g, const C *u, const C *aux, R *ta);
 SO_DECL(double, double complex, )
 SO_DECL(float, float complex, _f)
 

@@ -286,3 +286,109 @@ int S(so_cg)(const so_geom *g, const C *u, const R *ph, double mass, C *solution
 	*cg_return = cg;
 	return sqrt(current_res) <= res ? 1 : 0;
 }
+
+/* ------------------------------------------------------------------ fermion force outer products
+ * gl(3) fields (aux_u, pseudo_ipdot) use the su3_soa[8] layout with ALL three rows meaningful:
+ *   aux[((k*3 + r)*3 + c)*sizeh + i].   tamat_soa[8] (struct_c_def.h:45-51) as reals:
+ *   ta[k*8*sizeh + ...]: c01 complex @0, c02 @2*sizeh, c12 @4*sizeh, ic00 real @6*sizeh, ic11 @7*sizeh. */
+
+/* fermion_force_utilities.h:16-42  aux(idxh) += fer_l(idl) (x) [factor * conj(fer_r(idr))] */
+static inline void S(so_directprod)(const so_geom *g, C *auxk, long idxh, const C *fl, long idl, const C *fr,
+																		long idr, R factor)
+{
+	const long n = g->sizeh;
+	C r[3], l[3];
+	for (int c = 0; c < 3; c++) { r[c] = factor * CONJ(fr[c * n + idr]); l[c] = fl[c * n + idl]; }
+	for (int a = 0; a < 3; a++)
+		for (int c = 0; c < 3; c++) auxk[(a * 3 + c) * n + idxh] += l[a] * r[c];
+}
+
+static long S(so_nnp)(const so_geom *g, int d0, int d1, int d2, int d3, int mu)   /* geometry.c:49-61 */
+{
+	int c[4] = { d0, d1, d2, d3 };
+	c[mu] = (c[mu] == g->nd[mu] - 1) ? 0 : c[mu] + 1;
+	return so_snum(g, c[0], c[1], c[2], c[3]);
+}
+
+/* fermion_force_utilities.c:31-95: even sites  aux[2mu]  (x) += a * h(x+mu) (x) conj(s(x))
+ *                                  odd sites   aux[2mu+1](x) += -a * s(x+mu) (x) conj(h(x)) */
+void S(so_direct_product_of_fermions_into_auxmat)(const so_geom *g, const C *s, const C *h, C *aux, double a)
+{
+	const long n = g->sizeh;
+	for (int par = 0; par < 2; par++)
+		for (int d3 = g->d3_halo; d3 < g->nd[3] - g->d3_halo; d3++)
+			for (int d2 = 0; d2 < g->nd[2]; d2++)
+				for (int d1 = 0; d1 < g->nd[1]; d1++)
+					for (int hd0 = 0; hd0 < g->nd[0] / 2; hd0++) {
+						int d0 = 2 * hd0 + ((d1 + d2 + d3 + par) & 1);
+						long idxh = so_snum(g, d0, d1, d2, d3);
+						for (int mu = 0; mu < 4; mu++) {
+							long ip = S(so_nnp)(g, d0, d1, d2, d3, mu);
+							C *auxk = aux + (long) (2 * mu + par) * 9 * n;
+							if (par == 0) S(so_directprod)(g, auxk, idxh, h, ip, s, idxh, (R) a);
+							else S(so_directprod)(g, auxk, idxh, s, ip, h, idxh, (R) -a);
+						}
+					}
+}
+
+/* fermion_force_utilities.c:183-201 (acc_Doe without exchange: single-rank geometries only) */
+void S(so_compute_fermion_force)(const so_geom *g, const C *u, C *aux, const C *in_shiftmulti, C *s, C *h,
+																 const R *ph, int order, const double *ra_a)
+{
+	const long vs = 3 * g->sizeh;
+	for (int iter = 0; iter < order; iter++) {
+		S(so_axpy_like)(g, SO_ASSIGN, s, in_shiftmulti + iter * vs, 0, 0, 0, 0);
+		S(so_doe)(g, u, h, s, ph, g->d3_halo, g->d3_halo + g->loc_n[3]);
+		S(so_direct_product_of_fermions_into_auxmat)(g, s, h, aux, ra_a[iter]);
+	}
+}
+
+/* fermion_force_utilities.c:123-153 + .h:185-203: pseudo_ipdot += e^{i theta} aux over the local interior */
+void S(so_multiply_backfield_times_force)(const so_geom *g, const R *ph, const C *aux, C *pseudo)
+{
+	const long n = g->sizeh, lo = (long) g->d3_halo * g->vol3h, hi = (long) (g->nd[3] - g->d3_halo) * g->vol3h;
+	for (int k = 0; k < 8; k++)
+		for (long i = lo; i < hi; i++) {
+			R arg = ph[k * n + i];
+			C phase = RCOS(arg) + I * RSIN(arg);
+			for (int e = 0; e < 9; e++) pseudo[(k * 9 + e) * n + i] += aux[(k * 9 + e) * n + i] * phase;
+		}
+}
+
+/* fermion_force_utilities.c:155-180 */
+void S(so_accumulate_gl3soa_into_gl3soa)(const so_geom *g, const C *aux, C *pseudo)
+{
+	const long n = g->sizeh, lo = (long) g->d3_halo * g->vol3h, hi = (long) (g->nd[3] - g->d3_halo) * g->vol3h;
+	for (int k = 0; k < 8; k++)
+		for (long i = lo; i < hi; i++)
+			for (int e = 0; e < 9; e++) pseudo[(k * 9 + e) * n + i] += aux[(k * 9 + e) * n + i];
+}
+
+/* fermion_force_utilities.c:97-121 + .h:108-152: ipdot -= TA(U * aux), U's third row rebuilt */
+void S(so_multiply_conf_times_force_and_take_ta_nophase)(const so_geom *g, const C *u, const C *aux, R *ta)
+{
+	const long n = g->sizeh, lo = (long) g->d3_halo * g->vol3h, hi = (long) (g->nd[3] - g->d3_halo) * g->vol3h;
+	const R one_by_three = (R) 0.33333333333333333333333;   /* common_defines.h:65-66 */
+	for (int k = 0; k < 8; k++) {
+		const C *uk = u + (long) k * 9 * n, *ak = aux + (long) k * 9 * n;
+		R *tk = ta + (long) k * 8 * n;
+		C *c01 = (C *) tk, *c02 = (C *) (tk + 2 * n), *c12 = (C *) (tk + 4 * n);
+		R *ic00 = tk + 6 * n, *ic11 = tk + 7 * n;
+		for (long i = lo; i < hi; i++) {
+			C m[3][3], x[3][3], p[3][3];
+			for (int c = 0; c < 3; c++) { m[0][c] = uk[c * n + i]; m[1][c] = uk[(3 + c) * n + i]; }
+			m[2][0] = CONJ(m[0][1] * m[1][2] - m[0][2] * m[1][1]);
+			m[2][1] = CONJ(m[0][2] * m[1][0] - m[0][0] * m[1][2]);
+			m[2][2] = CONJ(m[0][0] * m[1][1] - m[0][1] * m[1][0]);
+			for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) x[r][c] = ak[(r * 3 + c) * n + i];
+			for (int r = 0; r < 3; r++)
+				for (int c = 0; c < 3; c++) p[r][c] = m[r][0] * x[0][c] + m[r][1] * x[1][c] + m[r][2] * x[2][c];
+			c01[i] -= HALF * (p[0][1] - CONJ(p[1][0]));
+			c02[i] -= HALF * (p[0][2] - CONJ(p[2][0]));
+			c12[i] -= HALF * (p[1][2] - CONJ(p[2][1]));
+			R tr = S(so_cimag)(p[0][0]) + S(so_cimag)(p[1][1]) + S(so_cimag)(p[2][2]);
+			ic00[i] -= S(so_cimag)(p[0][0]) - one_by_three * tr;
+			ic11[i] -= S(so_cimag)(p[1][1]) - one_by_three * tr;
+		}
+	}
+}

@@ -131,6 +131,25 @@ def main():
     rec = lat.new_vec()
     t = timeit(lambda: lat.recombine_shifted_vec3_to_vec3(sol, src, rec, approx), 10)
     out["recombine_ms"] = t
+    # ---- fermion force outer products (row N2) on the solutions just computed: ker_openacc_compute_fermion_force
+    # (N acc_Doe + outer products into aux_u), multiply_backfield_times_force, ..._take_ta_nophase.
+    # Algorithmic bytes per half-lattice index (FP64): Doe 928 per shift; outer products 2304 (aux_u read+write, 8 links
+    # x 9 x 16 B x 2) per PAIR of shifts + 192 per shift (s, h at the site and at the +mu neighbours, each vector once)
+    # + 96 for the final loc_s copy; the reference's structure moves 96 + 928 + 2304 + 192 per shift.
+    aux, pseudo, ta = lat.new_conf(), lat.new_conf(), lat.new_tamat()
+    fpars = lat.ferm_param(args.mass, ph, phf)
+    fpars.approx_md.approx_order = n
+    for i in range(n):
+        fpars.approx_md.RA_a[i] = approx.RA_a[i]
+    t = timeit(lambda: lat.ker_openacc_compute_fermion_force(u, aux, sol, s, h, fpars), 5)
+    fb = (928.0 * n + 2304.0 * ((n + 1) // 2) + 192.0 * n + 96.0) * interior
+    out["fermion_force"] = {"ms": t, "shifts": n, "hbm_GBps_per_gpu": fb / t / 1e6, "frac_of_measured_peak": fb / t / 1e6 / peak,
+                            "reference_structure_bytes_ratio": (3520.0 * n) / (fb / interior)}
+    t = timeit(lambda: lat.multiply_backfield_times_force(fpars, aux, pseudo), 10)
+    out["backfield_times_force"] = {"ms": t, "hbm_GBps_per_gpu": 3520.0 * interior / t / 1e6}
+    t = timeit(lambda: lat.multiply_conf_times_force_and_take_ta_nophase(u, pseudo, ta), 10)
+    out["take_ta"] = {"ms": t, "hbm_GBps_per_gpu": 2944.0 * interior / t / 1e6}
+    del aux, pseudo, ta
     if not args.skip_fp32:
         # FP32 CG-M (multishift_invert_f) to the reference's single-precision target (inverter_wrappers.c:62-64)
         solf, psf = lat.new_vec(n, single=True), lat.new_vec(n, single=True)

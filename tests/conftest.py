@@ -25,6 +25,11 @@ def golden_r2():
     return dict(np.load(os.path.join(GOLDEN_DIR, "ref_4x4x4x4_r2.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_force():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ref_force_4x4x4x4_r1.npz")))
+
+
 def relerr(a, b):
     """max |a-b| / max |b| -- the relative error used for every parity statement."""
     a = np.asarray(a); b = np.asarray(b)

@@ -97,6 +97,34 @@ def multi_rank(loc=(4, 4, 4, 4), nr=2):
     print("multi rank", loc, nr, "ms_cg", cg)
 
 
+def force_single(n=(4, 4, 4, 4)):
+    """Fermion-force outer products (fermion_force_utilities.c) on the 4^4 fixture of single_rank(): inputs are that
+    fixture's u, phases and multishift solutions (the vectors the MD force is really computed from)."""
+    R = RefLib(*n)
+    g = dict(np.load(os.path.join(HERE, "ref_%dx%dx%dx%d_r1.npz" % n)))
+    u, ph, phf, sh = g["u"], g["ph_bf"], g["phf_bf"], g["ms_out"]
+    d = {"ra_a": RA_A}
+    rng = np.random.default_rng(77)
+    aux0 = (rng.standard_normal((8, 3, 3, R.sizeh)) + 1j * rng.standard_normal((8, 3, 3, R.sizeh)))
+    ta0 = rng.standard_normal((8, 8, R.sizeh))
+    d["aux0"] = aux0; d["ta0"] = ta0
+    aux = aux0.copy()
+    s, h = R.compute_fermion_force(u, aux, sh, ph, RA_A)
+    d["force_aux"] = aux.copy(); d["force_loc_s"] = s; d["force_loc_h"] = h
+    one = aux0.copy(); R.direct_product(g["v"], g["w"], one, 0.37); d["direct_product"] = one
+    pseudo = aux0[::-1].copy(); R.multiply_backfield_times_force(ph, aux, pseudo); d["backfield"] = pseudo.copy()
+    R.accumulate_gl3(aux, pseudo); d["accumulated"] = pseudo.copy()
+    ta = ta0.copy(); R.take_ta(u, pseudo, ta); d["ta"] = ta
+    # FP32 twins (generated sp_fermion_force_utilities.c: pure float arithmetic)
+    uf, shf = u.astype(np.complex64), sh.astype(np.complex64)
+    auxf = aux0.astype(np.complex64)
+    R.compute_fermion_force(uf, auxf, shf, phf, RA_A); d["force_aux_f"] = auxf.copy()
+    pf = aux0[::-1].astype(np.complex64); R.multiply_backfield_times_force(phf, auxf, pf); d["backfield_f"] = pf.copy()
+    taf = ta0.astype(np.float32); R.take_ta(uf, pf, taf); d["ta_f"] = taf
+    np.savez_compressed(os.path.join(HERE, "ref_force_%dx%dx%dx%d_r1.npz" % n), **d)
+    print("force", n, float(np.abs(d["force_aux"]).max()), float(np.abs(ta).max()))
+
+
 class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
     _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
                 ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
@@ -135,10 +163,12 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force"]
     if "single" in which:
         single_rank()
     if "multi" in which:
         multi_rank()
     if "abi" in which:
         abi_and_approx()
+    if "force" in which:
+        force_single()

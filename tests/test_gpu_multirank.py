@@ -90,6 +90,19 @@ def _worker(rank, world, port, loc, mode, q):
         errs["cgm_sol"] = e
         errs["cgm_iters"] = abs(cg - cg_ref) / cg_ref
         errs["cgm_status"] = 0.0 if st == 1 else 1.0
+        # ---- fermion-force outer products (row N2): acc_Doe with its exchange + outer products over the interior
+        shg = gaussian_vec(G.sizeh, 5, n=3); ra = np.array([0.4, -1.1, 0.7])
+        auxg = np.zeros((8, 3, 3, G.sizeh), np.complex128)
+        G.compute_fermion_force(u, auxg, shg, phg, ra)
+        dsh = lat.to_device(np.stack([S.scatter_vec(rank, shg[i]) for i in range(3)]))
+        daux = lat.new_conf()
+        fp = lat.ferm_param(0.0507, dph); fp.approx_md.approx_order = 3
+        for i in range(3):
+            fp.approx_md.RA_a[i] = ra[i]
+        lat.ker_openacc_compute_fermion_force(du, daux, dsh, lat.new_vec(), lat.new_vec(), fp)
+        wantaux = S.scatter_conf(rank, auxg)
+        ilo, ihi = S.d3_halo * S.vol3h, (S.d3_halo + loc[3]) * S.vol3h
+        errs["force"] = _relerr(daux.cpu().numpy()[..., ilo:ihi], wantaux[..., ilo:ihi])
         lat.shutdown_multidev()
         dist.destroy_process_group()
         q.put((rank, errs, ""))
@@ -114,7 +127,7 @@ def _run(world, loc, mode):
     for rank, errs, tb in sorted(res):
         assert tb == "", tb
         assert errs["su3_borders_rows01"] == 0.0 and errs["fermion_borders"] == 0.0, (rank, errs)
-        for k in ("acc_Doe", "acc_Deo", "mdagm"):
+        for k in ("acc_Doe", "acc_Deo", "mdagm", "force"):
             assert errs[k] < 1e-13, (rank, k, errs)
         assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)

@@ -351,7 +351,8 @@ def test_streamed_host_round_trip(osb, loc_n, chunk, on_stream):
         hin = lat.host_array((3, lat.sizeh), np.complex128)
         hout = lat.host_array((3, lat.sizeh), np.complex128)
         tmp, plain = lat.new_vec(), lat.new_vec()
-        for rep, src in enumerate((c["v"], c["w"], c["v"])):
+        for rep, src in enumerate((c["v"], c["w"], c["v"], c["w"])):
+            lat.L.staple_set_streamed_mode(rep % 2)      # 0: copy-engine downloads, 1: Deo kernels store to the host
             hin.np[...] = src
             hout.np[...] = 0
             lat.acc_Doe_Deo_streamed(c["d_u"], hout, hin, tmp, c["d_ph"], chunk)
@@ -367,6 +368,7 @@ def test_streamed_host_round_trip(osb, loc_n, chunk, on_stream):
         lat.acc_Doe(c["d_u"], tmp, c["d_v"], c["d_ph"]); lat.acc_Deo(c["d_u"], plain, tmp, c["d_ph"])
         assert np.array_equal(dout.cpu().numpy(), plain.cpu().numpy())
         hin.free(); hout.free()
+        lat.L.staple_set_streamed_mode(0)
         torch.cuda.synchronize()
     lat.use_torch_stream()
 
