@@ -330,6 +330,34 @@ void find_min_max_eigenvalue_soloopenacc(su3_soa *u, ferm_param *pars, vec3_soa 
 STAPLE_FORCE_DECL(, su3_soa, vec3_soa, tamat_soa)
 STAPLE_FORCE_DECL(_f, su3_soa_f, vec3_soa_f, tamat_soa_f)
 
+/* "next" row N4: isotropic stout smearing, the producer of the links the operator reads.
+ * ref: OpenAcc/stouting.c:27-167, plaquettes.c:196-255 (staples), su3_utilities.c:210-237 (rho TA(U S)),
+ * cayley_hamilton.h:24-180 (exp).  ACTION_TYPE TLSM (C_ZERO = 5/3).  stout_wrapper reads the reference's globals
+ * act_params.{stout_steps,topo_action,topo_stout_steps}, gl_stout_rho / gl_topo_rho (action.h:6-23, main.c:276-277)
+ * and the parking arrays auxbis_conf_acc, glocal_staples, gipdot (+_f) of alloc_vars.h:23,54-55: all are WEAK
+ * definitions in the library, so the host program's own definitions win at link time; a host that binds the
+ * library dynamically sets them through these symbols.  tstout_conf_acc_arr holds stout_steps consecutive su3_soa[8]. */
+#ifndef ACTION_H_
+typedef struct action_param_t {             /* ref: OpenAcc/action.h:6-18 */
+	double beta; int stout_steps; double stout_rho;
+	int topo_action; double barrier; double width; char topo_file_path[20]; int topo_stout_steps; double topo_rho;
+} action_param;
+extern action_param act_params;
+extern double gl_stout_rho, gl_topo_rho;
+#endif
+extern su3_soa *auxbis_conf_acc, *glocal_staples;
+extern tamat_soa *gipdot;
+extern su3_soa_f *auxbis_conf_acc_f, *glocal_staples_f;
+extern tamat_soa_f *gipdot_f;
+#define STAPLE_STOUT_DECL(S, SU3, TAMAT) \
+	void calc_loc_staples_nnptrick_all_onlyferms##S(const SU3 *u, SU3 *loc_stap);                /* ref: plaquettes.c:196-255 */ \
+	void RHO_times_conf_times_staples_ta_part##S(const SU3 *u, const SU3 *loc_stap, TAMAT *tipdot, int istopo); /* ref: su3_utilities.c:210-237 */ \
+	void exp_minus_QA_times_conf##S(const SU3 *tu, const TAMAT *QA, SU3 *tu_out, SU3 *exp_aux);  /* ref: stouting.c:136-167 */ \
+	void stout_isotropic##S(const SU3 *u, SU3 *uprime, SU3 *local_staples, SU3 *auxiliary, TAMAT *tipdot, const int istopo); /* ref: stouting.c:74-100 */ \
+	void stout_wrapper##S(const SU3 *tconf_acc, SU3 *tstout_conf_acc_arr, const int istopo);     /* ref: stouting.c:27-72 */
+STAPLE_STOUT_DECL(, su3_soa, tamat_soa)
+STAPLE_STOUT_DECL(_f, su3_soa_f, tamat_soa_f)
+
 /* ------------------------------------------------------------------ introspection for benches/tests */
 /* statistics of the last multishift_invert[_f] call: iterations, sum over iterations of active
  * shifts (for the algorithmic-bytes roofline figure), device time of the loop in ms. */

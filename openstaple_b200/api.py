@@ -88,6 +88,12 @@ class InverterPackage(C.Structure):     # OpenAcc/inverter_package.h:12-29
                 ("out_f", C.c_void_p)]
 
 
+class ActionParam(C.Structure):         # OpenAcc/action.h:6-18
+    _fields_ = [("beta", C.c_double), ("stout_steps", C.c_int), ("stout_rho", C.c_double), ("topo_action", C.c_int),
+                ("barrier", C.c_double), ("width", C.c_double), ("topo_file_path", C.c_char * 20),
+                ("topo_stout_steps", C.c_int), ("topo_rho", C.c_double)]
+
+
 class InvTricks(C.Structure):           # Include/inverter_tricks.h:4-11
     _fields_ = [("singlePInvAccelMultiInv", C.c_int), ("useMixedPrecision", C.c_int),
                 ("mixedPrecisionDelta", C.c_double), ("restartingEvery", C.c_int)]
@@ -377,6 +383,36 @@ class Lattice:
         """tpars.approx_md holds the shifts' residues RA_a (fermion_force_utilities.c:195)."""
         getattr(self.L, "ker_openacc_compute_fermion_force" + _sfx(u))(
             _addr(u), _addr(aux_u), _addr(in_shiftmulti), _addr(loc_s), _addr(loc_h), C.addressof(tpars))
+
+    # ---- isotropic stout smearing (OpenAcc/stouting.h, plaquettes.h:18, su3_utilities.h:49)
+    def set_stout(self, rho, steps, auxbis=None, staples=None, ipdot=None, single=False):
+        """what main.c:276-277 and alloc_vars.c do for stout_wrapper: act_params.stout_rho/steps, gl_stout_rho and the
+        parking arrays auxbis_conf_acc, glocal_staples, gipdot (the library's weak globals)."""
+        ap = ActionParam.in_dll(self.L, "act_params")
+        ap.stout_rho, ap.stout_steps, ap.topo_action = rho, steps, 0
+        C.c_double.in_dll(self.L, "gl_stout_rho").value = rho
+        C.c_double.in_dll(self.L, "gl_topo_rho").value = rho
+        sfx = "_f" if single else ""
+        for name, arr in (("auxbis_conf_acc", auxbis), ("glocal_staples", staples), ("gipdot", ipdot)):
+            if arr is not None:
+                C.c_void_p.in_dll(self.L, name + sfx).value = _addr(arr)
+        self._keep.append((auxbis, staples, ipdot))
+
+    def calc_loc_staples_nnptrick_all_onlyferms(self, u, loc_stap):
+        getattr(self.L, "calc_loc_staples_nnptrick_all_onlyferms" + _sfx(u))(_addr(u), _addr(loc_stap))
+
+    def RHO_times_conf_times_staples_ta_part(self, u, loc_stap, tipdot, istopo=0):
+        getattr(self.L, "RHO_times_conf_times_staples_ta_part" + _sfx(u))(_addr(u), _addr(loc_stap), _addr(tipdot), int(istopo))
+
+    def exp_minus_QA_times_conf(self, tu, QA, tu_out, exp_aux):
+        getattr(self.L, "exp_minus_QA_times_conf" + _sfx(tu))(_addr(tu), _addr(QA), _addr(tu_out), _addr(exp_aux))
+
+    def stout_isotropic(self, u, uprime, local_staples, auxiliary, tipdot, istopo=0):
+        getattr(self.L, "stout_isotropic" + _sfx(u))(_addr(u), _addr(uprime), _addr(local_staples), _addr(auxiliary),
+                                                     _addr(tipdot), int(istopo))
+
+    def stout_wrapper(self, tconf_acc, tstout_conf_acc_arr, istopo=0):
+        getattr(self.L, "stout_wrapper" + _sfx(tconf_acc))(_addr(tconf_acc), _addr(tstout_conf_acc_arr), int(istopo))
 
     # ---- conversions (OpenAcc/float_double_conv.c)
     def convert_double_to_float_vec3_soa(self, d, f): self.L.convert_double_to_float_vec3_soa(_addr(d), _addr(f))

@@ -273,6 +273,7 @@ struct DslashArgs {
 	// (-> rank R), blocks [fb,2fb) the BOTTOM one (-> rank L), the rest the bulk -- faces are scheduled first,
 	// so their NVLink stores overlap the bulk of the same kernel
 	int fused;
+	int dbg;                  // diagnostics (STAPLE_DEBUG_HALO): bit 0 = skip the peer stores, bit 1 = skip the unpack copy
 	unsigned int face_blocks;
 	long top_lo, bot_lo;      // first idxh of the two surface slices; site_lo/nsites describe the bulk
 	cplx_t<T> *peer2;         // bottom face target (peer = top face target)

@@ -208,9 +208,13 @@ __device__ __forceinline__ bool grid_sum_finalize(double v[NV], double *partials
 __device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsigned long long seq, unsigned int *ticket,
 																						unsigned int nblocks, unsigned int *groups_done = nullptr)
 {
-	__threadfence_system();
+	// ONE system-scope fence per block, by the thread that takes the ticket: the barrier orders every thread's peer
+	// stores before it (the fence is cumulative), exactly the post pattern of NCCL's simple protocol.  A fence.sys by
+	// all 128 threads of each of the ~2000 face blocks floods the memory system with membars and was measured to
+	// cost more than the transfer itself.
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		__threadfence_system();
 		const unsigned int t = atomicAdd(ticket, 1u);
 		if (t == nblocks - 1) {
 			__threadfence_system();
@@ -343,6 +347,33 @@ void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
 	count_launch();
 }
 
+// copy of one staged slice (3 colour arrays of nv elements) into a halo slice of `out`: grid-stride, 4 sites x 3
+// colours = 12 independent 16-byte loads in flight per thread.  Not inlined: its registers must not weigh on the
+// 72-register budget of the operator itself.
+template <typename T>
+__device__ __noinline__ void unpack_copy(cplx_t<T> *dst, long n, const cplx_t<T> *src, unsigned int nv, unsigned int first,
+																				 unsigned int stride)
+{
+	using C = cplx_t<T>;
+	for (unsigned int t0 = first; t0 < nv; t0 += 4 * stride) {
+		C v[4][3];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const unsigned int tt = t0 + j * stride;
+#pragma unroll
+			for (int c = 0; c < 3; c++) v[j][c] = tt < nv ? __ldcg(src + c * nv + tt) : mk<T>(0, 0);
+		}
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const unsigned int tt = t0 + j * stride;
+			if (tt < nv) {
+#pragma unroll
+				for (int c = 0; c < 3; c++) dst[c * n + tt] = v[j][c];
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------ Dirac operator kernel
 // Fused Re(in0 . out): block partial -> deterministic grid sum; inside a CG-M solve the block that completes the
 // sum (alpha) also runs the recurrences that consume it, so no one-warp kernel sits between M^+M and the update
@@ -387,12 +418,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 			const unsigned long long seq = *a.seq_rw + 1;
 			face_wait(a.local_flags + which, seq);
 			const C *src = a.unpack_src + (seq & 1ull) * a.peer_parity_stride + which * a.slot_elems;
-			const unsigned int tt = (b - which * ub) * kBlock + threadIdx.x;
-			if (tt < (unsigned int) a.vol3h) {
-				const long dst = (which ? a.upper_lo : a.lower_lo) + tt;
-#pragma unroll
-				for (int c = 0; c < 3; c++) a.out[c * a.sizeh + dst] = __ldcg(src + c * a.vol3h + tt);
-			}
+			if (!(a.dbg & 2)) unpack_copy<T>(a.out + (which ? a.upper_lo : a.lower_lo), a.sizeh, src, (unsigned int) a.vol3h, (b - which * ub) * kBlock + threadIdx.x, ub * kBlock);
 			__syncthreads();
 			if (threadIdx.x == 0) {
 				__threadfence();
@@ -459,12 +485,16 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 			}
 			a.out[c * n + idx] = o;
 			if (a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
-			if (peer != nullptr) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
+			if (peer != nullptr && !(a.dbg & 1)) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
 	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks, a.fused == 2 ? a.unpack_ticket + 1 : nullptr);
 	if (EPI == EPI_MASS_DOT) dslash_finish_dot(a, dot);
 }
+
+// unpack blocks per halo: at most 2 per SM (grid-stride copy with 12 loads in flight per thread).  Thousands of
+// 128-thread blocks only add scheduling time to the tail; 74 were measured too few to cover the HBM latency.
+static inline unsigned int unpack_blocks_for(unsigned int face_blocks) { return face_blocks < 296u ? face_blocks : 296u; }
 
 unsigned int dslash_blocks(int d3lo, int d3hi)
 {
@@ -482,6 +512,8 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	if (d3hi <= d3lo) return;
 	DslashArgs<T> a;
 	a.peer = nullptr; a.peer_flag = nullptr; a.seq_ptr = nullptr; a.peer_parity_stride = 0; a.face_ticket = nullptr;
+	static const int dbg_halo = getenv("STAPLE_DEBUG_HALO") ? atoi(getenv("STAPLE_DEBUG_HALO")) : 0;   // timing experiments only: wrong halos
+	a.dbg = dbg_halo;
 	a.fused = 0; a.face_blocks = 0; a.top_lo = a.bot_lo = 0; a.peer2 = nullptr; a.peer_flag2 = nullptr; a.face_ticket2 = nullptr;
 	a.bulk_blocks = 0; a.unpack_blocks = 0; a.unpack_src = nullptr; a.slot_elems = 0; a.local_flags = nullptr; a.seq_rw = nullptr;
 	a.unpack_ticket = nullptr; a.lower_lo = a.upper_lo = 0;
@@ -494,7 +526,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 			a.fused = face == 4 ? 2 : 1; a.face_blocks = dslash_blocks(0, 1);
 			a.bulk_blocks = dslash_blocks(d3lo + 1, d3hi - 1);
 			if (face == 4) {
-				a.unpack_blocks = a.face_blocks;
+				a.unpack_blocks = unpack_blocks_for(a.face_blocks);
 				a.unpack_src = (const cplx_t<T> *) p.stage; a.slot_elems = (long) (p.slot_bytes / sizeof(cplx_t<T>));
 				a.local_flags = p.flags; a.seq_rw = p.d_seq; a.unpack_ticket = p.tickets + 2;
 				a.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; a.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
@@ -561,7 +593,7 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		// over NVLink while the bulk blocks of the same launch run; then the unpack of what the neighbours
 		// pushed.  No stream fork/join, no events.
 		if (c.p2p_unpack_in_kernel)
-			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * bs, 0, skip, c.stream, 4);
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * unpack_blocks_for(bs), 0, skip, c.stream, 4);
 		else {
 			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3);
 			p2p_unpack(out, sizeof(cplx_t<T>), c.stream, skip);

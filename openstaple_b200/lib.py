@@ -94,6 +94,11 @@ def _declare(L):
         getattr(L, "multiply_backfield_times_force" + s).argtypes = [vp, vp, vp]
         getattr(L, "accumulate_gl3soa_into_gl3soa" + s).argtypes = [vp, vp]
         getattr(L, "ker_openacc_compute_fermion_force" + s).argtypes = [vp, vp, vp, vp, vp, vp]
+        getattr(L, "calc_loc_staples_nnptrick_all_onlyferms" + s).argtypes = [vp, vp]
+        getattr(L, "RHO_times_conf_times_staples_ta_part" + s).argtypes = [vp, vp, vp, i]
+        getattr(L, "exp_minus_QA_times_conf" + s).argtypes = [vp, vp, vp, vp]
+        getattr(L, "stout_isotropic" + s).argtypes = [vp, vp, vp, vp, vp, i]
+        getattr(L, "stout_wrapper" + s).argtypes = [vp, vp, i]
         getattr(L, "communicate_fermion_borders" + s).argtypes = [vp]
         getattr(L, "communicate_su3_borders" + s).argtypes = [vp, i]
     for f in ("convert_float_to_double_vec3_soa", "convert_double_to_float_vec3_soa", "convert_float_to_double_su3_soa",

@@ -212,6 +212,31 @@ class RefLib:
     def take_ta(self, u, aux, ta):
         getattr(self.lib, "multiply_conf_times_force_and_take_ta_nophase" + self._sfx(u))(ptr(u), ptr(aux), ptr(ta))
 
+    # --- isotropic stout smearing (stouting.c, plaquettes.c:196-255, su3_utilities.c:210-237, cayley_hamilton.h)
+    def _stout_globals(self, rho, steps, like):
+        cd = like.dtype; rd = np.float32 if cd == np.complex64 else np.float64
+        self._stout_keep = [np.zeros((8, 3, 3, self.sizeh), cd), np.zeros((8, 3, 3, self.sizeh), cd), np.zeros((8, 8, self.sizeh), rd)]
+        a = [ptr(x) for x in self._stout_keep]
+        if cd == np.complex64:
+            self.lib.ref_set_stout(C.c_double(rho), C.c_int(steps), None, None, None, *a)
+        else:
+            self.lib.ref_set_stout(C.c_double(rho), C.c_int(steps), *a, None, None, None)
+
+    def stout_isotropic(self, u, rho):
+        """-> (uprime [rows 0,1 written], staples, exp_aux, tipdot) exactly as stout_isotropic leaves them"""
+        self._stout_globals(rho, 1, u)
+        rd = np.float32 if u.dtype == np.complex64 else np.float64
+        up = np.zeros_like(u); stap = np.zeros_like(u); aux = np.zeros_like(u); ta = np.zeros((8, 8, self.sizeh), rd)
+        getattr(self.lib, "stout_isotropic" + self._sfx(u))(ptr(u), ptr(up), ptr(stap), ptr(aux), ptr(ta), C.c_int(0))
+        return up, stap, aux, ta
+
+    def stout_wrapper(self, u, rho, steps):
+        """-> stout_conf_acc_arr [steps, 8, 3, 3, sizeh] (single rank: no border exchange involved)"""
+        self._stout_globals(rho, steps, u)
+        out = np.zeros((steps,) + u.shape, u.dtype)
+        getattr(self.lib, "stout_wrapper" + self._sfx(u))(ptr(u), ptr(out), C.c_int(0))
+        return out
+
     # --- reductions
     def l2norm2(self, a):
         return getattr(self.lib, "l2norm2_global" + self._sfx(a))(ptr(a))
@@ -354,6 +379,22 @@ class Restatement:
     def take_ta(self, u, aux, ta):
         getattr(self.lib, "so_multiply_conf_times_force_and_take_ta_nophase" + self._sfx(u))(
             self.gp(), ptr(u), ptr(aux), ptr(ta))
+
+    # isotropic stout smearing
+    def stout_isotropic(self, u, rho):
+        rd = np.float32 if u.dtype == np.complex64 else np.float64
+        up = np.zeros_like(u); stap = np.zeros_like(u); aux = np.zeros_like(u); ta = np.zeros((8, 8, self.sizeh), rd)
+        getattr(self.lib, "so_stout_isotropic" + self._sfx(u))(self.gp(), ptr(u), ptr(up), ptr(stap), ptr(aux), ptr(ta), C.c_double(rho))
+        return up, stap, aux, ta
+
+    def stout_wrapper(self, u, rho, steps):
+        """stouting.c:27-72 for a single rank: level l smears level l-1 (level 0 smears u)"""
+        out = np.zeros((steps,) + u.shape, u.dtype)
+        src = u
+        for l in range(steps):
+            out[l] = self.stout_isotropic(src, rho)[0]
+            src = out[l]
+        return out
 
     # multi-rank helpers (global <-> rank-local boxes)
     def scatter_vec(self, rank, gl):

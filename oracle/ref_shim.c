@@ -27,10 +27,32 @@
 #include "OpenAcc/inverter_wrappers.h"
 #include "OpenAcc/inverter_mixedp.h"
 #include "RationalApprox/rationalapprox.h"
+#include "OpenAcc/action.h"
+#include "OpenAcc/stouting.h"
 
 int verbosity_lv = 0;
 vec3_soa_f *aux1_f = NULL;                 /* alloc_vars globals used by inverter_wrappers.c:60-71 */
 vec3_soa_f *ferm_shiftmulti_acc_f = NULL;
+
+/* globals that main.c / alloc_vars.c define in the reference's own programs and stouting.c reads (stouting.c:27-72) */
+action_param act_params;
+su3_soa *auxbis_conf_acc = NULL, *glocal_staples = NULL;
+tamat_soa *gipdot = NULL;
+su3_soa_f *auxbis_conf_acc_f = NULL, *glocal_staples_f = NULL;
+tamat_soa_f *gipdot_f = NULL;
+/* only called for verbosity_lv > 4 (stouting.c:42-46); su3_measurements.c is not part of this build */
+void check_unitarity_device(const su3_soa *u, double *mx, double *avg) { *mx = 0; *avg = 0; }
+void check_unitarity_device_f(const su3_soa_f *u, double *mx, double *avg) { *mx = 0; *avg = 0; }
+
+/* stout parameters as main.c:276-277 sets them, and the parking arrays stout_wrapper takes from alloc_vars */
+void ref_set_stout(double rho, int steps, void *auxbis, void *staples, void *ipdot, void *auxbis_f, void *staples_f,
+									 void *ipdot_f)
+{
+	act_params.stout_rho = rho; act_params.stout_steps = steps; act_params.topo_action = 0;
+	gl_stout_rho = rho; gl_topo_rho = rho;
+	auxbis_conf_acc = (su3_soa *) auxbis; glocal_staples = (su3_soa *) staples; gipdot = (tamat_soa *) ipdot;
+	auxbis_conf_acc_f = (su3_soa_f *) auxbis_f; glocal_staples_f = (su3_soa_f *) staples_f; gipdot_f = (tamat_soa_f *) ipdot_f;
+}
 
 void ref_geometry(int *o)
 {

@@ -146,8 +146,14 @@ void so_exchange_halo(const so_geom *g, double complex **ranks, int ncomp_arrays
 #define RSIN sin
 #define CONJ conj
 #define HALF 0.5
+#define RPOW pow
+#define RACOS acos
+#define RSQRT sqrt
+#define RFABS fabs
 static inline double so_cimag(double complex z) { return cimag(z); }
 static inline float so_cimag_f(float complex z) { return cimagf(z); }
+static inline double so_creal(double complex z) { return creal(z); }
+static inline float so_creal_f(float complex z) { return crealf(z); }
 #include "staggered_oracle_impl.h"
 #undef R
 #undef C
@@ -156,6 +162,10 @@ static inline float so_cimag_f(float complex z) { return cimagf(z); }
 #undef RSIN
 #undef CONJ
 #undef HALF
+#undef RPOW
+#undef RACOS
+#undef RSQRT
+#undef RFABS
 
 #define R float
 #define C float complex
@@ -164,6 +174,10 @@ static inline float so_cimag_f(float complex z) { return cimagf(z); }
 #define RSIN sinf
 #define CONJ conjf
 #define HALF 0.5f
+#define RPOW powf
+#define RACOS acosf
+#define RSQRT sqrtf
+#define RFABS fabsf
 #include "staggered_oracle_impl.h"
 #undef R
 #undef C
@@ -172,6 +186,10 @@ static inline float so_cimag_f(float complex z) { return cimagf(z); }
 #undef RSIN
 #undef CONJ
 #undef HALF
+#undef RPOW
+#undef RACOS
+#undef RSQRT
+#undef RFABS
 
 /* float_double_conv.c:9-33 */
 void so_convert_d2f(long n, const double complex *d, float complex *f)

@@ -72,7 +72,11 @@ void so_compute_fermion_force##S(const so_geom *g, const C *u, C *aux, const C *
 		const R *ph, int order, const double *ra_a); \
 void so_multiply_backfield_times_force##S(const so_geom *g, const R *ph, const C *aux, C *pseudo); \
 void so_accumulate_gl3soa_into_gl3soa##S(const so_geom *g, const C *aux, C *pseudo); \
-void so_multiply_conf_times_force_and_take_ta_nophase##S(const so_geom *g, const C *u, const C *aux, R *ta);
+void so_multiply_conf_times_force_and_take_ta_nophase##S(const so_geom *g, const C *u, const C *aux, R *ta); \
+void so_calc_loc_staples_onlyferms##S(const so_geom *g, const C *u, C *stap); \
+void so_rho_times_conf_times_staples_ta_part##S(const so_geom *g, const C *u, const C *stap, R *ta, double rho); \
+void so_exp_minus_QA_times_conf##S(const so_geom *g, const C *u, const R *ta, C *uout, C *expaux); \
+void so_stout_isotropic##S(const so_geom *g, const C *u, C *uprime, C *stap, C *aux, R *ta, double rho);
 SO_DECL(double, double complex, )
 SO_DECL(float, float complex, _f)
 

@@ -392,3 +392,173 @@ void S(so_multiply_conf_times_force_and_take_ta_nophase)(const so_geom *g, const
 		}
 	}
 }
+
+/* ------------------------------------------------------------------ isotropic stout smearing
+ * Produces the smeared links the Dirac operator reads.  C_ZERO = 5/3 (ACTION_TYPE TLSM, common_defines.h:73). */
+#define SO_C_ZERO ((R) 5.0 * (R) 0.33333333333333333333333)
+
+static inline void S(so_load_link)(const C *uk, long n, long i, C m[3][3])   /* rows 0,1 + conj(r0 x r1) */
+{
+	for (int c = 0; c < 3; c++) { m[0][c] = uk[c * n + i]; m[1][c] = uk[(3 + c) * n + i]; }
+	m[2][0] = CONJ((m[0][1] * m[1][2]) - (m[0][2] * m[1][1]));
+	m[2][1] = CONJ((m[0][2] * m[1][0]) - (m[0][0] * m[1][2]));
+	m[2][2] = CONJ((m[0][0] * m[1][1]) - (m[0][1] * m[1][0]));
+}
+static inline void S(so_dagger)(C m[3][3])
+{
+	for (int r = 0; r < 3; r++) m[r][r] = CONJ(m[r][r]);
+	for (int r = 0; r < 3; r++)
+		for (int c = r + 1; c < 3; c++) { C t = CONJ(m[r][c]); m[r][c] = CONJ(m[c][r]); m[c][r] = t; }
+}
+/* first two rows of a*b, third row rebuilt (su3_utilities.h:660-750, :878-975) */
+static inline void S(so_mul2)(C a[3][3], C b[3][3], C o[3][3])
+{
+	for (int r = 0; r < 2; r++)
+		for (int c = 0; c < 3; c++) o[r][c] = a[r][0] * b[0][c] + a[r][1] * b[1][c] + a[r][2] * b[2][c];
+	o[2][0] = CONJ((o[0][1] * o[1][2]) - (o[0][2] * o[1][1]));
+	o[2][1] = CONJ((o[0][2] * o[1][0]) - (o[0][0] * o[1][2]));
+	o[2][2] = CONJ((o[0][0] * o[1][1]) - (o[0][1] * o[1][0]));
+}
+static long S(so_shift)(const so_geom *g, const int c0[4], int mu, int smu, int nu, int snu)   /* geometry.c:14-61 wrap */
+{
+	int c[4] = { c0[0], c0[1], c0[2], c0[3] };
+	if (smu) c[mu] = (c[mu] + smu + g->nd[mu]) % g->nd[mu];
+	if (snu) c[nu] = (c[nu] + snu + g->nd[nu]) % g->nd[nu];
+	return so_snum(g, c[0], c[1], c[2], c[3]);
+}
+
+/* plaquettes.c:196-255: loc_stap[2mu+p](x) += C_ZERO * sum_{nu != mu} [ U_nu(x+mu) U_mu(x+nu)^+ U_nu(x)^+
+ *                                                                    + U_nu(x+mu-nu)^+ U_mu(x-nu)^+ U_nu(x-nu) ] */
+void S(so_calc_loc_staples_onlyferms)(const so_geom *g, const C *u, C *stap)
+{
+	const long n = g->sizeh;
+	static const int perp[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
+	for (int d3 = g->d3_halo; d3 < g->nd[3] - g->d3_halo; d3++)
+		for (int d2 = 0; d2 < g->nd[2]; d2++)
+			for (int d1 = 0; d1 < g->nd[1]; d1++)
+				for (int d0 = 0; d0 < g->nd[0]; d0++) {
+					const int x[4] = { d0, d1, d2, d3 };
+					const long idxh = so_snum(g, d0, d1, d2, d3);
+					const int p = (d0 + d1 + d2 + d3) % 2;
+					for (int mu = 0; mu < 4; mu++) {
+						C *sk = stap + (long) (2 * mu + p) * 9 * n;
+						for (int it = 0; it < 3; it++) {
+							const int nu = perp[mu][it];
+							const long ipmu = S(so_shift)(g, x, mu, 1, nu, 0), ipnu = S(so_shift)(g, x, mu, 0, nu, 1);
+							const long imnu = S(so_shift)(g, x, mu, 0, nu, -1), ipmumnu = S(so_shift)(g, x, mu, 1, nu, -1);
+							C a[3][3], b[3][3], c[3][3], ab[3][3], abc[3][3];
+							/* right: U_nu(x+mu) [2nu+!p] * U_mu(x+nu)^+ [2mu+!p] * U_nu(x)^+ [2nu+p] */
+							S(so_load_link)(u + (long) (2 * nu + !p) * 9 * n, n, ipmu, a);
+							S(so_load_link)(u + (long) (2 * mu + !p) * 9 * n, n, ipnu, b); S(so_dagger)(b);
+							S(so_load_link)(u + (long) (2 * nu + p) * 9 * n, n, idxh, c); S(so_dagger)(c);
+							S(so_mul2)(a, b, ab); S(so_mul2)(ab, c, abc);
+							for (int e = 0; e < 9; e++) sk[e * n + idxh] += SO_C_ZERO * abc[e / 3][e % 3];
+							/* left: U_nu(x+mu-nu)^+ [2nu+p] * U_mu(x-nu)^+ [2mu+!p] * U_nu(x-nu) [2nu+!p] */
+							S(so_load_link)(u + (long) (2 * nu + p) * 9 * n, n, ipmumnu, a); S(so_dagger)(a);
+							S(so_load_link)(u + (long) (2 * mu + !p) * 9 * n, n, imnu, b); S(so_dagger)(b);
+							S(so_load_link)(u + (long) (2 * nu + !p) * 9 * n, n, imnu, c);
+							S(so_mul2)(a, b, ab); S(so_mul2)(ab, c, abc);
+							for (int e = 0; e < 9; e++) sk[e * n + idxh] += SO_C_ZERO * abc[e / 3][e % 3];
+						}
+					}
+				}
+}
+
+/* su3_utilities.c:210-237 + su3_utilities.h:1097-1150: tipdot = (rho/C_ZERO) TA(U * staples), assigned */
+void S(so_rho_times_conf_times_staples_ta_part)(const so_geom *g, const C *u, const C *stap, R *ta, double rho)
+{
+	const long n = g->sizeh, lo = (long) g->d3_halo * g->vol3h, hi = (long) (g->nd[3] - g->d3_halo) * g->vol3h;
+	const R one_by_three = (R) 0.33333333333333333333333, tmp = (R) rho / SO_C_ZERO;
+	for (int k = 0; k < 8; k++) {
+		R *tk = ta + (long) k * 8 * n;
+		C *c01 = (C *) tk, *c02 = (C *) (tk + 2 * n), *c12 = (C *) (tk + 4 * n);
+		R *ic00 = tk + 6 * n, *ic11 = tk + 7 * n;
+		for (long i = lo; i < hi; i++) {
+			C m[3][3], x[3][3], p[3][3];
+			S(so_load_link)(u + (long) k * 9 * n, n, i, m);
+			for (int e = 0; e < 9; e++) x[e / 3][e % 3] = stap[((long) k * 9 + e) * n + i];
+			for (int r = 0; r < 3; r++)
+				for (int c = 0; c < 3; c++) p[r][c] = m[r][0] * x[0][c] + m[r][1] * x[1][c] + m[r][2] * x[2][c];
+			c01[i] = tmp * (HALF * (p[0][1] - CONJ(p[1][0])));
+			c02[i] = tmp * (HALF * (p[0][2] - CONJ(p[2][0])));
+			c12[i] = tmp * (HALF * (p[1][2] - CONJ(p[2][1])));
+			R tr = S(so_cimag)(p[0][0]) + S(so_cimag)(p[1][1]) + S(so_cimag)(p[2][2]);
+			ic00[i] = tmp * (S(so_cimag)(p[0][0]) - one_by_three * tr);
+			ic11[i] = tmp * (S(so_cimag)(p[1][1]) - one_by_three * tr);
+		}
+	}
+}
+
+/* cayley_hamilton.h:24-180: rows 0,1 of exp(-QA) = exp(iQ), Q = i QA hermitian traceless (Morningstar-Peardon) */
+static void S(so_ch_exp)(C q01, C q02, C q12, R i00, R i11, C e[2][3])
+{
+	const R i22 = -i00 - i11;
+	R c0 = -S(so_creal)(i00 * i11 * i22 + 2 * S(so_cimag)(q01 * q12 * CONJ(q02)) - i00 * q12 * CONJ(q12)
+											- i11 * q02 * CONJ(q02) - q01 * CONJ(q01) * i22);
+	const R c1 = HALF * (2 * S(so_creal)(i00 * i00 + i11 * i11 + i00 * i11 + q01 * CONJ(q01) + q02 * CONJ(q02) + q12 * CONJ(q12)));
+	const R c0max = 2 * RPOW(c1 / 3, (R) 1.5);
+	C f0, f1, f2;
+	if (c1 < (R) 4.0e-3) {
+		f0 = (1 - c0 * c0 / 720) + ((R) 1.0 * I) * (-c0 * (1 - c1 * (1 - c1 / 42) / 20) / 6);
+		f1 = (c0 * (1 - c1 * (1 - 3 * c1 / 112) / 15) / 24) + ((R) 1.0 * I) * (1 - c1 * (1 - c1 * (1 - c1 / 42) / 20) / 6 - c0 * c0 / 5040);
+		f2 = (HALF * (-1 + c1 * (1 - c1 * (1 - c1 / 56) / 30) / 12 + c0 * c0 / 20160)) + ((R) 1.0 * I) * (HALF * (c0 * (1 - c1 * (1 - c1 / 48) / 21) / 60));
+	} else {
+		int sign = 1;
+		if (c0 < 0) { sign = -1; c0 = -c0; }
+		const R eps = (c0max - c0) / c0max;
+		R theta;
+		if (eps < 0) theta = 0;
+		else if (eps < 1e-3) theta = RSQRT(2 * eps) * (1 + ((R) 1.0 / 12 + ((R) 3.0 / 160 + ((R) 5.0 / 896 + ((R) 35.0 / 18432 + (R) 63.0 / 90112 * eps) * eps) * eps) * eps) * eps);
+		else theta = RACOS(c0 / c0max);
+		const R u = RSQRT(c1 / 3) * RCOS(theta / 3), w = RSQRT(c1) * RSIN(theta / 3);
+		const R u2 = u * u, w2 = w * w, u2mw2 = u2 - w2, w2p3u2 = w2 + 3 * u2, w2m3u2 = w2 - 3 * u2;
+		const R cu = RCOS(u), c2u = RCOS(2 * u), su = RSIN(u), s2u = RSIN(2 * u), cw = RCOS(w);
+		R xi0w;
+		if (RFABS(w) < (R) 0.05) { R t0 = w * w, t1 = 1 - t0 / 42, t2 = (R) 1.0 - t0 / 20 * t1; xi0w = 1 - t0 / 6 * t2; }
+		else xi0w = RSIN(w) / w;
+		const R denom = 1 / (9 * u * u - w * w);
+		f0 = (u2mw2 * c2u + cu * 8 * u2 * cw + 2 * su * u * w2p3u2 * xi0w) + ((R) 1.0 * I) * (u2mw2 * s2u + -su * 8 * u2 * cw + cu * 2 * u * w2p3u2 * xi0w);
+		f0 *= denom;
+		f1 = (2 * u * c2u + -cu * 2 * u * cw + -su * w2m3u2 * xi0w) + ((R) 1.0 * I) * (2 * u * s2u + su * 2 * u * RCOS(w) + -cu * w2m3u2 * xi0w);
+		f1 *= denom;
+		f2 = (c2u + -cu * cw + -3 * su * u * xi0w) + ((R) 1.0 * I) * (s2u + su * cw + -cu * 3 * u * xi0w);
+		f2 *= denom;
+		if (sign == -1) { f0 = CONJ(f0); f1 = -CONJ(f1); f2 = CONJ(f2); }
+	}
+	e[0][0] = f0 - f1 * i00 + f2 * (i00 * i00 + q01 * CONJ(q01) + q02 * CONJ(q02));
+	e[0][1] = (f1 * I) * q01 + f2 * (q02 * CONJ(q12) + ((R) -1.0 * I) * q01 * (i00 + i11));
+	e[0][2] = (f1 * I) * q02 + f2 * (-q01 * q12 + ((R) 1.0 * I) * q02 * i11);
+	e[1][0] = (-f1 * I) * CONJ(q01) + f2 * (q12 * CONJ(q02) + ((R) 1.0 * I) * CONJ(q01) * (i00 + i11));
+	e[1][1] = f0 - f1 * i11 + f2 * (i11 * i11 + q01 * CONJ(q01) + q12 * CONJ(q12));
+	e[1][2] = (f1 * I) * q12 + f2 * (((R) 1.0 * I) * i00 * q12 + q02 * CONJ(q01));
+}
+
+/* stouting.c:107-167: exp_aux = rows 0,1 of exp(-QA); u_out rows 0,1 = exp_aux * U (row 2 of both untouched) */
+void S(so_exp_minus_QA_times_conf)(const so_geom *g, const C *u, const R *ta, C *uout, C *expaux)
+{
+	const long n = g->sizeh, lo = (long) g->d3_halo * g->vol3h, hi = (long) (g->nd[3] - g->d3_halo) * g->vol3h;
+	for (int k = 0; k < 8; k++) {
+		const R *tk = ta + (long) k * 8 * n;
+		const C *c01 = (const C *) tk, *c02 = (const C *) (tk + 2 * n), *c12 = (const C *) (tk + 4 * n);
+		for (long i = lo; i < hi; i++) {
+			C e[2][3], m[3][3];
+			S(so_ch_exp)(c01[i], c02[i], c12[i], tk[6 * n + i], tk[7 * n + i], e);
+			S(so_load_link)(u + (long) k * 9 * n, n, i, m);
+			for (int r = 0; r < 2; r++)
+				for (int c = 0; c < 3; c++) {
+					expaux[((long) k * 9 + r * 3 + c) * n + i] = e[r][c];
+					uout[((long) k * 9 + r * 3 + c) * n + i] = e[r][0] * m[0][c] + e[r][1] * m[1][c] + e[r][2] * m[2][c];
+				}
+		}
+	}
+}
+
+/* stouting.c:74-100 */
+void S(so_stout_isotropic)(const so_geom *g, const C *u, C *uprime, C *stap, C *aux, R *ta, double rho)
+{
+	memset(stap, 0, sizeof(C) * 72 * g->sizeh);
+	S(so_calc_loc_staples_onlyferms)(g, u, stap);
+	S(so_rho_times_conf_times_staples_ta_part)(g, u, stap, ta, rho);
+	S(so_exp_minus_QA_times_conf)(g, u, ta, uprime, aux);
+}
+#undef SO_C_ZERO

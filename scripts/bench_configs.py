@@ -149,7 +149,14 @@ def main():
     out["backfield_times_force"] = {"ms": t, "hbm_GBps_per_gpu": 3520.0 * interior / t / 1e6}
     t = timeit(lambda: lat.multiply_conf_times_force_and_take_ta_nophase(u, pseudo, ta), 10)
     out["take_ta"] = {"ms": t, "hbm_GBps_per_gpu": 2944.0 * interior / t / 1e6}
-    del aux, pseudo, ta
+    # ---- isotropic stout smearing (row N4): one level.  Bytes per half-lattice index as the two kernels move them:
+    # staples+Q kernel reads the 8 links once (768) and writes staples (1152) + Q (512); exp kernel reads Q (512) + links
+    # (768), writes exp_aux rows 0,1 (768) + smeared links rows 0,1 (768) = 5248 B.  Arithmetic: ~2.7 kflop per link for the
+    # six staples + ~0.7 kflop for TA(U S), exp and exp*U => ~27 kflop per index: FP64-bound, not HBM-bound.
+    lat.set_stout(0.15, 1)
+    t = timeit(lambda: lat.stout_isotropic(u, aux, pseudo, rec_conf, ta, 0), 5) if (rec_conf := lat.new_conf()) is not None else 0
+    out["stout_isotropic"] = {"ms": t, "hbm_GBps_per_gpu": 5248.0 * interior / t / 1e6, "approx_fp64_tflops": 27.0e3 * interior / t / 1e9}
+    del aux, pseudo, ta, rec_conf
     if not args.skip_fp32:
         # FP32 CG-M (multishift_invert_f) to the reference's single-precision target (inverter_wrappers.c:62-64)
         solf, psf = lat.new_vec(n, single=True), lat.new_vec(n, single=True)

@@ -30,6 +30,11 @@ def golden_force():
     return dict(np.load(os.path.join(GOLDEN_DIR, "ref_force_4x4x4x4_r1.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_stout():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ref_stout_4x4x4x4_r1.npz")))
+
+
 def relerr(a, b):
     """max |a-b| / max |b| -- the relative error used for every parity statement."""
     a = np.asarray(a); b = np.asarray(b)

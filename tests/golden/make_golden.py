@@ -125,6 +125,24 @@ def force_single(n=(4, 4, 4, 4)):
     print("force", n, float(np.abs(d["force_aux"]).max()), float(np.abs(ta).max()))
 
 
+def stout_single(n=(4, 4, 4, 4)):
+    """Isotropic stout smearing (stouting.c) of the 4^4 fixture's links: one level with every intermediate the
+    reference leaves behind, and the two-level stout_wrapper output; rho = 0.15 (tools/test input files) and a tiny
+    rho that exercises the small-c1 branch of the Cayley-Hamilton exponential."""
+    R = RefLib(*n)
+    g = dict(np.load(os.path.join(HERE, "ref_%dx%dx%dx%d_r1.npz" % n)))
+    u = g["u"]
+    d = {"rho": 0.15, "rho_small": 1e-3}
+    up, stap, aux, ta = R.stout_isotropic(u, 0.15)
+    d.update(uprime=up, staples=stap, exp_aux=aux, tipdot=ta)
+    d["uprime_small"] = R.stout_isotropic(u, 1e-3)[0]
+    d["wrapper2"] = R.stout_wrapper(u, 0.15, 2)
+    upf, stapf, auxf, taf = R.stout_isotropic(u.astype(np.complex64), 0.15)
+    d.update(uprime_f=upf, tipdot_f=taf)
+    np.savez_compressed(os.path.join(HERE, "ref_stout_%dx%dx%dx%d_r1.npz" % n), **d)
+    print("stout", n, float(np.abs(ta).max()))
+
+
 class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
     _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
                 ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
@@ -163,7 +181,7 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi", "force"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout"]
     if "single" in which:
         single_rank()
     if "multi" in which:
@@ -172,3 +190,5 @@ if __name__ == "__main__":
         abi_and_approx()
     if "force" in which:
         force_single()
+    if "stout" in which:
+        stout_single()

@@ -103,6 +103,13 @@ def _worker(rank, world, port, loc, mode, q):
         wantaux = S.scatter_conf(rank, auxg)
         ilo, ihi = S.d3_halo * S.vol3h, (S.d3_halo + loc[3]) * S.vol3h
         errs["force"] = _relerr(daux.cpu().numpy()[..., ilo:ihi], wantaux[..., ilo:ihi])
+        # ---- stout smearing (row N4): two levels, link halos (thickness 2) exchanged after each (stouting.c:27-72)
+        wantst = G.stout_wrapper(u, 0.15, 2)
+        arr = torch.zeros((2, 8, 3, 3, S.sizeh), dtype=torch.complex128, device=lat.device)
+        lat.set_stout(0.15, 2, lat.new_conf(), lat.new_conf(), lat.new_tamat())
+        lat.stout_wrapper(du, arr, 0)
+        got = arr.cpu().numpy()
+        errs["stout"] = max(_relerr(got[l][:, :2], S.scatter_conf(rank, wantst[l])[:, :2]) for l in range(2))   # halos included
         lat.shutdown_multidev()
         dist.destroy_process_group()
         q.put((rank, errs, ""))
@@ -127,7 +134,7 @@ def _run(world, loc, mode):
     for rank, errs, tb in sorted(res):
         assert tb == "", tb
         assert errs["su3_borders_rows01"] == 0.0 and errs["fermion_borders"] == 0.0, (rank, errs)
-        for k in ("acc_Doe", "acc_Deo", "mdagm", "force"):
+        for k in ("acc_Doe", "acc_Deo", "mdagm", "force", "stout"):
             assert errs[k] < 1e-13, (rank, k, errs)
         assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)
