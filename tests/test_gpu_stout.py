@@ -61,7 +61,8 @@ def test_stout_vs_golden(osb, golden_r1, golden_stout):
     assert relerr(up.cpu().numpy(), gs["uprime_small"]) < 1e-13
     # FP32 twin
     duf = lat.to_device(g["u"].astype(np.complex64))
-    upf, stapf, auxf, taf = (lat.new_conf(single=True) for _ in range(3)) + (lat.new_tamat(single=True),)
+    upf, stapf, auxf = (lat.new_conf(single=True) for _ in range(3))
+    taf = lat.new_tamat(single=True)
     lat.set_stout(rho, 1)
     lat.stout_isotropic(duf, upf, stapf, auxf, taf, 0)
     assert relerr(upf.cpu().numpy(), gs["uprime_f"]) < 1e-6 and relerr(taf.cpu().numpy(), gs["tipdot_f"]) < 1e-6
