@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 					*a.seq_rw = seq;
 				}
 			}
-			if (EPI == EPI_MASS_DOT) dslash_finish_dot(a, 0.0);   // a zero partial, so that the ticket count stays gridDim.x
+			if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, 0.0);   // a zero partial, so that the ticket count stays gridDim.x
 			return;
 		}
 	}
@@ -484,12 +484,12 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
 			}
 			a.out[c * n + idx] = o;
-			if (a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
+			if (EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
 			if (peer != nullptr && !(a.dbg & 1)) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
 		}
 	}
 	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks, a.fused == 2 ? a.unpack_ticket + 1 : nullptr);
-	if (EPI == EPI_MASS_DOT) dslash_finish_dot(a, dot);
+	if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, dot);
 }
 
 // unpack blocks per halo: at most 2 per SM (grid-stride copy with 12 loads in flight per thread).  Thousands of
@@ -550,13 +550,13 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;
 	const unsigned int grid = a.fused ? 2 * a.face_blocks + a.bulk_blocks + 2 * a.unpack_blocks : dslash_blocks(d3lo, d3hi);
 #define STAPLE_LAUNCH(P, E) dslash_kernel<T, P, E><<<grid, kBlock, 0, s>>>(a)
+	// the mass epilogue without the dot product runs the EPI_MASS_DOT instantiation with the reduction switched off
+	// (a.partials == nullptr): one code path less, and that instantiation fits the 72-register budget without spills
 	if (par == 0) {
 		if (epi == EPI_NONE) STAPLE_LAUNCH(0, EPI_NONE);
-		else if (epi == EPI_MASS) STAPLE_LAUNCH(0, EPI_MASS);
 		else STAPLE_LAUNCH(0, EPI_MASS_DOT);
 	} else {
 		if (epi == EPI_NONE) STAPLE_LAUNCH(1, EPI_NONE);
-		else if (epi == EPI_MASS) STAPLE_LAUNCH(1, EPI_MASS);
 		else STAPLE_LAUNCH(1, EPI_MASS_DOT);
 	}
 #undef STAPLE_LAUNCH

@@ -3,7 +3,7 @@
 //   OpenAcc/plaquettes.c:196-255         calc_loc_staples_nnptrick_all_onlyferms  (+ su3_utilities.h:660-975)
 //   OpenAcc/su3_utilities.c:210-237      RHO_times_conf_times_staples_ta_part     (+ su3_utilities.h:1097-1150)
 //   OpenAcc/cayley_hamilton.h:24-180     CH_exponential_antihermitian_soa_nissalike (Morningstar-Peardon)
-// One thread per link (grid.y = 2*mu + parity).  The six staples of a link are accumulated in registers and,
+// One thread per half-lattice index, looping over its eight links.  The six staples of a link are accumulated in registers and,
 // inside stout_isotropic, projected straight to Q = (rho/C_ZERO) TA(U S): the reference's 8 x 6 read-modify-write
 // passes over the staple field become one store.  Neighbouring threads share 18 of the 19 links a thread reads, so
 // the kernel runs out of L1/L2 and is bound by FP64 arithmetic (~2.7 kflop per link), not by HBM.
@@ -42,19 +42,20 @@ template <typename C> __device__ __forceinline__ C cmul_(C a, C b) { C r; r.x = 
 template <typename C> __device__ __forceinline__ C conj_(C a) { a.y = -a.y; return a; }
 
 // rows 0,1 from memory, third row = conj(r0 x r1)   (su3_utilities.h, everywhere)
-template <typename T>
+template <typename T, bool THIRD = true>
 __device__ __forceinline__ void load_link(const cplx_t<T> *uk, long n, unsigned int i, cplx_t<T> m[3][3])
 {
 	using C = cplx_t<T>;
 #pragma unroll
 	for (int c = 0; c < 3; c++) { m[0][c] = __ldg(uk + c * n + i); m[1][c] = __ldg(uk + (3 + c) * n + i); }
+	if (!THIRD) return;            // a plain left factor only contributes its first two rows
 	C a, b;
 	a = cmul_(m[0][1], m[1][2]); b = cmul_(m[0][2], m[1][1]); m[2][0] = mks<T>(a.x - b.x, -(a.y - b.y));
 	a = cmul_(m[0][2], m[1][0]); b = cmul_(m[0][0], m[1][2]); m[2][1] = mks<T>(a.x - b.x, -(a.y - b.y));
 	a = cmul_(m[0][0], m[1][1]); b = cmul_(m[0][1], m[1][0]); m[2][2] = mks<T>(a.x - b.x, -(a.y - b.y));
 }
 // first two rows of op(a) * op(b), op = dagger where the flag says so; third row rebuilt
-template <typename T, bool DA, bool DB>
+template <typename T, bool DA, bool DB, bool THIRD = true>
 __device__ __forceinline__ void mul2(const cplx_t<T> a[3][3], const cplx_t<T> b[3][3], cplx_t<T> o[3][3])
 {
 	using C = cplx_t<T>;
@@ -71,6 +72,7 @@ __device__ __forceinline__ void mul2(const cplx_t<T> a[3][3], const cplx_t<T> b[
 			}
 			o[r][c] = acc;
 		}
+	if (!THIRD) return;            // an intermediate product that is only used as a plain left factor
 	C p, q;
 	p = cmul_(o[0][1], o[1][2]); q = cmul_(o[0][2], o[1][1]); o[2][0] = mks<T>(p.x - q.x, -(p.y - q.y));
 	p = cmul_(o[0][2], o[1][0]); q = cmul_(o[0][0], o[1][2]); o[2][1] = mks<T>(p.x - q.x, -(p.y - q.y));
@@ -103,77 +105,83 @@ __device__ __forceinline__ void store_ta(T *tk, long n, unsigned int i, const cp
 // MODE 1: the first two thirds of stout_isotropic  -- loc_stap  = C_ZERO * staples (the reference zeroes it first),
 //                                                     tipdot    = (rho/C_ZERO) TA(U * loc_stap)   (stouting.c:83-90)
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kStoutBlock) stout_staples_kernel(const cplx_t<T> *u, cplx_t<T> *stap, T *ta, T rho, StoutGeom g)
+__global__ void __launch_bounds__(kStoutBlock, 3) stout_staples_kernel(const cplx_t<T> *u, cplx_t<T> *stap, T *ta, T rho, StoutGeom g)
 {
 	using C = cplx_t<T>;
 	const unsigned int t = blockIdx.x * kStoutBlock + threadIdx.x;
 	if (t >= g.cnt) return;
 	const unsigned int idx = g.lo + t;
 	const long n = g.sizeh;
-	const int k = blockIdx.y, mu = k >> 1, p = k & 1;
 	const int nd0h = g.nd0 >> 1;
 	const int hd0 = idx % nd0h;
 	unsigned int q = idx / nd0h;
 	const int d1 = q % g.nd1; q /= g.nd1;
 	const int d2 = q % g.nd2;
 	const int d3 = q / g.nd2;
-	int x[4] = { 2 * hd0 + ((d1 + d2 + d3 + p) & 1), d1, d2, d3 };
 	const int nd[4] = { g.nd0, g.nd1, g.nd2, g.nd3 };
 	const T c_zero = (T) 5.0 * (T) 0.33333333333333333333333;   // C_ZERO, ACTION_TYPE TLSM (common_defines.h:73)
-	C s[3][3];
-#pragma unroll
-	for (int r = 0; r < 3; r++)
-#pragma unroll
-		for (int c = 0; c < 3; c++) s[r][c] = MODE == 0 ? stap[((long) k * 9 + r * 3 + c) * n + idx] : mks<T>(0, 0);
-	auto site = [&](int dmu, int nu, int dnu) {
-		int y[4] = { x[0], x[1], x[2], x[3] };
-		y[mu] = wrap(y[mu] + dmu, nd[mu]);
-		y[nu] = wrap(y[nu] + dnu, nd[nu]);
-		return snum_dev(g, y[0], y[1], y[2], y[3]);
-	};
+	// all eight links of this half-lattice index (both parities, four directions) in ONE thread: the 8 x 18 link
+	// reads around the two sites then hit L1/L2 while they are hot.  With the link index on grid.y instead, each
+	// of the eight sweeps re-streamed most of the configuration from HBM (ncu: 3.3 GB read for 0.4 GB of links).
 #pragma unroll 1
-	for (int it = 0; it < 3; it++) {
-		const int nu = it + (it >= mu ? 1 : 0);          // perp_dirs[mu][it]
-		C a[3][3], b[3][3], ab[3][3];
-		// right: U_nu(x+mu) U_mu(x+nu)^+ U_nu(x)^+
-		load_link<T>(u + (long) (2 * nu + !p) * 9 * n, n, site(1, nu, 0), a);
-		load_link<T>(u + (long) (2 * mu + !p) * 9 * n, n, site(0, nu, 1), b);
-		mul2<T, false, true>(a, b, ab);
-		load_link<T>(u + (long) (2 * nu + p) * 9 * n, n, idx, b);
-		mul2<T, false, true>(ab, b, a);
+	for (int k = 0; k < 8; k++) {
+		const int mu = k >> 1, p = k & 1;
+		const int x[4] = { 2 * hd0 + ((d1 + d2 + d3 + p) & 1), d1, d2, d3 };
+		C s[3][3];
 #pragma unroll
 		for (int r = 0; r < 3; r++)
 #pragma unroll
-			for (int c = 0; c < 3; c++) { s[r][c].x += c_zero * a[r][c].x; s[r][c].y += c_zero * a[r][c].y; }
-		// left: U_nu(x+mu-nu)^+ U_mu(x-nu)^+ U_nu(x-nu)
-		const unsigned int imnu = site(0, nu, -1);
-		load_link<T>(u + (long) (2 * nu + p) * 9 * n, n, site(1, nu, -1), a);
-		load_link<T>(u + (long) (2 * mu + !p) * 9 * n, n, imnu, b);
-		mul2<T, true, true>(a, b, ab);
-		load_link<T>(u + (long) (2 * nu + !p) * 9 * n, n, imnu, b);
-		mul2<T, false, false>(ab, b, a);
+			for (int c = 0; c < 3; c++) s[r][c] = MODE == 0 ? stap[((long) k * 9 + r * 3 + c) * n + idx] : mks<T>(0, 0);
+		auto site = [&](int dmu, int nu, int dnu) {
+			int y[4] = { x[0], x[1], x[2], x[3] };
+			y[mu] = wrap(y[mu] + dmu, nd[mu]);
+			y[nu] = wrap(y[nu] + dnu, nd[nu]);
+			return snum_dev(g, y[0], y[1], y[2], y[3]);
+		};
+#pragma unroll 1
+		for (int it = 0; it < 3; it++) {
+			const int nu = it + (it >= mu ? 1 : 0);          // perp_dirs[mu][it]
+			C a[3][3], b[3][3], ab[3][3];
+			// right: U_nu(x+mu) U_mu(x+nu)^+ U_nu(x)^+
+			load_link<T, false>(u + (long) (2 * nu + !p) * 9 * n, n, site(1, nu, 0), a);
+			load_link<T>(u + (long) (2 * mu + !p) * 9 * n, n, site(0, nu, 1), b);
+			mul2<T, false, true, false>(a, b, ab);
+			load_link<T>(u + (long) (2 * nu + p) * 9 * n, n, idx, b);
+			mul2<T, false, true>(ab, b, a);
+#pragma unroll
+			for (int r = 0; r < 3; r++)
+#pragma unroll
+				for (int c = 0; c < 3; c++) { s[r][c].x += c_zero * a[r][c].x; s[r][c].y += c_zero * a[r][c].y; }
+			// left: U_nu(x+mu-nu)^+ U_mu(x-nu)^+ U_nu(x-nu)
+			const unsigned int imnu = site(0, nu, -1);
+			load_link<T>(u + (long) (2 * nu + p) * 9 * n, n, site(1, nu, -1), a);
+			load_link<T>(u + (long) (2 * mu + !p) * 9 * n, n, imnu, b);
+			mul2<T, true, true, false>(a, b, ab);
+			load_link<T>(u + (long) (2 * nu + !p) * 9 * n, n, imnu, b);
+			mul2<T, false, false>(ab, b, a);
+#pragma unroll
+			for (int r = 0; r < 3; r++)
+#pragma unroll
+				for (int c = 0; c < 3; c++) { s[r][c].x += c_zero * a[r][c].x; s[r][c].y += c_zero * a[r][c].y; }
+		}
 #pragma unroll
 		for (int r = 0; r < 3; r++)
 #pragma unroll
-			for (int c = 0; c < 3; c++) { s[r][c].x += c_zero * a[r][c].x; s[r][c].y += c_zero * a[r][c].y; }
-	}
+			for (int c = 0; c < 3; c++) stap[((long) k * 9 + r * 3 + c) * n + idx] = s[r][c];
+		if (MODE == 1) {
+			C m[3][3], pr[3][3];
+			load_link<T>(u + (long) k * 9 * n, n, idx, m);
 #pragma unroll
-	for (int r = 0; r < 3; r++)
+			for (int r = 0; r < 3; r++)
 #pragma unroll
-		for (int c = 0; c < 3; c++) stap[((long) k * 9 + r * 3 + c) * n + idx] = s[r][c];
-	if (MODE == 1) {
-		C m[3][3], pr[3][3];
-		load_link<T>(u + (long) k * 9 * n, n, idx, m);
-#pragma unroll
-		for (int r = 0; r < 3; r++)
-#pragma unroll
-			for (int c = 0; c < 3; c++) {
-				C acc = cmul_(m[r][0], s[0][c]);
-				const C b1 = cmul_(m[r][1], s[1][c]), b2 = cmul_(m[r][2], s[2][c]);
-				acc.x += b1.x; acc.y += b1.y; acc.x += b2.x; acc.y += b2.y;
-				pr[r][c] = acc;
-			}
-		store_ta<T, true>(ta + (long) k * 8 * n, n, idx, pr, rho / c_zero);
+				for (int c = 0; c < 3; c++) {
+					C acc = cmul_(m[r][0], s[0][c]);
+					const C b1 = cmul_(m[r][1], s[1][c]), b2 = cmul_(m[r][2], s[2][c]);
+					acc.x += b1.x; acc.y += b1.y; acc.x += b2.x; acc.y += b2.y;
+					pr[r][c] = acc;
+				}
+			store_ta<T, true>(ta + (long) k * 8 * n, n, idx, pr, rho / c_zero);
+		}
 	}
 }
 
@@ -304,7 +312,7 @@ static void stout_isotropic_t(const cplx_t<T> *u, cplx_t<T> *uprime, cplx_t<T> *
 	const T rho = (T) (istopo ? gl_topo_rho : gl_stout_rho);
 	// set_su3_soa_to_zero(local_staples) (stouting.c:85): the halo slices of the parking field are zero afterwards
 	STAPLE_CUDA_CHECK(cudaMemsetAsync(stap, 0, sizeof(cplx_t<T>) * 72 * g.sizeh, ctx().stream));
-	stout_staples_kernel<T, 1><<<grid, kStoutBlock, 0, ctx().stream>>>(u, stap, ta, rho, g);
+	stout_staples_kernel<T, 1><<<grid.x, kStoutBlock, 0, ctx().stream>>>(u, stap, ta, rho, g);
 	stout_exp_kernel<T><<<grid, kStoutBlock, 0, ctx().stream>>>(u, ta, uprime, aux, g);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch(2);
@@ -329,7 +337,7 @@ void communicate_su3_borders_f(su3_soa_f *lnh_conf, int thickness);
 	{                                                                                                                         \
 		require_init("calc_loc_staples_nnptrick_all_onlyferms");                                                                \
 		const StoutGeom g = stout_geom();                                                                                       \
-		stout_staples_kernel<T, 0><<<dim3((g.cnt + kStoutBlock - 1) / kStoutBlock, 8), kStoutBlock, 0, ctx().stream>>>(         \
+		stout_staples_kernel<T, 0><<<(g.cnt + kStoutBlock - 1) / kStoutBlock, kStoutBlock, 0, ctx().stream>>>(                  \
 			CD(u), D(loc_stap), nullptr, (T) 0, g);                                                                               \
 		STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();                                                                  \
 	}                                                                                                                         \
