@@ -255,6 +255,20 @@ class Lattice:
     def to_device(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
+    def load_configuration(self, path, fmt="ildg"):
+        """Read a GLOBAL configuration file (ILDG/LIME or the reference's ASCII format, openstaple_b200/io.py), cut out
+        this rank's local+halo box (halos included, Mpi/communications.c:1104-1148) and upload it in the su3_soa[8]
+        layout -> (device tensor [8,3,3,sizeh], conf_id)."""
+        from . import io as sio
+        dims = (self.loc_n[0], self.loc_n[1], self.loc_n[2], self.loc_n[3] * self.nranks)
+        if fmt == "ildg":
+            conf, cid = sio.read_su3_soa_ildg_binary(path, dims)
+        else:
+            conf, cid, _ = sio.read_su3_soa_ASCII(path, dims)
+        if self.nranks > 1:
+            conf = sio.send_lnh_subconf_to_buffer(conf, self.rank, self.loc_n, self.nranks, self.halo_width)
+        return self.to_device(conf), cid
+
     def host_array(self, shape, dtype):
         return HostArray(self, shape, dtype)
 

@@ -29,6 +29,9 @@
 #include "RationalApprox/rationalapprox.h"
 #include "OpenAcc/action.h"
 #include "OpenAcc/stouting.h"
+#include "OpenAcc/alloc_settings.h"
+#include "OpenAcc/io.h"
+#include "Include/setting_file_parser.h"
 
 int verbosity_lv = 0;
 vec3_soa_f *aux1_f = NULL;                 /* alloc_vars globals used by inverter_wrappers.c:60-71 */
@@ -52,6 +55,16 @@ void ref_set_stout(double rho, int steps, void *auxbis, void *staples, void *ipd
 	gl_stout_rho = rho; gl_topo_rho = rho;
 	auxbis_conf_acc = (su3_soa *) auxbis; glocal_staples = (su3_soa *) staples; gipdot = (tamat_soa *) ipdot;
 	auxbis_conf_acc_f = (su3_soa_f *) auxbis_f; glocal_staples_f = (su3_soa_f *) staples_f; gipdot_f = (tamat_soa_f *) ipdot_f;
+}
+
+/* globals read by io.c's writers (io.c:56-66, :498): no flavours, empty embedded input file */
+alloc_settings alloc_info;
+ferm_param *fermions_parameters = NULL;
+char input_file_str[MAXLINES * MAXLINELENGTH];
+void ref_set_io(double beta, const char *input_file)
+{
+	act_params.beta = beta; alloc_info.NDiffFlavs = 0;
+	strncpy(input_file_str, input_file, sizeof(input_file_str) - 1);
 }
 
 void ref_geometry(int *o)

@@ -143,6 +143,31 @@ def stout_single(n=(4, 4, 4, 4)):
     print("stout", n, float(np.abs(ta).max()))
 
 
+def io_single(n=(4, 4, 4, 4)):
+    """On-disk formats (io.c): the reference writes the 4^4 fixture's links as ASCII and as ILDG, and reads both
+    files back; the file bytes and the read-back arrays are the fixture."""
+    import tempfile
+    R = RefLib(*n)
+    g = dict(np.load(os.path.join(HERE, "ref_%dx%dx%dx%d_r1.npz" % n)))
+    u = np.ascontiguousarray(g["u"])
+    R.lib.ref_set_io(C.c_double(3.7), b"# embedded input file\nnx 4\n")
+    d = {"beta": 3.7, "conf_id": 7, "input_file": "# embedded input file\nnx 4\n"}
+    with tempfile.TemporaryDirectory() as td:
+        pa, pi = os.path.join(td, "conf.ascii").encode(), os.path.join(td, "conf.ildg").encode()
+        assert R.lib.print_su3_soa_ASCII(ptr(u), pa, C.c_int(7), None) == 0
+        assert R.lib.print_su3_soa_ildg_binary(ptr(u), pi, C.c_int(7)) == 0
+        d["ascii_bytes"] = np.frombuffer(open(pa, "rb").read(), dtype=np.uint8)
+        d["ildg_bytes"] = np.frombuffer(open(pi, "rb").read(), dtype=np.uint8)
+        back = np.zeros_like(u); cid = C.c_int(0)
+        assert R.lib.read_su3_soa_ASCII(ptr(back), pa, C.byref(cid)) == 0
+        d["ascii_read_back"] = back.copy(); d["ascii_conf_id"] = cid.value
+        back = np.zeros_like(u); cid = C.c_int(0)
+        assert R.lib.read_su3_soa_ildg_binary(ptr(back), pi, C.byref(cid)) == 0
+        d["ildg_read_back"] = back.copy(); d["ildg_conf_id"] = cid.value
+    np.savez_compressed(os.path.join(HERE, "ref_io_%dx%dx%dx%d_r1.npz" % n), **d)
+    print("io", n, d["ascii_bytes"].size, d["ildg_bytes"].size, cid.value)
+
+
 class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
     _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
                 ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
@@ -181,7 +206,7 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "io"]
     if "single" in which:
         single_rank()
     if "multi" in which:
@@ -192,3 +217,5 @@ if __name__ == "__main__":
         force_single()
     if "stout" in which:
         stout_single()
+    if "io" in which:
+        io_single()

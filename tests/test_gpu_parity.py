@@ -501,3 +501,19 @@ def test_multishift_fused_tail_matches_separate_kernels(osb, single):
     assert res[0][0] == res[1][0]
     assert np.array_equal(res[0][1], res[1][1])
     assert res[0][2] < res[1][2]          # 4 instead of 6 launches per iteration
+
+
+def test_load_configuration_from_ildg_and_ascii(osb, tmp_path):
+    """N5: a configuration file goes straight into the su3_soa[8] layout the kernels read"""
+    from openstaple_b200 import io as sio
+    c = make_case(osb, (4, 4, 4, 8))
+    lat, S = c["lat"], c["S"]
+    want = S.dslash("deo", c["u"], c["v"], c["ph"])
+    for fmt, writer in (("ildg", lambda p: sio.print_su3_soa_ildg_binary(c["u"], p, (4, 4, 4, 8), 12)),
+                        ("ascii", lambda p: sio.print_su3_soa_ASCII(c["u"], p, (4, 4, 4, 8), 12))):
+        p = str(tmp_path / ("conf." + fmt)); writer(p)
+        du, cid = lat.load_configuration(p, fmt)
+        assert cid == 12
+        out = lat.new_vec()
+        lat.acc_Deo(du, out, c["d_v"], c["d_ph"])
+        assert relerr(out.cpu().numpy(), want) < (TOL64 if fmt == "ildg" else 1e-12)    # ASCII keeps 18 decimals
