@@ -51,6 +51,8 @@ typedef struct su3_soa_f_t su3_soa_f;
 typedef struct float_soa_t float_soa;
 typedef struct tamat_soa_t tamat_soa;       /* ref: OpenAcc/struct_c_def.h:45-51  {c01,c02,c12 complex[sizeh]; ic00,ic11 double[sizeh]} */
 typedef struct tamat_soa_f_t tamat_soa_f;
+typedef struct thmat_soa_t thmat_soa;       /* ref: OpenAcc/struct_c_def.h:52-58  {c01,c02,c12 complex[sizeh]; rc00,rc11 double[sizeh]} */
+typedef struct thmat_soa_f_t thmat_soa_f;
 
 #ifndef MAX_APPROX_ORDER
 #define MAX_APPROX_ORDER 25                 /* ref: RationalApprox/rationalapprox.h:8 */
@@ -357,6 +359,20 @@ extern tamat_soa_f *gipdot_f;
 	void stout_wrapper##S(const SU3 *tconf_acc, SU3 *tstout_conf_acc_arr, const int istopo);     /* ref: stouting.c:27-72 */
 STAPLE_STOUT_DECL(, su3_soa, tamat_soa)
 STAPLE_STOUT_DECL(_f, su3_soa_f, tamat_soa_f)
+
+/* N4, force side: Sigma' -> Sigma through one smearing level (the stouted fermion force).
+ * ref: OpenAcc/stouting.c:171-548 (compute_lambda), :550-1305 (compute_sigma), OpenAcc/fermion_force.c:52-163 (the chain);
+ * border exchanges of gl(3), tamat and thmat fields: Mpi/communications.c (thickness 1 inside the chain). */
+#define STAPLE_SF_DECL(S, SU3, TAMAT, THMAT) \
+	void compute_lambda##S(THMAT *L, const SU3 *SP, const SU3 *U, const TAMAT *QA, SU3 *TMP);                 /* ref: stouting.c:516-548 */ \
+	void compute_sigma##S(const THMAT *L, const SU3 *U, SU3 *S_, const TAMAT *QA, SU3 *TMP, const int istopo); /* ref: stouting.c:1175-1305 */ \
+	void communicate_gl3_borders##S(SU3 *lnh_conf, int thickness); \
+	void communicate_tamat_soa_borders##S(TAMAT *lnh_ipdot, int thickness); \
+	void communicate_thmat_soa_borders##S(THMAT *lnh_ipdot, int thickness); \
+	void compute_sigma_from_sigma_prime_backinto_sigma_prime##S(SU3 *Sigma, THMAT *Lambda, TAMAT *QA, const SU3 *U, SU3 *TMP, \
+																															 const int istopo);                          /* ref: fermion_force.c:52-163 */
+STAPLE_SF_DECL(, su3_soa, tamat_soa, thmat_soa)
+STAPLE_SF_DECL(_f, su3_soa_f, tamat_soa_f, thmat_soa_f)
 
 /* ------------------------------------------------------------------ introspection for benches/tests */
 /* statistics of the last multishift_invert[_f] call: iterations, sum over iterations of active

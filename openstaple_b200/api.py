@@ -428,6 +428,17 @@ class Lattice:
     def stout_wrapper(self, tconf_acc, tstout_conf_acc_arr, istopo=0):
         getattr(self.L, "stout_wrapper" + _sfx(tconf_acc))(_addr(tconf_acc), _addr(tstout_conf_acc_arr), int(istopo))
 
+    # ---- stouted fermion force: Sigma' -> Sigma (OpenAcc/stouting.h, fermion_force.c:52-163)
+    def compute_lambda(self, L, SP, U, QA, TMP):
+        getattr(self.L, "compute_lambda" + _sfx(U))(_addr(L), _addr(SP), _addr(U), _addr(QA), _addr(TMP))
+
+    def compute_sigma(self, L, U, S, QA, TMP, istopo=0):
+        getattr(self.L, "compute_sigma" + _sfx(U))(_addr(L), _addr(U), _addr(S), _addr(QA), _addr(TMP), int(istopo))
+
+    def compute_sigma_from_sigma_prime_backinto_sigma_prime(self, Sigma, Lambda, QA, U, TMP, istopo=0):
+        getattr(self.L, "compute_sigma_from_sigma_prime_backinto_sigma_prime" + _sfx(U))(
+            _addr(Sigma), _addr(Lambda), _addr(QA), _addr(U), _addr(TMP), int(istopo))
+
     # ---- conversions (OpenAcc/float_double_conv.c)
     def convert_double_to_float_vec3_soa(self, d, f): self.L.convert_double_to_float_vec3_soa(_addr(d), _addr(f))
     def convert_float_to_double_vec3_soa(self, f, d): self.L.convert_float_to_double_vec3_soa(_addr(f), _addr(d))

@@ -99,6 +99,11 @@ def _declare(L):
         getattr(L, "exp_minus_QA_times_conf" + s).argtypes = [vp, vp, vp, vp]
         getattr(L, "stout_isotropic" + s).argtypes = [vp, vp, vp, vp, vp, i]
         getattr(L, "stout_wrapper" + s).argtypes = [vp, vp, i]
+        getattr(L, "compute_lambda" + s).argtypes = [vp, vp, vp, vp, vp]
+        getattr(L, "compute_sigma" + s).argtypes = [vp, vp, vp, vp, vp, i]
+        getattr(L, "compute_sigma_from_sigma_prime_backinto_sigma_prime" + s).argtypes = [vp, vp, vp, vp, vp, i]
+        for f in ("communicate_gl3_borders", "communicate_tamat_soa_borders", "communicate_thmat_soa_borders"):
+            getattr(L, f + s).argtypes = [vp, i]
         getattr(L, "communicate_fermion_borders" + s).argtypes = [vp]
         getattr(L, "communicate_su3_borders" + s).argtypes = [vp, i]
     for f in ("convert_float_to_double_vec3_soa", "convert_double_to_float_vec3_soa", "convert_float_to_double_su3_soa",

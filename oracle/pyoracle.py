@@ -237,6 +237,21 @@ class RefLib:
         getattr(self.lib, "stout_wrapper" + self._sfx(u))(ptr(u), ptr(out), C.c_int(0))
         return out
 
+    # --- stout force chain (stouting.c:171-1305)
+    def compute_lambda(self, sp, u, ta):
+        """-> (Lambda thmat [8,8,sizeh], TMP)"""
+        rd = np.float32 if u.dtype == np.complex64 else np.float64
+        lam = np.zeros((8, 8, self.sizeh), rd); tmp = np.zeros_like(u)
+        getattr(self.lib, "compute_lambda" + self._sfx(u))(ptr(lam), ptr(sp), ptr(u), ptr(ta), ptr(tmp))
+        return lam, tmp
+
+    def compute_sigma(self, lam, u, sg, ta, rho):
+        """Sigma' (sg) -> Sigma in place; -> TMP"""
+        self._stout_globals(rho, 1, u)
+        tmp = np.zeros_like(u)
+        getattr(self.lib, "compute_sigma" + self._sfx(u))(ptr(lam), ptr(u), ptr(sg), ptr(ta), ptr(tmp), C.c_int(0))
+        return tmp
+
     # --- reductions
     def l2norm2(self, a):
         return getattr(self.lib, "l2norm2_global" + self._sfx(a))(ptr(a))
@@ -395,6 +410,18 @@ class Restatement:
             out[l] = self.stout_isotropic(src, rho)[0]
             src = out[l]
         return out
+
+    # stout force chain
+    def compute_lambda(self, sp, u, ta):
+        rd = np.float32 if u.dtype == np.complex64 else np.float64
+        lam = np.zeros((8, 8, self.sizeh), rd); tmp = np.zeros_like(u)
+        getattr(self.lib, "so_compute_lambda" + self._sfx(u))(self.gp(), ptr(lam), ptr(sp), ptr(u), ptr(ta), ptr(tmp))
+        return lam, tmp
+
+    def compute_sigma(self, lam, u, sg, ta, rho):
+        tmp = np.zeros_like(u)
+        getattr(self.lib, "so_compute_sigma" + self._sfx(u))(self.gp(), ptr(lam), ptr(u), ptr(sg), ptr(ta), ptr(tmp), C.c_double(rho))
+        return tmp
 
     # multi-rank helpers (global <-> rank-local boxes)
     def scatter_vec(self, rank, gl):

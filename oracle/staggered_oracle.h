@@ -76,7 +76,9 @@ void so_multiply_conf_times_force_and_take_ta_nophase##S(const so_geom *g, const
 void so_calc_loc_staples_onlyferms##S(const so_geom *g, const C *u, C *stap); \
 void so_rho_times_conf_times_staples_ta_part##S(const so_geom *g, const C *u, const C *stap, R *ta, double rho); \
 void so_exp_minus_QA_times_conf##S(const so_geom *g, const C *u, const R *ta, C *uout, C *expaux); \
-void so_stout_isotropic##S(const so_geom *g, const C *u, C *uprime, C *stap, C *aux, R *ta, double rho);
+void so_stout_isotropic##S(const so_geom *g, const C *u, C *uprime, C *stap, C *aux, R *ta, double rho); \
+void so_compute_lambda##S(const so_geom *g, R *lam, const C *sp, const C *u, const R *ta, C *tmp); \
+void so_compute_sigma##S(const so_geom *g, const R *lam, const C *u, C *sg, const R *ta, C *tmp, double rho);
 SO_DECL(double, double complex, )
 SO_DECL(float, float complex, _f)
 

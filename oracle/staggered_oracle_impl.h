@@ -562,3 +562,197 @@ void S(so_stout_isotropic)(const so_geom *g, const C *u, C *uprime, C *stap, C *
 	S(so_exp_minus_QA_times_conf)(g, u, ta, uprime, aux);
 }
 #undef SO_C_ZERO
+
+/* ------------------------------------------------------------------ stout force chain Sigma' -> Sigma (stouting.c:171-1305)
+ * thmat_soa[8] (struct_c_def.h:52-58) as reals, same packing as tamat: c01 @0, c02 @2*sizeh, c12 @4*sizeh (complex),
+ * rc00 @6*sizeh, rc11 @7*sizeh.  The reference spells every 3x3 product out on the packed components; here the
+ * same algebra is done on full matrices: Q = i*QA (hermitian, traceless), Lambda hermitian traceless.
+ * Pinned against the reference build to rounding (1e-14), not bit for bit -- the operation order differs. */
+static void S(so_q_from_qa)(const R *tk, long n, long i, C q[3][3])   /* Q = i * QA */
+{
+	const C c01 = ((const C *) tk)[i], c02 = ((const C *) (tk + 2 * n))[i], c12 = ((const C *) (tk + 4 * n))[i];
+	const R i00 = tk[6 * n + i], i11 = tk[7 * n + i];
+	q[0][0] = -i00; q[1][1] = -i11; q[2][2] = i00 + i11;
+	q[0][1] = I * c01; q[1][0] = -I * CONJ(c01);
+	q[0][2] = I * c02; q[2][0] = -I * CONJ(c02);
+	q[1][2] = I * c12; q[2][1] = -I * CONJ(c12);
+}
+static void S(so_herm_from_thmat)(const R *tk, long n, long i, C l[3][3])
+{
+	const C c01 = ((const C *) tk)[i], c02 = ((const C *) (tk + 2 * n))[i], c12 = ((const C *) (tk + 4 * n))[i];
+	const R r00 = tk[6 * n + i], r11 = tk[7 * n + i];
+	l[0][0] = r00; l[1][1] = r11; l[2][2] = -r00 - r11;
+	l[0][1] = c01; l[1][0] = CONJ(c01); l[0][2] = c02; l[2][0] = CONJ(c02); l[1][2] = c12; l[2][1] = CONJ(c12);
+}
+static void S(so_mm)(C a[3][3], C b[3][3], C o[3][3])
+{
+	for (int r = 0; r < 3; r++)
+		for (int c = 0; c < 3; c++) o[r][c] = a[r][0] * b[0][c] + a[r][1] * b[1][c] + a[r][2] * b[2][c];
+}
+/* Cayley-Hamilton coefficients f_j and their derivatives b_1j, b_2j (stouting.c:179-327, hep-lat/0311018 eqs. 57-69) */
+static void S(so_ch_coeffs)(C q[3][3], C f[3], C b1[3], C b2[3])
+{
+	C q2[3][3]; S(so_mm)(q, q, q2);
+	R c0 = S(so_creal)(q[0][0] * (q[1][1] * q[2][2] - q[1][2] * q[2][1]) - q[0][1] * (q[1][0] * q[2][2] - q[1][2] * q[2][0])
+										 + q[0][2] * (q[1][0] * q[2][1] - q[1][1] * q[2][0]));          /* det Q */
+	const R c1 = HALF * S(so_creal)(q2[0][0] + q2[1][1] + q2[2][2]);                     /* Tr Q^2 / 2 */
+	const R c0max = 2 * RPOW(c1 / 3, (R) 1.5);
+	if (c1 < (R) 4e-3) {
+		f[0] = (1 - c0 * c0 / 720) + I * (-c0 * (1 - c1 * (1 - c1 / 42) / 20) / 6);
+		f[1] = (c0 * (1 - c1 * (1 - 3 * c1 / 112) / 15) / 24) + I * (1 - c1 * (1 - c1 * (1 - c1 / 42) / 20) / 6 - c0 * c0 / 5040);
+		f[2] = (HALF * (-1 + c1 * (1 - c1 * (1 - c1 / 56) / 30) / 12 + c0 * c0 / 20160)) + I * (HALF * (c0 * (1 - c1 * (1 - c1 / 48) / 21) / 60));
+		b1[0] = 0 + I * (c0 / 120 * (1 - c1 / 21));
+		b1[1] = (-c0 / 360 * (1 - 3 * c1 / 56)) + I * ((R) -1.0 / 6 * (1 - c1 / 10 * ((R) 1.0 - c1 / 28)));
+		b1[2] = (HALF * ((R) 1.0 / 12 * (1 - 2 * c1 / 30 * (1 - 3 * c1 / 112)))) + I * (HALF * (-c0 / 1260 * (1 - c1 / 24)));
+		b2[0] = (-c0 / 360) + I * ((R) -1.0 / 6 * (1 - c1 / 20 * (1 - c1 / 42)));
+		b2[1] = ((R) 1.0 / 24 * (1 - c1 / 15 * (1 - 3 * c1 / 112))) + I * (-c0 / 2520);
+		b2[2] = (HALF * c0 / 10080) + I * (HALF * ((R) 1.0 / 60 * (1 - c1 / 21 * (1 - c1 / 48))));
+		return;
+	}
+	int sign = 1;
+	if (c0 < 0) { sign = -1; c0 = -c0; }
+	const R eps = (c0max - c0) / c0max;
+	R theta;
+	if (eps < 0) theta = 0;
+	else if (eps < 1e-3) theta = RSQRT(2 * eps) * (1 + ((R) 1.0 / 12 + ((R) 3.0 / 160 + ((R) 5.0 / 896 + ((R) 35.0 / 18432 + (R) 63.0 / 90112 * eps) * eps) * eps) * eps) * eps);
+	else theta = RACOS(c0 / c0max);
+	const R u = RSQRT(c1 / 3) * RCOS(theta / 3), w = RSQRT(c1) * RSIN(theta / 3);
+	const R u2 = u * u, w2 = w * w, u2mw2 = u2 - w2, w2p3u2 = w2 + 3 * u2, w2m3u2 = w2 - 3 * u2;
+	const R cu = RCOS(u), c2u = RCOS(2 * u), su = RSIN(u), s2u = RSIN(2 * u), cw = RCOS(w);
+	R xi0w, xi1w;
+	if (RFABS(w) < (R) 0.05) { R t0 = w * w, t1 = 1 - t0 / 42, t2 = (R) 1.0 - t0 / 20 * t1; xi0w = 1 - t0 / 6 * t2; }
+	else xi0w = RSIN(w) / w;
+	if (RFABS(w) < (R) 0.05) xi1w = -(1 - w2 * (1 - w2 * (1 - w2 / 54) / 28) / 10) / 3;
+	else xi1w = cw / w2 - RSIN(w) / (w2 * w);
+	const R denom = 1 / (9 * u * u - w * w);
+	f[0] = ((u2mw2 * c2u + cu * 8 * u2 * cw + 2 * su * u * w2p3u2 * xi0w) + I * (u2mw2 * s2u + -su * 8 * u2 * cw + cu * 2 * u * w2p3u2 * xi0w)) * denom;
+	f[1] = ((2 * u * c2u + -cu * 2 * u * cw + -su * w2m3u2 * xi0w) + I * (2 * u * s2u + su * 2 * u * cw + -cu * w2m3u2 * xi0w)) * denom;
+	f[2] = ((c2u + -cu * cw + -3 * su * u * xi0w) + I * (s2u + su * cw + -cu * 3 * u * xi0w)) * denom;
+	C r1[3], r2[3];
+	r1[0] = (2 * c2u * u + s2u * (-2 * u2 + 2 * w2) + 2 * cu * u * (8 * cw + 3 * u2 * xi0w + w2 * xi0w) + su * (-8 * cw * u2 + 18 * u2 * xi0w + 2 * w2 * xi0w))
+		+ I * (-8 * cw * (2 * su * u + cu * u2) + 2 * (s2u * u + c2u * u2 - c2u * w2) + 2 * (9 * cu * u2 - 3 * su * u * u2 + cu * w2 - su * u * w2) * xi0w);
+	r1[1] = (2 * c2u - 4 * s2u * u + su * (2 * cw * u + 6 * u * xi0w) + cu * (-2 * cw + 3 * u2 * xi0w - w2 * xi0w))
+		+ I * (2 * s2u + 4 * c2u * u + 2 * cw * (su + cu * u) + (6 * cu * u - 3 * su * u2 + su * w2) * xi0w);
+	r1[2] = (-2 * s2u + cw * su - 3 * (su + cu * u) * xi0w) + I * (2 * c2u + cu * cw + (-3 * cu + 3 * su * u) * xi0w);
+	r2[0] = (-2 * c2u + 2 * cw * su * u + 2 * su * u * xi0w - 8 * cu * u2 * xi0w + 6 * su * u * u2 * xi1w)
+		+ I * (2 * (-s2u + 4 * su * u2 * xi0w + cu * u * (cw + xi0w + 3 * u2 * xi1w)));
+	r2[1] = (2 * cu * u * xi0w + su * (-cw - xi0w + 3 * u2 * xi1w)) + I * (-2 * su * u * xi0w - cu * (cw + xi0w - 3 * u2 * xi1w));
+	r2[2] = (cu * xi0w - 3 * su * u * xi1w) + I * (-(su * xi0w) - 3 * cu * u * xi1w);
+	for (int j = 0; j < 3; j++) {
+		b1[j] = HALF * denom * denom * (2 * u * r1[j] + (3 * u * u - w * w) * r2[j] - 2 * (15 * u * u + w * w) * f[j]);   /* (57) */
+		b2[j] = HALF * denom * denom * (r1[j] - 3 * u * r2[j] - 24 * u * f[j]);                                            /* (58) */
+	}
+	if (sign == -1) {
+		b1[0] = CONJ(b1[0]); b1[1] = -CONJ(b1[1]); b1[2] = CONJ(b1[2]);
+		b2[0] = -CONJ(b2[0]); b2[1] = CONJ(b2[1]); b2[2] = -CONJ(b2[2]);
+		f[0] = CONJ(f[0]); f[1] = -CONJ(f[1]); f[2] = CONJ(f[2]);
+	}
+}
+
+/* stouting.c:171-548: Lambda = traceless hermitian part of
+ * Gamma = Tr(B1 U Sigma') Q + Tr(B2 U Sigma') Q^2 + f1 U Sigma' + f2 (Q U Sigma' + U Sigma' Q);  TMP is left = U Sigma' */
+void S(so_compute_lambda)(const so_geom *g, R *lam, const C *sp, const C *u, const R *ta, C *tmp)
+{
+	const long n = g->sizeh, lo = (long) g->d3_halo * g->vol3h, hi = (long) (g->nd[3] - g->d3_halo) * g->vol3h;
+	const R one_by_three = (R) 0.33333333333333333333333;
+	for (int k = 0; k < 8; k++)
+		for (long i = lo; i < hi; i++) {
+			C q[3][3], q2[3][3], f[3], b1[3], b2[3], m[3][3], s[3][3], us[3][3], B[3][3], t[3][3], gm[3][3], qus[3][3], usq[3][3];
+			S(so_q_from_qa)(ta + (long) k * 8 * n, n, i, q);
+			S(so_ch_coeffs)(q, f, b1, b2);
+			S(so_mm)(q, q, q2);
+			S(so_load_link)(u + (long) k * 9 * n, n, i, m);
+			for (int e = 0; e < 9; e++) s[e / 3][e % 3] = sp[((long) k * 9 + e) * n + i];
+			S(so_mm)(m, s, us);
+			C tr[2];
+			for (int w = 0; w < 2; w++) {
+				const C *b = w ? b2 : b1;
+				for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) B[r][c] = (r == c ? b[0] : 0) + b[1] * q[r][c] + b[2] * q2[r][c];
+				S(so_mm)(B, us, t);
+				tr[w] = t[0][0] + t[1][1] + t[2][2];
+			}
+			S(so_mm)(q, us, qus); S(so_mm)(us, q, usq);
+			for (int r = 0; r < 3; r++)
+				for (int c = 0; c < 3; c++) {
+					gm[r][c] = tr[0] * q[r][c] + tr[1] * q2[r][c] + f[1] * us[r][c] + f[2] * (qus[r][c] + usq[r][c]);
+					tmp[((long) k * 9 + r * 3 + c) * n + i] = us[r][c];
+				}
+			R *lk = lam + (long) k * 8 * n;
+			lk[6 * n + i] = (2 * S(so_creal)(gm[0][0]) - S(so_creal)(gm[1][1]) - S(so_creal)(gm[2][2])) * one_by_three;
+			lk[7 * n + i] = (2 * S(so_creal)(gm[1][1]) - S(so_creal)(gm[0][0]) - S(so_creal)(gm[2][2])) * one_by_three;
+			((C *) lk)[i] = (gm[0][1] + CONJ(gm[1][0])) * HALF;
+			((C *) (lk + 2 * n))[i] = (gm[0][2] + CONJ(gm[2][0])) * HALF;
+			((C *) (lk + 4 * n))[i] = (gm[1][2] + CONJ(gm[2][1])) * HALF;
+		}
+}
+
+/* stouting.c:550-1305: Sigma = Sigma' exp(iQ) + i rho sum_{nu != mu} [ right and left staples with one Lambda inserted ]
+ *   right, A = U_nu(x+mu), B = U_mu(x+nu)^+, C = U_nu(x)^+ :  ABC (L_mu(x) - L_nu(x)) + L_nu(x+mu) ABC - A B L_mu(x+nu) C
+ *   left,  A = U_nu(x+mu-nu)^+, B = U_mu(x-nu)^+, C = U_nu(x-nu) :
+ *                           A B (L_nu(x-nu) - L_mu(x-nu)) C + A B C L_mu(x) - A L_nu(x+mu-nu) B C
+ * TMP is left = exp(iQ). */
+void S(so_compute_sigma)(const so_geom *g, const R *lam, const C *u, C *sg, const R *ta, C *tmp, double rho)
+{
+	const long n = g->sizeh;
+	static const int perp[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
+	const C irho = I * (R) rho;
+	for (int d3 = g->d3_halo; d3 < g->nd[3] - g->d3_halo; d3++)
+		for (int d2 = 0; d2 < g->nd[2]; d2++)
+			for (int d1 = 0; d1 < g->nd[1]; d1++)
+				for (int d0 = 0; d0 < g->nd[0]; d0++) {
+					const int x[4] = { d0, d1, d2, d3 };
+					const long idxh = so_snum(g, d0, d1, d2, d3);
+					const int p = (d0 + d1 + d2 + d3) % 2;
+					for (int mu = 0; mu < 4; mu++) {
+						const int k = 2 * mu + p;
+						C q[3][3], q2[3][3], f[3], b1[3], b2[3], e[3][3], s[3][3], res[3][3];
+						S(so_q_from_qa)(ta + (long) k * 8 * n, n, idxh, q);
+						S(so_ch_coeffs)(q, f, b1, b2);
+						S(so_mm)(q, q, q2);
+						for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) e[r][c] = (r == c ? f[0] : 0) + f[1] * q[r][c] + f[2] * q2[r][c];
+						e[2][0] = CONJ(e[0][1] * e[1][2] - e[0][2] * e[1][1]);      /* third row rebuilt (:642-644) */
+						e[2][1] = CONJ(e[0][2] * e[1][0] - e[0][0] * e[1][2]);
+						e[2][2] = CONJ(e[0][0] * e[1][1] - e[0][1] * e[1][0]);
+						for (int t = 0; t < 9; t++) { s[t / 3][t % 3] = sg[((long) k * 9 + t) * n + idxh]; tmp[((long) k * 9 + t) * n + idxh] = e[t / 3][t % 3]; }
+						S(so_mm)(s, e, res);
+						C lmu[3][3]; S(so_herm_from_thmat)(lam + (long) k * 8 * n, n, idxh, lmu);
+						for (int it = 0; it < 3; it++) {
+							const int nu = perp[mu][it];
+							const long ipmu = S(so_shift)(g, x, mu, 1, nu, 0), ipnu = S(so_shift)(g, x, mu, 0, nu, 1);
+							const long imnu = S(so_shift)(g, x, mu, 0, nu, -1), ipmumnu = S(so_shift)(g, x, mu, 1, nu, -1);
+							C a[3][3], b[3][3], c[3][3], ab[3][3], abc[3][3], l1[3][3], l2[3][3], t1[3][3], t2[3][3];
+							/* right */
+							S(so_load_link)(u + (long) (2 * nu + !p) * 9 * n, n, ipmu, a);
+							S(so_load_link)(u + (long) (2 * mu + !p) * 9 * n, n, ipnu, b); S(so_dagger)(b);
+							S(so_load_link)(u + (long) (2 * nu + p) * 9 * n, n, idxh, c); S(so_dagger)(c);
+							S(so_mm)(a, b, ab); S(so_mm)(ab, c, abc);
+							S(so_herm_from_thmat)(lam + (long) (2 * nu + p) * 8 * n, n, idxh, l1);             /* E = L_nu(x) */
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) l2[r][cc] = lmu[r][cc] - l1[r][cc];
+							S(so_mm)(abc, l2, t1);
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) res[r][cc] += irho * t1[r][cc];
+							S(so_herm_from_thmat)(lam + (long) (2 * nu + !p) * 8 * n, n, ipmu, l1);            /* F = L_nu(x+mu) */
+							S(so_mm)(l1, abc, t1);
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) res[r][cc] += irho * t1[r][cc];
+							S(so_herm_from_thmat)(lam + (long) (2 * mu + !p) * 8 * n, n, ipnu, l1);            /* G = L_mu(x+nu) */
+							S(so_mm)(ab, l1, t1); S(so_mm)(t1, c, t2);
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) res[r][cc] -= irho * t2[r][cc];
+							/* left */
+							S(so_load_link)(u + (long) (2 * nu + p) * 9 * n, n, ipmumnu, a); S(so_dagger)(a);
+							S(so_load_link)(u + (long) (2 * mu + !p) * 9 * n, n, imnu, b); S(so_dagger)(b);
+							S(so_load_link)(u + (long) (2 * nu + !p) * 9 * n, n, imnu, c);
+							S(so_mm)(a, b, ab); S(so_mm)(ab, c, abc);
+							S(so_herm_from_thmat)(lam + (long) (2 * nu + !p) * 8 * n, n, imnu, l1);            /* G = L_nu(x-nu) */
+							S(so_herm_from_thmat)(lam + (long) (2 * mu + !p) * 8 * n, n, imnu, l2);            /* E = L_mu(x-nu) */
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) l1[r][cc] -= l2[r][cc];
+							S(so_mm)(ab, l1, t1); S(so_mm)(t1, c, t2);
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) res[r][cc] += irho * t2[r][cc];
+							S(so_mm)(abc, lmu, t1);                                                              /* D = L_mu(x) */
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) res[r][cc] += irho * t1[r][cc];
+							S(so_herm_from_thmat)(lam + (long) (2 * nu + p) * 8 * n, n, ipmumnu, l1);          /* F = L_nu(x+mu-nu) */
+							S(so_mm)(a, l1, t1); S(so_mm)(t1, b, t2); S(so_mm)(t2, c, t1);
+							for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) res[r][cc] -= irho * t1[r][cc];
+						}
+						for (int t = 0; t < 9; t++) sg[((long) k * 9 + t) * n + idxh] = res[t / 3][t % 3];
+					}
+				}
+}

@@ -35,6 +35,11 @@ def golden_stout():
     return dict(np.load(os.path.join(GOLDEN_DIR, "ref_stout_4x4x4x4_r1.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_stoutforce():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ref_stoutforce_4x4x4x4_r1.npz")))
+
+
 def relerr(a, b):
     """max |a-b| / max |b| -- the relative error used for every parity statement."""
     a = np.asarray(a); b = np.asarray(b)

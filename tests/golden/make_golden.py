@@ -143,6 +143,27 @@ def stout_single(n=(4, 4, 4, 4)):
     print("stout", n, float(np.abs(ta).max()))
 
 
+def stoutforce_single(n=(4, 4, 4, 4)):
+    """Sigma' -> Sigma through one stout level (stouting.c:171-1305) on the 4^4 fixture: Q from stout_single(),
+    a random gl(3) Sigma' as the force arriving from the level above."""
+    R = RefLib(*n)
+    g = dict(np.load(os.path.join(HERE, "ref_%dx%dx%dx%d_r1.npz" % n)))
+    gs = dict(np.load(os.path.join(HERE, "ref_stout_%dx%dx%dx%d_r1.npz" % n)))
+    u, ta, rho = g["u"], gs["tipdot"], float(gs["rho"])
+    rng = np.random.default_rng(91)
+    sp = rng.standard_normal((8, 3, 3, R.sizeh)) + 1j * rng.standard_normal((8, 3, 3, R.sizeh))
+    d = {"sigma_prime": sp, "rho": rho}
+    lam, tmp = R.compute_lambda(sp, u, ta)
+    d["lambda"] = lam; d["lambda_tmp"] = tmp
+    sg = sp.copy(); tmp2 = R.compute_sigma(lam, u, sg, ta, rho)
+    d["sigma"] = sg; d["sigma_tmp"] = tmp2
+    uf, taf, spf = u.astype(np.complex64), gs["tipdot_f"], sp.astype(np.complex64)
+    lamf, _ = R.compute_lambda(spf, uf, taf); d["lambda_f"] = lamf
+    sgf = spf.copy(); R.compute_sigma(lamf, uf, sgf, taf, rho); d["sigma_f"] = sgf
+    np.savez_compressed(os.path.join(HERE, "ref_stoutforce_%dx%dx%dx%d_r1.npz" % n), **d)
+    print("stoutforce", n, float(np.abs(lam).max()), float(np.abs(sg).max()))
+
+
 def io_single(n=(4, 4, 4, 4)):
     """On-disk formats (io.c): the reference writes the 4^4 fixture's links as ASCII and as ILDG, and reads both
     files back; the file bytes and the read-back arrays are the fixture."""
@@ -206,7 +227,7 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "io"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io"]
     if "single" in which:
         single_rank()
     if "multi" in which:
@@ -217,5 +238,7 @@ if __name__ == "__main__":
         force_single()
     if "stout" in which:
         stout_single()
+    if "stoutforce" in which:
+        stoutforce_single()
     if "io" in which:
         io_single()

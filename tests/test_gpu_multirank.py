@@ -110,6 +110,17 @@ def _worker(rank, world, port, loc, mode, q):
         lat.stout_wrapper(du, arr, 0)
         got = arr.cpu().numpy()
         errs["stout"] = max(_relerr(got[l][:, :2], S.scatter_conf(rank, wantst[l])[:, :2]) for l in range(2))   # halos included
+        # ---- stouted force chain Sigma' -> Sigma with its four border exchanges (fermion_force.c:52-163)
+        spg = gaussian_vec(G.sizeh, 6, n=24).reshape(8, 3, 3, G.sizeh).copy()
+        tag = G.stout_isotropic(u, 0.15)[3]
+        lamg, _ = G.compute_lambda(spg, u, tag)
+        sgg = spg.copy(); G.compute_sigma(lamg, u, sgg, tag, 0.15)
+        lat.set_stout(0.15, 1)
+        dsg = lat.to_device(S.scatter_conf(rank, spg))
+        lat.compute_sigma_from_sigma_prime_backinto_sigma_prime(dsg, lat.new_tamat(), lat.new_tamat(), du, lat.new_conf(), 0)
+        wsg = S.scatter_conf(rank, sgg)
+        flo, fhi = (S.d3_halo - 1) * S.vol3h, (S.d3_halo + loc[3] + 1) * S.vol3h      # interior + the exchanged halo slice
+        errs["stout_force"] = _relerr(dsg.cpu().numpy()[..., flo:fhi], wsg[..., flo:fhi])
         lat.shutdown_multidev()
         dist.destroy_process_group()
         q.put((rank, errs, ""))
@@ -134,7 +145,7 @@ def _run(world, loc, mode):
     for rank, errs, tb in sorted(res):
         assert tb == "", tb
         assert errs["su3_borders_rows01"] == 0.0 and errs["fermion_borders"] == 0.0, (rank, errs)
-        for k in ("acc_Doe", "acc_Deo", "mdagm", "force", "stout"):
+        for k in ("acc_Doe", "acc_Deo", "mdagm", "force", "stout", "stout_force"):
             assert errs[k] < 1e-13, (rank, k, errs)
         assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)

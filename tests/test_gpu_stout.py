@@ -88,3 +88,53 @@ def test_stout_properties_32(osb):
     o1, o2 = lat.new_vec(), lat.new_vec()
     lat.acc_Deo(u, o1, v, ph); lat.acc_Deo(up, o2, v, ph)
     assert float((o1 - o2).abs().max()) > 1e-2
+
+
+# ----------------------------------------------------------------------------- force side: Sigma' -> Sigma
+def _thmat(lat, single=False):
+    return lat.new_tamat(single=single)          # thmat_soa[8] has the tamat packing (struct_c_def.h:45-58)
+
+
+@pytest.mark.parametrize("rho", [0.15, 2e-3])
+@pytest.mark.parametrize("loc_n", [(8, 8, 8, 8), (8, 4, 6, 10)])
+def test_stout_force_vs_oracle(osb, loc_n, rho):
+    from oracle.pyoracle import gaussian_vec
+    lat = osb.Lattice(loc_n); S = Restatement(*loc_n); n = S.sizeh
+    u = random_su3_conf(n, 62)
+    sp = gaussian_vec(n, 63, n=24).reshape(8, 3, 3, n).copy()
+    ta = S.stout_isotropic(u, rho)[3]
+    wlam, wtmp = S.compute_lambda(sp, u, ta)
+    wsg = sp.copy(); wtmp2 = S.compute_sigma(wlam, u, wsg, ta, rho)
+    lat.set_stout(rho, 1)
+    du, dsp, dta = lat.to_device(u), lat.to_device(sp), lat.to_device(ta)
+    lam, tmp = _thmat(lat), lat.new_conf()
+    lat.compute_lambda(lam, dsp, du, dta, tmp)
+    assert relerr(lam.cpu().numpy(), wlam) < 1e-13 and relerr(tmp.cpu().numpy(), wtmp) < 1e-13
+    lat.compute_sigma(lat.to_device(wlam), du, dsp, dta, tmp, 0)
+    assert relerr(dsp.cpu().numpy(), wsg) < 1e-13 and relerr(tmp.cpu().numpy(), wtmp2) < 1e-13
+    # the whole chain of fermion_force.c:52-163 from U and Sigma' alone
+    sg, lam2, qa, tmp3 = lat.to_device(sp), _thmat(lat), lat.new_tamat(), lat.new_conf()
+    lat.compute_sigma_from_sigma_prime_backinto_sigma_prime(sg, lam2, qa, du, tmp3, 0)
+    assert relerr(qa.cpu().numpy(), ta) < 1e-13 and relerr(lam2.cpu().numpy(), wlam) < 1e-13
+    assert relerr(sg.cpu().numpy(), wsg) < 1e-13
+
+
+def test_stout_force_vs_golden(osb, golden_r1, golden_stout, golden_stoutforce):
+    g, gs, gf = golden_r1, golden_stout, golden_stoutforce
+    lat = osb.Lattice((4, 4, 4, 4))
+    lat.set_stout(float(gf["rho"]), 1)
+    du, dta = lat.to_device(g["u"]), lat.to_device(gs["tipdot"])
+    lam, tmp = _thmat(lat), lat.new_conf()
+    lat.compute_lambda(lam, lat.to_device(gf["sigma_prime"]), du, dta, tmp)
+    assert relerr(lam.cpu().numpy(), gf["lambda"]) < 1e-13 and relerr(tmp.cpu().numpy(), gf["lambda_tmp"]) < 1e-13
+    sg = lat.to_device(gf["sigma_prime"])
+    lat.compute_sigma(lat.to_device(gf["lambda"]), du, sg, dta, tmp, 0)
+    assert relerr(sg.cpu().numpy(), gf["sigma"]) < 1e-13 and relerr(tmp.cpu().numpy(), gf["sigma_tmp"]) < 1e-13
+    # FP32 twin (5e-6: the b_ij coefficients are ill-conditioned in float, see tests/test_oracle_vs_reference.py)
+    duf, dtaf = lat.to_device(g["u"].astype(np.complex64)), lat.to_device(gs["tipdot_f"])
+    lamf, tmpf = _thmat(lat, single=True), lat.new_conf(single=True)
+    lat.compute_lambda(lamf, lat.to_device(gf["sigma_prime"].astype(np.complex64)), duf, dtaf, tmpf)
+    assert relerr(lamf.cpu().numpy(), gf["lambda_f"]) < 5e-6
+    sgf = lat.to_device(gf["sigma_prime"].astype(np.complex64))
+    lat.compute_sigma(lat.to_device(gf["lambda_f"]), duf, sgf, dtaf, tmpf, 0)
+    assert relerr(sgf.cpu().numpy(), gf["sigma_f"]) < 5e-6
