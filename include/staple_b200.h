@@ -235,6 +235,14 @@ void acc_Doe_d3c(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const doub
 void acc_Deo_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *backfield, int off3, int thick3);
 void acc_Doe_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, const float_soa *backfield, int off3, int thick3);
 
+/* The operator "with a field" of the magnetic-susceptibility measurement (ref: OpenAcc/field_times_fermion_matrix.c:77-232,
+ * matvecmul.h:176-260): every link's phase e^{i backfield} is multiplied by the complex per-link field field_re + i field_im
+ * (double_soa[8] each, same k = 2*dir+parity indexing).  FP64 only, as in the reference. */
+void acc_Deo_wf_unsafe(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *phases, const double_soa *field_re, const double_soa *field_im);
+void acc_Doe_wf_unsafe(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *phases, const double_soa *field_re, const double_soa *field_im);
+void acc_Deo_wf(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *phases, const double_soa *field_re, const double_soa *field_im);
+void acc_Doe_wf(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *phases, const double_soa *field_re, const double_soa *field_im);
+
 /* out = (m^2 [+shift]) in - Deo Doe in ; temp1 = odd-site scratch.  ref: fermion_matrix.c:723-746 */
 void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars);
 void fermion_matrix_multiplication_shifted(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars, double shift);
@@ -266,7 +274,7 @@ STAPLE_BLAS_DECL(vec3_soa_f, _f)
 /* ------------------------------------------------------------------ precision conversion (ref: OpenAcc/float_double_conv.c:9-150) */
 void convert_float_to_double_vec3_soa(const vec3_soa_f *f_var, vec3_soa *d_var);
 void convert_double_to_float_vec3_soa(const vec3_soa *d_var, vec3_soa_f *f_var);
-void convert_float_to_double_su3_soa(const su3_soa_f *f_var, su3_soa *d_var);   /* one su3_soa; call 8x for a conf */
+void convert_float_to_double_su3_soa(const su3_soa_f *f_var, su3_soa *d_var);   /* all 8 links of a conf, rows r0,r1,r2 (ref: :94-150) */
 void convert_double_to_float_su3_soa(const su3_soa *d_var, su3_soa_f *f_var);
 void convert_float_to_double_real_soa(const float_soa *f_var, double_soa *d_var);
 void convert_double_to_float_real_soa(const double_soa *d_var, float_soa *f_var);
@@ -373,6 +381,42 @@ STAPLE_STOUT_DECL(_f, su3_soa_f, tamat_soa_f)
 																															 const int istopo);                          /* ref: fermion_force.c:52-163 */
 STAPLE_SF_DECL(, su3_soa, tamat_soa, thmat_soa)
 STAPLE_SF_DECL(_f, su3_soa_f, tamat_soa_f, thmat_soa_f)
+
+/* ------------------------------------------------------------------ callers of the path: whole fermion force, even/odd inversion */
+/* The MD fermion force from thin links to the momenta's time derivative (ref: OpenAcc/fermion_force.c:166-357, called by
+ * md_integrator.c:536-715): stout_wrapper -> for every flavour and pseudofermion inverter_multishift_wrapper on approx_md +
+ * ker_openacc_compute_fermion_force, multiply_backfield_times_force per flavour -> Sigma' -> Sigma through every stout
+ * level -> multiply_conf_times_force_and_take_ta_nophase.  Argument list = the reference's with STOUT_FERMIONS defined
+ * (common_defines.h:58).  Globals read like the reference: act_params.stout_steps, inverter_tricks, md_parameters.
+ * recycleInvsForce (the reference's recycle branch exits with "not implemented correctly", so does this), the parking
+ * arrays aux_th / aux_ta (alloc_vars.h:56-57) and conf_acc_f (FP32 links when singlePInvAccelMultiInv is set);
+ * nMdInversionPerformed is incremented.  All are WEAK in the library.  debug_settings diagnostics / dbg prints
+ * (fermion_force.c:325-354) are not part of the path and are not written.  The _f twin (generated sp_fermion_force.c:
+ * 158-300) calls multishift_invert_f directly and takes `float res`. */
+#ifndef MD_PARAMETERS_H
+typedef struct md_param_t {                 /* ref: OpenAcc/md_parameters.h:6-19 */
+	int no_md; int gauge_scale; double t; double residue_metro; double expected_max_eigenvalue; int singlePrecMD;
+	double residue_md; int max_cg_iterations; int recycleInvsForce; int extrapolateInvsForce;
+} md_param;
+extern md_param md_parameters;
+extern int nMdInversionPerformed;
+#endif
+extern thmat_soa *aux_th;
+extern tamat_soa *aux_ta;
+extern thmat_soa_f *aux_th_f;
+extern tamat_soa_f *aux_ta_f;
+extern su3_soa_f *conf_acc_f;
+void fermion_force_soloopenacc(su3_soa *tconf_acc, su3_soa *tstout_conf_acc_arr, su3_soa *gl3_aux, tamat_soa *tipdot_acc,
+															 ferm_param *tfermion_parameters, int tNDiffFlavs, const vec3_soa *ferm_in_acc, double res,
+															 su3_soa *taux_conf_acc, vec3_soa *tferm_shiftmulti_acc, inverter_package ipt, const int max_cg);
+void fermion_force_soloopenacc_f(su3_soa_f *tconf_acc, su3_soa_f *tstout_conf_acc_arr, su3_soa_f *gl3_aux, tamat_soa_f *tipdot_acc,
+																 ferm_param *tfermion_parameters, int tNDiffFlavs, const vec3_soa_f *ferm_in_acc, float res,
+																 su3_soa_f *taux_conf_acc, vec3_soa_f *tferm_shiftmulti_acc, inverter_package ipt, const int max_cg);
+/* Full-lattice solve (D + m) out = in from the even/odd solver (ref: Meas/ferm_meas.c:50-72):
+ * phi_e = m in_e - Deo in_o ; out_e = (M^+M)^-1 phi_e (inverter_wrapper, CONVERGENCE_CRITICAL) ; out_o = (in_o - Doe out_e)/m.
+ * phi_e / phi_o are parking vectors. */
+void eo_inversion(inverter_package ip, ferm_param *tfermions_parameters, double res, int max_cg, vec3_soa *in_e, vec3_soa *in_o,
+									vec3_soa *out_e, vec3_soa *out_o, vec3_soa *phi_e, vec3_soa *phi_o);
 
 /* ------------------------------------------------------------------ introspection for benches/tests */
 /* statistics of the last multishift_invert[_f] call: iterations, sum over iterations of active

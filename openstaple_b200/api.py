@@ -94,6 +94,12 @@ class ActionParam(C.Structure):         # OpenAcc/action.h:6-18
                 ("topo_stout_steps", C.c_int), ("topo_rho", C.c_double)]
 
 
+class MdParam(C.Structure):             # OpenAcc/md_parameters.h:6-19
+    _fields_ = [("no_md", C.c_int), ("gauge_scale", C.c_int), ("t", C.c_double), ("residue_metro", C.c_double),
+                ("expected_max_eigenvalue", C.c_double), ("singlePrecMD", C.c_int), ("residue_md", C.c_double),
+                ("max_cg_iterations", C.c_int), ("recycleInvsForce", C.c_int), ("extrapolateInvsForce", C.c_int)]
+
+
 class InvTricks(C.Structure):           # Include/inverter_tricks.h:4-11
     _fields_ = [("singlePInvAccelMultiInv", C.c_int), ("useMixedPrecision", C.c_int),
                 ("mixedPrecisionDelta", C.c_double), ("restartingEvery", C.c_int)]
@@ -300,6 +306,16 @@ class Lattice:
     def acc_Deo_d3m(self, u, out, inp, backfield): self._dslash("acc_Deo_d3m", u, out, inp, backfield)
     def acc_Doe_d3m(self, u, out, inp, backfield): self._dslash("acc_Doe_d3m", u, out, inp, backfield)
 
+    # ---- operator "with a field" (OpenAcc/field_times_fermion_matrix.h:20-50), FP64 only
+    def _dslash_wf(self, name, u, out, inp, phases, field_re, field_im):
+        f = getattr(self.L, name); f.argtypes = [C.c_void_p] * 6; f.restype = None
+        f(_addr(u), _addr(out), _addr(inp), _addr(phases), _addr(field_re), _addr(field_im))
+
+    def acc_Deo_wf(self, u, out, inp, phases, field_re, field_im): self._dslash_wf("acc_Deo_wf", u, out, inp, phases, field_re, field_im)
+    def acc_Doe_wf(self, u, out, inp, phases, field_re, field_im): self._dslash_wf("acc_Doe_wf", u, out, inp, phases, field_re, field_im)
+    def acc_Deo_wf_unsafe(self, u, out, inp, phases, field_re, field_im): self._dslash_wf("acc_Deo_wf_unsafe", u, out, inp, phases, field_re, field_im)
+    def acc_Doe_wf_unsafe(self, u, out, inp, phases, field_re, field_im): self._dslash_wf("acc_Doe_wf_unsafe", u, out, inp, phases, field_re, field_im)
+
     def acc_Deo_d3c(self, u, out, inp, backfield, off3, thick3):
         getattr(self.L, "acc_Deo_d3c" + _sfx(inp))(_addr(u), _addr(out), _addr(inp), _addr(backfield), off3, thick3)
 
@@ -444,10 +460,11 @@ class Lattice:
     def convert_float_to_double_vec3_soa(self, f, d): self.L.convert_float_to_double_vec3_soa(_addr(f), _addr(d))
 
     def convert_double_to_float_su3_soa(self, d, f):
-        """whole conf[8] (the reference converts one su3_soa per call)."""
-        sd, sf = 9 * self.sizeh * 16, 9 * self.sizeh * 8
-        for k in range(8):
-            self.L.convert_double_to_float_su3_soa(_addr(d) + k * sd, _addr(f) + k * sf)
+        """whole conf[8] in one call, like the reference (float_double_conv.c:122-150)."""
+        self.L.convert_double_to_float_su3_soa(_addr(d), _addr(f))
+
+    def convert_float_to_double_su3_soa(self, f, d):
+        self.L.convert_float_to_double_su3_soa(_addr(f), _addr(d))
 
     def convert_double_to_float_real_soa(self, d, f):
         for k in range(8):
@@ -510,6 +527,47 @@ class Lattice:
         f.restype = C.c_int
         return f(ip, C.addressof(pars), _addr(out), _addr(inp), float(res), int(max_cg), float(shift),
                  int(convergence_importance))
+
+    # ---- callers of the path: whole MD fermion force (OpenAcc/fermion_force.h:23-37), eo_inversion (Meas/ferm_meas.h)
+    def ferm_param_array(self, flavours):
+        """ferm_param[nflav] as fermion_force_soloopenacc walks it; flavours: list of dict(mass, phases, phases_f,
+        number_of_ps, first_ps, ra_a, ra_b) with approx_md = (ra_a, ra_b)."""
+        arr = (FermParam * len(flavours))()
+        for p, fl in zip(arr, flavours):
+            p.ferm_mass = fl["mass"]; p.degeneracy = 1; p.name = b"flavour"
+            p.number_of_ps = fl.get("number_of_ps", 1); p.index_of_the_first_ps = fl.get("first_ps", 0)
+            p.phases = _addr(fl.get("phases")); p.phases_f = _addr(fl.get("phases_f"))
+            p.approx_md.approx_order = len(fl["ra_b"])
+            for i, (a, b) in enumerate(zip(fl["ra_a"], fl["ra_b"])):
+                p.approx_md.RA_a[i] = a; p.approx_md.RA_b[i] = b
+        self._keep.append((arr, flavours))
+        return arr
+
+    def set_force_globals(self, aux_th=None, aux_ta=None, conf_acc_f=None, single=False, recycleInvsForce=0):
+        """the parking arrays fermion_force_soloopenacc takes from alloc_vars (aux_th, aux_ta [+_f], conf_acc_f) and
+        md_parameters.recycleInvsForce -- the library's weak globals."""
+        sfx = "_f" if single else ""
+        for name, arr in (("aux_th" + sfx, aux_th), ("aux_ta" + sfx, aux_ta), ("conf_acc_f", conf_acc_f)):
+            if arr is not None:
+                C.c_void_p.in_dll(self.L, name).value = _addr(arr)
+        MdParam.in_dll(self.L, "md_parameters").recycleInvsForce = recycleInvsForce
+        self._keep.append((aux_th, aux_ta, conf_acc_f))
+
+    def fermion_force_soloopenacc(self, tconf_acc, tstout_conf_acc_arr, gl3_aux, tipdot_acc, tfermion_parameters, tNDiffFlavs,
+                                  ferm_in_acc, res, taux_conf_acc, tferm_shiftmulti_acc, ipt, max_cg):
+        single = _sfx(tconf_acc) == "_f"
+        f = getattr(self.L, "fermion_force_soloopenacc" + ("_f" if single else ""))
+        f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_float if single else C.c_double, C.c_void_p, C.c_void_p,
+                                         InverterPackage, C.c_int]
+        f.restype = None
+        f(_addr(tconf_acc), _addr(tstout_conf_acc_arr), _addr(gl3_aux), _addr(tipdot_acc), C.addressof(tfermion_parameters),
+          int(tNDiffFlavs), _addr(ferm_in_acc), float(res), _addr(taux_conf_acc), _addr(tferm_shiftmulti_acc), ipt, int(max_cg))
+
+    def eo_inversion(self, ip, pars, res, max_cg, in_e, in_o, out_e, out_o, phi_e, phi_o):
+        f = self.L.eo_inversion
+        f.argtypes = [InverterPackage, C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 6; f.restype = None
+        f(ip, C.addressof(pars), float(res), int(max_cg), _addr(in_e), _addr(in_o), _addr(out_e), _addr(out_o),
+          _addr(phi_e), _addr(phi_o))
 
     def set_sp_globals(self, aux1_f, ferm_shiftmulti_acc_f):
         self._keep.append((aux1_f, ferm_shiftmulti_acc_f))

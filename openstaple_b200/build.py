@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstaple_b200.so")
-SOURCES = ["staple_core.cu", "staple_kernels.cu", "staple_solvers.cu", "staple_force.cu", "staple_stout.cu", "staple_stout_force.cu"]
+SOURCES = ["staple_core.cu", "staple_kernels.cu", "staple_solvers.cu", "staple_force.cu", "staple_stout.cu", "staple_stout_force.cu", "staple_callers.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

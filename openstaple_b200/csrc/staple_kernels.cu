@@ -646,6 +646,100 @@ template void launch_dslash<float>(int, int, const float2 *, float2 *, const flo
 																	 const float2 *, double, int, int, int, unsigned int, unsigned int, const int *,
 																	 cudaStream_t, int);
 
+// ------------------------------------------------------------------ operator "with a field" (magnetic susceptibility)
+// field_times_fermion_matrix.c:77-196 with matvecmul.h:176-260: the same stencil with every link's U(1) phase multiplied by a
+// complex per-link field (field_re + i field_im)[k][idx_mat] -- "not in U(1) anymore".  FP64 only (the reference generates
+// no _f twin).  Algorithmic bytes per site: 928 + 8 x 16 (the field) = 1056.  A measurement-side sibling of the hot kernel,
+// kept out of dslash_kernel so that the hot instantiations stay exactly as tuned.
+template <bool DAG>
+__device__ __forceinline__ void hop_wf(double2 acc[3], const double2 *__restrict__ uk, const double *__restrict__ phk,
+																			 const double *__restrict__ frk, const double *__restrict__ fik, unsigned int im,
+																			 const double2 *__restrict__ in, unsigned int iv, long n)
+{
+	using C = double2;
+	const double th = ld_stream(phk + im), fr = ld_stream(frk + im), fi = ld_stream(fik + im);
+	const C m00 = ld_stream(uk + im), m01 = ld_stream(uk + n + im), m02 = ld_stream(uk + 2 * n + im);
+	const C m10 = ld_stream(uk + 3 * n + im), m11 = ld_stream(uk + 4 * n + im), m12 = ld_stream(uk + 5 * n + im);
+	const C v0 = ld_cached(in + iv), v1 = ld_cached(in + n + iv), v2 = ld_cached(in + 2 * n + iv);
+	double s, c;
+	sincos_t(th, &s, &c);
+	const C ph = cmul(mk<double>(c, s), mk<double>(fr, fi));      // matvecmul.h:188-189
+	const C x0 = cross(m01, m12, m02, m11);
+	const C x1 = cross(m02, m10, m00, m12);
+	const C x2 = cross(m00, m11, m01, m10);
+	if (!DAG) {
+		const C w0 = cmul(v0, ph), w1 = cmul(v1, ph), w2 = cmul(v2, ph);
+		cfma(acc[0], m00, w0); cfma(acc[0], m01, w1); cfma(acc[0], m02, w2);
+		cfma(acc[1], m10, w0); cfma(acc[1], m11, w1); cfma(acc[1], m12, w2);
+		cfma_ca(acc[2], x0, w0); cfma_ca(acc[2], x1, w1); cfma_ca(acc[2], x2, w2);
+	} else {
+		const C p = mk<double>(-ph.x, ph.y);                        // -conj(phase): backward hops are subtracted
+		const C w0 = cmul(v0, p), w1 = cmul(v1, p), w2 = cmul(v2, p);
+		cfma_ca(acc[0], m00, w0); cfma_ca(acc[0], m10, w1); cfma(acc[0], x0, w2);
+		cfma_ca(acc[1], m01, w0); cfma_ca(acc[1], m11, w1); cfma(acc[1], x1, w2);
+		cfma_ca(acc[2], m02, w0); cfma_ca(acc[2], m12, w1); cfma(acc[2], x2, w2);
+	}
+}
+
+struct DslashWfArgs {
+	const double2 *u, *in; double2 *out;
+	const double *ph, *fre, *fim;
+	long site_lo, nsites, sizeh, vol3h;
+	int nd0h, nd1, nd2, nd3;
+};
+
+template <int PAR>
+__global__ void __launch_bounds__(kBlock) dslash_wf_kernel(const DslashWfArgs a)
+{
+	using C = double2;
+	const unsigned int t = blockIdx.x * kBlock + threadIdx.x;
+	if (t >= (unsigned int) a.nsites) return;
+	const unsigned int idx = (unsigned int) a.site_lo + t;
+	const long n = a.sizeh;
+	const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
+	const unsigned int hd0 = idx % nd0h;
+	unsigned int q = idx / nd0h;
+	const unsigned int d1 = q % nd1; q /= nd1;
+	const unsigned int d2 = q % nd2;
+	const unsigned int d3 = q / nd2;
+	const unsigned int rp = (d1 + d2 + d3 + PAR) & 1u;
+	const unsigned int s1 = nd0h, s2 = nd0h * nd1, s3 = (unsigned int) a.vol3h;
+	const unsigned int i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
+	const unsigned int i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
+	const unsigned int i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
+	const unsigned int i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
+	const unsigned int i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
+	const unsigned int i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
+	const unsigned int i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
+	const unsigned int i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
+	C acc[3];
+	acc[0] = mk<double>(0, 0); acc[1] = mk<double>(0, 0); acc[2] = mk<double>(0, 0);
+	const long un = 9 * n;
+#define STAPLE_WF(DAG, K, IM, IV) hop_wf<DAG>(acc, a.u + (K) * un, a.ph + (K) * n, a.fre + (K) * n, a.fim + (K) * n, IM, a.in, IV, n)
+	STAPLE_WF(true, 1 - PAR, i0m, i0m); STAPLE_WF(true, 3 - PAR, i1m, i1m);        // field_times_fermion_matrix.c:104-111
+	STAPLE_WF(true, 5 - PAR, i2m, i2m); STAPLE_WF(true, 7 - PAR, i3m, i3m);
+	STAPLE_WF(false, 0 + PAR, idx, i0p); STAPLE_WF(false, 2 + PAR, idx, i1p);      // :117-124
+	STAPLE_WF(false, 4 + PAR, idx, i2p); STAPLE_WF(false, 6 + PAR, idx, i3p);
+#undef STAPLE_WF
+#pragma unroll
+	for (int c = 0; c < 3; c++) a.out[c * n + idx] = mk<double>(acc[c].x * 0.5, acc[c].y * 0.5);   // :128-130
+}
+
+static void launch_dslash_wf(int par, const double2 *u, double2 *out, const double2 *in, const double *ph, const double *fre,
+														 const double *fim)
+{
+	const Geom &g = ctx().g;
+	DslashWfArgs a;
+	a.u = u; a.in = in; a.out = out; a.ph = ph; a.fre = fre; a.fim = fim;
+	a.site_lo = (long) g.d3_halo * g.vol3h; a.nsites = (long) g.loc_n3 * g.vol3h; a.sizeh = g.sizeh; a.vol3h = g.vol3h;
+	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3;
+	const unsigned int grid = dslash_blocks(g.d3_halo, g.d3_halo + g.loc_n3);
+	if (par == 0) dslash_wf_kernel<0><<<grid, kBlock, 0, ctx().stream>>>(a);
+	else dslash_wf_kernel<1><<<grid, kBlock, 0, ctx().stream>>>(a);
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch();
+}
+
 // ------------------------------------------------------------------ BLAS-1 element-wise kernels
 // All arithmetic in double with double factors, stored back in T: this is what the reference's FP32
 // twin does too (float complex * double promotes; double_to_single_transformer.py leaves
@@ -903,6 +997,21 @@ void acc_Doe_d3c_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, co
 	launch_dslash<float>(1, EPI_NONE, CDF(u), DF(out), CDF(in), (const float *) dev(bf, "backfield"), nullptr, 0.0, off3, off3 + thick3, -1, 0, 0, nullptr, ctx().stream);
 }
 
+// field_times_fermion_matrix.c:77-232
+#define STAPLE_WF_DEF(NAME, PAR, EXCHANGE)                                                                                    \
+	void NAME(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const double_soa *phases, const double_soa *field_re,        \
+						const double_soa *field_im)                                                                                       \
+	{                                                                                                                           \
+		require_init(#NAME);                                                                                                      \
+		launch_dslash_wf(PAR, CDD(u), DD(out), CDD(in), (const double *) dev(phases, "phases"),                                   \
+										 (const double *) dev(field_re, "field_re"), (const double *) dev(field_im, "field_im"));                 \
+		if (EXCHANGE && ctx().nranks > 1) communicate_fermion_borders(out);                                                       \
+	}
+STAPLE_WF_DEF(acc_Deo_wf_unsafe, 0, false)
+STAPLE_WF_DEF(acc_Doe_wf_unsafe, 1, false)
+STAPLE_WF_DEF(acc_Deo_wf, 0, true)
+STAPLE_WF_DEF(acc_Doe_wf, 1, true)
+
 // deo_doe_test.c's host round trip (update device; acc_Doe; acc_Deo; update host) pipelined over d3 chunks.
 // Chunk k of Doe reads `in` chunks k-1,k,k+1 (periodic), chunk k of Deo reads the Doe output of k-1,k,k+1: both
 // are issued on the compute stream as soon as the last chunk they depend on has been uploaded / computed, and
@@ -1153,9 +1262,9 @@ void convert_float_to_double_vec3_soa(const vec3_soa_f *f, vec3_soa *d)
 void convert_double_to_float_vec3_soa(const vec3_soa *d, vec3_soa_f *f)
 { require_init("convert_double_to_float_vec3_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 6 * ctx().g.sizeh); }
 void convert_float_to_double_su3_soa(const su3_soa_f *f, su3_soa *d)
-{ require_init("convert_float_to_double_su3_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 18 * ctx().g.sizeh); }
+{ require_init("convert_float_to_double_su3_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 8 * 18 * ctx().g.sizeh); }
 void convert_double_to_float_su3_soa(const su3_soa *d, su3_soa_f *f)
-{ require_init("convert_double_to_float_su3_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 18 * ctx().g.sizeh); }
+{ require_init("convert_double_to_float_su3_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 8 * 18 * ctx().g.sizeh); }
 void convert_float_to_double_real_soa(const float_soa *f, double_soa *d)
 { require_init("convert_float_to_double_real_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), ctx().g.sizeh); }
 void convert_double_to_float_real_soa(const double_soa *d, float_soa *f)

@@ -36,7 +36,7 @@ CF="-O3 -std=gnu99 -fcommon -w -fPIC -I$HERE/mpi_stub -I$SCR/src -DACTION_TYPE=T
 SRCS="OpenAcc/fermion_matrix OpenAcc/sp_fermion_matrix OpenAcc/fermionic_utilities OpenAcc/sp_fermionic_utilities
  OpenAcc/inverter_multishift_full OpenAcc/sp_inverter_multishift_full OpenAcc/inverter_full OpenAcc/sp_inverter_full
  OpenAcc/inverter_mixedp OpenAcc/inverter_package OpenAcc/inverter_wrappers OpenAcc/float_double_conv OpenAcc/geometry
- OpenAcc/find_min_max OpenAcc/io OpenAcc/stouting OpenAcc/sp_stouting OpenAcc/plaquettes OpenAcc/sp_plaquettes OpenAcc/su3_utilities OpenAcc/sp_su3_utilities OpenAcc/fermion_force_utilities OpenAcc/sp_fermion_force_utilities OpenAcc/backfield OpenAcc/sp_backfield OpenAcc/backfield_parameters
+ OpenAcc/find_min_max OpenAcc/io OpenAcc/stouting OpenAcc/sp_stouting OpenAcc/plaquettes OpenAcc/sp_plaquettes OpenAcc/su3_utilities OpenAcc/sp_su3_utilities OpenAcc/fermion_force_utilities OpenAcc/sp_fermion_force_utilities OpenAcc/backfield OpenAcc/sp_backfield OpenAcc/backfield_parameters OpenAcc/fermion_force OpenAcc/sp_fermion_force OpenAcc/field_times_fermion_matrix Meas/ferm_meas
  RationalApprox/rationalapprox tests_and_benchmarks/test_and_benchmarks Mpi/multidev Mpi/communications Mpi/sp_communications Include/inverter_tricks"
 pids=()
 for f in $SRCS; do

@@ -252,6 +252,73 @@ class RefLib:
         getattr(self.lib, "compute_sigma" + self._sfx(u))(ptr(lam), ptr(u), ptr(sg), ptr(ta), ptr(tmp), C.c_int(0))
         return tmp
 
+    # --- the callers of the path: whole fermion force (fermion_force.c:166-357), eo_inversion (Meas/ferm_meas.c:50-72)
+    def _package(self, u, nshifts, single_too=False, u_f=None):
+        """inverter_package with scratch vectors (kept alive on self); -> None (the shim holds the package)"""
+        n = self.sizeh
+        d = [np.zeros((3, n), np.complex128) for _ in range(4)]
+        st = np.zeros((max(nshifts, 1), 3, n), np.complex128)
+        self._ip_keep = [d, st]
+        self.lib.ref_ip_dp(ptr(u), ptr(st), C.c_int(nshifts), *[ptr(x) for x in d])
+        f = [np.zeros((3, n), np.complex64) for _ in range(5)]
+        st_f = np.zeros((max(nshifts, 1), 3, n), np.complex64)
+        self._ip_keep += [f, st_f, u_f]
+        self.lib.ref_ip_sp(ptr(u_f), ptr(st_f), C.c_int(nshifts), *[ptr(x) for x in f])
+
+    def _flavours(self, flavours, single):
+        """flavours: list of dict(mass, ph, number_of_ps, first_ps, ra_a, ra_b) -> ferm_param[nflav]"""
+        self.lib.ref_ferm_param_array_new.restype = C.c_void_p
+        arr = C.c_void_p(self.lib.ref_ferm_param_array_new(C.c_int(len(flavours))))
+        self._fl_keep = []
+        for i, fl in enumerate(flavours):
+            a = np.ascontiguousarray(fl["ra_a"], np.float64); b = np.ascontiguousarray(fl["ra_b"], np.float64)
+            ph = np.ascontiguousarray(fl["ph"], np.float32 if single else np.float64)
+            self._fl_keep += [a, b, ph]
+            self.lib.ref_ferm_param_array_set(arr, C.c_int(i), C.c_double(fl["mass"]), None if single else ptr(ph),
+                                              ptr(ph) if single else None, C.c_int(fl["number_of_ps"]),
+                                              C.c_int(fl["first_ps"]), C.c_int(len(a)), ptr(a), ptr(b))
+        return arr
+
+    def fermion_force(self, u, flavours, ferm_in, res, max_cg, rho, steps):
+        """fermion_force_soloopenacc[_f] (dtype of u selects): -> (ipdot tamat [8,8,sizeh], gl3_aux, stout levels)"""
+        single = u.dtype == np.complex64
+        cd = u.dtype; rd = np.float32 if single else np.float64
+        n = self.sizeh
+        self._stout_globals(rho, steps, u)
+        th, ta = np.zeros((8, 8, n), rd), np.zeros((8, 8, n), rd)
+        a = (None, None, ptr(th), ptr(ta), None) if single else (ptr(th), ptr(ta), None, None, None)
+        self.lib.ref_set_force_globals(*a)
+        nsh = max(len(fl["ra_b"]) for fl in flavours)
+        if single:
+            self._package(np.zeros_like(u, dtype=np.complex128), nsh, u_f=u)
+        else:
+            self._package(u, nsh)
+        pars = self._flavours(flavours, single)
+        stout = np.zeros((max(steps, 1),) + u.shape, cd)
+        gl3, taux = np.zeros_like(u), np.zeros_like(u)
+        ipdot = np.zeros((8, 8, n), rd)
+        shiftmulti = np.zeros((nsh, 3, n), cd)
+        ferm_in = np.ascontiguousarray(ferm_in, cd)
+        fn = self.lib.ref_fermion_force_f if single else self.lib.ref_fermion_force
+        fn(ptr(u), ptr(stout), ptr(gl3), ptr(ipdot), pars, C.c_int(len(flavours)), ptr(ferm_in), C.c_double(res),
+           ptr(taux), ptr(shiftmulti), C.c_int(max_cg))
+        return ipdot, gl3, stout
+
+    def eo_inversion(self, u, ph, mass, in_e, in_o, res, max_cg):
+        """-> (out_e, out_o): (D + m)(out_e, out_o) = (in_e, in_o)"""
+        self._package(u, 1)
+        pars = self.ferm_param(mass, ph)
+        out_e, out_o, phi_e, phi_o = (np.zeros_like(in_e) for _ in range(4))
+        self.lib.ref_eo_inversion(pars, C.c_double(res), C.c_int(max_cg), ptr(in_e), ptr(in_o), ptr(out_e), ptr(out_o),
+                                  ptr(phi_e), ptr(phi_o))
+        return out_e, out_o
+
+    def dslash_wf(self, name, u, inp, ph, fre, fim):
+        """name in acc_Deo_wf, acc_Doe_wf, acc_Deo_wf_unsafe, acc_Doe_wf_unsafe (field_times_fermion_matrix.c)"""
+        out = np.zeros_like(inp)
+        getattr(self.lib, name)(ptr(u), ptr(out), ptr(inp), ptr(ph), ptr(fre), ptr(fim))
+        return out
+
     # --- reductions
     def l2norm2(self, a):
         return getattr(self.lib, "l2norm2_global" + self._sfx(a))(ptr(a))
@@ -422,6 +489,60 @@ class Restatement:
         tmp = np.zeros_like(u)
         getattr(self.lib, "so_compute_sigma" + self._sfx(u))(self.gp(), ptr(lam), ptr(u), ptr(sg), ptr(ta), ptr(tmp), C.c_double(rho))
         return tmp
+
+    def sigma_prime_to_sigma(self, sigma, u, rho):
+        """compute_sigma_from_sigma_prime_backinto_sigma_prime (fermion_force.c:52-163), single rank: staples of U,
+        Q = rho TA(U staples), Lambda from Sigma', Sigma in place.  -> (Lambda, Q)"""
+        rd = np.float32 if u.dtype == np.complex64 else np.float64
+        sfx = self._sfx(u)
+        tmp = np.zeros_like(u); qa = np.zeros((8, 8, self.sizeh), rd)
+        getattr(self.lib, "so_calc_loc_staples_onlyferms" + sfx)(self.gp(), ptr(u), ptr(tmp))
+        getattr(self.lib, "so_rho_times_conf_times_staples_ta_part" + sfx)(self.gp(), ptr(u), ptr(tmp), ptr(qa), C.c_double(rho))
+        lam = np.zeros((8, 8, self.sizeh), rd)
+        getattr(self.lib, "so_compute_lambda" + sfx)(self.gp(), ptr(lam), ptr(sigma), ptr(u), ptr(qa), ptr(tmp))
+        getattr(self.lib, "so_compute_sigma" + sfx)(self.gp(), ptr(lam), ptr(u), ptr(sigma), ptr(qa), ptr(tmp), C.c_double(rho))
+        return lam, qa
+
+    # --- the callers of the path (single rank)
+    def fermion_force(self, u, flavours, ferm_in, res, max_cg, rho, steps):
+        """fermion_force_soloopenacc (fermion_force.c:166-357) from the restated steps, in the reference's order.
+        flavours: list of dict(mass, ph, number_of_ps, first_ps, ra_a, ra_b).  -> (ipdot, gl3_aux, stout levels, [cg])"""
+        rd = np.float32 if u.dtype == np.complex64 else np.float64
+        stout = self.stout_wrapper(u, rho, steps) if steps > 0 else np.zeros((1,) + u.shape, u.dtype)     # :197
+        conf = stout[steps - 1] if steps > 0 else u                                                       # :198-201
+        gl3 = np.zeros_like(u); ipdot = np.zeros((8, 8, self.sizeh), rd); cgs = []
+        for fl in flavours:
+            taux = np.zeros_like(u)                                                                       # :226
+            ph = np.ascontiguousarray(fl["ph"], rd)
+            for ips in range(fl["number_of_ps"]):
+                out, cg, ok, _ = self.multishift_invert(conf, ph, fl["mass"], fl["ra_b"],
+                                                        np.ascontiguousarray(ferm_in[fl["first_ps"] + ips], u.dtype), res, max_cg)
+                cgs.append(cg)
+                self.compute_fermion_force(conf, taux, out, ph, fl["ra_a"])                               # :249
+            self.multiply_backfield_times_force(ph, taux, gl3)                                            # :257
+        for lvl in range(steps, 1, -1):                                                                   # :275-292
+            self.sigma_prime_to_sigma(gl3, stout[lvl - 2], rho)
+        if steps > 0:
+            self.sigma_prime_to_sigma(gl3, u, rho)                                                        # :294-300
+        self.take_ta(u, gl3, ipdot)                                                                       # :306
+        return ipdot, gl3, stout, cgs
+
+    def eo_inversion(self, u, ph, mass, in_e, in_o, res, max_cg, restarting_every=10000):
+        """Meas/ferm_meas.c:50-72 with inverter_wrapper -> ker_invert_openacc (useMixedPrecision = 0)"""
+        phi_e = self.dslash("deo", u, in_o, ph)
+        self.axpy_like("fact1_minus_in2", phi_e, in_e, f1=mass)            # phi_e = m in_e - phi_e
+        out_e, cg, ok = self.cg(u, ph, mass, phi_e, res, max_cg, 0.0, restarting_every)
+        phi_o = self.dslash("doe", u, out_e, ph)
+        out_o = np.zeros_like(in_o)
+        self.axpy_like("in1_minus_in2_allxfact", out_o, in_o, phi_o, f1=1.0 / mass)
+        return out_e, out_o, cg
+
+    def dslash_wf(self, which, u, inp, ph, fre, fim):
+        """which: 'deo' | 'doe' (field_times_fermion_matrix.c:77-196)"""
+        out = np.zeros_like(inp)
+        getattr(self.lib, "so_" + which + "_wf")(self.gp(), ptr(u), ptr(out), ptr(inp), ptr(ph), ptr(fre), ptr(fim),
+                                                 C.c_int(self.d3_halo), C.c_int(self.d3_halo + self.loc_n[3]))
+        return out
 
     # multi-rank helpers (global <-> rank-local boxes)
     def scatter_vec(self, rank, gl):

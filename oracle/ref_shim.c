@@ -32,6 +32,13 @@
 #include "OpenAcc/alloc_settings.h"
 #include "OpenAcc/io.h"
 #include "Include/setting_file_parser.h"
+#include "Include/debug.h"
+#include "Include/montecarlo_parameters.h"
+#include "OpenAcc/md_parameters.h"
+#include "OpenAcc/fermion_force.h"
+#include "OpenAcc/sp_fermion_force.h"
+#include "OpenAcc/field_times_fermion_matrix.h"
+#include "Meas/ferm_meas.h"
 
 int verbosity_lv = 0;
 vec3_soa_f *aux1_f = NULL;                 /* alloc_vars globals used by inverter_wrappers.c:60-71 */
@@ -218,6 +225,62 @@ int ref_inverter_wrapper(ferm_param *pars, vec3_soa *out, const vec3_soa *in, do
 int ref_inverter_mixed_precision(ferm_param *pars, vec3_soa *solution, const vec3_soa *in,
 																 double res, int max_cg, double shift, int *cg_return)
 { return inverter_mixed_precision(the_ip, pars, solution, in, res, max_cg, shift, cg_return); }
+
+/* ---- the two callers of the path: fermion_force_soloopenacc (OpenAcc/fermion_force.c:166-357) and eo_inversion
+ * (Meas/ferm_meas.c:50-72).  Globals that md_parameters.c / alloc_vars.c / debug.c / main.c define in the reference's
+ * own programs; the dbg/diagnostic hooks are never reached with debug_settings zeroed (fermion_force.c:258,325). */
+md_param md_parameters;
+int nMdInversionPerformed = 0;
+debug_settings_t debug_settings;
+int md_dbg_print_count = 0, md_diag_count_fermion = 0, ipdot_f_reset = 0;
+mc_params_t mc_params;
+tamat_soa *aux_ta = NULL, *ipdot_f_old = NULL; thmat_soa *aux_th = NULL;
+tamat_soa_f *aux_ta_f = NULL, *ipdot_f_old_f = NULL; thmat_soa_f *aux_th_f = NULL;
+su3_soa_f *conf_acc_f = NULL;
+su3_soa *gstout_conf_acc_arr = NULL;
+vec3_soa *ferm_shiftmulti_acc = NULL, *kloc_r = NULL, *kloc_h = NULL, *kloc_s = NULL, *kloc_p = NULL;
+vec3_soa_f *kloc_r_f = NULL, *kloc_h_f = NULL, *kloc_s_f = NULL, *kloc_p_f = NULL;
+static void unreachable(const char *what) { printf("oracle shim: %s is not part of this build\n", what); exit(1); }
+void dbg_print_su3_soa(su3_soa *const c, const char *n, int i) { unreachable("dbg_print_su3_soa"); }
+void dbg_print_su3_soa_f(su3_soa_f *const c, const char *n, int i) { unreachable("dbg_print_su3_soa_f"); }
+double calc_force_norm(const tamat_soa *t) { unreachable("calc_force_norm"); return 0; }
+double calc_diff_force_norm(const tamat_soa *t, const tamat_soa *o) { unreachable("calc_diff_force_norm"); return 0; }
+void copy_ipdot_into_old(const tamat_soa *t, tamat_soa *o) { unreachable("copy_ipdot_into_old"); }
+float calc_force_norm_f(const tamat_soa_f *t) { unreachable("calc_force_norm_f"); return 0; }
+float calc_diff_force_norm_f(const tamat_soa_f *t, const tamat_soa_f *o) { unreachable("calc_diff_force_norm_f"); return 0; }
+void copy_ipdot_into_old_f(const tamat_soa_f *t, tamat_soa_f *o) { unreachable("copy_ipdot_into_old_f"); }
+void generate_vec3_soa_gauss(vec3_soa *const v) { unreachable("generate_vec3_soa_gauss"); }
+void generate_vec3_soa_z2noise(vec3_soa *const v) { unreachable("generate_vec3_soa_z2noise"); }
+
+void ref_set_force_globals(void *th, void *ta, void *th_f, void *ta_f, void *conf_f)
+{
+	aux_th = (thmat_soa *) th; aux_ta = (tamat_soa *) ta; aux_th_f = (thmat_soa_f *) th_f; aux_ta_f = (tamat_soa_f *) ta_f;
+	conf_acc_f = (su3_soa_f *) conf_f;
+	memset(&md_parameters, 0, sizeof(md_parameters)); memset(&debug_settings, 0, sizeof(debug_settings));
+	nMdInversionPerformed = 0;
+}
+int ref_md_inversions_performed(void) { return nMdInversionPerformed; }
+
+/* an array of flavours as fermion_force_soloopenacc walks it (fermion_parameters.h:9-41) */
+ferm_param *ref_ferm_param_array_new(int n) { return (ferm_param *) calloc(n, sizeof(ferm_param)); }
+void ref_ferm_param_array_set(ferm_param *arr, int i, double mass, double_soa *phases, float_soa *phases_f, int number_of_ps,
+															int index_of_the_first_ps, int order, const double *a, const double *b)
+{
+	ferm_param *p = &arr[i];
+	p->ferm_mass = mass; p->phases = phases; p->phases_f = phases_f; p->degeneracy = 1; sprintf(p->name, "flav%d", i);
+	p->number_of_ps = number_of_ps; p->index_of_the_first_ps = index_of_the_first_ps;
+	p->approx_md.approx_order = order; p->approx_md.RA_a0 = 0;
+	for (int k = 0; k < order; k++) { p->approx_md.RA_a[k] = a[k]; p->approx_md.RA_b[k] = b[k]; }
+}
+void ref_fermion_force(su3_soa *conf, su3_soa *stout_arr, su3_soa *gl3_aux, tamat_soa *ipdot, ferm_param *pars, int nflav,
+											 const vec3_soa *ferm_in, double res, su3_soa *taux, vec3_soa *shiftmulti, int max_cg)
+{ fermion_force_soloopenacc(conf, stout_arr, gl3_aux, ipdot, pars, nflav, ferm_in, res, taux, shiftmulti, the_ip, max_cg); }
+void ref_fermion_force_f(su3_soa_f *conf, su3_soa_f *stout_arr, su3_soa_f *gl3_aux, tamat_soa_f *ipdot, ferm_param *pars, int nflav,
+												 const vec3_soa_f *ferm_in, double res, su3_soa_f *taux, vec3_soa_f *shiftmulti, int max_cg)
+{ fermion_force_soloopenacc_f(conf, stout_arr, gl3_aux, ipdot, pars, nflav, ferm_in, (float) res, taux, shiftmulti, the_ip, max_cg); }
+void ref_eo_inversion(ferm_param *pars, double res, int max_cg, vec3_soa *in_e, vec3_soa *in_o, vec3_soa *out_e, vec3_soa *out_o,
+											vec3_soa *phi_e, vec3_soa *phi_o)
+{ eo_inversion(the_ip, pars, res, max_cg, in_e, in_o, out_e, out_o, phi_e, phi_o); }
 
 #ifdef MULTIDEVICE
 /* ---- single-process mailbox MPI ------------------------------------------------

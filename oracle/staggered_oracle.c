@@ -191,6 +191,57 @@ static inline float so_creal_f(float complex z) { return crealf(z); }
 #undef RSQRT
 #undef RFABS
 
+/* "wf" = with a field: the operator with every link's U(1) phase multiplied by a complex per-link field (the derivative of
+ * the phase for the magnetic susceptibility), matvecmul.h:176-260 and field_times_fermion_matrix.c:77-196.  FP64 only
+ * (the reference generates no _f twin of this file).  par = parity of the output sites. */
+static void so_dslash_wf(const so_geom *g, int par, const double complex *u, double complex *out, const double complex *in,
+												 const double *ph, const double *fre, const double *fim, int d3lo, int d3hi)
+{
+	const long n = g->sizeh;
+	const int nd[4] = { g->nd[0], g->nd[1], g->nd[2], g->nd[3] };
+	for (int d3 = d3lo; d3 < d3hi; d3++)
+		for (int d2 = 0; d2 < nd[2]; d2++)
+			for (int d1 = 0; d1 < nd[1]; d1++)
+				for (int hd0 = 0; hd0 < nd[0] / 2; hd0++) {
+					int c[4] = { 2 * hd0 + ((d1 + d2 + d3 + par) & 1), d1, d2, d3 };
+					long idx = so_snum(g, c[0], c[1], c[2], c[3]);
+					double complex acc[3] = { 0, 0, 0 };
+					for (int fwd = 0; fwd < 2; fwd++)          /* backward hops subtracted first (:104-111), then forward (:117-124) */
+						for (int mu = 0; mu < 4; mu++) {
+							int cn[4] = { c[0], c[1], c[2], c[3] };
+							if (fwd) cn[mu] = (c[mu] == nd[mu] - 1) ? 0 : c[mu] + 1; else cn[mu] = (c[mu] == 0) ? nd[mu] - 1 : c[mu] - 1;
+							long in_idx = so_snum(g, cn[0], cn[1], cn[2], cn[3]);
+							int k = fwd ? 2 * mu + par : 2 * mu + 1 - par;
+							long im = fwd ? idx : in_idx;
+							const double complex *um = u + (long) k * 9 * n;
+							double arg = ph[(long) k * n + im];
+							double complex phase = cos(arg) + I * sin(arg);
+							phase *= (fre[(long) k * n + im] + I * fim[(long) k * n + im]);     /* not in U(1) anymore */
+							if (!fwd) phase = conj(phase);
+							double complex v0 = in[in_idx] * phase, v1 = in[n + in_idx] * phase, v2 = in[2 * n + in_idx] * phase;
+							double complex m00 = um[im], m01 = um[n + im], m02 = um[2 * n + im];
+							double complex m10 = um[3 * n + im], m11 = um[4 * n + im], m12 = um[5 * n + im];
+							double complex m20 = conj(m01 * m12 - m02 * m11), m21 = conj(m02 * m10 - m00 * m12), m22 = conj(m00 * m11 - m01 * m10);
+							if (fwd) {
+								acc[0] += m00 * v0 + m01 * v1 + m02 * v2;
+								acc[1] += m10 * v0 + m11 * v1 + m12 * v2;
+								acc[2] += m20 * v0 + m21 * v1 + m22 * v2;
+							} else {
+								acc[0] -= conj(m00) * v0 + conj(m10) * v1 + conj(m20) * v2;
+								acc[1] -= conj(m01) * v0 + conj(m11) * v1 + conj(m21) * v2;
+								acc[2] -= conj(m02) * v0 + conj(m12) * v1 + conj(m22) * v2;
+							}
+						}
+					out[idx] = acc[0] * 0.5; out[n + idx] = acc[1] * 0.5; out[2 * n + idx] = acc[2] * 0.5;
+				}
+}
+void so_deo_wf(const so_geom *g, const double complex *u, double complex *out, const double complex *in, const double *ph,
+							 const double *fre, const double *fim, int d3lo, int d3hi)
+{ so_dslash_wf(g, 0, u, out, in, ph, fre, fim, d3lo, d3hi); }
+void so_doe_wf(const so_geom *g, const double complex *u, double complex *out, const double complex *in, const double *ph,
+							 const double *fre, const double *fim, int d3lo, int d3hi)
+{ so_dslash_wf(g, 1, u, out, in, ph, fre, fim, d3lo, d3hi); }
+
 /* float_double_conv.c:9-33 */
 void so_convert_d2f(long n, const double complex *d, float complex *f)
 { for (long i = 0; i < n; i++) f[i] = (float) creal(d[i]) + (float) cimag(d[i]) * I; }

@@ -82,6 +82,12 @@ void so_compute_sigma##S(const so_geom *g, const R *lam, const C *u, C *sg, cons
 SO_DECL(double, double complex, )
 SO_DECL(float, float complex, _f)
 
+/* operator "with a field" (field_times_fermion_matrix.c:77-196), FP64 only */
+void so_deo_wf(const so_geom *g, const double complex *u, double complex *out, const double complex *in, const double *ph,
+							 const double *fre, const double *fim, int d3lo, int d3hi);
+void so_doe_wf(const so_geom *g, const double complex *u, double complex *out, const double complex *in, const double *ph,
+							 const double *fre, const double *fim, int d3lo, int d3hi);
+
 void so_convert_d2f(long n, const double complex *d, float complex *f);
 void so_convert_f2d(long n, const float complex *f, double complex *d);
 

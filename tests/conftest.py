@@ -44,3 +44,18 @@ def relerr(a, b):
     """max |a-b| / max |b| -- the relative error used for every parity statement."""
     a = np.asarray(a); b = np.asarray(b)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="session")
+def golden_callers():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ref_callers_4x4x4x4_r1.npz")))
+
+
+def callers_flavours(gc, single=False):
+    """the flavour list of tests/golden/make_golden.py:callers_single from the fixture's own arrays"""
+    fl = []
+    for i in range(2):
+        fl.append(dict(mass=float(gc["fl%d_mass" % i]), ph=gc[("phf%d" if single else "ph%d") % i],
+                       number_of_ps=int(gc["fl%d_number_of_ps" % i]), first_ps=int(gc["fl%d_first_ps" % i]),
+                       ra_a=gc["fl%d_ra_a" % i], ra_b=gc["fl%d_ra_b" % i]))
+    return fl

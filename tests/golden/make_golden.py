@@ -189,6 +189,43 @@ def io_single(n=(4, 4, 4, 4)):
     print("io", n, d["ascii_bytes"].size, d["ildg_bytes"].size, cid.value)
 
 
+# flavours of the whole-force fixture: light (charge 2, two pseudofermions) and heavy (charge -1, one)
+FORCE_FLAVOURS = [dict(mass=0.0507, charge=2.0, number_of_ps=2, first_ps=0, ra_a=[0.11, 0.23, 0.37], ra_b=[0.003, 0.04, 0.5]),
+                  dict(mass=0.12, charge=-1.0, number_of_ps=1, first_ps=2, ra_a=[0.3, -0.2], ra_b=[0.01, 0.2])]
+
+
+def callers_single(n=(4, 4, 4, 4)):
+    """The two callers of the path on the 4^4 fixture: fermion_force_soloopenacc (fermion_force.c:166-357; two flavours,
+    three pseudofermions, rho = 0.15, two / zero stout levels, FP64 and the _f twin), eo_inversion (Meas/ferm_meas.c:50-72)
+    and the operator with a field (field_times_fermion_matrix.c)."""
+    R = RefLib(*n)
+    g = dict(np.load(os.path.join(HERE, "ref_%dx%dx%dx%d_r1.npz" % n)))
+    u = g["u"]
+    fin = np.stack([g["v"], g["w"], gaussian_vec(R.sizeh, 14)])
+    d = {"ferm_in": fin, "rho": 0.15, "res": 1e-10, "res_f": 1e-5}
+    fl = []; flf = []
+    for i, f in enumerate(FORCE_FLAVOURS):
+        ph = R.phases(EB, MU, f["charge"]); phf = R.phases_f(EB, MU, f["charge"])
+        d["ph%d" % i] = ph; d["phf%d" % i] = phf
+        for k in ("mass", "number_of_ps", "first_ps", "ra_a", "ra_b"):
+            d["fl%d_%s" % (i, k)] = np.array(f[k])
+        fl.append(dict(f, ph=ph)); flf.append(dict(f, ph=phf))
+    for steps in (2, 0):
+        ipdot, gl3, stout = R.fermion_force(u, fl, fin, 1e-10, 5000, 0.15, steps)
+        d["ipdot_s%d" % steps] = ipdot; d["gl3_s%d" % steps] = gl3
+    ipdot, gl3, _ = R.fermion_force(u.astype(np.complex64), flf, fin.astype(np.complex64), 1e-5, 5000, 0.15, 2)
+    d["ipdot_s2_f"] = ipdot
+    oe, oo = R.eo_inversion(u, d["ph0"], MASS, g["v"], g["w"], 1e-10, 5000)
+    d["eo_out_e"] = oe; d["eo_out_o"] = oo
+    rng = np.random.default_rng(15)
+    fre, fim = rng.standard_normal((8, R.sizeh)), rng.standard_normal((8, R.sizeh))
+    d["field_re"] = fre; d["field_im"] = fim
+    d["deo_wf"] = R.dslash_wf("acc_Deo_wf", u, g["v"], d["ph0"], fre, fim)
+    d["doe_wf"] = R.dslash_wf("acc_Doe_wf", u, g["v"], d["ph0"], fre, fim)
+    np.savez_compressed(os.path.join(HERE, "ref_callers_%dx%dx%dx%d_r1.npz" % n), **d)
+    print("callers", n, float(np.abs(d["ipdot_s2"]).max()), float(np.abs(d["ipdot_s0"]).max()), float(np.abs(oe).max()))
+
+
 class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
     _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
                 ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
@@ -227,7 +264,7 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io", "callers"]
     if "single" in which:
         single_rank()
     if "multi" in which:
@@ -242,3 +279,5 @@ if __name__ == "__main__":
         stoutforce_single()
     if "io" in which:
         io_single()
+    if "callers" in which:
+        callers_single()

@@ -58,12 +58,16 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) > 126, syms
     for s_ in ("ker_openacc_compute_fermion_force", "ker_openacc_compute_fermion_force_f", "set_tamat_soa_to_zero",
                "multiply_conf_times_force_and_take_ta_nophase_f", "staple_acc_Doe_Deo_streamed", "stout_wrapper", "stout_isotropic_f",
-               "calc_loc_staples_nnptrick_all_onlyferms", "exp_minus_QA_times_conf"):
+               "calc_loc_staples_nnptrick_all_onlyferms", "exp_minus_QA_times_conf", "fermion_force_soloopenacc",
+               "fermion_force_soloopenacc_f", "eo_inversion", "acc_Deo_wf", "acc_Doe_wf", "acc_Deo_wf_unsafe", "acc_Doe_wf_unsafe"):
         assert s_ in syms, s_
     missing = [s for s in syms if not hasattr(L, s)]
     assert not missing, missing
-    for g in ("verbosity_lv", "multishift_invert_iterations"):
+    for g in ("verbosity_lv", "multishift_invert_iterations", "nMdInversionPerformed"):
         C.c_int.in_dll(L, g)
+    for g in ("aux_th", "aux_ta", "aux_th_f", "aux_ta_f", "conf_acc_f", "auxbis_conf_acc", "glocal_staples", "gipdot"):
+        assert C.c_void_p.in_dll(L, g).value is None          # the reference's parking-array globals, unset until the host sets them
+    assert C.sizeof(osb.api.MdParam) == 64 and osb.api.MdParam.recycleInvsForce.offset == 52   # md_parameters.h:6-19
     InvTricks.in_dll(L, "inverter_tricks")
     assert b"sm_100a" in L.staple_version()
     # the reference's own entry-point names are all there (fermion_matrix.h, fermionic_utilities.h, inverter_*.h)
