@@ -53,6 +53,10 @@ typedef struct tamat_soa_t tamat_soa;       /* ref: OpenAcc/struct_c_def.h:45-51
 typedef struct tamat_soa_f_t tamat_soa_f;
 typedef struct thmat_soa_t thmat_soa;       /* ref: OpenAcc/struct_c_def.h:52-58  {c01,c02,c12 complex[sizeh]; rc00,rc11 double[sizeh]} */
 typedef struct thmat_soa_f_t thmat_soa_f;
+typedef struct vec3_t vec3;                 /* ref: OpenAcc/struct_c_def.h:29-33  one colour vector by value {complex c0,c1,c2}, host side */
+typedef struct vec3_f_t vec3_f;
+typedef struct dcomplex_soa_t dcomplex_soa; /* ref: OpenAcc/struct_c_def.h:21-23  {complex c[sizeh]} */
+typedef struct fcomplex_soa_t fcomplex_soa;
 
 #ifndef MAX_APPROX_ORDER
 #define MAX_APPROX_ORDER 25                 /* ref: RationalApprox/rationalapprox.h:8 */
@@ -210,10 +214,14 @@ void communicate_su3_borders(su3_soa *lnh_conf, int thickness);   /* ref: :306-3
 void communicate_su3_borders_hostonly(su3_soa *lnh_conf, int thickness); /* ref: :319-332 */
 void communicate_fermion_borders_f(vec3_soa_f *lnh_fermion);      /* generated Mpi/sp_communications.c */
 void communicate_su3_borders_f(su3_soa_f *lnh_conf, int thickness);
+void communicate_fermion_borders_hostonly_f(vec3_soa_f *lnh_fermion);
+void communicate_su3_borders_hostonly_f(su3_soa_f *lnh_conf, int thickness);
 /* ref: :257-271 / :273-303 take MPI_Request arrays; here the requests are CUDA events owned by the
  * library: *_async starts the exchange on the comm stream, staple_wait_borders() joins it. */
 void communicate_fermion_borders_async(vec3_soa *lnh_fermion, void *unused_send_req, void *unused_recv_req);
 void communicate_su3_borders_async(su3_soa *lnh_conf, int thickness, void *unused_send_req, void *unused_recv_req);
+void communicate_fermion_borders_async_f(vec3_soa_f *lnh_fermion, void *unused_send_req, void *unused_recv_req);
+void communicate_su3_borders_async_f(su3_soa_f *lnh_conf, int thickness, void *unused_send_req, void *unused_recv_req);
 void staple_wait_borders(void);
 
 /* ------------------------------------------------------------------ Dirac operator  (ref: OpenAcc/fermion_matrix.h:20-106) */
@@ -247,7 +255,7 @@ void acc_Doe_wf(const su3_soa *u, vec3_soa *out, const vec3_soa *in, const doubl
 void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars);
 void fermion_matrix_multiplication_shifted(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1, ferm_param *pars, double shift);
 void fermion_matrix_multiplication_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars);
-void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars, double shift);
+void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars, float shift);   /* float: generated sp_fermion_matrix.h */
 
 /* ------------------------------------------------------------------ BLAS-1  (ref: OpenAcc/fermionic_utilities.h:38-123) */
 #define STAPLE_BLAS_DECL(V, S) \
@@ -276,6 +284,14 @@ void convert_float_to_double_vec3_soa(const vec3_soa_f *f_var, vec3_soa *d_var);
 void convert_double_to_float_vec3_soa(const vec3_soa *d_var, vec3_soa_f *f_var);
 void convert_float_to_double_su3_soa(const su3_soa_f *f_var, su3_soa *d_var);   /* all 8 links of a conf, rows r0,r1,r2 (ref: :94-150) */
 void convert_double_to_float_su3_soa(const su3_soa *d_var, su3_soa_f *f_var);
+void convert_float_to_double_tamat_soa(const tamat_soa_f *f_var, tamat_soa *d_var);   /* all 8 links (ref: :150-185) */
+void convert_double_to_float_tamat_soa(const tamat_soa *d_var, tamat_soa_f *f_var);
+void convert_float_to_double_thmat_soa(const thmat_soa_f *f_var, thmat_soa *d_var);   /* ref: :187-228 */
+void convert_double_to_float_thmat_soa(const thmat_soa *d_var, thmat_soa_f *f_var);
+void convert_float_to_double_complex_soa(const fcomplex_soa *f_var, dcomplex_soa *d_var);   /* ref: :48-70 */
+void convert_double_to_float_complex_soa(const dcomplex_soa *d_var, fcomplex_soa *f_var);
+void convert_float_to_double_vec3(const vec3_f *f_var, vec3 *d_var);                  /* host structs, ref: :34-47 */
+void convert_double_to_float_vec3(const vec3 *d_var, vec3_f *f_var);
 void convert_float_to_double_real_soa(const float_soa *f_var, double_soa *d_var);
 void convert_double_to_float_real_soa(const double_soa *d_var, float_soa *f_var);
 
@@ -318,6 +334,7 @@ void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f
 
 /* "next" row N1.  ref: OpenAcc/find_min_max.c:21-117 */
 double ker_find_max_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p);
+double ker_find_min_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p, double max);   /* ref: :62-98 */
 void find_min_max_eigenvalue_soloopenacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h,
 																				 vec3_soa *loc_p1, vec3_soa *loc_p2, double *minmax);
 

@@ -466,6 +466,18 @@ class Lattice:
     def convert_float_to_double_su3_soa(self, f, d):
         self.L.convert_float_to_double_su3_soa(_addr(f), _addr(d))
 
+    def convert_double_to_float_tamat_soa(self, d, f):          # tamat_soa[8] / thmat_soa[8]: [8, 8, sizeh] reals
+        self.L.convert_double_to_float_tamat_soa(_addr(d), _addr(f))
+
+    def convert_float_to_double_tamat_soa(self, f, d):
+        self.L.convert_float_to_double_tamat_soa(_addr(f), _addr(d))
+
+    def convert_double_to_float_thmat_soa(self, d, f):
+        self.L.convert_double_to_float_thmat_soa(_addr(d), _addr(f))
+
+    def convert_float_to_double_thmat_soa(self, f, d):
+        self.L.convert_float_to_double_thmat_soa(_addr(f), _addr(d))
+
     def convert_double_to_float_real_soa(self, d, f):
         for k in range(8):
             self.L.convert_double_to_float_real_soa(_addr(d) + k * self.sizeh * 8, _addr(f) + k * self.sizeh * 4)
@@ -575,6 +587,11 @@ class Lattice:
 
     def ker_find_max_eigenvalue_openacc(self, u, pars, loc_r, loc_h, loc_p):
         return self.L.ker_find_max_eigenvalue_openacc(_addr(u), C.addressof(pars), _addr(loc_r), _addr(loc_h), _addr(loc_p))
+
+    def ker_find_min_eigenvalue_openacc(self, u, pars, loc_r, loc_h, loc_p, mx):
+        f = self.L.ker_find_min_eigenvalue_openacc
+        f.argtypes = [C.c_void_p] * 5 + [C.c_double]; f.restype = C.c_double
+        return f(_addr(u), C.addressof(pars), _addr(loc_r), _addr(loc_h), _addr(loc_p), float(mx))
 
     def last_solve_stats(self):
         it = C.c_int(0); act = C.c_longlong(0); ms = C.c_double(0)

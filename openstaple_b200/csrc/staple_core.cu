@@ -561,6 +561,23 @@ void communicate_su3_borders_async(su3_soa *u, int thickness, void *, void *)
 	su3_borders(dev(u, "lnh_conf"), 16, thickness, ctx().s_comm);
 	STAPLE_CUDA_CHECK(cudaEventRecord(ctx().ev_comm, ctx().s_comm));
 }
+// generated Mpi/sp_communications.c twins
+void communicate_fermion_borders_hostonly_f(vec3_soa_f *f) { communicate_fermion_borders_f(f); }
+void communicate_su3_borders_hostonly_f(su3_soa_f *u, int thickness) { communicate_su3_borders_f(u, thickness); }
+void communicate_fermion_borders_async_f(vec3_soa_f *f, void *, void *)
+{
+	require_init("communicate_fermion_borders_async_f");
+	fork_comm();
+	fermion_borders(dev(f, "lnh_fermion"), 8, ctx().s_comm);
+	STAPLE_CUDA_CHECK(cudaEventRecord(ctx().ev_comm, ctx().s_comm));
+}
+void communicate_su3_borders_async_f(su3_soa_f *u, int thickness, void *, void *)
+{
+	require_init("communicate_su3_borders_async_f");
+	fork_comm();
+	su3_borders(dev(u, "lnh_conf"), 8, thickness, ctx().s_comm);
+	STAPLE_CUDA_CHECK(cudaEventRecord(ctx().ev_comm, ctx().s_comm));
+}
 void staple_wait_borders(void)
 {
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(ctx().stream, ctx().ev_comm, 0));

@@ -1194,7 +1194,7 @@ void fermion_matrix_multiplication_f(const su3_soa_f *u, vec3_soa_f *out, const 
 										 pars->ferm_mass * pars->ferm_mass, -1, nullptr);
 }
 void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1,
-																						 ferm_param *pars, double shift)
+																						 ferm_param *pars, float shift)
 {
 	require_init("fermion_matrix_multiplication_shifted_f");
 	apply_mdagm<float>(CDF(u), DF(out), CDF(in), DF(temp1), (const float *) dev(pars->phases_f, "pars->phases_f"),
@@ -1269,6 +1269,33 @@ void convert_float_to_double_real_soa(const float_soa *f, double_soa *d)
 { require_init("convert_float_to_double_real_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), ctx().g.sizeh); }
 void convert_double_to_float_real_soa(const double_soa *d, float_soa *f)
 { require_init("convert_double_to_float_real_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), ctx().g.sizeh); }
+
+// tamat_soa[8] / thmat_soa[8]: three complex and two real arrays per link = 8 reals per site and link, all 8 links per call
+// (float_double_conv.c:150-228); dcomplex_soa: one complex array (:48-70)
+void convert_float_to_double_tamat_soa(const tamat_soa_f *f, tamat_soa *d)
+{ require_init("convert_float_to_double_tamat_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 8 * 8 * ctx().g.sizeh); }
+void convert_double_to_float_tamat_soa(const tamat_soa *d, tamat_soa_f *f)
+{ require_init("convert_double_to_float_tamat_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 8 * 8 * ctx().g.sizeh); }
+void convert_float_to_double_thmat_soa(const thmat_soa_f *f, thmat_soa *d)
+{ require_init("convert_float_to_double_thmat_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 8 * 8 * ctx().g.sizeh); }
+void convert_double_to_float_thmat_soa(const thmat_soa *d, thmat_soa_f *f)
+{ require_init("convert_double_to_float_thmat_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 8 * 8 * ctx().g.sizeh); }
+void convert_float_to_double_complex_soa(const fcomplex_soa *f, dcomplex_soa *d)
+{ require_init("convert_float_to_double_complex_soa"); convert<float, double>((const float *) dev(f, "f_var"), (double *) dev(d, "d_var"), 2 * ctx().g.sizeh); }
+void convert_double_to_float_complex_soa(const dcomplex_soa *d, fcomplex_soa *f)
+{ require_init("convert_double_to_float_complex_soa"); convert<double, float>((const double *) dev(d, "d_var"), (float *) dev(f, "f_var"), 2 * ctx().g.sizeh); }
+
+// one colour vector held by value on the HOST (struct_c_def.h:29-33): plain casts, no device work (float_double_conv.c:34-47)
+void convert_float_to_double_vec3(const vec3_f *f, vec3 *d)
+{
+	const float *s = (const float *) f; double *o = (double *) d;
+	for (int i = 0; i < 6; i++) o[i] = (double) s[i];
+}
+void convert_double_to_float_vec3(const vec3 *d, vec3_f *f)
+{
+	const double *s = (const double *) d; float *o = (float *) f;
+	for (int i = 0; i < 6; i++) o[i] = (float) s[i];
+}
 
 void combine_add_in2_into_in1_mixed_precision(vec3_soa *in1, const vec3_soa_f *in2)
 {

@@ -255,6 +255,11 @@ template <> struct PhasesOf<float> { static const float *get(ferm_param *p) { re
 
 enum { SLOT_TMP = 0, SLOT_DELTA = 1, SLOT_SRC = 2, SLOT_ALPHA = 3, SLOT_LAMBDA = 4 };
 
+// the reference's generated FP32 operator takes `float shift` (sp_fermion_matrix.c:735-746): every double shift its FP32
+// callers pass (sp_inverter_full.c:58,78,114, sp_inverter_multishift_full.c:217, inverter_mixedp.c:101) is rounded to float
+template <typename T> static inline double shift_as_seen(double shift) { return shift; }
+template <> inline double shift_as_seen<float>(double shift) { return (double) (float) shift; }
+
 template <typename T>
 static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox *approx, cplx_t<T> *out,
 													 const cplx_t<T> *in, double residuo, cplx_t<T> *loc_r, cplx_t<T> *loc_h, cplx_t<T> *loc_s,
@@ -392,7 +397,7 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	if (verbosity_lv > 2 && 0 == c.myrank) printf("Relative Res:");
 	for (int i = 0; i < order; i++) {
 		blas<T>(OP_ASSIGN, loc_p, out + (long) i * 3 * n, nullptr, nullptr, 0.0);
-		apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2 + approx->RA_b[i], -1, nullptr);
+		apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2 + shift_as_seen<T>(approx->RA_b[i]), -1, nullptr);
 		blas<T>(OP_IN1_MINUS_IN2, loc_h, in, loc_s, nullptr, 0.0);
 		const double giustoono = reduce_global<T>(RED_L2NORM2, loc_h, nullptr).re / source_norm;
 		check *= (giustoono <= 1) ? 1 : 0;
@@ -414,7 +419,7 @@ static int cg_impl(const cplx_t<T> *u, ferm_param *pars, cplx_t<T> *solution, co
 {
 	Ctx &c = ctx();
 	const T *ph = PhasesOf<T>::get(pars);
-	const double m2 = pars->ferm_mass * pars->ferm_mass + shift;
+	const double m2 = pars->ferm_mass * pars->ferm_mass + shift_as_seen<T>(shift);
 	int cg = 0;
 	double delta, alpha, lambda = 0, omega, gammag;
 	const double source_norm = reduce_global<T>(RED_L2NORM2, in, nullptr).re;
@@ -512,6 +517,7 @@ int inverter_mixed_precision(inverter_package ip, ferm_param *pars, vec3_soa *so
 	const double *ph = (const double *) dev(pars->phases, "pars->phases");
 	const float *ph_f = (const float *) dev(pars->phases_f, "pars->phases_f");
 	const double m2 = pars->ferm_mass * pars->ferm_mass + shift;
+	const double m2_f = pars->ferm_mass * pars->ferm_mass + shift_as_seen<float>(shift);   // inverter_mixedp.c:101
 	const long n = c.g.sizeh;
 	int cg = 0, magicTouchCount = 0;
 	double delta, alpha, lambda, omega, gammag, lastMaxResNorm = 0;
@@ -526,7 +532,7 @@ int inverter_mixed_precision(inverter_package ip, ferm_param *pars, vec3_soa *so
 	if (verbosity_lv > 3 && 0 == c.myrank) printf("STARTING CG:\nCG\tR - mixed precision\n");
 	do {
 		cg++;
-		apply_mdagm<float>(u_f, loc_s, loc_p, loc_h, ph_f, m2, SLOT_ALPHA, nullptr);
+		apply_mdagm<float>(u_f, loc_s, loc_p, loc_h, ph_f, m2_f, SLOT_ALPHA, nullptr);
 		fetch_results(SLOT_ALPHA, 1, &alpha);
 		omega = delta / alpha;
 		blas<float>(OP_IN1XFACTOR_PLUS_IN2, out, loc_p, out, nullptr, omega);
@@ -683,6 +689,32 @@ double ker_find_max_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *l
 		loop_count++;
 	} while (old_norm > 1.0e-5);
 	return norm;
+}
+
+// find_min_max.c:62-98, literally: power iteration on (max - m^2) - Deo Doe (loc_p = start vector); returns max - norm.
+// (Its top eigenvalue is ~2 max - 2 m^2, so the value is ~ m^2 - max rather than lambda_min; the reference's
+// find_min_max_eigenvalue_soloopenacc does not call it and takes m^2 as the lower bound.  Same numbers as the reference.)
+double ker_find_min_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p, double max)
+{
+	require_init("ker_find_min_eigenvalue_openacc");
+	int loop_count = 0;
+	double norm, inorm, old_norm;
+	const double m2 = pars->ferm_mass * pars->ferm_mass;
+	const double delta = max - m2;
+	norm = sqrt(l2norm2_global(loc_p));
+	do {
+		inorm = 1.0 / norm;
+		multiply_fermion_x_doublefactor(loc_p, inorm);
+		assign_in_to_out(loc_p, loc_r);
+		old_norm = norm;
+		// literally the reference's call (:87): (m2 + delta - m2) r - Deo Doe r
+		fermion_matrix_multiplication_shifted(u, loc_p, loc_r, loc_h, pars, delta - m2);
+		norm = sqrt(l2norm2_global(loc_p));
+		old_norm = fabs(old_norm - norm);
+		old_norm /= norm;
+		loop_count++;
+	} while (old_norm > 1.0e-5);
+	return max - norm;
 }
 
 // find_min_max.c:100-117

@@ -64,7 +64,7 @@ def _declare(L):
         for f in ("acc_Deo_d3c", "acc_Doe_d3c"):
             getattr(L, f + s).argtypes = [vp, vp, vp, vp, i, i]; getattr(L, f + s).restype = None
         getattr(L, "fermion_matrix_multiplication" + s).argtypes = [vp, vp, vp, vp, vp]
-        getattr(L, "fermion_matrix_multiplication_shifted" + s).argtypes = [vp, vp, vp, vp, vp, d]
+        getattr(L, "fermion_matrix_multiplication_shifted" + s).argtypes = [vp, vp, vp, vp, vp, C.c_float if s else d]
         getattr(L, "scal_prod_global" + s).argtypes = [vp, vp]; getattr(L, "scal_prod_global" + s).restype = DComplex
         getattr(L, "real_scal_prod_global" + s).argtypes = [vp, vp]; getattr(L, "real_scal_prod_global" + s).restype = d
         getattr(L, "l2norm2_global" + s).argtypes = [vp]; getattr(L, "l2norm2_global" + s).restype = d
@@ -106,6 +106,10 @@ def _declare(L):
             getattr(L, f + s).argtypes = [vp, i]
         getattr(L, "communicate_fermion_borders" + s).argtypes = [vp]
         getattr(L, "communicate_su3_borders" + s).argtypes = [vp, i]
+    for f in ("convert_float_to_double_tamat_soa", "convert_double_to_float_tamat_soa", "convert_float_to_double_thmat_soa",
+              "convert_double_to_float_thmat_soa", "convert_float_to_double_complex_soa", "convert_double_to_float_complex_soa",
+              "convert_float_to_double_vec3", "convert_double_to_float_vec3"):
+        getattr(L, f).argtypes = [vp, vp]; getattr(L, f).restype = None
     for f in ("convert_float_to_double_vec3_soa", "convert_double_to_float_vec3_soa", "convert_float_to_double_su3_soa",
               "convert_double_to_float_su3_soa", "convert_float_to_double_real_soa", "convert_double_to_float_real_soa",
               "combine_add_in2_into_in1_mixed_precision"):

@@ -186,6 +186,11 @@ class RefLib:
         pars = self.ferm_param(mass, ph)
         return self.lib.ker_find_max_eigenvalue_openacc(ptr(u), pars, ptr(r), ptr(h), ptr(p))
 
+    def min_eigenvalue(self, u, ph, mass, start, mx):
+        p = start.copy(); r = np.zeros_like(p); h = np.zeros_like(p)
+        self.lib.ker_find_min_eigenvalue_openacc.restype = C.c_double
+        return self.lib.ker_find_min_eigenvalue_openacc(ptr(u), self.ferm_param(mass, ph), ptr(r), ptr(h), ptr(p), C.c_double(mx))
+
     # --- fermion-force outer products (fermion_force_utilities.c)
     def compute_fermion_force(self, u, aux, shiftmulti, ph, ra_a):
         """ker_openacc_compute_fermion_force: aux (gl3 field [8,3,3,sizeh]) accumulated in place; -> (loc_s, loc_h)."""
@@ -439,6 +444,18 @@ class Restatement:
     def max_eigenvalue(self, u, ph, mass, start):
         p = start.copy(); r = np.zeros_like(p); h = np.zeros_like(p)
         return self.lib.so_find_max_eigenvalue(self.gp(), ptr(u), ptr(ph), C.c_double(mass), ptr(r), ptr(h), ptr(p), None)
+
+    def min_eigenvalue(self, u, ph, mass, start, mx):
+        """ker_find_min_eigenvalue_openacc (find_min_max.c:62-98): power iteration on max - M^+M from `start`"""
+        p = start.copy(); m2 = mass * mass; delta = mx - m2
+        norm = np.sqrt(self.l2norm2(p))
+        while True:
+            self.axpy_like("scale", p, f1=1.0 / norm)
+            r = p.copy(); old = norm
+            p = self.mdagm(u, r, ph, mass, delta - m2)
+            norm = np.sqrt(self.l2norm2(p))
+            if abs(old - norm) / norm <= 1.0e-5:
+                return mx - norm
 
     # fermion-force outer products (tamat_soa[8] as reals [8, 8, sizeh], see staggered_oracle_impl.h)
     def compute_fermion_force(self, u, aux, shiftmulti, ph, ra_a):

@@ -116,7 +116,8 @@ void S(so_fermion_matrix_multiplication_shifted)(const so_geom *g, const C *u, C
 	int lo = g->d3_halo, hi = g->d3_halo + g->loc_n[3];
 	S(so_doe)(g, u, tmp, in, ph, lo, hi);
 	S(so_deo)(g, u, out, tmp, ph, lo, hi);
-	S(so_axpy_like)(g, SO_IN1XMASS_MINUS_IN2, out, in, 0, 0, mass * mass + shift, 0);
+	/* the generated FP32 twin takes `float shift` (sp_fermion_matrix.c:735-746): its callers' double shifts are rounded */
+	S(so_axpy_like)(g, SO_IN1XMASS_MINUS_IN2, out, in, 0, 0, mass * mass + (R) shift, 0);
 }
 
 /* reductions, fermionic_utilities.c:32-175 (+ fermionic_utilities.h:15-35): double accumulators */

@@ -9,6 +9,7 @@ numpy RNG stream.
 """
 import ctypes as C
 import os
+import re
 import sys
 
 import numpy as np
@@ -226,6 +227,39 @@ def callers_single(n=(4, 4, 4, 4)):
     print("callers", n, float(np.abs(d["ipdot_s2"]).max()), float(np.abs(d["ipdot_s0"]).max()), float(np.abs(oe).max()))
 
 
+# headers of the reference that declare the hot path and its callers -- generated sp_* twins included
+PROTO_HEADERS = ["OpenAcc/fermion_matrix.h", "OpenAcc/sp_fermion_matrix.h", "OpenAcc/fermionic_utilities.h", "OpenAcc/sp_fermionic_utilities.h",
+                 "OpenAcc/inverter_multishift_full.h", "OpenAcc/sp_inverter_multishift_full.h", "OpenAcc/inverter_full.h",
+                 "OpenAcc/sp_inverter_full.h", "OpenAcc/inverter_mixedp.h", "OpenAcc/inverter_wrappers.h", "OpenAcc/inverter_package.h",
+                 "OpenAcc/float_double_conv.h", "OpenAcc/find_min_max.h", "OpenAcc/fermion_force_utilities.h",
+                 "OpenAcc/sp_fermion_force_utilities.h", "OpenAcc/fermion_force.h", "OpenAcc/sp_fermion_force.h", "OpenAcc/stouting.h",
+                 "OpenAcc/sp_stouting.h", "OpenAcc/plaquettes.h", "OpenAcc/sp_plaquettes.h", "OpenAcc/su3_utilities.h",
+                 "OpenAcc/sp_su3_utilities.h", "OpenAcc/field_times_fermion_matrix.h", "Mpi/communications.h", "Mpi/sp_communications.h",
+                 "Mpi/multidev.h", "Meas/ferm_meas.h"]
+
+
+def reference_prototypes():
+    """Every function prototype the reference's own headers declare for the path (preprocessed with the build's -D flags,
+    MULTIDEVICE on), normalised by tests/prototypes.py -> tests/golden/ref_prototypes.json.  Pins the C ABI: names,
+    argument order, argument and return types (tests/test_abi_and_host.py compares include/staple_b200.h against it)."""
+    import json
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from prototypes import preprocess, prototypes
+    from oracle.pyoracle import build_ref
+    build_ref(4, 4, 4, 4, 2)                                  # makes sure the scratch copy with the generated sp_* headers exists
+    scr = os.path.join(os.environ.get("STAPLE_ORACLE_SCRATCH", os.path.join(os.environ.get("TMPDIR", "/tmp"), "staple_oracle_src")), "src")
+    flags = ["-fcommon", "-I" + os.path.join(HERE, "..", "..", "oracle", "mpi_stub"), "-I" + scr, "-DACTION_TYPE=TLSM", "-DNREPLICAS=1",
+             "-DLOC_N0=4", "-DLOC_N1=4", "-DLOC_N2=4", "-DLOC_N3=4", "-DNRANKS_D3=2", "-DCOMMIT_HASH=oracle"]
+    flags += ["-D%s%s=8" % (a, b) for a in ("DEODOE", "IMPSTAP", "STAP", "SIGMA") for b in ("TILE0", "TILE1", "TILE2", "GANG3")]
+    per_header = {}
+    for h in PROTO_HEADERS:
+        names = set(re.findall(r"\b([A-Za-z_]\w*)\s*\(", open(os.path.join(scr, h)).read()))
+        pr = prototypes(preprocess('#include "%s"\n' % h, flags))
+        per_header[h] = {k: v for k, v in sorted(pr.items()) if k in names and not k.startswith(("MPI_", "__"))}
+    json.dump(per_header, open(os.path.join(HERE, "ref_prototypes.json"), "w"), indent=0, sort_keys=True)
+    print("prototypes", sum(len(v) for v in per_header.values()))
+
+
 class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
     _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
                 ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
@@ -264,7 +298,7 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io", "callers"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io", "callers", "prototypes"]
     if "single" in which:
         single_rank()
     if "multi" in which:
@@ -281,3 +315,5 @@ if __name__ == "__main__":
         io_single()
     if "callers" in which:
         callers_single()
+    if "prototypes" in which:
+        reference_prototypes()

@@ -161,3 +161,42 @@ def test_geometry_plan_worked_example_and_rejections(golden_r2):
             osb.geometry_plan(*bad)
     with pytest.raises(ValueError):
         osb.geometry_plan((8, 8, 8, 8), 2, halo_width=1)     # Wilson multi-rank flips parities (io.c:595-597)
+
+
+# ----------------------------------------------------------------------------- prototypes against the reference's headers
+# headers whose EVERY function must be exported (the subsystems the library replaces, SURVEY 8b + the "next" rows built)
+COMPLETE_HEADERS = ["OpenAcc/fermion_matrix.h", "OpenAcc/sp_fermion_matrix.h", "OpenAcc/fermionic_utilities.h",
+                    "OpenAcc/sp_fermionic_utilities.h", "OpenAcc/inverter_multishift_full.h", "OpenAcc/sp_inverter_multishift_full.h",
+                    "OpenAcc/inverter_full.h", "OpenAcc/sp_inverter_full.h", "OpenAcc/inverter_mixedp.h", "OpenAcc/inverter_wrappers.h",
+                    "OpenAcc/inverter_package.h", "OpenAcc/float_double_conv.h", "OpenAcc/find_min_max.h",
+                    "OpenAcc/fermion_force_utilities.h", "OpenAcc/sp_fermion_force_utilities.h", "OpenAcc/fermion_force.h",
+                    "OpenAcc/sp_fermion_force.h", "OpenAcc/stouting.h", "OpenAcc/sp_stouting.h", "OpenAcc/field_times_fermion_matrix.h"]
+# the only deliberate differences: C99 `double complex` returned as an ABI-identical {re, im} struct; MPI_Request arrays are
+# opaque pointers here (the requests are CUDA events owned by the library)
+TYPE_ALIAS = {"d_complex": "staple_dcomplex", "MPI_Request*": "void*"}
+
+
+def test_prototypes_match_reference_headers():
+    """names, argument order, argument types and return types of every entry point against the reference's own headers
+    (tests/golden/ref_prototypes.json, written by tests/golden/make_golden.py:reference_prototypes)."""
+    import json
+    from prototypes import preprocess, prototypes
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_prototypes.json")))
+    ours = prototypes(preprocess('#include "%s"\n' % os.path.join(ROOT, "include", "staple_b200.h")))
+    alias = lambda t: TYPE_ALIAS.get(t, t)
+    checked, bad, missing = 0, [], []
+    for hdr, protos in ref.items():
+        for name, (rt, params) in protos.items():
+            if name not in ours:
+                if hdr in COMPLETE_HEADERS:
+                    missing.append((hdr, name))
+                continue
+            o_rt, o_params = ours[name]
+            if alias(rt) != o_rt or [alias(p) for p in params] != o_params:
+                bad.append((name, ours[name], [rt, params]))
+            checked += 1
+    assert not bad, bad
+    assert not missing, missing
+    assert checked >= 145, checked
+    L = osb.load_library()
+    assert not [n for hdr in COMPLETE_HEADERS for n in ref[hdr] if not hasattr(L, n)]

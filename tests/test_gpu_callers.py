@@ -156,3 +156,38 @@ def test_convert_su3_covers_all_links(osb):
     back = lat.new_conf()
     lat.convert_float_to_double_su3_soa(uf, back)
     assert np.array_equal(back.cpu().numpy(), u.astype(np.complex64).astype(np.complex128))
+
+
+def test_tamat_thmat_conversions(osb):
+    lat = osb.Lattice((4, 4, 6, 8))
+    rng = np.random.default_rng(5)
+    ta = rng.standard_normal((8, 8, lat.sizeh))
+    d = lat.to_device(ta); f = lat.new_tamat(single=True); back = lat.new_tamat()
+    lat.convert_double_to_float_tamat_soa(d, f)
+    assert np.array_equal(f.cpu().numpy(), ta.astype(np.float32))
+    lat.convert_float_to_double_tamat_soa(f, back)
+    assert np.array_equal(back.cpu().numpy(), ta.astype(np.float32).astype(np.float64))
+    f.zero_(); lat.convert_double_to_float_thmat_soa(d, f)
+    assert np.array_equal(f.cpu().numpy(), ta.astype(np.float32))
+    back.zero_(); lat.convert_float_to_double_thmat_soa(f, back)
+    assert np.array_equal(back.cpu().numpy(), ta.astype(np.float32).astype(np.float64))
+    # host-side single colour vector (vec3 by value)
+    v = np.array([1.5 + 2j, -3.25 + 0.125j, 1 / 3 + 1j / 7]); vf = np.zeros(3, np.complex64); vd = np.zeros(3, np.complex128)
+    lat.L.convert_double_to_float_vec3(v.ctypes.data, vf.ctypes.data); lat.L.convert_float_to_double_vec3(vf.ctypes.data, vd.ctypes.data)
+    assert np.array_equal(vf, v.astype(np.complex64)) and np.array_equal(vd, vf.astype(np.complex128))
+
+
+def test_min_eigenvalue(osb):
+    """ker_find_min_eigenvalue_openacc (find_min_max.c:62-98) against the restatement: a converged power iteration,
+    stopped by a 1e-5 criterion on both sides -> 1e-9 on the value"""
+    loc_n = (8, 8, 8, 8)
+    lat = osb.Lattice(loc_n); S = Restatement(*loc_n)
+    u = random_su3_conf(S.sizeh, 96); w = gaussian_vec(S.sizeh, 97); ph = S.phases(0, EB, 1.0, 2.0)
+    mx = S.max_eigenvalue(u, ph, 0.3, w)
+    want = S.min_eigenvalue(u, ph, 0.3, w, mx * 1.1)
+    du, dph = lat.to_device(u), lat.to_device(ph)
+    pars = lat.ferm_param(0.3, dph)
+    got_max = lat.ker_find_max_eigenvalue_openacc(du, pars, lat.new_vec(), lat.new_vec(), lat.to_device(w))
+    got = lat.ker_find_min_eigenvalue_openacc(du, pars, lat.new_vec(), lat.new_vec(), lat.to_device(w), mx * 1.1)
+    print("eigenvalues: max %.12g (oracle %.12g)  min %.12g (oracle %.12g)" % (got_max, mx, got, want))
+    assert abs(got_max / mx - 1) < 1e-9 and abs(got / want - 1) < 1e-9
