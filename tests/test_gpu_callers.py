@@ -179,7 +179,7 @@ def test_tamat_thmat_conversions(osb):
 
 def test_min_eigenvalue(osb):
     """ker_find_min_eigenvalue_openacc (find_min_max.c:62-98) against the restatement: a converged power iteration,
-    stopped by a 1e-5 criterion on both sides -> 1e-9 on the value"""
+    stopped by a 1e-5 relative criterion on both sides (one iteration more or less moves the value by up to that) -> 3e-5"""
     loc_n = (8, 8, 8, 8)
     lat = osb.Lattice(loc_n); S = Restatement(*loc_n)
     u = random_su3_conf(S.sizeh, 96); w = gaussian_vec(S.sizeh, 97); ph = S.phases(0, EB, 1.0, 2.0)
@@ -190,4 +190,4 @@ def test_min_eigenvalue(osb):
     got_max = lat.ker_find_max_eigenvalue_openacc(du, pars, lat.new_vec(), lat.new_vec(), lat.to_device(w))
     got = lat.ker_find_min_eigenvalue_openacc(du, pars, lat.new_vec(), lat.new_vec(), lat.to_device(w), mx * 1.1)
     print("eigenvalues: max %.12g (oracle %.12g)  min %.12g (oracle %.12g)" % (got_max, mx, got, want))
-    assert abs(got_max / mx - 1) < 1e-9 and abs(got / want - 1) < 1e-9
+    assert abs(got_max / mx - 1) < 3e-5 and abs(got / want - 1) < 3e-5
