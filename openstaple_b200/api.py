@@ -512,11 +512,13 @@ class Lattice:
         self.L.setup_inverter_package_dp.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4
         self.L.setup_inverter_package_dp(C.addressof(ip), _addr(u), _addr(ferm_shift_temp), nshifts, _addr(loc_r),
                                          _addr(loc_h), _addr(loc_s), _addr(loc_p))
+        ip._refs_dp = (u, ferm_shift_temp, loc_r, loc_h, loc_s, loc_p)     # the struct holds raw addresses only
 
     def setup_inverter_package_sp(self, ip, u_f, ferm_shift_temp_f, nshifts, loc_r_f, loc_h_f, loc_s_f, loc_p_f, out_f):
         self.L.setup_inverter_package_sp.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5
         self.L.setup_inverter_package_sp(C.addressof(ip), _addr(u_f), _addr(ferm_shift_temp_f), nshifts, _addr(loc_r_f),
                                          _addr(loc_h_f), _addr(loc_s_f), _addr(loc_p_f), _addr(out_f))
+        ip._refs_sp = (u_f, ferm_shift_temp_f, loc_r_f, loc_h_f, loc_s_f, loc_p_f, out_f)
 
     def inverter_mixed_precision(self, ip, pars, solution, inp, res, max_cg, shift):
         f = self.L.inverter_mixed_precision
