@@ -121,6 +121,34 @@ def _worker(rank, world, port, loc, mode, q):
         wsg = S.scatter_conf(rank, sgg)
         flo, fhi = (S.d3_halo - 1) * S.vol3h, (S.d3_halo + loc[3] + 1) * S.vol3h      # interior + the exchanged halo slice
         errs["stout_force"] = _relerr(dsg.cpu().numpy()[..., flo:fhi], wsg[..., flo:fhi])
+        # ---- operator with a field (field_times_fermion_matrix.c): exchange through communicate_fermion_borders
+        def scat(a):        # any [..., gl_sizeh] field -> this rank's local+halo box: whole d3 slices (communications.c:1104-1257)
+            a2 = a.reshape(-1, G.sizeh); o = np.zeros((a2.shape[0], S.sizeh), a.dtype)
+            for d3 in range(S.nd[3]):
+                g3 = (d3 + loc[3] * rank - S.d3_halo) % (loc[3] * world)
+                o[:, d3 * S.vol3h:(d3 + 1) * S.vol3h] = a2[:, g3 * S.vol3h:(g3 + 1) * S.vol3h]
+            return o.reshape(a.shape[:-1] + (S.sizeh,))
+        rng = np.random.default_rng(7); freg, fimg = rng.standard_normal((8, G.sizeh)), rng.standard_normal((8, G.sizeh))
+        out = lat.new_vec()
+        lat.acc_Deo_wf(du, out, dv, dph, lat.to_device(scat(freg)), lat.to_device(scat(fimg)))
+        want = S.scatter_vec(rank, G.dslash_wf("deo", u, v, phg, freg, fimg))
+        errs["deo_wf"] = _relerr(out.cpu().numpy()[:, r1lo:r1hi], want[:, r1lo:r1hi])
+        # ---- the whole MD fermion force (fermion_force.c:166-357): smearing, CG-M, outer products, Sigma' -> Sigma, TA
+        fin = gaussian_vec(G.sizeh, 8, n=1)
+        flg = [dict(mass=0.08, ph=phg, number_of_ps=1, first_ps=0, ra_a=[0.4, 0.1], ra_b=[0.02, 0.3])]
+        want_ipdot = G.fermion_force(u, flg, fin, 1e-10, 5000, 0.12, 1)[0]
+        lat.set_stout(0.12, 1, lat.new_conf(), lat.new_conf(), lat.new_tamat())
+        lat.set_force_globals(aux_th=lat.new_tamat(), aux_ta=lat.new_tamat())
+        fpars = lat.ferm_param_array([dict(mass=0.08, phases=dph, number_of_ps=1, first_ps=0, ra_a=[0.4, 0.1], ra_b=[0.02, 0.3])])
+        ip = osb.InverterPackage()
+        lat.setup_inverter_package_dp(ip, du, lat.new_vec(2), 2, lat.new_vec(), lat.new_vec(), lat.new_vec(), lat.new_vec())
+        ipdot = lat.new_tamat()
+        lat.fermion_force_soloopenacc(du, torch.zeros((1, 8, 3, 3, S.sizeh), dtype=torch.complex128, device=lat.device), lat.new_conf(),
+                                      ipdot, fpars, 1, lat.to_device(np.stack([S.scatter_vec(rank, fin[0])])), 1e-10, lat.new_conf(),
+                                      lat.new_vec(2), ip, 5000)
+        # tamat_soa packs three COMPLEX arrays and two real ones per link: slice by site field by field
+        errs["full_force"] = max(_relerr(a[..., ilo:ihi], scat(np.ascontiguousarray(b))[..., ilo:ihi])
+                                 for a, b in zip(osb.tamat_fields(ipdot), osb.tamat_fields(want_ipdot)))
         lat.shutdown_multidev()
         dist.destroy_process_group()
         q.put((rank, errs, ""))
@@ -149,6 +177,8 @@ def _run(world, loc, mode):
             assert errs[k] < 1e-13, (rank, k, errs)
         assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)
+        assert errs["deo_wf"] < 1e-13 and errs["full_force"] < 1e-7, (rank, errs)      # force: iterative solves to 1e-10 inside
+    print("multi-rank errors:", sorted(res)[0][1])
 
 
 @pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3))],
