@@ -119,8 +119,22 @@ typedef struct inv_tricks_t {               /* ref: Include/inverter_tricks.h:4-
 extern inv_tricks inverter_tricks;          /* weak in the library; the host's definition wins */
 #endif
 
-/* complex return values: {re, im} pairs, ABI-identical to C99 `double complex` */
+/* complex return values: {re, im} pairs, ABI-identical to C99 `double complex` (x86-64 SysV: both travel in xmm0:xmm1).
+ * A C translation unit that has <complex.h> in scope (every reference source has, through struct_c_def.h) sees the
+ * reference's own return type, so this header and the reference's fermionic_utilities.h can be included together. */
 typedef struct { double re, im; } staple_dcomplex;
+#if !defined(__cplusplus) && defined(_Complex_I)
+typedef double _Complex staple_dcomplex_ret;
+#else
+typedef staple_dcomplex staple_dcomplex_ret;
+#endif
+/* MPI_Request arrays of the reference's *_async exchanges (ignored here: the requests are CUDA events owned by the
+ * library); typed as the host's MPI_Request when <mpi.h> is in scope so that communications.h can be included too */
+#if defined(MPI_VERSION) || defined(MPI_COMM_WORLD)
+typedef MPI_Request staple_request;
+#else
+typedef void staple_request;
+#endif
 
 #ifndef INVERTER_SUCCESS
 #define INVERTER_SUCCESS 1                  /* ref: OpenAcc/inverter_full.h:12-13 */
@@ -218,10 +232,10 @@ void communicate_fermion_borders_hostonly_f(vec3_soa_f *lnh_fermion);
 void communicate_su3_borders_hostonly_f(su3_soa_f *lnh_conf, int thickness);
 /* ref: :257-271 / :273-303 take MPI_Request arrays; here the requests are CUDA events owned by the
  * library: *_async starts the exchange on the comm stream, staple_wait_borders() joins it. */
-void communicate_fermion_borders_async(vec3_soa *lnh_fermion, void *unused_send_req, void *unused_recv_req);
-void communicate_su3_borders_async(su3_soa *lnh_conf, int thickness, void *unused_send_req, void *unused_recv_req);
-void communicate_fermion_borders_async_f(vec3_soa_f *lnh_fermion, void *unused_send_req, void *unused_recv_req);
-void communicate_su3_borders_async_f(su3_soa_f *lnh_conf, int thickness, void *unused_send_req, void *unused_recv_req);
+void communicate_fermion_borders_async(vec3_soa *lnh_fermion, staple_request *unused_send_req, staple_request *unused_recv_req);
+void communicate_su3_borders_async(su3_soa *lnh_conf, int thickness, staple_request *unused_send_req, staple_request *unused_recv_req);
+void communicate_fermion_borders_async_f(vec3_soa_f *lnh_fermion, staple_request *unused_send_req, staple_request *unused_recv_req);
+void communicate_su3_borders_async_f(su3_soa_f *lnh_conf, int thickness, staple_request *unused_send_req, staple_request *unused_recv_req);
 void staple_wait_borders(void);
 
 /* ------------------------------------------------------------------ Dirac operator  (ref: OpenAcc/fermion_matrix.h:20-106) */
@@ -259,7 +273,7 @@ void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out
 
 /* ------------------------------------------------------------------ BLAS-1  (ref: OpenAcc/fermionic_utilities.h:38-123) */
 #define STAPLE_BLAS_DECL(V, S) \
-	staple_dcomplex scal_prod_global##S(const V *in_vect1, const V *in_vect2);            /* ref: fermionic_utilities.c:85-100,126-146 */ \
+	staple_dcomplex_ret scal_prod_global##S(const V *in_vect1, const V *in_vect2);            /* ref: fermionic_utilities.c:85-100,126-146 */ \
 	double real_scal_prod_global##S(const V *in_vect1, const V *in_vect2);                /* ref: :101-110,147-161 */ \
 	double l2norm2_global##S(const V *in_vect1);                                          /* ref: :111-120,162-175 */ \
 	void combine_in1xfactor_plus_in2##S(const V *in_vect1, const double factor, const V *in_vect2, V *out);       /* ref: :180-193 */ \

@@ -173,7 +173,7 @@ COMPLETE_HEADERS = ["OpenAcc/fermion_matrix.h", "OpenAcc/sp_fermion_matrix.h", "
                     "OpenAcc/sp_fermion_force.h", "OpenAcc/stouting.h", "OpenAcc/sp_stouting.h", "OpenAcc/field_times_fermion_matrix.h"]
 # the only deliberate differences: C99 `double complex` returned as an ABI-identical {re, im} struct; MPI_Request arrays are
 # opaque pointers here (the requests are CUDA events owned by the library)
-TYPE_ALIAS = {"d_complex": "staple_dcomplex", "MPI_Request*": "void*"}
+TYPE_ALIAS = {"d_complex": "staple_dcomplex_ret", "MPI_Request*": "staple_request*"}
 
 
 def test_prototypes_match_reference_headers():
@@ -200,3 +200,40 @@ def test_prototypes_match_reference_headers():
     assert checked >= 145, checked
     L = osb.load_library()
     assert not [n for hdr in COMPLETE_HEADERS for n in ref[hdr] if not hasattr(L, n)]
+
+
+# ----------------------------------------------------------------------------- a C host program links and runs
+REF_SCRATCH = os.path.join(os.environ.get("STAPLE_ORACLE_SCRATCH", os.path.join(os.environ.get("TMPDIR", "/tmp"), "staple_oracle_src")), "src")
+
+
+def _gcc_host(tmp_path, extra, link=True):
+    import subprocess
+    libdir = os.path.join(ROOT, "openstaple_b200")
+    exe = str(tmp_path / ("host" if link else "host.o"))
+    cmd = ["gcc", "-std=gnu99", "-Wall", "-Werror=implicit-function-declaration", "-I" + os.path.join(ROOT, "include")] + extra + \
+          [os.path.join(ROOT, "tests", "c_host", "host_link.c"), "-o", exe]
+    cmd += ["-L" + libdir, "-lstaple_b200", "-Wl,-rpath," + libdir] if link else ["-c"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+def test_c_host_program_links_and_runs(tmp_path):
+    """INTEGRATION.md in practice: gcc compiles a C host against include/staple_b200.h, the link step resolves the entry points
+    from libstaple_b200.so, and the program runs (host-side geometry arithmetic only -- no GPU)."""
+    import subprocess
+    osb.load_library()
+    exe = _gcc_host(tmp_path, [])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("nd3 12 sizeh 3072 r0 512 2560 r1 256 2816 linked 49 "), r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_SCRATCH, "OpenAcc")), reason="reference headers (scratch copy with the generated sp_* twins) not present")
+def test_header_coexists_with_reference_headers(tmp_path):
+    """a translation unit may include the reference's own headers AND include/staple_b200.h: every declaration compatible
+    (double complex return of scal_prod_global, MPI_Request* of the async exchanges, struct guards)"""
+    flags = ["-DWITH_REFERENCE_HEADERS", "-fcommon", "-w", "-I" + os.path.join(ROOT, "oracle", "mpi_stub"), "-I" + REF_SCRATCH,
+             "-DACTION_TYPE=TLSM", "-DNREPLICAS=1", "-DLOC_N0=8", "-DLOC_N1=8", "-DLOC_N2=8", "-DLOC_N3=8", "-DNRANKS_D3=2", "-DCOMMIT_HASH=t"]
+    flags += ["-D%s%s=8" % (a, b) for a in ("DEODOE", "IMPSTAP", "STAP", "SIGMA") for b in ("TILE0", "TILE1", "TILE2", "GANG3")]
+    _gcc_host(tmp_path, flags, link=False)
