@@ -27,7 +27,19 @@ void require_init(const char *fn)
 		exit(1);
 	}
 }
-void count_launch(int n) { g_ctx.launches += n; }
+// Blocking mode (staple_set_blocking): every entry point returns with its device work finished, which is what the
+// reference's synchronous OpenACC `kernels` regions give a host program that reads results (managed memory, gettimeofday
+// timers) right after a call.  Launches that are being captured into a CUDA graph are left alone: the solver that captures
+// them synchronises when it replays.
+static bool g_blocking = false;
+void blocking_point()
+{
+	if (!g_blocking) return;
+	cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+	if (cudaStreamIsCapturing(g_ctx.stream, &st) != cudaSuccess) { cudaGetLastError(); return; }
+	if (st == cudaStreamCaptureStatusNone) STAPLE_CUDA_CHECK(cudaDeviceSynchronize());
+}
+void count_launch(int n) { g_ctx.launches += n; blocking_point(); }
 
 // ------------------------------------------------------------------ present table
 struct Entry { size_t bytes; char *dptr; bool owned_host; };
@@ -345,6 +357,20 @@ void staple_acc_update_host(void *host, size_t bytes)
 	STAPLE_CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
 }
 
+void staple_set_blocking(int on) { g_blocking = on != 0; }
+
+// SURVEY 8b option (i): one address valid on host and device.  The reference's `#pragma acc update host/device` (no-ops
+// under gcc) become page migrations, so an UNMODIFIED host program runs against the library with only this allocator
+// behind posix_memalign_wrapper -- together with staple_set_blocking(1).
+int staple_posix_memalign_managed(void **memptr, size_t alignment, size_t size)
+{
+	(void) alignment;   // cudaMallocManaged returns memory aligned to at least 256 bytes (the reference asks for 128)
+	void *p = nullptr;
+	if (cudaMallocManaged(&p, size ? size : 1, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return 12; /* ENOMEM */ }
+	*memptr = p;
+	return 0;
+}
+
 int staple_posix_memalign(void **memptr, size_t alignment, size_t size)
 {
 	(void) alignment;   // cudaHostAlloc returns page-aligned memory (>= the reference's ALIGN 128)
@@ -362,6 +388,13 @@ int staple_posix_memalign(void **memptr, size_t alignment, size_t size)
 void staple_free(void *memptr)
 {
 	if (!memptr) return;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, memptr) == cudaSuccess && at.type == cudaMemoryTypeManaged) {   // staple_posix_memalign_managed
+		cudaDeviceSynchronize(); cudaFree(memptr);
+		for (auto &e : g_devcache) e = 0;            // cached "is a device address" answers may lie inside the freed block
+		return;
+	}
+	cudaGetLastError();
 	bool owned = false;
 	{
 		std::lock_guard<std::mutex> lk(g_present_mu);

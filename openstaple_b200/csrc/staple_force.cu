@@ -224,12 +224,12 @@ extern "C" {
 	void set_tamat_soa_to_zero##S(TAMAT *matrix)                                                                            \
 	{                                                                                                                       \
 		require_init("set_tamat_soa_to_zero");                                                                                \
-		STAPLE_CUDA_CHECK(cudaMemsetAsync(dev(matrix, "matrix"), 0, sizeof(T) * 8 * 8 * ctx().g.sizeh, ctx().stream));        \
+		STAPLE_CUDA_CHECK(cudaMemsetAsync(dev(matrix, "matrix"), 0, sizeof(T) * 8 * 8 * ctx().g.sizeh, ctx().stream)); blocking_point(); \
 	}                                                                                                                       \
 	void set_su3_soa_to_zero##S(SU3 *matrix)                                                                                \
 	{                                                                                                                       \
 		require_init("set_su3_soa_to_zero");                                                                                  \
-		STAPLE_CUDA_CHECK(cudaMemsetAsync(dev(matrix, "matrix"), 0, sizeof(C2) * 8 * 9 * ctx().g.sizeh, ctx().stream));       \
+		STAPLE_CUDA_CHECK(cudaMemsetAsync(dev(matrix, "matrix"), 0, sizeof(C2) * 8 * 9 * ctx().g.sizeh, ctx().stream)); blocking_point(); \
 	}                                                                                                                       \
 	void direct_product_of_fermions_into_auxmat##S(const VEC3 *loc_s, const VEC3 *loc_h, SU3 *aux_u,                        \
 																								 const RationalApprox *approx, int iter)                                  \

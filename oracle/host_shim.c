@@ -1,0 +1,55 @@
+/* TEST INFRASTRUCTURE ONLY -- the ONE file that is not the reference's in oracle/_ref/<prog>_staple_<geom>
+ * (oracle/build_ref_host.sh).  It stands in for src/Include/memory_wrapper.c, the allocation choke point every lattice
+ * array of the reference goes through (alloc_vars.c), and does what INTEGRATION.md section 2 asks of a maintainer:
+ *   (a) hand the compile-time geometry to the library once (staple_init_geometry),
+ *   (b) allocate through the library -- CUDA managed memory, so the host program's `#pragma acc update host/device`
+ *       (no-ops under gcc) need no replacement: one address is valid on both sides,
+ *   and ask for the reference's synchronous semantics (staple_set_blocking).
+ * Everything else in that binary -- main(), the input-file parser, the dSFMT generators, backfield phases, IO -- is the
+ * reference's own object code; the hot path is libstaple_b200.so. */
+#include <stdio.h>
+#include <stdlib.h>
+#include "staple_b200.h"
+
+struct memory_allocated_t { void *ptr; const char *varname; size_t size; struct memory_allocated_t *next; };   /* memory_wrapper.h:15-22 */
+struct memory_allocated_t *memory_allocated_base = NULL;
+size_t memory_used = 0;
+size_t max_memory_used = 0;
+
+static void init_once(void)
+{
+	static int done = 0;
+	if (done) return;
+	done = 1;
+	const char *dev = getenv("STAPLE_DEVICE");
+	if (staple_init_geometry(LOC_N0, LOC_N1, LOC_N2, LOC_N3, 1, 2 /* HALO_WIDTH, TLSM */, dev ? atoi(dev) : 0) != 0) {
+		fprintf(stderr, "host_shim: staple_init_geometry failed\n"); exit(1);
+	}
+	staple_set_blocking(1);
+	fprintf(stderr, "host_shim: hot path served by %s\n", staple_version());
+}
+
+/* memory_wrapper.c:14-31 */
+int posix_memalign_wrapper(void **memptr, size_t alignment, size_t size, const char *varname)
+{
+	init_once();
+	int res = staple_posix_memalign_managed(memptr, alignment, size);
+	memory_used += size;
+	if (memory_used > max_memory_used) max_memory_used = memory_used;
+	struct memory_allocated_t *all = (struct memory_allocated_t *) malloc(sizeof(struct memory_allocated_t));
+	all->ptr = *memptr; all->varname = varname; all->size = size; all->next = memory_allocated_base;
+	memory_allocated_base = all;
+	return res;
+}
+
+/* memory_wrapper.c:33-57 */
+void free_wrapper(void *memptr)
+{
+	struct memory_allocated_t *all = memory_allocated_base, *prev = NULL;
+	while (all != NULL && all->ptr != memptr) { prev = all; all = all->next; }
+	if (all == NULL) { fprintf(stderr, "host_shim: failed to find pointer %p in the list while freeing\n", memptr); exit(1); }
+	memory_used -= all->size;
+	if (prev != NULL) prev->next = all->next; else memory_allocated_base = all->next;
+	staple_free(all->ptr);
+	free(all);
+}

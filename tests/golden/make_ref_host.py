@@ -1,0 +1,119 @@
+"""Generates tests/golden/ref_host/*: the input files for the reference's OWN test programs (deo_doe_test,
+inverter_multishift_test; built unmodified by oracle/build_ref_host.sh) and the results the pure-reference CPU build of
+those programs writes.  tests/test_gpu_reference_host.py runs the SAME programs linked against libstaple_b200.so on the
+B200 with the same input files and compares the files they write.  Run in the dev container only:
+
+    python tests/golden/make_ref_host.py
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = os.environ.get("STAPLE_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "ref_host")
+GEOM = (8, 8, 8, 8)
+
+
+def make_input(n, deo_doe_iterations=3, ms_repetitions=1, benchmark=1, max_cg=40, save=1):
+    """build/input.example with: this geometry on one rank, identity direction map, the flavours and background field of
+    tools/test (charges, chemical potential, E and B fields: general U(1) phases), no replicas section, results saved"""
+    t = open(os.path.join(REF, "build", "input.example")).read()
+    t = t[:t.index("#---- Hasenbusch Parallel Tempering params")]
+    flav = open(os.path.join(REF, "tools", "test", "fermion_parameters.set")).read().strip() + "\n\n"
+    t = re.sub(r"FlavourParameters\n.*?(?=BackgroundFieldParameters)", "", t, flags=re.S)
+    t = t.replace("BackgroundFieldParameters", flav + "BackgroundFieldParameters", 1)
+
+    def put(key, val):
+        nonlocal t
+        t, k = re.subn(r"^(%s\s+)\S+" % re.escape(key), lambda m: m.group(1) + str(val), t, count=1, flags=re.M)
+        assert k == 1, key
+    for key, val in (("ex", 5), ("ey", -5), ("ez", 1), ("bx", -5), ("by", 5), ("bz", 3), ("nx", n[0]), ("ny", n[1]), ("nz", n[2]),
+                     ("nt", n[3]), ("xmap", 0), ("ymap", 1), ("zmap", 2), ("tmap", 3), ("NRanks", 1), ("NProcPerNode", 1),
+                     ("residue_md", "1.0e-4"), ("residue_metro", "1.0e-8"), ("ExpMaxEigenvalue", "5.5"), ("EpsGen", "3.0"),
+                     ("UseILDG", 0), ("VerbosityLv", 1), ("SaveDiagnostics", 0), ("DeoDoeIterations", deo_doe_iterations),
+                     ("MultiShiftInverterRepetitions", ms_repetitions), ("BenchmarkMode", benchmark), ("SaveResults", save),
+                     ("MaxCGIterations", max_cg), ("useMixedPrecision", 0), ("FakeShift", "1.0e-2")):
+        put(key, val)
+    return t
+
+
+def read_vec3_ascii(path, single=False):
+    """print_vec3_soa_wrapper's global ASCII format (io.c:553-614): one `re<TAB>im` line per colour and even site"""
+    a = np.loadtxt(path, dtype=np.float64)
+    return (a[:, 0] + 1j * a[:, 1]).reshape(-1, 3)
+
+
+def run(prog, input_text, extra_files=()):
+    exe = os.path.join(ROOT, "oracle", "_ref", "%s_ref_%dx%dx%dx%d" % ((prog,) + GEOM))
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "in.set"), "w").write(input_text)
+        for name, text in extra_files:
+            open(os.path.join(td, name), "w").write(text)
+        r = subprocess.run([exe, "in.set"], cwd=td, capture_output=True, text=True, timeout=3600)
+        files = {f: os.path.join(td, f) for f in os.listdir(td)}
+        return r, {f: open(p, "rb").read() for f, p in files.items() if os.path.getsize(p) < 64 << 20}
+
+
+def remez_text(r):
+    """the .REMEZ layout the reference's reader parses (rationalapprox.c:96-106), from the numbers its own reader returned"""
+    t = "\nApproximation to f(x) = (x)^(%d/%d)\n" % (r["num"], r["den"])
+    t += "Order: %d\nLambda Min: %.16e\nLambda Max: %.16e\n" % (r["order"], r["lmin"], r["lmax"])
+    t += "GMP Remez Precision: %d\nError: %.16e\nRA_a0 = %.16e\n" % (r["prec"], r["error"], r["a0"])
+    for i, (x, y) in enumerate(zip(r["a"], r["b"])):
+        t += "RA_a[%d] = %.16e, RA_b[%d] = %.16e\n" % (i, x, i, y)
+    return t
+
+
+def read_ratapproxes():
+    """tools/test/ratapproxes/*.REMEZ through the reference's own reader -> {file name: numbers}"""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    from make_golden import _RA
+    from oracle.pyoracle import RefLib
+    R = RefLib(4, 4, 4, 4)
+    out = {}
+    d = os.path.join(REF, "tools", "test", "ratapproxes")
+    for f in sorted(os.listdir(d)):
+        r = _RA()
+        R.lib.ref_approx_read(C.byref(r), os.path.join(d, f).encode())
+        out[f] = dict(num=r.exponent_num, den=r.exponent_den, order=r.approx_order, lmin=r.lambda_min, lmax=r.lambda_max,
+                      prec=r.gmp_remez_precision, error=r.error, a0=r.RA_a0, a=list(r.RA_a[:r.approx_order]), b=list(r.RA_b[:r.approx_order]))
+    return out
+
+
+if __name__ == "__main__":
+    subprocess.run([os.path.join(ROOT, "oracle", "build_ref_host.sh")] + [str(x) for x in GEOM], check=True)
+    os.makedirs(OUT, exist_ok=True)
+    text = make_input(GEOM)
+    open(os.path.join(OUT, "deo_doe_%dx%dx%dx%d.set" % GEOM), "w").write(text)
+    r, files = run("deo_doe_test", text)
+    assert r.returncode == 0 and "Test completed" in r.stdout, r.stdout[-2000:]
+    d = {}
+    with tempfile.TemporaryDirectory() as td:
+        for f in ("test_fermion", "test_fermion_result_doe2", "test_fermion_result_deo2", "test_fermion_result_fulldirac2",
+                  "sp_test_fermion_result_doe2", "sp_test_fermion_result_deo2", "sp_test_fermion_result_fulldirac2"):
+            open(os.path.join(td, f), "wb").write(files[f])
+            d[f] = read_vec3_ascii(os.path.join(td, f))
+    # inverter_multishift_test in benchmark mode: 15 equal shifts, MaxCGIterations iterations (its residue is 2e-144)
+    approx = read_ratapproxes()
+    import json
+    json.dump(approx, open(os.path.join(OUT, "ratapproxes.json"), "w"), indent=0, sort_keys=True)
+    extra = [(name, remez_text(r)) for name, r in approx.items()]
+    r, files = run("inverter_multishift_test", text, extra)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    print(r.stdout[-1200:])
+    shifts = sorted(f for f in files if re.match(r"fermion_shift_\d+\.dat$", f))
+    with tempfile.TemporaryDirectory() as td:
+        for f in shifts[:3]:
+            open(os.path.join(td, f), "wb").write(files[f])
+            d["ms_" + f.replace(".dat", "")] = read_vec3_ascii(os.path.join(td, f))
+    d["ms_nshift_files"] = len(shifts)
+    np.savez_compressed(os.path.join(OUT, "ref_host_results_%dx%dx%dx%d.npz" % GEOM), **d)
+    print(sorted(files)); print({k: getattr(v, "shape", v) for k, v in d.items()})
