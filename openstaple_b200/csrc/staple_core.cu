@@ -231,6 +231,7 @@ int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo
 	STAPLE_CUDA_CHECK(cudaGetDevice(&c.device));
 	Geom &g = c.g;
 	fill_geom(g, n0, n1, n2, n3, nranks_d3, halo_width);
+	release_streamed_state();      // cached schedules carry the previous geometry in their kernel arguments
 	if (!c.own_stream) {
 		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
 		STAPLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.s_p, cudaStreamNonBlocking));
@@ -277,11 +278,26 @@ int staple_geometry_plan(const int loc_n[4], int nranks_d3, int halo_width, long
 	return 0;
 }
 
+// Releases everything the library owns: rank layer, streams, events, reduction scratch, solver control blocks, cached
+// graphs.  The present table (device mirrors of host arrays) belongs to the caller's arrays and goes with staple_free /
+// staple_acc_exit_data.  staple_init_geometry may be called again afterwards.
 void staple_shutdown(void)
 {
 	Ctx &c = ctx();
 	if (!c.inited) return;
 	cudaDeviceSynchronize();
+	shutdown_multidev();
+	release_solver_state();
+	release_streamed_state();
+	cudaStream_t *streams[] = { &c.own_stream, &c.s_p, &c.s_m, &c.s_comm };
+	for (auto s : streams) { if (*s) cudaStreamDestroy(*s); *s = nullptr; }
+	cudaEvent_t *evs[] = { &c.ev_fork, &c.ev_p, &c.ev_m, &c.ev_comm, &c.ev_misc };
+	for (auto e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+	cudaFree(c.d_tickets); cudaFree(c.d_results); cudaFree(c.d_partials); cudaFreeHost(c.h_results);
+	c.d_tickets = nullptr; c.d_results = nullptr; c.d_partials = nullptr; c.h_results = nullptr; c.max_partials = 0;
+	c.stream = nullptr; c.cgm_hook = nullptr; c.out_host_hook = nullptr;
+	for (auto &e : g_devcache) e = 0;
+	cudaGetLastError();
 	c.inited = false;
 }
 

@@ -332,6 +332,8 @@ staple_dcomplex reduce_global(RedOp op, const cplx_t<T> *a, const cplx_t<T> *b);
 void fetch_results(int slot, int ndoubles, double *host_out);   // all-reduce + D2H + sync
 
 void count_launch(int n = 1);
+void release_solver_state();      // staple_solvers.cu: CG-M control block, snapshot buffers, timing events
+void release_streamed_state();    // staple_kernels.cu: cached graphs of staple_acc_Doe_Deo_streamed
 void blocking_point();            // staple_set_blocking(1): wait for the device here (no-op otherwise and during graph capture)
 
 }   // namespace staple

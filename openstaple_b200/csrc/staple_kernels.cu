@@ -947,6 +947,22 @@ using namespace staple;
 #define CDD(p) ((const double2 *) dev(p, #p))
 #define CDF(p) ((const float2 *) dev(p, #p))
 
+// captured schedules of staple_acc_Doe_Deo_streamed, keyed by buffers + chunking (geometry is baked into their kernel nodes:
+// staple_init_geometry and staple_shutdown flush them)
+struct StreamedGraph { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs, mode; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
+static StreamedGraph g_streamed_cache[4] = {};
+static int g_streamed_next = 0;
+namespace staple {
+void release_streamed_state()
+{
+	for (auto &e : g_streamed_cache) {
+		if (e.exec) cudaGraphExecDestroy(e.exec);
+		e = StreamedGraph{};
+	}
+	g_streamed_next = 0;
+}
+}   // namespace staple
+
 extern "C" {
 
 // ---- operator variants.  `unsafe`: whole local interior, no exchange; bulk/d3p/d3m/d3c: d3 sub-ranges
@@ -1133,9 +1149,9 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	// depends on the pointers and the chunking, so it is captured ONCE into a CUDA graph (three streams, copy
 	// nodes included) and replayed with a single launch.  The legacy default stream cannot be captured: direct
 	// issue there.
-	struct Cached { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs, mode; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
-	static Cached cache[4] = {};
-	static int cache_next = 0;
+	using Cached = StreamedGraph;
+	Cached (&cache)[4] = g_streamed_cache;
+	int &cache_next = g_streamed_next;
 	Cached *hit = nullptr;
 	if (st != nullptr && c.use_graphs && !trace) {
 		for (auto &e : cache)

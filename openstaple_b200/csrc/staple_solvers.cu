@@ -249,6 +249,15 @@ static void ensure_ctl()
 	STAPLE_CUDA_CHECK(cudaEventCreate(&g_ev_t1));
 }
 
+void release_solver_state()        // staple_shutdown
+{
+	if (!g_d_ctl) return;
+	cudaFree(g_d_ctl); cudaFreeHost(g_h_ctl);
+	for (int i = 0; i < 2; i++) cudaEventDestroy(g_ev_snap[i]);
+	cudaEventDestroy(g_ev_t0); cudaEventDestroy(g_ev_t1);
+	g_d_ctl = nullptr; g_h_ctl = nullptr; g_ev_snap[0] = g_ev_snap[1] = g_ev_t0 = g_ev_t1 = nullptr;
+}
+
 template <typename T> struct PhasesOf;
 template <> struct PhasesOf<double> { static const double *get(ferm_param *p) { return (const double *) dev(p->phases, "pars->phases"); } };
 template <> struct PhasesOf<float> { static const float *get(ferm_param *p) { return (const float *) dev(p->phases_f, "pars->phases_f"); } };

@@ -191,3 +191,32 @@ def test_min_eigenvalue(osb):
     got = lat.ker_find_min_eigenvalue_openacc(du, pars, lat.new_vec(), lat.new_vec(), lat.to_device(w), mx * 1.1)
     print("eigenvalues: max %.12g (oracle %.12g)  min %.12g (oracle %.12g)" % (got_max, mx, got, want))
     assert abs(got_max / mx - 1) < 3e-5 and abs(got / want - 1) < 3e-5
+
+
+def test_shutdown_releases_and_reinit_works(osb):
+    """staple_shutdown frees the library's streams, scratch and cached graphs; staple_init_geometry brings everything back"""
+    loc_n = (8, 8, 8, 8)
+    S = Restatement(*loc_n)
+    u = random_su3_conf(S.sizeh, 31); v = gaussian_vec(S.sizeh, 32); ph = S.phases(0, EB, 1.0, 2.0)
+    want = S.mdagm(u, v, ph, 0.0507)
+    for _ in range(2):
+        lat = osb.Lattice(loc_n)
+        du, dv, dph = lat.to_device(u), lat.to_device(v), lat.to_device(ph)
+        out, tmp = lat.new_vec(), lat.new_vec()
+        lat.fermion_matrix_multiplication(du, out, dv, tmp, lat.ferm_param(0.0507, dph))
+        assert relerr(out.cpu().numpy(), want) < 1e-13
+        sol, ps = lat.new_vec(2), lat.new_vec(2)
+        r, h, s, p = (lat.new_vec() for _ in range(4))
+        st, cg = lat.multishift_invert(du, lat.ferm_param(0.0507, dph), osb.RationalApprox.make(1.0, np.ones(2), np.array([0.01, 0.5])),
+                                       sol, dv, 1e-8, r, h, s, p, ps, 5000)
+        assert st == 1 and cg > 10
+        lat.synchronize()
+        lat.L.staple_shutdown()
+    # a compute call after shutdown fails loudly (subprocess: the library exits)
+    import subprocess
+    import sys
+    code = ("import openstaple_b200 as o, torch\nlat = o.Lattice((4, 4, 4, 4)); v = lat.new_vec(); lat.L.staple_shutdown()\n"
+            "lat.L.l2norm2_global(v.data_ptr())\nprint('SURVIVED')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       cwd=__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    assert r.returncode != 0 and "SURVIVED" not in r.stdout and "staple_init_geometry" in r.stderr
