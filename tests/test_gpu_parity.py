@@ -255,6 +255,34 @@ def test_multishift_vs_oracle_8(osb):
     assert cg2 == 37
 
 
+@pytest.mark.parametrize("order", [1, 25])
+@pytest.mark.parametrize("single", [False, True])
+def test_multishift_extreme_orders(osb, order, single):
+    """approx_order = 1 and = MAX_APPROX_ORDER (rationalapprox.h:8), both precisions, against the oracle: iteration counts, every
+    shifted solution, and the recombination with 25 terms"""
+    c = make_case(osb, (4, 4, 4, 4), seed=5)
+    lat, S = c["lat"], c["S"]
+    shifts = np.array([0.05]) if order == 1 else np.geomspace(1e-4, 5.0, 25)
+    ra = np.linspace(0.2, 1.4, order)
+    mass, res = 0.0507, (1e-5 if single else 1e-9)
+    u, v, ph = (c["uf"], c["vf"], c["phf"]) if single else (c["u"], c["v"], c["ph"])
+    want, cg_ref, ok, _ = S.multishift_invert(u, ph, mass, shifts, v, res, 10000)
+    pars = lat.ferm_param(mass, c["d_ph"], c["d_phf"])
+    approx = osb.RationalApprox.make(0.3, ra, shifts)
+    out, ps = lat.new_vec(order, single=single), lat.new_vec(order, single=single)
+    r, h, s_, p = (lat.new_vec(single=single) for _ in range(4))
+    d_u, d_v = (c["d_uf"], c["d_vf"]) if single else (c["d_u"], c["d_v"])
+    st, cg = lat.multishift_invert(d_u, pars, approx, out, d_v, res, r, h, s_, p, ps, 10000)
+    # +-2 % of the oracle's count; a 69-iteration FP32 solve is shorter than 2 % resolves, so at least two iterations of slack
+    assert st == osb.INVERTER_SUCCESS and abs(cg - cg_ref) <= max(2, 0.02 * cg_ref), (cg, cg_ref)
+    got = out.cpu().numpy()
+    tol = 2e-3 if single else 1e-6          # iterative solutions: residual x condition number, not rounding
+    assert max(relerr(got[i], want[i]) for i in range(order)) < tol
+    rec = lat.new_vec(single=single)
+    lat.recombine_shifted_vec3_to_vec3(out, d_v, rec, approx)
+    assert relerr(rec.cpu().numpy(), S.recombine(got, v, 0.3, ra)) < (TOL32 if single else TOL64)
+
+
 def test_cg_and_mixed(osb, golden_r1):
     g = golden_r1
     lat = osb.Lattice((4, 4, 4, 4))
