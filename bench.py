@@ -158,6 +158,10 @@ def run_reference(args, emit):
         run = lambda u, a, b, ph: (R.dslash("doe", u, a, ph, out=b), R.dslash("deo", u, b, ph, out=a))
         ph = R.phases(0)
     u = random_su3_conf(R.sizeh, 1); a = gaussian_vec(R.sizeh, 2); b = np.zeros_like(a)
+    # Bounded sample: the reference's build is single-threaded (OpenACC pragmas ignored, no OpenMP anywhere in the tree), one
+    # Doe+Deo pair on 32^4 takes 0.4-1 s, so at most 12 timed pairs (2 warm-up) of ONE rank's slab are run whatever K, W and N
+    # are; its throughput is size-independent (bandwidth-bound stencil), so the figure stands for the whole workload.
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
     steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
     for _ in range(warm):
         run(u, a, b, ph)
@@ -167,14 +171,24 @@ def run_reference(args, emit):
     dt = (time.perf_counter() - t0) / steps
     gflops = 2 * FLOP_PER_SITE * R.sizeh / dt / 1e9
     line = {"impl": "reference", "metric": "deo_doe_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3 * world, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "deo_doe %s FP64 (Doe+Deo per step)" % args.lattice},
+            "config": workload_config(args.lattice, loc, world, "none (single host process)"),
             "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": kind,
-                             "sample": "%d Doe+Deo pairs on the full %s lattice, 1 host thread" % (steps, args.lattice)},
+                             "sample": "%d Doe+Deo pairs (of the %d steps asked for) on one %s slab, timed on 1 host thread -- the gcc "
+                                       "build of the reference is single-threaded; ms_per_step = that time x %d slab(s)"
+                                       % (steps, args.steps, args.lattice, world)},
             "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def workload_config(lattice, loc, world, halo):
+    """the `config` object of both arms: the workload BASELINE.json's metric is quoted on (configs[1]) and how it is laid out"""
+    return {"workload": "deo_doe %s per GPU, FP64, one acc_Doe + one acc_Deo per step, D3 slabs over %d GPU(s)" % (lattice, world),
+            "global_lattice": "%dx%dx%dx%d" % (loc[0], loc[1], loc[2], loc[3] * world), "halo": halo,
+            "l2_policy": "inputs larger than L2 (links 384 MiB read per application at 32^4 vs 126 MB L2)",
+            "flop_per_site": FLOP_PER_SITE, "bytes_per_site": BYTES_PER_SITE_FP64}
 
 
 def cpu_baseline(args, loc, u_host, v_host, ph_host):
@@ -396,12 +410,8 @@ def main():
         line = {"metric": "deo_doe_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "deo_doe %s per GPU, FP64, one acc_Doe + one acc_Deo per step, D3 slabs over %d GPU(s)"
-                                       % (args.lattice, world),
-                           "global_lattice": "%dx%dx%dx%d" % (loc[0], loc[1], loc[2], loc[3] * world),
-                           "halo": ("nvlink peer stores fused in the surface kernels" if getattr(lat, "p2p", False) else "nccl send/recv") if world > 1 else "none",
-                           "l2_policy": "inputs larger than L2 (links 384 MiB read per application at 32^4 vs 126 MB L2)",
-                           "flop_per_site": FLOP_PER_SITE, "bytes_per_site": BYTES_PER_SITE_FP64},
+                "config": workload_config(args.lattice, loc, world, ("nvlink peer stores fused in the surface kernels" if getattr(lat, "p2p", False)
+                                                                      else "nccl send/recv") if world > 1 else "none"),
                 "hbm_GBps": BYTES_PER_SITE_FP64 * sites_per_step / world / (ms_step * 1e-3) / 1e9,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "mdagm": {"ms": ms_mdagm, "algorithmic_GBps": 1904.0 * interior / (ms_mdagm * 1e-3) / 1e9,

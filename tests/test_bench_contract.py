@@ -1,0 +1,56 @@
+"""bench.py's JSON contract (task statement, section 4): the reference arm is run for real on the CPU (one bounded sample),
+the product arm's line is checked on the latest committed B200 run (profiles/), and both must describe the same workload."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+
+
+def _latest_product_line():
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_bench_n1.json")))
+    assert files
+    return json.loads(open(files[-1]).read().strip().splitlines()[-1])
+
+
+def test_product_line_carries_the_contract():
+    d = _latest_product_line()
+    assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    assert d["metric"] == "deo_doe_gflops" and d["unit"] == "GFLOP/s" and d["dtype"] == "f64" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.5 < r["frac"] <= 1.05
+    c = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("reference", "port") and c["cores"] == 1
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
+    assert e["h2d_bytes_per_step"] == 48 * 524288 and e["d2h_bytes_per_step"] == 48 * 524288 and 0 < e["value"] < d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_32x32x32x32_r1.so")), reason="no reference build for 32^4")
+def test_reference_arm_runs_on_the_cpu_and_matches_the_workload():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                   # ONE JSON line on stdout
+    d = json.loads(lines[0])
+    assert BASE_KEYS | {"impl"} <= set(d) and d["impl"] == "reference"
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert 0.05 < d["value"] < 50                            # a single CPU thread: order 1 GFLOP/s
+    p = _latest_product_line()
+    for k in ("metric", "unit", "higher_is_better", "dtype", "scaling"):
+        assert d[k] == p[k], k
+    for k in ("workload", "global_lattice", "flop_per_site", "bytes_per_site"):
+        assert d["config"][k] == p["config"][k], k
