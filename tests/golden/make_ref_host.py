@@ -40,7 +40,9 @@ def make_input(n, deo_doe_iterations=3, ms_repetitions=1, benchmark=1, max_cg=40
                      ("MultiShiftInverterRepetitions", ms_repetitions), ("BenchmarkMode", benchmark), ("SaveResults", save),
                      ("MaxCGIterations", max_cg), ("useMixedPrecision", 0), ("FakeShift", "1.0e-2")):
         put(key, val)
-    return t
+    # keep only what the parser reads: section names and `key value` pairs (the example's commentary stays in the reference)
+    lines = [l.split("#")[0].rstrip() for l in t.splitlines()]
+    return "\n".join(re.sub(r"\s+", " ", l) for l in lines if l.strip()) + "\n"
 
 
 def read_vec3_ascii(path, single=False):
