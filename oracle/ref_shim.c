@@ -284,13 +284,13 @@ void ref_eo_inversion(ferm_param *pars, double res, int max_cg, vec3_soa *in_e, 
 
 #ifdef MULTIDEVICE
 /* ---- single-process mailbox MPI ------------------------------------------------
- * Sends are copied into a mailbox keyed by (src,dst,tag); receives are served from
- * it if the matching message is already there, otherwise they are left pending
- * (nonblocking) or skipped (blocking).  Running the reference's exchange routine
- * twice for every rank therefore completes all transfers with the reference's own
- * offsets, counts, tags and neighbour ranks. */
-#define MB_MAX 4096
-typedef struct { int src, dst, tag; size_t bytes; void *data; } mb_msg;
+ * Sends are appended to a FIFO keyed by (src,dst,tag) -- MPI's non-overtaking order: the reference re-uses tags 0-5 for every
+ * component array of a field; receives take the OLDEST matching message if one is there, otherwise they are left pending
+ * (nonblocking) or skipped (blocking).  Running the reference's exchange routine twice for every rank therefore completes
+ * all transfers with the reference's own offsets, counts, tags and neighbour ranks (the second pass re-sends the same
+ * interior slices, which the exchange never modifies).  ref_mailbox_clear() before every exchange drops what is left. */
+#define MB_MAX 8192
+typedef struct { int src, dst, tag, live; size_t bytes; void *data; } mb_msg;
 static mb_msg mb[MB_MAX]; static int mb_n = 0;
 typedef struct { int src, tag; size_t bytes; void *dst; int live; } mb_pend;
 static mb_pend pend[MB_MAX]; static int pend_n = 0;
@@ -306,21 +306,16 @@ long ref_mailbox_missing(void) { long m = mb_missing; mb_missing = 0; return m; 
 static size_t dtsize(MPI_Datatype t) { return (size_t) t; }
 static void mb_post(const void *buf, size_t bytes, int dst, int tag)
 {
-	for (int i = 0; i < mb_n; i++)
-		if (mb[i].src == devinfo.myrank && mb[i].dst == dst && mb[i].tag == tag) {
-			if (mb[i].bytes != bytes) { mb[i].data = realloc(mb[i].data, bytes); mb[i].bytes = bytes; }
-			memcpy(mb[i].data, buf, bytes); return;
-		}
 	if (mb_n == MB_MAX) { printf("oracle mailbox full\n"); exit(1); }
-	mb[mb_n].src = devinfo.myrank; mb[mb_n].dst = dst; mb[mb_n].tag = tag; mb[mb_n].bytes = bytes;
+	mb[mb_n].src = devinfo.myrank; mb[mb_n].dst = dst; mb[mb_n].tag = tag; mb[mb_n].bytes = bytes; mb[mb_n].live = 1;
 	mb[mb_n].data = malloc(bytes); memcpy(mb[mb_n].data, buf, bytes); mb_n++;
 }
 static int mb_fetch(void *buf, size_t bytes, int src, int tag)
 {
 	for (int i = 0; i < mb_n; i++)
-		if (mb[i].src == src && mb[i].dst == devinfo.myrank && mb[i].tag == tag) {
+		if (mb[i].live && mb[i].src == src && mb[i].dst == devinfo.myrank && mb[i].tag == tag) {
 			if (mb[i].bytes != bytes) { printf("oracle mailbox size mismatch\n"); exit(1); }
-			memcpy(buf, mb[i].data, bytes); return 1;
+			memcpy(buf, mb[i].data, bytes); mb[i].live = 0; return 1;
 		}
 	mb_missing++; return 0;
 }

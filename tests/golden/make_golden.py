@@ -260,6 +260,44 @@ def reference_prototypes():
     print("prototypes", sum(len(v) for v in per_header.values()))
 
 
+def border_fields(sizeh, rank):
+    """deterministic local boxes for the border-exchange fixture: every element names its rank, array and site"""
+    idx = np.arange(sizeh, dtype=np.float64)
+    conf = np.zeros((8, 3, 3, sizeh), np.complex128)
+    for k in range(8):
+        for r in range(3):
+            for c in range(3):
+                conf[k, r, c] = (1000.0 * rank + 100 * k + 10 * r + c) + 1e-4 * idx + 1j * (idx + 0.5 * rank)
+    ta = np.zeros((8, 8, sizeh), np.float64)
+    for k in range(8):
+        for j in range(8):
+            ta[k, j] = 7000.0 * rank + 100 * k + j + 1e-4 * idx
+    return conf, ta
+
+
+def borders_multi(loc=(4, 4, 4, 4), nr=2):
+    """the reference's own border exchanges (communications.c) between two ranks run in one process through the mailbox MPI of
+    oracle/ref_shim.c: su3 (thickness 2 and 1), gl3, tamat, thmat (thickness 1)"""
+    R = RefLib(*loc, nr)
+    d = {"loc_n": np.array(loc), "nranks": nr, "sizeh": R.sizeh}
+
+    def exchange(fn, arrays, *extra):
+        R.lib.ref_mailbox_clear()
+        for _ in range(2):
+            for r in range(nr):
+                R.set_rank(r); getattr(R.lib, fn)(ptr(arrays[r]), *extra)
+        return arrays
+    for name, fn, which, extra in (("su3_t2", "communicate_su3_borders", 0, (C.c_int(2),)), ("su3_t1", "communicate_su3_borders", 0, (C.c_int(1),)),
+                                   ("gl3_t1", "communicate_gl3_borders", 0, (C.c_int(1),)), ("tamat_t1", "communicate_tamat_soa_borders", 1, (C.c_int(1),)),
+                                   ("thmat_t1", "communicate_thmat_soa_borders", 1, (C.c_int(1),))):
+        arrays = [border_fields(R.sizeh, r)[which].copy() for r in range(nr)]
+        exchange(fn, arrays, *extra)
+        for r in range(nr):
+            d["%s_r%d" % (name, r)] = arrays[r]
+    np.savez_compressed(os.path.join(HERE, "ref_borders_%dx%dx%dx%d_r%d.npz" % (loc + (nr,))), **d)
+    print("borders", loc, nr, R.sizeh)
+
+
 class _RA(C.Structure):      # RationalApprox/rationalapprox.h:15-26 (layout checked by ref_abi below)
     _fields_ = [("exponent_num", C.c_int), ("exponent_den", C.c_int), ("approx_order", C.c_int),
                 ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("gmp_remez_precision", C.c_int),
@@ -298,7 +336,7 @@ def abi_and_approx():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io", "callers", "prototypes"]
+    which = sys.argv[1:] or ["single", "multi", "abi", "force", "stout", "stoutforce", "io", "callers", "prototypes", "borders"]
     if "single" in which:
         single_rank()
     if "multi" in which:
@@ -317,3 +355,5 @@ if __name__ == "__main__":
         callers_single()
     if "prototypes" in which:
         reference_prototypes()
+    if "borders" in which:
+        borders_multi()

@@ -72,3 +72,46 @@ def test_two_rank_halo_exchange_and_reductions_gloo():
         assert err == "", err
         assert ok_halo, "rank %d: halo slices differ from the reference's exchange" % rank
         assert ok_norm and ok_max
+
+
+def _borders_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import torch
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from make_golden import border_fields
+        from openstaple_b200 import sharding as sh
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_borders_4x4x4x4_r2.npz")))
+        loc = tuple(int(x) for x in g["loc_n"]); sizeh = int(g["sizeh"])
+        bad = []
+        for name, fn, which, thickness in (("su3_t2", sh.communicate_su3_borders_hostonly, 0, 2), ("su3_t1", sh.communicate_su3_borders_hostonly, 0, 1),
+                                           ("gl3_t1", sh.communicate_gl3_borders, 0, 1), ("tamat_t1", sh.communicate_tamat_soa_borders, 1, 1),
+                                           ("thmat_t1", sh.communicate_thmat_soa_borders, 1, 1)):
+            t = torch.from_numpy(border_fields(sizeh, rank)[which].copy())
+            fn(dist, t, loc, thickness)
+            if not np.array_equal(t.numpy(), g["%s_r%d" % (name, rank)]):
+                bad.append(name)
+        dist.destroy_process_group()
+        q.put((rank, bad, ""))
+    except Exception:      # pragma: no cover
+        import traceback
+        q.put((rank, ["exception"], traceback.format_exc()))
+
+
+def test_two_rank_link_and_force_border_exchanges_gloo():
+    """host-side su3 (thickness 2 and 1), gl3, tamat and thmat border exchanges over gloo land byte-identical to the reference's
+    own exchanges between two ranks (tests/golden/make_golden.py:borders_multi, mailbox MPI)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue(); port = _free_port(); world = 2
+    procs = [ctx.Process(target=_borders_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, bad, err in sorted(res):
+        assert err == "", err
+        assert bad == [], (rank, bad)
