@@ -20,7 +20,7 @@ OUT = os.path.join(HERE, "ref_host")
 GEOM = (8, 8, 8, 8)
 
 
-def make_input(n, deo_doe_iterations=3, ms_repetitions=1, benchmark=1, max_cg=40, save=1):
+def make_input(n, deo_doe_iterations=3, ms_repetitions=1, benchmark=1, max_cg=40, save=1, eps_gen="3.0"):
     """build/input.example with: this geometry on one rank, identity direction map, the flavours and background field of
     tools/test (charges, chemical potential, E and B fields: general U(1) phases), no replicas section, results saved"""
     t = open(os.path.join(REF, "build", "input.example")).read()
@@ -35,7 +35,7 @@ def make_input(n, deo_doe_iterations=3, ms_repetitions=1, benchmark=1, max_cg=40
         assert k == 1, key
     for key, val in (("ex", 5), ("ey", -5), ("ez", 1), ("bx", -5), ("by", 5), ("bz", 3), ("nx", n[0]), ("ny", n[1]), ("nz", n[2]),
                      ("nt", n[3]), ("xmap", 0), ("ymap", 1), ("zmap", 2), ("tmap", 3), ("NRanks", 1), ("NProcPerNode", 1),
-                     ("residue_md", "1.0e-4"), ("residue_metro", "1.0e-8"), ("ExpMaxEigenvalue", "5.5"), ("EpsGen", "3.0"),
+                     ("residue_md", "1.0e-4"), ("residue_metro", "1.0e-8"), ("ExpMaxEigenvalue", "5.5"), ("EpsGen", eps_gen),
                      ("UseILDG", 0), ("VerbosityLv", 1), ("SaveDiagnostics", 0), ("DeoDoeIterations", deo_doe_iterations),
                      ("MultiShiftInverterRepetitions", ms_repetitions), ("BenchmarkMode", benchmark), ("SaveResults", save),
                      ("MaxCGIterations", max_cg), ("useMixedPrecision", 0), ("FakeShift", "1.0e-2")):
@@ -117,5 +117,20 @@ if __name__ == "__main__":
             open(os.path.join(td, f), "wb").write(files[f])
             d["ms_" + f.replace(".dat", "")] = read_vec3_ascii(os.path.join(td, f))
     d["ms_nshift_files"] = len(shifts)
+    # the same program with BenchmarkMode 0: first flavour's approx_md, rescaled with the largest eigenvalue that
+    # find_min_max_eigenvalue_soloopenacc measures (inverter_multishift_test.c:248-267), again MaxCGIterations iterations
+    # (a smoother configuration: with EpsGen 3 the largest eigenvalue, 6.97, is outside what the shipped approximations cover)
+    text0 = make_input(GEOM, benchmark=0, eps_gen="0.1")
+    open(os.path.join(OUT, "inverter_mode0_%dx%dx%dx%d.set" % GEOM), "w").write(text0)
+    r, files = run("inverter_multishift_test", text0, extra)
+    assert r.returncode == 0 and "NOT ENTERING BENCHMARK MODE" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    m = re.search(r"Found eigenvalues of dirac operator: (\S+),\s+(\S+)", r.stdout)
+    d["ms0_minmax"] = np.array([float(m.group(1)), float(m.group(2))])
+    shifts0 = sorted((f for f in files if re.match(r"fermion_shift_\d+\.dat$", f)), key=lambda f: int(re.findall(r"\d+", f)[0]))
+    with tempfile.TemporaryDirectory() as td:
+        for f in (shifts0[0], shifts0[len(shifts0) // 2], shifts0[-1]):
+            open(os.path.join(td, f), "wb").write(files[f])
+            d["ms0_" + f.replace(".dat", "")] = read_vec3_ascii(os.path.join(td, f))
+    d["ms0_nshift_files"] = len(shifts0)
     np.savez_compressed(os.path.join(OUT, "ref_host_results_%dx%dx%dx%d.npz" % GEOM), **d)
     print(sorted(files)); print({k: getattr(v, "shape", v) for k, v in d.items()})

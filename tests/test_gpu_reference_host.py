@@ -44,11 +44,11 @@ def _remez_text(r):
     return t
 
 
-def _run(prog, td):
+def _run(prog, td, input_file=None):
     exe = _exe(prog)
     if not os.path.exists(exe):
         pytest.skip("no %s (built by oracle/build_ref_host.sh where the reference is present)" % os.path.basename(exe))
-    open(os.path.join(td, "in.set"), "w").write(open(os.path.join(HOST_DIR, "deo_doe_%s.set" % GEOM)).read())
+    open(os.path.join(td, "in.set"), "w").write(open(os.path.join(HOST_DIR, input_file or "deo_doe_%s.set" % GEOM)).read())
     for name, r in json.load(open(os.path.join(HOST_DIR, "ratapproxes.json"))).items():
         open(os.path.join(td, name), "w").write(_remez_text(r))
     env = dict(os.environ)
