@@ -48,7 +48,12 @@ def build(force=False, verbose=False, extra_flags=(), out=None, tag="obj", only=
 
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
-    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
+    # -Bsymbolic-functions: calls between the library's own entry points (stout_wrapper -> stout_isotropic -> calc_loc_staples_...,
+    # the force chain, the wrappers) bind inside the .so.  A host program keeps files such as plaquettes.c / su3_utilities.c that
+    # define a few of the same names; without this flag its CPU definitions would interpose on the library's internal calls.
+    # Data symbols (verbosity_lv, act_params, inverter_tricks, ... weak here) are NOT bound locally: the host's definitions win.
+    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-Bsymbolic-functions",
+                                                 "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)

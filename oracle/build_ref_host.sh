@@ -58,20 +58,23 @@ REPLACED=" Include/memory_wrapper OpenAcc/fermion_matrix OpenAcc/sp_fermion_matr
  OpenAcc/inverter_package OpenAcc/inverter_wrappers OpenAcc/float_double_conv OpenAcc/find_min_max OpenAcc/fermion_force OpenAcc/sp_fermion_force
  OpenAcc/fermion_force_utilities OpenAcc/sp_fermion_force_utilities OpenAcc/field_times_fermion_matrix OpenAcc/stouting OpenAcc/sp_stouting "
 pids=()
-for f in $COMMON tests_and_benchmarks/deo_doe_test tests_and_benchmarks/inverter_multishift_test; do
+for f in $COMMON tests_and_benchmarks/deo_doe_test tests_and_benchmarks/inverter_multishift_test OpenAcc/main; do
   gcc $CF -c "$SCR/src/$f.c" -o "$OBJ/$(echo $f | tr / _).o" & pids+=($!)
 done
 gcc -O2 -std=gnu99 -w -I"$HERE/mpi_stub" -c "$HERE/mpi_stub/mpi_single.c" -o "$OBJ/mpi_single.o" & pids+=($!)
 gcc -O2 -std=gnu99 -w -I"$HERE/../include" -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -c "$HERE/host_shim.c" -o "$OBJ/host_shim.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 ALL=""; KEPT=""
+REPLACED=" $(echo $REPLACED) "     # one space between names, whatever the line breaks above
 for f in $COMMON; do
   o="$OBJ/$(echo $f | tr / _).o"; ALL="$ALL $o"
   case "$REPLACED" in *" $f "*) ;; *) KEPT="$KEPT $o";; esac
 done
-for prog in deo_doe_test inverter_multishift_test; do
-  gcc -o "$HERE/_ref/${prog}_ref_$GEOM" "$OBJ/tests_and_benchmarks_$prog.o" $ALL "$OBJ/mpi_single.o" -lm
-  gcc -o "$HERE/_ref/${prog}_staple_$GEOM" "$OBJ/tests_and_benchmarks_$prog.o" $KEPT "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
+# the third program is the reference's production main (OpenAcc/main.c: the whole RHMC), same two ways
+for prog in deo_doe_test inverter_multishift_test main; do
+  mo="$OBJ/tests_and_benchmarks_$prog.o"; [ $prog = main ] && mo="$OBJ/OpenAcc_main.o"
+  gcc -o "$HERE/_ref/${prog}_ref_$GEOM" "$mo" $ALL "$OBJ/mpi_single.o" -lm
+  gcc -o "$HERE/_ref/${prog}_staple_$GEOM" "$mo" $KEPT "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
       -L"$LIBDIR" -lstaple_b200 -Wl,-rpath,'$ORIGIN/../../openstaple_b200' -lm
 done
-echo "built $HERE/_ref/{deo_doe_test,inverter_multishift_test}_{ref,staple}_$GEOM"
+echo "built $HERE/_ref/{deo_doe_test,inverter_multishift_test,main}_{ref,staple}_$GEOM"

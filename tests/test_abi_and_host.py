@@ -237,3 +237,18 @@ def test_header_coexists_with_reference_headers(tmp_path):
              "-DACTION_TYPE=TLSM", "-DNREPLICAS=1", "-DLOC_N0=8", "-DLOC_N1=8", "-DLOC_N2=8", "-DLOC_N3=8", "-DNRANKS_D3=2", "-DCOMMIT_HASH=t"]
     flags += ["-D%s%s=8" % (a, b) for a in ("DEODOE", "IMPSTAP", "STAP", "SIGMA") for b in ("TILE0", "TILE1", "TILE2", "GANG3")]
     _gcc_host(tmp_path, flags, link=False)
+
+
+def test_library_internal_calls_cannot_be_interposed():
+    """A host program keeps reference files (plaquettes.c, su3_utilities.c, ferm_meas.c) that define a few names the library also
+    exports.  The library is linked -Bsymbolic-functions: calls between its own entry points carry no PLT relocation (they can
+    not be captured by the host's CPU definitions -- no accidental CPU fallback), while the reference's data globals stay
+    pre-emptible so that the host's own definitions are the ones the library reads."""
+    import subprocess
+    rel = subprocess.run(["readelf", "-rW", osb.library_path()], capture_output=True, text=True).stdout
+    plt = [l.split()[4] for l in rel.splitlines() if "JUMP_SLO" in l and len(l.split()) > 4]
+    own = set(declared_symbols())
+    assert not [s for s in plt if s.split("@")[0] in own], [s for s in plt if s.split("@")[0] in own]
+    glob = " ".join(l for l in rel.splitlines() if "GLOB_DAT" in l)
+    for g in ("verbosity_lv", "inverter_tricks", "act_params", "md_parameters", "aux_th", "aux_ta", "conf_acc_f", "gl_stout_rho"):
+        assert g in glob, g
