@@ -90,7 +90,50 @@ def read_ratapproxes():
     return out
 
 
+def parse_rhmc(stdout, gauge_obs_text):
+    """what a trajectory of the reference's main leaves behind: the gauge_obs rows (iteration, accepted, plaquette, rectangle,
+    Polyakov loop), the Metropolis energy differences and the CG-M iteration counts per trajectory"""
+    rows = [[float(x) for x in l.split()] for l in gauge_obs_text.splitlines() if l.strip() and not l.startswith("#")]
+    return {"gauge_obs": rows,
+            "delta_action": [float(x) for x in re.findall(r"DELTA_ACTION = (-?[0-9.eE+-]+?)\. ", stdout)],
+            "cgm_md": [int(x) for x in re.findall(r"CG-M iterations\[MD\]: (\d+)", stdout)],
+            "cgm_fi": [int(x) for x in re.findall(r"CG-M iterations\[FI\]: (\d+)", stdout)],
+            "cgm_li": [int(x) for x in re.findall(r"CG-M iterations\[LI\]: (\d+)", stdout)]}
+
+
+def rhmc(n=(4, 4, 4, 4)):
+    """The reference's production program (OpenAcc/main.c): three RHMC trajectories (one thermalisation + two with the
+    Metropolis test) of 2+1 stout-smeared flavours from a near-cold start; zero background field so that the spectrum stays
+    inside the shipped approximations on this tiny lattice."""
+    import json
+    subprocess.run([os.path.join(ROOT, "oracle", "build_ref_host.sh")] + [str(x) for x in n], check=True)
+    t = make_input(n, benchmark=0, eps_gen="0.1")
+    for k in ("ex", "ey", "ez", "bx", "by", "bz"):
+        t = re.sub(r"^(%s )\S+" % k, r"\g<1>0", t, count=1, flags=re.M)
+    t = re.sub(r"^(MuOverPiT )\S+", r"\g<1>0", t, flags=re.M)
+    for k, v in (("Ntraj", 3), ("ThermNtraj", 1), ("NmdSteps", 8), ("GaugeSubSteps", 3), ("TrajLength", "0.5"), ("VerbosityLv", 1),
+                 ("SaveConfInterval", 100), ("StoreConfInterval", 100), ("MeasEvery", 1000000), ("SaveAllAtEnd", 0), ("MeasCool", 0),
+                 ("MeasStout", 0), ("CoolMeasSteps", 0), ("StoutMeasSteps", 0)):
+        t, c = re.subn(r"^(%s )\S+" % k, lambda m: m.group(1) + str(v), t, count=1, flags=re.M)
+        assert c == 1, k
+    name = "rhmc_%dx%dx%dx%d" % n
+    open(os.path.join(OUT, name + ".set"), "w").write(t)
+    exe = os.path.join(ROOT, "oracle", "_ref", "main_ref_%dx%dx%dx%d" % n)
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "in.set"), "w").write(t)
+        for fname, r in read_ratapproxes().items():
+            open(os.path.join(td, fname), "w").write(remez_text(r))
+        r = subprocess.run([exe, "in.set"], cwd=td, capture_output=True, text=True, timeout=3600)
+        assert r.returncode == 0, r.stdout[-3000:]
+        obs = [f for f in os.listdir(td) if f.startswith("gauge_obs")]
+        res = parse_rhmc(r.stdout, open(os.path.join(td, obs[0])).read())
+    json.dump(res, open(os.path.join(OUT, name + ".json"), "w"), indent=1)
+    print("rhmc", res)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["rhmc"]:
+        rhmc(); sys.exit(0)
     subprocess.run([os.path.join(ROOT, "oracle", "build_ref_host.sh")] + [str(x) for x in GEOM], check=True)
     os.makedirs(OUT, exist_ok=True)
     text = make_input(GEOM)
@@ -134,3 +177,4 @@ if __name__ == "__main__":
     d["ms0_nshift_files"] = len(shifts0)
     np.savez_compressed(os.path.join(OUT, "ref_host_results_%dx%dx%dx%d.npz" % GEOM), **d)
     print(sorted(files)); print({k: getattr(v, "shape", v) for k, v in d.items()})
+    rhmc()

@@ -1,0 +1,77 @@
+"""The reference's PRODUCTION program -- OpenAcc/main.c, the whole RHMC: heat bath, molecular dynamics with the stouted
+fermion force of 2+1 flavours, Metropolis test, gauge measurements -- built unmodified by oracle/build_ref_host.sh with the
+replaced subsystems left out and libstaple_b200.so linked instead.  Its gauge sector (gauge force, link update, plaquettes)
+is the reference's own CPU object code working on CUDA managed memory; every fermionic step (smearing, CG-M, force, Sigma'
+-> Sigma, heat-bath and action inversions, reductions) runs on the B200 through the C ABI.  Three trajectories on 4^4 are
+compared with what the pure-reference CPU build of the same program produced from the same input file
+(tests/golden/ref_host/rhmc_4x4x4x4.json, written by tests/golden/make_ref_host.py): gauge_obs rows, Metropolis energy
+differences, acceptances, CG-M iteration counts.
+
+Tolerances: the two runs do the same arithmetic up to rounding, but MD solves stop at residue 1e-4 -- one iteration more or
+less in a single solve moves the force by ~1e-5 -- so plaquette / rectangle 1e-5 relative, Delta H 1e-3 absolute, iteration
+counts 2 %.
+
+Status: written at the end of round 1 after the GPU budget was spent; the pure-reference half is exercised on the CPU
+(tests/test_reference_host_cpu.py), the first B200 run of the library-linked half is the driver's.  Hence xfail(strict=False):
+XPASS is the expected outcome, an XFAIL is a finding for the next round, neither hides the other GPU tests (sorted last)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from test_gpu_reference_host import HOST_DIR, _remez_text
+
+pytestmark = pytest.mark.gpu
+GEOM = "4x4x4x4"
+
+
+def parse_rhmc(stdout, gauge_obs_text):
+    import re
+    rows = [[float(x) for x in l.split()] for l in gauge_obs_text.splitlines() if l.strip() and not l.startswith("#")]
+    return {"gauge_obs": rows,
+            "delta_action": [float(x) for x in re.findall(r"DELTA_ACTION = (-?[0-9.eE+-]+?)\. ", stdout)],
+            "cgm_md": [int(x) for x in re.findall(r"CG-M iterations\[MD\]: (\d+)", stdout)],
+            "cgm_fi": [int(x) for x in re.findall(r"CG-M iterations\[FI\]: (\d+)", stdout)],
+            "cgm_li": [int(x) for x in re.findall(r"CG-M iterations\[LI\]: (\d+)", stdout)]}
+
+
+def run_main(kind, td):
+    exe = os.path.join(ROOT, "oracle", "_ref", "main_%s_%s" % (kind, GEOM))
+    if not os.path.exists(exe):
+        pytest.skip("no " + os.path.basename(exe))
+    open(os.path.join(td, "in.set"), "w").write(open(os.path.join(HOST_DIR, "rhmc_%s.set" % GEOM)).read())
+    for name, r in json.load(open(os.path.join(HOST_DIR, "ratapproxes.json"))).items():
+        open(os.path.join(td, name), "w").write(_remez_text(r))
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(x for x in (env.get("LD_LIBRARY_PATH", ""), "/usr/local/cuda/lib64") if x)
+    r = subprocess.run([exe, "in.set"], cwd=td, capture_output=True, text=True, timeout=1800, env=env)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    obs = [f for f in os.listdir(td) if f.startswith("gauge_obs")]
+    return r, parse_rhmc(r.stdout, open(os.path.join(td, obs[0])).read())
+
+
+def compare(got, want):
+    assert len(got["gauge_obs"]) == len(want["gauge_obs"]) == 3
+    for a, b in zip(got["gauge_obs"], want["gauge_obs"]):
+        assert a[0] == b[0] and a[1] == b[1], (a, b)                              # iteration, accepted
+        assert abs(a[2] / b[2] - 1) < 1e-5 and abs(a[3] / b[3] - 1) < 1e-5, (a, b)   # plaquette, rectangle
+        assert abs(a[4] - b[4]) < 1e-5 and abs(a[5] - b[5]) < 1e-5, (a, b)           # Polyakov loop
+    assert len(got["delta_action"]) == len(want["delta_action"]) == 2
+    assert all(abs(a - b) < 1e-3 for a, b in zip(got["delta_action"], want["delta_action"])), (got["delta_action"], want["delta_action"])
+    for k in ("cgm_md", "cgm_fi", "cgm_li"):
+        assert len(got[k]) == len(want[k])
+        assert all(abs(a - b) <= max(2, 0.02 * b) for a, b in zip(got[k], want[k])), (k, got[k], want[k])
+
+
+@pytest.mark.xfail(strict=False, reason="first B200 run of this test is the driver's (see the module docstring)")
+def test_reference_rhmc_main_with_the_library(tmp_path):
+    want = json.load(open(os.path.join(HOST_DIR, "rhmc_%s.json" % GEOM)))
+    r, got = run_main("staple", str(tmp_path))
+    assert "hot path served by staple_b200" in r.stderr
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        json.dump({"got": got, "want": want}, open(os.path.join(out, "reference_rhmc_main_%s.json" % GEOM), "w"), indent=1)
+    print("library-linked main:", got)
+    compare(got, want)

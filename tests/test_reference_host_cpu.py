@@ -54,3 +54,15 @@ def test_library_linked_program_has_no_cpu_fallback(tmp_path):
     r = subprocess.run([exe, "in.set"], cwd=td, capture_output=True, text=True, timeout=900)
     assert r.returncode != 0 and "libstaple_b200: CUDA error" in r.stderr, r.stderr[-1500:]
     assert not os.path.exists(os.path.join(td, "test_fermion_result_doe2"))
+
+
+def test_pure_reference_rhmc_main_reproduces_fixture(tmp_path):
+    """the CPU half of tests/test_gpu_zz_reference_rhmc.py: the pure-reference build of OpenAcc/main.c reproduces the committed
+    trajectory observables exactly (and the comparison code of the GPU test is exercised)"""
+    import json
+    import test_gpu_zz_reference_rhmc as T
+    want = json.load(open(os.path.join(HOST_DIR, "rhmc_%s.json" % T.GEOM)))
+    r, got = T.run_main("ref", str(tmp_path))
+    assert got == want
+    T.compare(got, want)
+    assert all(row[1] == 1.0 for row in got["gauge_obs"]) and got["cgm_md"][0] > 100        # accepted trajectories, real solves
