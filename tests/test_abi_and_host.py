@@ -252,3 +252,31 @@ def test_library_internal_calls_cannot_be_interposed():
     glob = " ".join(l for l in rel.splitlines() if "GLOB_DAT" in l)
     for g in ("verbosity_lv", "inverter_tricks", "act_params", "md_parameters", "aux_th", "aux_ta", "conf_acc_f", "gl_stout_rho"):
         assert g in glob, g
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under openstaple_b200/ (Python or CUDA) may import, link or call it, and
+    bench.py reaches it only in its cpu_baseline / --impl reference legs"""
+    import ast
+    pkg = os.path.join(ROOT, "openstaple_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                for needle in ("pyoracle", "staggered_oracle", "oracle/", "oracle.", "_ref/", "libref_", "import oracle", "from oracle"):
+                    assert needle not in txt, (os.path.join(dirpath, f), needle)
+    needed = subprocess_out(["readelf", "-d", osb.library_path()])
+    assert "oracle" not in needed and "libref" not in needed
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    users = set()
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("oracle"):
+                users.add(fn.name)
+    assert users <= {"run_reference", "cpu_baseline"}, users
+    assert not [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n)]
+
+
+def subprocess_out(cmd):
+    import subprocess
+    return subprocess.run(cmd, capture_output=True, text=True).stdout
