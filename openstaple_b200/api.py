@@ -275,6 +275,13 @@ class Lattice:
             conf = sio.send_lnh_subconf_to_buffer(conf, self.rank, self.loc_n, self.nranks, self.halo_width)
         return self.to_device(conf), cid
 
+    def calc_u1_phases(self, bf_pars=(0, 0, 0, 0, 0, 0), im_chem_pot=0.0, ferm_charge=0.0, single=False):
+        """this rank's phase field (OpenAcc/backfield.c:20-187, host side: openstaple_b200/backfield.py) uploaded as
+        double_soa[8] / float_soa[8] -> device tensor [8, sizeh]"""
+        from .backfield import calc_u1_phases
+        return self.to_device(calc_u1_phases(self.loc_n, bf_pars, im_chem_pot, ferm_charge, self.nranks, self.rank,
+                                             self.halo_width, single))
+
     def host_array(self, shape, dtype):
         return HostArray(self, shape, dtype)
 
