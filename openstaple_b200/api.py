@@ -69,6 +69,46 @@ class RationalApprox(C.Structure):      # RationalApprox/rationalapprox.h:15-26
         return out
 
 
+    def renormalized(self):
+        """renormalize_rational_approximation, rationalapprox.c:197-222: the same approximation with lambda_max = 1"""
+        out = RationalApprox()
+        power = self.exponent_num / self.exponent_den
+        out.exponent_num, out.exponent_den, out.approx_order = self.exponent_num, self.exponent_den, self.approx_order
+        out.gmp_remez_precision, out.error = self.gmp_remez_precision, self.error
+        ratio = 1 / self.lambda_max
+        eps = ratio ** power
+        out.RA_a0 = self.RA_a0 * eps
+        for k in range(self.approx_order):
+            out.RA_a[k] = self.RA_a[k] * ratio * eps
+            out.RA_b[k] = self.RA_b[k] * ratio
+        out.lambda_min, out.lambda_max = self.lambda_min * ratio, 1.0
+        return out
+
+    def evaluate(self, x):
+        """rational_approx_evaluate, rationalapprox.c:225-237: RA_a0 + sum_i RA_a[i] / (x + RA_b[i])"""
+        res = self.RA_a0
+        for k in range(self.approx_order):
+            res += self.RA_a[k] / (x + self.RA_b[k])
+        return res
+
+    def filename(self):
+        """rational_approx_filename, rationalapprox.c:44-70: the name the reference looks a mother approximation up by"""
+        import math
+        return "approx_%d_over_%d_mlogerr_%1.1f_mloglm_%1.1f.REMEZ" % (
+            self.exponent_num, self.exponent_den, -math.log(self.error) / math.log(10.0), -math.log(self.lambda_min) / math.log(10.0))
+
+    def save(self, path):
+        """rationalapprox_save, rationalapprox.c:120-143: byte-identical .REMEZ text"""
+        with open(path, "w") as f:
+            f.write("\nApproximation to f(x) = (x)^(%i/%i)\n" % (self.exponent_num, self.exponent_den))
+            f.write("Order: %i\n" % self.approx_order)
+            f.write("Lambda Min: %18.16e\nLambda Max: %18.16e\n" % (self.lambda_min, self.lambda_max))
+            f.write("GMP Remez Precision: %i\nError: %18.16e\n" % (self.gmp_remez_precision, self.error))
+            f.write("RA_a0 = %18.16e\n" % self.RA_a0)
+            for i in range(self.approx_order):
+                f.write("RA_a[%d] = %18.16e, RA_b[%d] = %18.16e\n" % (i, self.RA_a[i], i, self.RA_b[i]))
+
+
 class FermParam(C.Structure):           # Include/fermion_parameters.h:9-41
     _fields_ = [("ferm_mass", C.c_double), ("degeneracy", C.c_int), ("number_of_ps", C.c_int),
                 ("name", C.c_char * 30), ("ferm_charge", C.c_double), ("ferm_im_chem_pot", C.c_double),

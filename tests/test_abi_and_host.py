@@ -280,3 +280,47 @@ def test_product_never_touches_the_oracle():
 def subprocess_out(cmd):
     import subprocess
     return subprocess.run(cmd, capture_output=True, text=True).stdout
+
+
+def _approx_from_numbers(r):
+    a = RationalApprox.make(r["a0"], r["a"], r["b"], r["num"], r["den"])
+    a.lambda_min, a.lambda_max, a.gmp_remez_precision, a.error = r["lmin"], r["lmax"], r["prec"], r["error"]
+    return a
+
+
+def test_rational_approx_host_functions():
+    """filename / evaluate / renormalized / save of RationalApprox (rationalapprox.c:44-70, 120-143, 197-237) on the six
+    approximations of tools/test (numbers parsed by the reference's own reader, tests/golden/ref_host/ratapproxes.json):
+    against the reference build where it is present, and against x^(num/den) within the approximation's own error"""
+    import json
+    from oracle.pyoracle import ref_lib_path
+    approxes = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_host", "ratapproxes.json")))
+    lib = C.CDLL(ref_lib_path(4, 4, 4, 4)) if os.path.exists(ref_lib_path(4, 4, 4, 4)) else None
+    if lib is not None:
+        lib.rational_approx_evaluate.restype = C.c_double; lib.rational_approx_filename.restype = C.c_char_p
+    for fname, r in approxes.items():
+        a = _approx_from_numbers(r)
+        p = a.exponent_num / a.exponent_den
+        for x in (a.lambda_min * 1.01, 1e-3, 0.1, 1.0):
+            if x >= a.lambda_min:
+                assert abs(a.evaluate(x) / x ** p - 1) < 3 * a.error, (fname, x)
+        n = a.renormalized()
+        assert n.lambda_max == 1.0 and abs(n.evaluate(0.5) / 0.5 ** p - 1) < 3 * a.error
+        assert a.filename().startswith("approx_%d_over_%d_mlogerr_" % (a.exponent_num, a.exponent_den)) and a.filename().endswith(fname[-17:])
+        if lib is None:
+            continue
+        ref = RationalApprox.from_buffer_copy(a)
+        assert lib.rational_approx_filename(C.c_double(a.error), C.c_int(a.exponent_num), C.c_int(a.exponent_den),
+                                            C.c_double(a.lambda_min)).decode() == a.filename()
+        for x in (1e-5, 0.003, 0.5, 1.0):
+            assert lib.rational_approx_evaluate(C.byref(ref), C.c_double(x)) == a.evaluate(x)
+        out = RationalApprox(); lib.renormalize_rational_approximation(C.byref(ref), C.byref(out))
+        assert np.allclose(np.array(n.RA_a[:n.approx_order]), np.array(out.RA_a[:n.approx_order]), rtol=1e-15, atol=0)
+        assert np.allclose(np.array(n.RA_b[:n.approx_order]), np.array(out.RA_b[:n.approx_order]), rtol=1e-15, atol=0)
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            p1, p2 = os.path.join(td, "a"), os.path.join(td, "b")
+            a.save(p1); lib.rationalapprox_save(p2.encode(), C.byref(ref))
+            assert open(p1, "rb").read() == open(p2, "rb").read()
+            back = RationalApprox.read(p1)
+            assert bytes(back) == bytes(a)
