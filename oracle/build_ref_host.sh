@@ -10,25 +10,29 @@
 # The second binary is the drop-in claim made executable: the reference's host program, its parser, generators and file
 # writers, running its hot path on the B200 through the C ABI.  Both travel to the GPU box as binaries (oracle/_ref is
 # git-ignored, not gpurun-ignored); tests/test_gpu_reference_host.py runs them there and compares their output files.
-# usage: oracle/build_ref_host.sh N0 N1 N2 N3
+# With a fifth argument NRANKS_D3 > 1 the programs are built for that many D3 slabs against oracle/mpi_mini (a minimal MPI over
+# local sockets: the image has none) and get the suffix _rN; run them with oracle/mpi_mini/mpirun.py -n N.
+# usage: oracle/build_ref_host.sh N0 N1 N2 N3 [NRANKS_D3=1]
 set -euo pipefail
 REF=${STAPLE_REFERENCE:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
-N0=$1; N1=$2; N2=$3; N3=$4
+N0=$1; N1=$2; N2=$3; N3=$4; NR=${5:-1}
 GEOM=${N0}x${N1}x${N2}x${N3}
+MPIDIR=$HERE/mpi_stub; MPISRC=$HERE/mpi_stub/mpi_single.c
+if [ "$NR" -gt 1 ]; then GEOM=${GEOM}_r$NR; MPIDIR=$HERE/mpi_mini; MPISRC=$HERE/mpi_mini/mpi_mini.c; fi
 mkdir -p "$HERE/_ref"
 [ -d "$REF/src" ] || { echo "reference not present at $REF (prebuilt oracle/_ref is used as is)"; exit 0; }
-"$HERE/build_ref.sh" $N0 $N1 $N2 $N3 1 > /dev/null        # makes sure the scratch copy with the generated sp_* files exists
+"$HERE/build_ref.sh" $N0 $N1 $N2 $N3 $NR > /dev/null        # makes sure the scratch copy with the generated sp_* files exists
 SCR=${STAPLE_ORACLE_SCRATCH:-${TMPDIR:-/tmp}/staple_oracle_src}
 LIBDIR=$(cd "$HERE/../openstaple_b200" && pwd)
 [ -f "$LIBDIR/libstaple_b200.so" ] || { echo "build libstaple_b200.so first"; exit 1; }
 STAMP="$HERE/_ref/deo_doe_test_staple_$GEOM"
-if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/host_shim.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
+if [ -f "$STAMP" ] && [ "$STAMP" -nt "$MPISRC" ] && [ "$STAMP" -nt "$HERE/host_shim.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 T=8
-CF="-O3 -std=gnu99 -fcommon -w -I$HERE/mpi_stub -I$SCR/src -DACTION_TYPE=TLSM -DNREPLICAS=1 \
- -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -DNRANKS_D3=1 -DCOMMIT_HASH=oracle \
+CF="-O3 -std=gnu99 -fcommon -w -I$MPIDIR -I$SCR/src -DACTION_TYPE=TLSM -DNREPLICAS=1 \
+ -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -DNRANKS_D3=$NR -DCOMMIT_HASH=oracle \
  -DDEODOETILE0=$T -DDEODOETILE1=$T -DDEODOETILE2=$T -DDEODOEGANG3=$T -DIMPSTAPTILE0=$T -DIMPSTAPTILE1=$T \
  -DIMPSTAPTILE2=$T -DIMPSTAPGANG3=$T -DSTAPTILE0=$T -DSTAPTILE1=$T -DSTAPTILE2=$T -DSTAPGANG3=$T \
  -DSIGMATILE0=$T -DSIGMATILE1=$T -DSIGMATILE2=$T -DSIGMAGANG3=$T"
@@ -58,11 +62,12 @@ REPLACED=" Include/memory_wrapper OpenAcc/fermion_matrix OpenAcc/sp_fermion_matr
  OpenAcc/inverter_package OpenAcc/inverter_wrappers OpenAcc/float_double_conv OpenAcc/find_min_max OpenAcc/fermion_force OpenAcc/sp_fermion_force
  OpenAcc/fermion_force_utilities OpenAcc/sp_fermion_force_utilities OpenAcc/field_times_fermion_matrix OpenAcc/stouting OpenAcc/sp_stouting "
 pids=()
-for f in $COMMON tests_and_benchmarks/deo_doe_test tests_and_benchmarks/inverter_multishift_test OpenAcc/main; do
+# DbgTools/debugger_hook.c is main's libdbghook.a (src/Makefile.am:176,187,216)
+for f in $COMMON tests_and_benchmarks/deo_doe_test tests_and_benchmarks/inverter_multishift_test OpenAcc/main DbgTools/debugger_hook; do
   gcc $CF -c "$SCR/src/$f.c" -o "$OBJ/$(echo $f | tr / _).o" & pids+=($!)
 done
-gcc -O2 -std=gnu99 -w -I"$HERE/mpi_stub" -c "$HERE/mpi_stub/mpi_single.c" -o "$OBJ/mpi_single.o" & pids+=($!)
-gcc -O2 -std=gnu99 -w -I"$HERE/../include" -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -c "$HERE/host_shim.c" -o "$OBJ/host_shim.o" & pids+=($!)
+gcc -O2 -std=gnu99 -w -I"$MPIDIR" -c "$MPISRC" -o "$OBJ/mpi_single.o" & pids+=($!)
+gcc -O2 -std=gnu99 -w -I"$MPIDIR" -I"$HERE/../include" -DNRANKS_D3=$NR -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -c "$HERE/host_shim.c" -o "$OBJ/host_shim.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 ALL=""; KEPT=""
 REPLACED=" $(echo $REPLACED) "     # one space between names, whatever the line breaks above
@@ -72,9 +77,9 @@ for f in $COMMON; do
 done
 # the third program is the reference's production main (OpenAcc/main.c: the whole RHMC), same two ways
 for prog in deo_doe_test inverter_multishift_test main; do
-  mo="$OBJ/tests_and_benchmarks_$prog.o"; [ $prog = main ] && mo="$OBJ/OpenAcc_main.o"
-  gcc -o "$HERE/_ref/${prog}_ref_$GEOM" "$mo" $ALL "$OBJ/mpi_single.o" -lm
-  gcc -o "$HERE/_ref/${prog}_staple_$GEOM" "$mo" $KEPT "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
+  mo="$OBJ/tests_and_benchmarks_$prog.o"; [ $prog = main ] && mo="$OBJ/OpenAcc_main.o $OBJ/DbgTools_debugger_hook.o"
+  gcc -o "$HERE/_ref/${prog}_ref_$GEOM" $mo $ALL "$OBJ/mpi_single.o" -lm
+  gcc -o "$HERE/_ref/${prog}_staple_$GEOM" $mo $KEPT "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
       -L"$LIBDIR" -lstaple_b200 -Wl,-rpath,'$ORIGIN/../../openstaple_b200' -lm
 done
 echo "built $HERE/_ref/{deo_doe_test,inverter_multishift_test,main}_{ref,staple}_$GEOM"

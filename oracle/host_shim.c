@@ -9,6 +9,12 @@
  * reference's own object code; the hot path is libstaple_b200.so. */
 #include <stdio.h>
 #include <stdlib.h>
+#ifndef NRANKS_D3
+#define NRANKS_D3 1
+#endif
+#if NRANKS_D3 > 1
+#include "mpi.h"
+#endif
 #include "staple_b200.h"
 
 /* statistics main.c prints (main.c:274,1245); the test programs never read them, so only the totals are kept */
@@ -22,9 +28,23 @@ static void init_once(void)
 	if (done) return;
 	done = 1;
 	const char *dev = getenv("STAPLE_DEVICE");
-	if (staple_init_geometry(LOC_N0, LOC_N1, LOC_N2, LOC_N3, 1, 2 /* HALO_WIDTH, TLSM */, dev ? atoi(dev) : 0) != 0) {
+	int rank = 0, nranks = 1;
+#if NRANKS_D3 > 1
+	/* the reference has called pre_init_multidev1D / init_multidev1D (MPI_Init included) before its first allocation */
+	MPI_Comm_rank(MPI_COMM_WORLD, &rank); MPI_Comm_size(MPI_COMM_WORLD, &nranks);
+	if (nranks != NRANKS_D3) { fprintf(stderr, "host_shim: built for %d ranks, started with %d\n", NRANKS_D3, nranks); exit(1); }
+#endif
+	if (staple_init_geometry(LOC_N0, LOC_N1, LOC_N2, LOC_N3, nranks, 2 /* HALO_WIDTH, TLSM */, (dev ? atoi(dev) : 0) + rank) != 0) {
 		fprintf(stderr, "host_shim: staple_init_geometry failed\n"); exit(1);
 	}
+#if NRANKS_D3 > 1
+	{	/* rank 0 makes the NCCL id, MPI carries it, every rank joins the D3 ring */
+		char id[128];
+		if (rank == 0) staple_nccl_unique_id(id);
+		MPI_Bcast(id, 128, MPI_CHAR, 0, MPI_COMM_WORLD);
+		staple_init_multidev1D(rank, nranks, id, 1);
+	}
+#endif
 	staple_set_blocking(1);
 	fprintf(stderr, "host_shim: hot path served by %s\n", staple_version());
 }

@@ -1,0 +1,34 @@
+"""Multi-GPU drop-in, executed (needs 2 GPUs; skipped otherwise): the reference's deo_doe_test built for NRANKS_D3 = 2 and
+linked against libstaple_b200.so runs as two processes, one per GPU, under oracle/mpi_mini -- the reference's own MPI code
+scatters the configuration and gathers the results through rank 0, oracle/host_shim.c hands the NCCL id around with MPI_Bcast
+and calls staple_init_multidev1D, the operator and its halo exchange run in the library (NCCL over
+NVLink).  The global result files are compared with the SINGLE-rank pure-reference build reading the configuration and source
+the two GPU ranks saved: FP64 relative 1e-13.
+
+Written at the end of round 1 after the GPU budget was spent (the CPU half, tests/test_reference_host_multirank_cpu.py, runs the
+pure-reference two-rank program through the same launcher): xfail(strict=False) until its first run on a 2-GPU box."""
+import os
+
+import numpy as np
+import pytest
+
+from test_reference_host_multirank_cpu import FILES, run_single_rank_on_saved_inputs, run_two_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.xfail(strict=False, reason="first multi-GPU run of this test is pending (see the module docstring); XPASS expected")
+def test_two_gpu_reference_deo_doe_program(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(x for x in (env.get("LD_LIBRARY_PATH", ""), "/usr/local/cuda/lib64") if x)
+    td = str(tmp_path)
+    two = run_two_ranks("staple", td, env=env)
+    assert "hot path served by staple_b200" in open(os.path.join(td, "stderr.0")).read()
+    one = run_single_rank_on_saved_inputs(td)
+    for f in FILES:
+        e = float(np.abs(two[f] - one[f]).max() / np.abs(one[f]).max())
+        print("%s: %.1e" % (f, e))
+        assert e < 1e-13, (f, e)
