@@ -26,7 +26,8 @@ mkdir -p "$HERE/_ref"
 SCR=${STAPLE_ORACLE_SCRATCH:-${TMPDIR:-/tmp}/staple_oracle_src}
 LIBDIR=$(cd "$HERE/../openstaple_b200" && pwd)
 [ -f "$LIBDIR/libstaple_b200.so" ] || { echo "build libstaple_b200.so first"; exit 1; }
-STAMP="$HERE/_ref/deo_doe_test_staple_$GEOM"
+PROGLIST=${PROGS:-deo_doe_test inverter_multishift_test main}
+STAMP="$HERE/_ref/${PROGLIST##* }_staple_$GEOM"          # the program linked last
 if [ -f "$STAMP" ] && [ "$STAMP" -nt "$MPISRC" ] && [ "$STAMP" -nt "$HERE/host_shim.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
@@ -76,10 +77,10 @@ for f in $COMMON; do
   case "$REPLACED" in *" $f "*) ;; *) KEPT="$KEPT $o";; esac
 done
 # the third program is the reference's production main (OpenAcc/main.c: the whole RHMC), same two ways
-for prog in deo_doe_test inverter_multishift_test main; do
+for prog in $PROGLIST; do      # PROGS="deo_doe_test" builds a subset
   mo="$OBJ/tests_and_benchmarks_$prog.o"; [ $prog = main ] && mo="$OBJ/OpenAcc_main.o $OBJ/DbgTools_debugger_hook.o"
   gcc -o "$HERE/_ref/${prog}_ref_$GEOM" $mo $ALL "$OBJ/mpi_single.o" -lm
   gcc -o "$HERE/_ref/${prog}_staple_$GEOM" $mo $KEPT "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
       -L"$LIBDIR" -lstaple_b200 -Wl,-rpath,'$ORIGIN/../../openstaple_b200' -lm
 done
-echo "built $HERE/_ref/{deo_doe_test,inverter_multishift_test,main}_{ref,staple}_$GEOM"
+echo "built $HERE/_ref/{${PROGS:-deo_doe_test,inverter_multishift_test,main}}_{ref,staple}_$GEOM"
