@@ -29,10 +29,13 @@ def two_rank_input():
     return t
 
 
-def run_two_ranks(kind, td, env=None):
+MS_FILES = ("fermion_shift_0.dat", "fermion_shift_7.dat", "fermion_shift_14.dat")
+
+
+def run_two_ranks(kind, td, env=None, prog="deo_doe_test", files=FILES):
     import json
     from mpirun import launch
-    exe = os.path.join(REF, "deo_doe_test_%s_8x8x8x8_r2" % kind)
+    exe = os.path.join(REF, "%s_%s_8x8x8x8_r2" % (prog, kind))
     if not os.path.exists(exe):
         pytest.skip("no " + os.path.basename(exe))
     open(os.path.join(td, "in.set"), "w").write(two_rank_input())
@@ -41,21 +44,21 @@ def run_two_ranks(kind, td, env=None):
     rc = launch(2, [exe, "in.set"], cwd=td, env=env, timeout=900)
     assert rc == 0, (open(os.path.join(td, "stdout.0")).read()[-2000:], open(os.path.join(td, "stderr.0")).read()[-2000:],
                      open(os.path.join(td, "stderr.1")).read()[-2000:])
-    return {f: _read_vec3_ascii(os.path.join(td, f)) for f in FILES}
+    return {f: _read_vec3_ascii(os.path.join(td, f)) for f in files}
 
 
-def run_single_rank_on_saved_inputs(td):
-    exe = os.path.join(REF, "deo_doe_test_ref_8x8x8x16")
+def run_single_rank_on_saved_inputs(td, prog="deo_doe_test", files=FILES):
+    exe = os.path.join(REF, "%s_ref_8x8x8x16" % prog)
     if not os.path.exists(exe):
         pytest.skip("no " + os.path.basename(exe))
     sd = os.path.join(td, "single"); os.makedirs(sd)
-    for f in ("save_conf", "test_fermion"):
+    for f in ["save_conf", "test_fermion"] + [f for f in os.listdir(td) if f.endswith(".REMEZ")]:
         os.link(os.path.join(td, f), os.path.join(sd, f))
     t = re.sub(r"^(NRanks|NProcPerNode) \S+", r"\g<1> 1", two_rank_input(), flags=re.M)
     open(os.path.join(sd, "in.set"), "w").write(t)
     r = subprocess.run([exe, "in.set"], cwd=sd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "Fermion READ : OK" in r.stdout and "Read : OK" in r.stdout, r.stdout[-2000:]
-    return {f: _read_vec3_ascii(os.path.join(sd, f)) for f in FILES}
+    return {f: _read_vec3_ascii(os.path.join(sd, f)) for f in files}
 
 
 def test_mini_mpi_unit(tmp_path):
@@ -76,3 +79,15 @@ def test_reference_two_rank_run_equals_its_single_rank_run(tmp_path):
     for f in FILES:
         e = float(np.abs(two[f] - one[f]).max() / np.abs(one[f]).max())
         assert e < 1e-15, (f, e)
+
+
+def test_reference_two_rank_multishift_equals_its_single_rank_run(tmp_path):
+    """inverter_multishift_test, benchmark mode (15 equal shifts, MaxCGIterations iterations): two ranks with an MPI_Allreduce
+    per scalar product against one rank on the same configuration and source.  The sums are accumulated in a different order
+    (two partial sums instead of one), so agreement is to rounding amplified by 40 CG iterations, not to the bit."""
+    td = str(tmp_path)
+    two = run_two_ranks("ref", td, prog="inverter_multishift_test", files=MS_FILES)
+    one = run_single_rank_on_saved_inputs(td, prog="inverter_multishift_test", files=MS_FILES)
+    for f in MS_FILES:
+        e = float(np.abs(two[f] - one[f]).max() / np.abs(one[f]).max())
+        assert e < 1e-11, (f, e)
