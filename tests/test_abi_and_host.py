@@ -324,3 +324,73 @@ def test_rational_approx_host_functions():
             assert open(p1, "rb").read() == open(p2, "rb").read()
             back = RationalApprox.read(p1)
             assert bytes(back) == bytes(a)
+
+
+def test_ctypes_signatures_match_the_header():
+    """every argtypes list openstaple_b200/lib.py declares has as many entries as the C prototype has parameters, floating-point
+    parameters are bound as c_double / c_float (not as integers or pointers) and by-value structs are not bound as pointers"""
+    from prototypes import preprocess, prototypes
+    L = osb.load_library()
+    ours = prototypes(preprocess('#include "%s"\n' % os.path.join(ROOT, "include", "staple_b200.h")))
+    checked = 0
+    for name, (rt, params) in ours.items():
+        f = getattr(L, name, None)
+        if f is None or f.argtypes is None:
+            continue
+        assert len(f.argtypes) == len(params), (name, len(f.argtypes), params)
+        for a, p in zip(f.argtypes, params):
+            if p == "double":
+                assert a is C.c_double, (name, p, a)
+            elif p == "float":
+                assert a is C.c_float, (name, p, a)
+            elif p in ("int", "constint"):
+                assert a is C.c_int, (name, p, a)
+            elif p == "inverter_package":
+                assert issubclass(a, C.Structure), (name, p, a)
+        if rt == "double":
+            assert f.restype is C.c_double, name
+        checked += 1
+    assert checked > 100, checked
+
+
+def test_lazily_bound_api_calls_match_the_header():
+    """the Lattice methods that set argtypes at call time (by-value inverter_package, float res, ...) are driven against a
+    recording stand-in for the library: the argtypes they set and the number of arguments they pass equal the C prototype"""
+    from prototypes import preprocess, prototypes
+    from openstaple_b200.api import Lattice, InverterPackage
+    ours = prototypes(preprocess('#include "%s"\n' % os.path.join(ROOT, "include", "staple_b200.h")))
+    calls = {}
+
+    class Fn:
+        def __init__(self, name):
+            self.name, self.argtypes, self.restype = name, None, None
+
+        def __call__(self, *a):
+            calls[self.name] = (self.argtypes, len(a))
+            return 0
+
+    class Lib:
+        def __getattr__(self, name):
+            f = Fn(name); object.__setattr__(self, name, f); return f
+
+    lat = Lattice.__new__(Lattice); lat.L = Lib(); lat._keep = []; lat.sizeh = 16
+    ip, pars, approx = InverterPackage(), FermParam(), RationalApprox.make(1.0, [1.0], [0.1])
+    arr = (FermParam * 1)()
+    lat.eo_inversion(ip, pars, 1e-8, 10, 1, 2, 3, 4, 5, 6)
+    lat.fermion_force_soloopenacc(1, 2, 3, 4, arr, 1, 5, 1e-6, 6, 7, ip, 100)
+    lat.inverter_wrapper(ip, pars, 1, 2, 1e-8, 10, 0.0, 0)
+    lat.inverter_multishift_wrapper(ip, pars, approx, 1, 2, 1e-8, 10, 0)
+    lat.inverter_mixed_precision(ip, pars, 1, 2, 1e-8, 10, 0.0)
+    lat.acc_Deo_wf(1, 2, 3, 4, 5, 6); lat.acc_Doe_wf_unsafe(1, 2, 3, 4, 5, 6)
+    lat.ker_find_min_eigenvalue_openacc(1, pars, 2, 3, 4, 5.0)
+    lat.setup_inverter_package_dp(ip, 1, 2, 3, 4, 5, 6, 7); lat.setup_inverter_package_sp(ip, 1, 2, 3, 4, 5, 6, 7, 8)
+    assert len(calls) == 10, sorted(calls)
+    for name, (argtypes, nargs) in calls.items():
+        params = ours[name][1]
+        assert nargs == len(params), (name, nargs, params)
+        assert argtypes is not None and len(argtypes) == len(params), (name, argtypes, params)
+        for a, p in zip(argtypes, params):
+            if p == "double":
+                assert a is C.c_double, (name, p)
+            if p == "inverter_package":
+                assert a is InverterPackage, (name, p)
