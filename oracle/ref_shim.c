@@ -99,6 +99,17 @@ void ref_abi(long *o)
 	o[22] = offsetof(vec3_soa, c1); o[23] = offsetof(su3_soa, r1);
 }
 
+/* the globals' structs the library reads from the HOST program's own definitions (action.h:6-18, md_parameters.h:6-19) */
+void ref_abi2(long *o)
+{
+	o[0] = sizeof(action_param); o[1] = offsetof(action_param, stout_steps); o[2] = offsetof(action_param, stout_rho);
+	o[3] = offsetof(action_param, topo_action); o[4] = offsetof(action_param, topo_file_path);
+	o[5] = offsetof(action_param, topo_stout_steps); o[6] = offsetof(action_param, topo_rho);
+	o[7] = sizeof(md_param); o[8] = offsetof(md_param, residue_metro); o[9] = offsetof(md_param, singlePrecMD);
+	o[10] = offsetof(md_param, max_cg_iterations); o[11] = offsetof(md_param, recycleInvsForce);
+	o[12] = sizeof(tamat_soa); o[13] = offsetof(tamat_soa, ic00); o[14] = sizeof(thmat_soa); o[15] = offsetof(thmat_soa, rc00);
+}
+
 /* index helpers straight from the reference's header-only geometry (geometry_multidev.h:209-262) */
 int ref_snum_acc(int d0, int d1, int d2, int d3) { return snum_acc(d0, d1, d2, d3); }
 int ref_lnh_to_gl_snum(int d0, int d1, int d2, int d3, int rank)

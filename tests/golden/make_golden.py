@@ -317,7 +317,8 @@ def abi_and_approx():
     rescale_rational_approximation (:145-194) applied to them."""
     R = RefLib(4, 4, 4, 4)
     o = (C.c_long * 24)(); R.lib.ref_abi(o)
-    d = {"abi": np.array(list(o)), "abi_sizeh": R.sizeh}
+    o2 = (C.c_long * 16)(); R.lib.ref_abi2(o2)
+    d = {"abi": np.array(list(o)), "abi_sizeh": R.sizeh, "abi2": np.array(list(o2))}
     ref = os.environ.get("STAPLE_REFERENCE", "/root/reference")
     files = {"m14": "saved_approxs/approx_-1_over_4_order_19_mloglm_6.4.REMEZ",
              "p18": "saved_approxs/approx_1_over_8_order_19_mloglm_6.4.REMEZ",

@@ -106,6 +106,34 @@ def test_struct_layouts_match_reference(abi):
     assert C.sizeof(InvTricks) == a[20] and InvTricks.mixedPrecisionDelta.offset == a[21]
 
 
+def test_host_global_struct_layouts_match_reference(abi):
+    """act_params and md_parameters are read by the library from the HOST program's own objects (weak/pre-emptible globals):
+    the layouts include/staple_b200.h declares must be the reference's (action.h:6-18, md_parameters.h:6-19); tamat/thmat packing"""
+    from openstaple_b200.api import ActionParam, MdParam
+    a = [int(x) for x in abi["abi2"]]; S = int(abi["abi_sizeh"])
+    assert C.sizeof(ActionParam) == a[0]
+    assert (ActionParam.stout_steps.offset, ActionParam.stout_rho.offset, ActionParam.topo_action.offset,
+            ActionParam.topo_file_path.offset, ActionParam.topo_stout_steps.offset, ActionParam.topo_rho.offset) == tuple(a[1:7])
+    assert C.sizeof(MdParam) == a[7]
+    assert (MdParam.residue_metro.offset, MdParam.singlePrecMD.offset, MdParam.max_cg_iterations.offset,
+            MdParam.recycleInvsForce.offset) == tuple(a[8:12])
+    assert a[12] == 64 * S and a[13] == 48 * S and a[14] == 64 * S and a[15] == 48 * S      # 3 complex + 2 real arrays per link
+    # ... and the C declarations of the header itself, compiled
+    import subprocess, tempfile
+    src = r'''#include <stdio.h>
+#include <stddef.h>
+#include "staple_b200.h"
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(action_param), offsetof(action_param, stout_steps),
+  offsetof(action_param, stout_rho), offsetof(action_param, topo_action), offsetof(action_param, topo_file_path),
+  offsetof(action_param, topo_stout_steps), offsetof(action_param, topo_rho), sizeof(md_param), offsetof(md_param, residue_metro),
+  offsetof(md_param, singlePrecMD), offsetof(md_param, max_cg_iterations), offsetof(md_param, recycleInvsForce)); return 0; }'''
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "a.c"), "w").write(src)
+        subprocess.run(["gcc", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), os.path.join(td, "a.c"), "-o", os.path.join(td, "a")], check=True)
+        out = subprocess.run([os.path.join(td, "a")], capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == a[:12]
+
+
 def write_remez(path, g, tag):
     """the .REMEZ text layout the reference's reader expects (rationalapprox.c:96-106)."""
     with open(path, "w") as f:
