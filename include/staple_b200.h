@@ -353,6 +353,8 @@ int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalA
 int inverter_wrapper(inverter_package ip, ferm_param *pars, vec3_soa *out, const vec3_soa *in, double res,
 										 int max_cg, double shift, int convergence_importance);
 void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f);
+extern vec3_soa_f *aux1_f, *ferm_shiftmulti_acc_f;   /* weak in the library: a host program's own definitions (alloc_vars.c) are used when
+                                                        staple_set_sp_globals() was not called */
 
 /* "next" row N1.  ref: OpenAcc/find_min_max.c:21-117 */
 double ker_find_max_eigenvalue_openacc(su3_soa *u, ferm_param *pars, vec3_soa *loc_r, vec3_soa *loc_h, vec3_soa *loc_p);

@@ -475,7 +475,11 @@ using namespace staple;
 #define CDD(p) ((const double2 *) dev(p, #p))
 #define CDF(p) ((const float2 *) dev(p, #p))
 
-static vec3_soa_f *g_aux1_f = nullptr, *g_ferm_shiftmulti_acc_f = nullptr;   // alloc_vars globals
+static vec3_soa_f *g_aux1_f = nullptr, *g_ferm_shiftmulti_acc_f = nullptr;   // staple_set_sp_globals
+extern "C" {
+__attribute__((weak)) vec3_soa_f *aux1_f = nullptr;                  // alloc_vars.h globals; the host program's definitions win
+__attribute__((weak)) vec3_soa_f *ferm_shiftmulti_acc_f = nullptr;
+}
 
 extern "C" {
 
@@ -644,6 +648,10 @@ int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalA
 	require_init("inverter_multishift_wrapper");
 	int total_iterations = 0, cg_return = 0, temp_conv_check;
 	if (inverter_tricks.singlePInvAccelMultiInv) {
+		// the reference reads the alloc_vars globals aux1_f / ferm_shiftmulti_acc_f (inverter_wrappers.c:60-71): a host program that
+		// defines them (they are weak here) needs no staple_set_sp_globals() call
+		if (!g_aux1_f) g_aux1_f = aux1_f;
+		if (!g_ferm_shiftmulti_acc_f) g_ferm_shiftmulti_acc_f = ferm_shiftmulti_acc_f;
 		if (!g_aux1_f || !g_ferm_shiftmulti_acc_f) {
 			fprintf(stderr, "inverter_multishift_wrapper: singlePInvAccelMultiInv needs staple_set_sp_globals(aux1_f, ferm_shiftmulti_acc_f)\n");
 			exit(1);
