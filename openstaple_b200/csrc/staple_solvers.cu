@@ -650,18 +650,18 @@ int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalA
 	if (inverter_tricks.singlePInvAccelMultiInv) {
 		// the reference reads the alloc_vars globals aux1_f / ferm_shiftmulti_acc_f (inverter_wrappers.c:60-71): a host program that
 		// defines them (they are weak here) needs no staple_set_sp_globals() call
-		if (!g_aux1_f) g_aux1_f = aux1_f;
-		if (!g_ferm_shiftmulti_acc_f) g_ferm_shiftmulti_acc_f = ferm_shiftmulti_acc_f;
-		if (!g_aux1_f || !g_ferm_shiftmulti_acc_f) {
+		vec3_soa_f *const sp_in = g_aux1_f ? g_aux1_f : aux1_f;
+		vec3_soa_f *const sp_out = g_ferm_shiftmulti_acc_f ? g_ferm_shiftmulti_acc_f : ferm_shiftmulti_acc_f;
+		if (!sp_in || !sp_out) {
 			fprintf(stderr, "inverter_multishift_wrapper: singlePInvAccelMultiInv needs staple_set_sp_globals(aux1_f, ferm_shiftmulti_acc_f)\n");
 			exit(1);
 		}
-		convert_double_to_float_vec3_soa(in, g_aux1_f);
+		convert_double_to_float_vec3_soa(in, sp_in);
 		float singlePMultiInvTargetRes = 8e-7f * sqrtf((float) ctx().g.sizeh);
 		if (singlePMultiInvTargetRes < res) singlePMultiInvTargetRes = res;
 		if (0 == ctx().myrank && verbosity_lv > 3)
 			printf("Multishift inverter, single precision, target res %e\n", singlePMultiInvTargetRes);
-		temp_conv_check = multishift_invert_f(ip.u_f, pars, approx, g_ferm_shiftmulti_acc_f, g_aux1_f, singlePMultiInvTargetRes,
+		temp_conv_check = multishift_invert_f(ip.u_f, pars, approx, sp_out, sp_in, singlePMultiInvTargetRes,
 																					ip.loc_r_f, ip.loc_h_f, ip.loc_s_f, ip.loc_p_f, ip.ferm_shift_temp_f, max_cg,
 																					&cg_return);
 		convergence_messages(convergence_importance, temp_conv_check);
@@ -670,7 +670,7 @@ int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalA
 		for (int ishift = 0; ishift < approx->approx_order; ishift++) {
 			const double bshift = approx->RA_b[ishift];
 			if (verbosity_lv > 0) printf("Shift %d, %f\n", ishift, bshift);
-			vec3_soa_f *src = (vec3_soa_f *) ((char *) g_ferm_shiftmulti_acc_f + ishift * vbytes_f);
+			vec3_soa_f *src = (vec3_soa_f *) ((char *) sp_out + ishift * vbytes_f);
 			vec3_soa *dst = (vec3_soa *) ((char *) out + ishift * vbytes_d);
 			convert_float_to_double_vec3_soa(src, dst);
 			// the reference adds the stale cg_return here (inverter_wrappers.c:91-95); the wrapper's own
