@@ -131,9 +131,34 @@ def rhmc(n=(4, 4, 4, 4)):
     print("rhmc", res)
 
 
+def rhmc_two_ranks(loc=(4, 4, 4, 4)):
+    """the same RHMC input on two D3 slabs (global 4x4x4x8): the pure-reference NRANKS_D3 = 2 build of main as two processes
+    under oracle/mpi_mini"""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "mpi_mini"))
+    from mpirun import launch
+    subprocess.run([os.path.join(ROOT, "oracle", "build_ref_host.sh")] + [str(x) for x in loc] + ["2"], check=True, env=dict(os.environ, PROGS="main"))
+    t = open(os.path.join(OUT, "rhmc_%dx%dx%dx%d.set" % loc)).read()
+    for k, v in (("nt", 2 * loc[3]), ("NRanks", 2), ("NProcPerNode", 2)):
+        t, c = re.subn(r"^(%s )\S+" % k, lambda m: m.group(1) + str(v), t, count=1, flags=re.M)
+        assert c == 1, k
+    name = "rhmc_%dx%dx%dx%d_r2" % loc
+    open(os.path.join(OUT, name + ".set"), "w").write(t)
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "in.set"), "w").write(t)
+        for fname, r in read_ratapproxes().items():
+            open(os.path.join(td, fname), "w").write(remez_text(r))
+        rc = launch(2, [os.path.join(ROOT, "oracle", "_ref", "main_ref_%dx%dx%dx%d_r2" % loc), "in.set"], cwd=td)
+        assert rc == 0, open(os.path.join(td, "stdout.0")).read()[-3000:]
+        obs = [f for f in os.listdir(td) if f.startswith("gauge_obs")]
+        res = parse_rhmc(open(os.path.join(td, "stdout.0")).read(), open(os.path.join(td, obs[0])).read())
+    json.dump(res, open(os.path.join(OUT, name + ".json"), "w"), indent=1)
+    print("rhmc two ranks", res)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["rhmc"]:
-        rhmc(); sys.exit(0)
+        rhmc(); rhmc_two_ranks(); sys.exit(0)
     subprocess.run([os.path.join(ROOT, "oracle", "build_ref_host.sh")] + [str(x) for x in GEOM], check=True)
     os.makedirs(OUT, exist_ok=True)
     text = make_input(GEOM)
@@ -178,3 +203,4 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(OUT, "ref_host_results_%dx%dx%dx%d.npz" % GEOM), **d)
     print(sorted(files)); print({k: getattr(v, "shape", v) for k, v in d.items()})
     rhmc()
+    rhmc_two_ranks()

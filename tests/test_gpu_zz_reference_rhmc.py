@@ -37,19 +37,34 @@ def parse_rhmc(stdout, gauge_obs_text):
             "cgm_li": [int(x) for x in re.findall(r"CG-M iterations\[LI\]: (\d+)", stdout)]}
 
 
-def run_main(kind, td):
-    exe = os.path.join(ROOT, "oracle", "_ref", "main_%s_%s" % (kind, GEOM))
+def run_main(kind, td, ranks=1):
+    """ranks = 2: the NRANKS_D3 = 2 build as two processes under oracle/mpi_mini (rank r on GPU r for the library-linked one)"""
+    sfx = GEOM if ranks == 1 else "%s_r%d" % (GEOM, ranks)
+    exe = os.path.join(ROOT, "oracle", "_ref", "main_%s_%s" % (kind, sfx))
     if not os.path.exists(exe):
         pytest.skip("no " + os.path.basename(exe))
-    open(os.path.join(td, "in.set"), "w").write(open(os.path.join(HOST_DIR, "rhmc_%s.set" % GEOM)).read())
+    open(os.path.join(td, "in.set"), "w").write(open(os.path.join(HOST_DIR, "rhmc_%s.set" % sfx)).read())
     for name, r in json.load(open(os.path.join(HOST_DIR, "ratapproxes.json"))).items():
         open(os.path.join(td, name), "w").write(_remez_text(r))
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = ":".join(x for x in (env.get("LD_LIBRARY_PATH", ""), "/usr/local/cuda/lib64") if x)
-    r = subprocess.run([exe, "in.set"], cwd=td, capture_output=True, text=True, timeout=1800, env=env)
-    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    if ranks == 1:
+        r = subprocess.run([exe, "in.set"], cwd=td, capture_output=True, text=True, timeout=1800, env=env)
+        assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+        stdout, stderr = r.stdout, r.stderr
+    else:
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "mpi_mini"))
+        from mpirun import launch
+        rc = launch(ranks, [exe, "in.set"], cwd=td, env=env, timeout=1800)
+        stdout, stderr = open(os.path.join(td, "stdout.0")).read(), open(os.path.join(td, "stderr.0")).read()
+        assert rc == 0, (stdout[-3000:], stderr[-3000:], open(os.path.join(td, "stderr.1")).read()[-2000:])
     obs = [f for f in os.listdir(td) if f.startswith("gauge_obs")]
-    return r, parse_rhmc(r.stdout, open(os.path.join(td, obs[0])).read())
+
+    class R:
+        pass
+    r = R(); r.stdout, r.stderr = stdout, stderr
+    return r, parse_rhmc(stdout, open(os.path.join(td, obs[0])).read())
 
 
 def compare(got, want):
@@ -74,4 +89,17 @@ def test_reference_rhmc_main_with_the_library(tmp_path):
     if os.path.isdir(out):
         json.dump({"got": got, "want": want}, open(os.path.join(out, "reference_rhmc_main_%s.json" % GEOM), "w"), indent=1)
     print("library-linked main:", got)
+    compare(got, want)
+
+
+@pytest.mark.xfail(strict=False, reason="first multi-GPU run of this test is pending (see the module docstring); XPASS expected")
+def test_reference_rhmc_main_with_the_library_two_gpus(tmp_path):
+    """the same program on two D3 slabs, one process per GPU under oracle/mpi_mini, against the pure-reference two-rank run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    want = json.load(open(os.path.join(HOST_DIR, "rhmc_%s_r2.json" % GEOM)))
+    r, got = run_main("staple", str(tmp_path), ranks=2)
+    assert "hot path served by staple_b200" in r.stderr
+    print("library-linked main, 2 ranks:", got)
     compare(got, want)

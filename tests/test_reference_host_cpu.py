@@ -66,3 +66,13 @@ def test_pure_reference_rhmc_main_reproduces_fixture(tmp_path):
     assert got == want
     T.compare(got, want)
     assert all(row[1] == 1.0 for row in got["gauge_obs"]) and got["cgm_md"][0] > 100        # accepted trajectories, real solves
+
+
+def test_pure_reference_two_rank_rhmc_main_reproduces_fixture(tmp_path):
+    """... and on two D3 slabs as two processes under oracle/mpi_mini (the CPU half of the 2-GPU test)"""
+    import json
+    import test_gpu_zz_reference_rhmc as T
+    want = json.load(open(os.path.join(HOST_DIR, "rhmc_%s_r2.json" % T.GEOM)))
+    r, got = T.run_main("ref", str(tmp_path), ranks=2)
+    assert got == want
+    T.compare(got, want)
