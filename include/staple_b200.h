@@ -145,6 +145,14 @@ typedef void staple_request;
 #define CONVERGENCE_NONCRITICAL 0
 #endif
 
+#ifndef TESTS_AND_BENCHMARK_H_
+typedef struct diracTimes_t {               /* ref: tests_and_benchmarks/test_and_benchmarks.h:37-42 */
+	double totTransferTime;                   /* wall time rank 0 spent in the BLOCKING fermion halo exchange of acc_Deo/acc_Doe */
+	unsigned int count;                       /* (fermion_matrix.c:196-205, :252-259; "makes sense only without async communications") */
+} diracTimeContainer;
+extern diracTimeContainer dirac_times;      /* weak in the library; the host's definition (test_and_benchmarks.c:30) wins */
+#endif
+
 extern int verbosity_lv;                    /* ref: Include/common_defines.h:88 (weak in the library) */
 extern int multishift_invert_iterations;    /* ref: OpenAcc/inverter_wrappers.c:43 */
 
@@ -223,10 +231,16 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 /* Optional (collective, after staple_init_multidev1D): fermion halos through NVLink peer memory instead of
  * ncclSend/Recv -- the surface kernels of acc_Deo/acc_Doe store their slice straight into the neighbour's
  * staging area (CUDA IPC) and raise a flag; returns 1 if active, 0 if it fell back to NCCL.
- * on = 1: acc_Deo/acc_Doe with their exchange are ONE kernel (face blocks first, bulk, unpack blocks last);
+ * on = 1: acc_Deo/acc_Doe with their exchange are ONE kernel (face blocks first, bulk, unpack blocks last), and the
+ *         solvers leave the halos of their intermediate vectors in the staging area, where the next kernel consumes them;
  * on = 2: the reference's three-queue structure (d3p, d3m, bulk on separate streams) with peer stores;
- * on = 3: one operator kernel + a separate unpack kernel.  Global sums use the same mailboxes. */
+ * on = 3: one operator kernel + a separate unpack kernel;  on = 4: like 1 without the staged halos inside the solvers.
+ * Global sums use the same mailboxes. */
 int staple_enable_p2p(int on);
+/* Every in-kernel wait of the peer-memory channels is for a flag that a PEER GPU writes; it is bounded: after `seconds`
+ * (default 60; 0 = wait for ever, which is what MPI_Wait does) the waiting kernel prints what it was waiting for and
+ * traps, so a dead rank surfaces as a CUDA error on the survivors instead of a hang. */
+void staple_set_spin_timeout(double seconds);
 void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
 int staple_myrank(void);
 

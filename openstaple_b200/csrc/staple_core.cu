@@ -13,6 +13,7 @@ extern "C" {
 __attribute__((weak)) int verbosity_lv = 0;                                // common_defines.h:88
 __attribute__((weak)) inv_tricks inverter_tricks = { 0, 0, 0.1, 10000 };   // inverter_tricks.h:4-11
 int multishift_invert_iterations = 0;                                     // inverter_wrappers.c:43
+__attribute__((weak)) diracTimeContainer dirac_times = { 0.0, 0u };       // tests_and_benchmarks/test_and_benchmarks.c:30
 }
 
 namespace staple {
@@ -210,6 +211,23 @@ static void fill_geom(Geom &g, int n0, int n1, int n2, int n3, int nranks_d3, in
 	g.r1_hi = g.sizeh - g.r1_lo;
 }
 
+// the peer-memory mailbox belongs to ONE geometry (staging slots and chunk flags are sized by vol3h): collective release
+static void release_p2p()
+{
+	Ctx &c = ctx();
+	if (!c.p2p.mailbox) { c.p2p = P2P(); return; }
+	cudaDeviceSynchronize();
+	if (c.comm && c.comm->comm) {                          // peers are done with our memory
+		double *p = result(kResultSlots - 1);
+		STAPLE_NCCL_CHECK(c.comm, c.comm->AllReduce(p, p, 1, ncclDouble, ncclSum, c.comm->comm, c.s_comm));
+		STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.s_comm));
+	}
+	for (int r = 0; r < c.nranks; r++)
+		if (r != c.myrank && c.p2p.peer_mailbox[r]) cudaIpcCloseMemHandle(c.p2p.peer_mailbox[r]);
+	cudaFree(c.p2p.mailbox); cudaFree(c.p2p.tickets); cudaFree(c.p2p.d_seq);
+	c.p2p = P2P();
+}
+
 }   // namespace staple
 
 using namespace staple;
@@ -217,7 +235,7 @@ using namespace staple;
 // ====================================================================== C ABI
 extern "C" {
 
-const char *staple_version(void) { return "staple_b200 0.1 (sm_100a)"; }
+const char *staple_version(void) { return "staple_b200 0.2 (sm_100a)"; }
 
 int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo_width, int device)
 {
@@ -230,6 +248,14 @@ int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo
 	if (device >= 0) STAPLE_CUDA_CHECK(cudaSetDevice(device));
 	STAPLE_CUDA_CHECK(cudaGetDevice(&c.device));
 	Geom &g = c.g;
+	{	// a new geometry invalidates everything that was sized or captured for the old one: the peer-memory mailbox (staging
+		// slots of 3*vol3h elements -- a larger lattice would write past them in the NEIGHBOURS' memory) and, when the number of
+		// ranks changes, the communicator.  Collective, like the staple_init_geometry calls of an SPMD host program are.
+		Geom ng;
+		fill_geom(ng, n0, n1, n2, n3, nranks_d3, halo_width);
+		if (c.inited && c.p2p.mailbox && (ng.vol3h != c.p2p.vol3h || ng.nranks != c.nranks)) release_p2p();
+		if (c.inited && c.comm && ng.nranks != c.nranks) shutdown_multidev();
+	}
 	fill_geom(g, n0, n1, n2, n3, nranks_d3, halo_width);
 	release_streamed_state();      // cached schedules carry the previous geometry in their kernel arguments
 	if (!c.own_stream) {
@@ -246,8 +272,8 @@ int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo
 		STAPLE_CUDA_CHECK(cudaHostAlloc(&c.h_results, sizeof(double) * 2 * kResultSlots, cudaHostAllocDefault));
 		c.stream = c.own_stream;
 	}
-	{	// one partial per 128-site CTA of the largest fused-reduction launch
-		const long need = g.sizeh / 128 + 4096;
+	{	// one partial per operator CTA of the largest fused-reduction launch (+ face and unpack blocks of a segmented launch)
+		const long need = g.sizeh / kDslashBlock + 4096;
 		if (need > c.max_partials) {
 			if (c.d_partials) STAPLE_CUDA_CHECK(cudaFree(c.d_partials));
 			c.max_partials = need;
@@ -441,6 +467,7 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 		fprintf(stderr, "MPI%02d - NRANKS_D3 = %d, nranks = %d\n", myrank, c.g.nranks, nranks);
 		exit(1);
 	}
+	if (c.comm) shutdown_multidev();                 // a second call replaces the rank layer (mailbox, communicator) instead of leaking it
 	c.myrank = myrank; c.nranks = nranks;
 	c.rank_L = (myrank + (nranks - 1)) % nranks;   // multidev.c:60-61 (SALAMINO ring)
 	c.rank_R = (myrank + 1) % nranks;
@@ -474,14 +501,19 @@ int staple_enable_p2p(int on)
 	if (!on || c.nranks <= 1) { p.on = false; return 0; }
 	c.p2p_single_launch = (on != 2);                   // 2: keep the reference's d3p/d3m/bulk three-queue structure
 	c.p2p_unpack_in_kernel = (on != 3);                // 3: single operator launch + separate unpack kernel
+	c.p2p_lazy = (on == 1);                            // 1: the solvers consume intermediate halos from the staging area
+	const Geom &g = c.g;
+	if (p.mailbox && p.vol3h != g.vol3h) release_p2p();  // built for another geometry (staple_init_geometry does this too)
 	if (p.stage_L) { p.on = true; return 1; }          // already mapped
 	if (!c.comm) { fprintf(stderr, "libstaple_b200: staple_enable_p2p before staple_init_multidev1D\n"); exit(1); }
 	if (c.nranks > kMaxRanks) { fprintf(stderr, "libstaple_b200: peer-memory channels support up to %d ranks\n", kMaxRanks); return 0; }
-	const Geom &g = c.g;
+	p.vol3h = g.vol3h;
+	p.nfb = (g.vol3h + kDslashBlock - 1) / kDslashBlock;
 	p.slot_bytes = (size_t) 3 * g.vol3h * 16;
-	const size_t mb_bytes = kMailboxStage + 4 * p.slot_bytes;
+	p.stage_off = kMailboxHeader + (((size_t) 2 * p.nfb * sizeof(unsigned long long) + 1023) / 1024) * 1024;
+	const size_t mb_bytes = p.stage_off + 4 * p.slot_bytes;
 	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.mailbox, mb_bytes));
-	STAPLE_CUDA_CHECK(cudaMemset(p.mailbox, 0, kMailboxStage));
+	STAPLE_CUDA_CHECK(cudaMemset(p.mailbox, 0, p.stage_off));
 	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 4 * sizeof(unsigned int)));
 	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 4 * sizeof(unsigned int)));
 	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.d_seq, 2 * sizeof(unsigned long long)));
@@ -523,26 +555,27 @@ int staple_enable_p2p(int on)
 			return 0;
 		}
 	}
-	p.stage = p.mailbox + kMailboxStage;
-	p.flags = (unsigned long long *) (p.mailbox + kMailboxHaloFlags);
-	p.stage_L = p.peer_mailbox[c.rank_L] + kMailboxStage; p.stage_R = p.peer_mailbox[c.rank_R] + kMailboxStage;
-	p.flags_L = (unsigned long long *) (p.peer_mailbox[c.rank_L] + kMailboxHaloFlags);
-	p.flags_R = (unsigned long long *) (p.peer_mailbox[c.rank_R] + kMailboxHaloFlags);
+	p.stage = p.mailbox + p.stage_off;
+	p.flags = (unsigned long long *) (p.mailbox + kMailboxHeader);
+	p.stage_L = p.peer_mailbox[c.rank_L] + p.stage_off; p.stage_R = p.peer_mailbox[c.rank_R] + p.stage_off;
+	p.flags_L = (unsigned long long *) (p.peer_mailbox[c.rank_L] + kMailboxHeader);
+	p.flags_R = (unsigned long long *) (p.peer_mailbox[c.rank_R] + kMailboxHeader);
 	p.on = true;
 	return 1;
+}
+
+void staple_set_spin_timeout(double seconds)
+{
+	require_init("staple_set_spin_timeout");
+	const unsigned long long ns = seconds <= 0 ? 0ull : (unsigned long long) (seconds * 1e9);
+	set_spin_timeout_kernels(ns);
+	set_spin_timeout_solvers(ns);
 }
 
 void shutdown_multidev(void)
 {
 	Ctx &c = ctx();
-	if (c.p2p.mailbox) {
-		cudaDeviceSynchronize();
-		if (c.comm && c.comm->comm) nccl_barrier(c.s_comm);   // peers are done with our memory
-		for (int r = 0; r < c.nranks; r++)
-			if (r != c.myrank && c.p2p.peer_mailbox[r]) cudaIpcCloseMemHandle(c.p2p.peer_mailbox[r]);
-		cudaFree(c.p2p.mailbox); cudaFree(c.p2p.tickets); cudaFree(c.p2p.d_seq);
-		c.p2p = P2P();
-	}
+	release_p2p();
 	if (c.comm && c.comm->comm) {
 		cudaDeviceSynchronize();
 		c.comm->CommDestroy(c.comm->comm);

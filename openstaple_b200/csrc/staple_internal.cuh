@@ -39,28 +39,34 @@ struct CgmCtl; // CG-M control block, below
 
 // Peer-memory channels over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank owns ONE
 // shared "mailbox" allocation:
-//   halo flags[2] | reduction flags[2 parities][kMaxRanks] | reduction boxes[2][kMaxRanks][2 doubles] |
-//   halo staging stage[2 parities][2 slots][3 colours x vol3h x 16 B]
+//   header (reduction flags[2 parities][kMaxRanks] | reduction boxes[2][kMaxRanks][2 doubles]) |
+//   halo flags[2 slots][nfb] | halo staging stage[2 parities][2 slots][3 colours x vol3h x 16 B]
 // Halo slot 0 receives the data of this rank's LOWER fermion halo (written by rank L's top-face blocks),
-// slot 1 the UPPER halo (written by rank R's bottom-face blocks).  Exchange / reduction number s uses
-// parity s&1, which makes both channels write-after-read safe without a handshake.
-// The sequence numbers live in DEVICE memory (d_seq, d_redq) and are advanced by the consuming kernels,
-// so a captured CUDA graph of solver iterations replays correctly.
+// slot 1 the UPPER halo (written by rank R's bottom-face blocks).  The unit of the protocol is one CTA of the
+// operator (kDslashBlock consecutive sites of a d3 slice, nfb = ceil(vol3h / kDslashBlock) of them per face):
+// the CTA that computed those sites stores them into the neighbour's staging slot and then publishes the exchange
+// number in the neighbour's flag[slot][j]; whoever consumes sites of chunk j waits for that one flag.  There is no
+// group barrier, no ticket and no wait on a block of the same launch anywhere.  Exchange number s uses staging
+// parity s&1, which makes the channel write-after-read safe without a handshake.
+// The sequence numbers live in DEVICE memory (d_seq, d_redq) and are advanced by kernels, so a captured CUDA graph
+// of solver iterations replays correctly.
 constexpr int kMaxRanks = 16;
-constexpr size_t kMailboxHaloFlags = 0, kMailboxRedFlags = 64, kMailboxRedBox = 64 + 2 * kMaxRanks * 8,
-								 kMailboxStage = 1024;
+constexpr size_t kMailboxRedFlags = 64, kMailboxRedBox = 64 + 2 * kMaxRanks * 8, kMailboxHeader = 1024;
 struct P2P {
 	bool on = false;
 	char *mailbox = nullptr;                  // local, cudaMalloc (IPC exported)
 	char *peer_mailbox[kMaxRanks] = {};       // every rank's mailbox as mapped here ([myrank] = local)
-	char *stage = nullptr;                    // = mailbox + kMailboxStage
-	unsigned long long *flags = nullptr;      // = mailbox + kMailboxHaloFlags
+	char *stage = nullptr;                    // local staging = mailbox + stage_off
+	unsigned long long *flags = nullptr;      // local per-chunk flags [2 slots][nfb]
 	char *stage_L = nullptr, *stage_R = nullptr;
 	unsigned long long *flags_L = nullptr, *flags_R = nullptr;
-	unsigned int *tickets = nullptr;          // local [4]: top face, bottom face, unpack
+	unsigned int *tickets = nullptr;          // local [4]: [0] launch ticket of the operator, [2] unpack kernel
 	unsigned long long *d_seq = nullptr;      // local: number of completed halo exchanges
 	unsigned long long *d_redq = nullptr;     // local: number of completed reductions
 	size_t slot_bytes = 0;                    // 3 * vol3h * 16
+	size_t stage_off = 0;                     // byte offset of the staging area in every mailbox
+	long nfb = 0;                             // chunks (operator CTAs) per face
+	long vol3h = 0;                           // the geometry the mailbox was built for
 };
 // by-value kernel argument of the peer-memory all-reduce
 struct RedView {
@@ -68,6 +74,17 @@ struct RedView {
 	unsigned long long *q;
 	double *box[kMaxRanks];                   // reduction boxes of every rank (parity 0 base)
 	unsigned long long *flags[kMaxRanks];
+};
+// by-value kernel argument: consumer's view of the LOCAL staging area (a vector whose halo slices were pushed by the
+// neighbours but not copied into the vector: "staged" halos)
+struct HaloView {
+	int on;                                   // 0: halos are in the vector itself
+	int chunk;                                // sites per flag (operator CTA size)
+	const char *stage_lo, *stage_hi;          // parity-0 bases of slot 0 (lower halo) / slot 1 (upper halo)
+	const unsigned long long *flag_lo, *flag_hi;
+	const unsigned long long *seq;            // exchange counter: the staged halos belong to exchange *seq
+	long parity_bytes;                        // bytes between the parity-0 and parity-1 staging
+	long lower_lo, upper_lo, vol3h;           // first idxh of the lower / upper fermion halo slice
 };
 
 struct Ctx {
@@ -91,6 +108,7 @@ struct Ctx {
 	bool use_graphs = true;          // CG-M iteration batches as CUDA graphs (single GPU, non-default stream)
 	bool p2p_unpack_in_kernel = true; // ... and the unpack blocks ride in the same launch
 	bool p2p_single_launch = true;   // acc_Deo/acc_Doe as one kernel + unpack (false: d3p/d3m/bulk on three streams)
+	bool p2p_lazy = true;            // solvers leave intermediate halos in the staging area and consume them there
 	// set by the CG-M solver around its iteration batches: fuse the after-alpha recurrences into the Deo tail
 	CgmCtl *cgm_hook = nullptr;
 	void *out_host_hook = nullptr;   // staple_acc_Doe_Deo_streamed: the Deo chunk kernels also store their result in host memory
@@ -128,7 +146,50 @@ void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s);
 RedView make_redview();
 inline RedView single_rank_redview() { RedView v; v.nranks = 1; v.myrank = 0; v.q = nullptr; return v; }
 
+// operator CTA size = sites per halo chunk (scripts/tune_dslash.py sweeps it; 128 is the measured optimum)
+#ifndef STAPLE_DSLASH_BLOCK
+#define STAPLE_DSLASH_BLOCK 128
+#endif
+constexpr int kDslashBlock = STAPLE_DSLASH_BLOCK;
+
 #ifdef __CUDACC__
+// Every in-kernel wait is for a flag that a PEER GPU writes (never for a block of the same launch), so forward progress
+// does not depend on block scheduling order; it does depend on the peer being alive.  The spin is bounded: after
+// g_spin_timeout_ns (staple_set_spin_timeout, default 60 s; 0 = unbounded, MPI_Wait semantics) the kernel reports what it
+// was waiting for and traps, which surfaces on the host as a CUDA error instead of a hang.
+// (no relocatable device code in this build: the variable and the cold path exist once per translation unit that waits --
+// staple_kernels.cu and staple_solvers.cu -- and staple_set_spin_timeout sets both copies)
+static __device__ unsigned long long g_spin_timeout_ns = 60ull * 1000000000ull;
+static __device__ __noinline__ void spin_timeout_trap(int what, unsigned long long have, unsigned long long want)
+{
+	printf("libstaple_b200: FATAL: block %u waited more than %llu s for a peer GPU (%s: have %llu, want %llu) -- is a rank dead, or "
+				 "did the ranks issue different call sequences?  (staple_set_spin_timeout changes the limit)\n",
+				 blockIdx.x, g_spin_timeout_ns / 1000000000ull, what == 1 ? "halo chunk flag" : "reduction mailbox", have, want);
+	__trap();
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+// what: 1 halo chunk flag, 2 reduction mailbox
+__device__ __forceinline__ void wait_flag_sys(const unsigned long long *flag, unsigned long long want, int what)
+{
+	unsigned long long v, t0 = 0;
+	unsigned int spins = 0;
+	for (;;) {
+		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+		if (v >= want) return;
+		__nanosleep(spins < 32 ? 20 : 200);
+		if ((++spins & 0x3fffu) == 0) {            // look at the clock every ~3 ms
+			const unsigned long long now = globaltimer_ns(), lim = *(volatile unsigned long long *) &g_spin_timeout_ns;
+			if (t0 == 0) t0 = now;
+			else if (lim != 0 && now - t0 > lim) spin_timeout_trap(what, v, want);
+		}
+	}
+}
+
 // One warp: every rank stores its value into every rank's box (lane = destination rank), waits for all
 // contributions to its own box and adds them in rank order -- bit-identical results everywhere, about one
 // NVLink round trip, and usable as the prologue of a kernel that consumes the sum (no separate launch).
@@ -143,11 +204,7 @@ __device__ __forceinline__ void p2p_allreduce_warp(double *vals, int nd, const R
 		b[1] = nd > 1 ? vals[1] : 0.0;
 		__threadfence_system();
 		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(v.flags[lane] + par * kMaxRanks + v.myrank), "l"(q) : "memory");
-		const unsigned long long *f = v.flags[v.myrank] + par * kMaxRanks + lane;
-		unsigned long long got;
-		do {
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
-		} while (got < q);
+		wait_flag_sys(v.flags[v.myrank] + par * kMaxRanks + lane, q, 2);
 	}
 	__syncwarp();
 	if (lane == 0) {
@@ -262,56 +319,65 @@ struct DslashArgs {
 	const int *skip;          // device flag: nonzero -> kernel is a no-op (solver overrun)
 	CgmCtl *cgm;              // EPI_MASS_DOT only: the block that completes the alpha sum also advances the CG-M recurrences
 	RedView cgm_red;
-	// fused halo push (surface launches of exactly one d3 slice): the slice is ALSO stored into the
-	// neighbour's staging slot through its NVLink mapping, then the neighbour's flag is set to peer_seq
-	cplx_t<T> *peer;          // [3][vol3h] in the neighbour's memory (parity-0 slot), or null
-	unsigned long long *peer_flag;
-	const unsigned long long *seq_ptr;   // device counter of completed exchanges; this one is *seq_ptr + 1
-	long peer_parity_stride;             // elements between the parity-0 and parity-1 slot
-	unsigned int *face_ticket;
-	// single-launch operator with fused halo push (fused != 0): blocks [0,fb) compute the TOP interior slice
-	// (-> rank R), blocks [fb,2fb) the BOTTOM one (-> rank L), the rest the bulk -- faces are scheduled first,
-	// so their NVLink stores overlap the bulk of the same kernel
-	int fused;
-	int dbg;                  // diagnostics (STAPLE_DEBUG_HALO): bit 0 = skip the peer stores, bit 1 = skip the unpack copy
-	unsigned int face_blocks;
-	long top_lo, bot_lo;      // first idxh of the two surface slices; site_lo/nsites describe the bulk
-	cplx_t<T> *peer2;         // bottom face target (peer = top face target)
-	unsigned long long *peer_flag2;
-	unsigned int *face_ticket2;
-	// ... and, scheduled last, 2*unpack_blocks blocks that wait for the neighbours' flags and copy the two staged
-	// slices into the halo slices of `out`: a whole acc_Deo/acc_Doe with its exchange is ONE launch
-	unsigned int bulk_blocks, unpack_blocks;
-	const cplx_t<T> *unpack_src;       // local staging, parity-0 slot 0 (slot 1 follows after slot_elems)
-	long slot_elems;
-	const unsigned long long *local_flags;
-	unsigned long long *seq_rw;        // the exchange counter, advanced by the last unpack block
-	unsigned int *unpack_ticket;       // [0] ticket of the unpack blocks, [1] number of face groups that have signalled
-	long lower_lo, upper_lo;           // first idxh of the lower / upper halo slice
-	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites)
+	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites) of a plain launch / of the bulk segment
 	int nd0h, nd1, nd2, nd3;
 	long vol3h, sizeh;
+	// ---- D3 slabs over NVLink peer memory (mr != 0): the launch is segmented by block index into
+	//   [nb_top blocks: TOP interior slice -> rank R's slot 0] [nb_bot: BOTTOM interior slice -> rank L's slot 1]
+	//   [nb_bulk: the slices in between] [2*nb_unpack: copy of the staged halos of THIS exchange into `out`]
+	// any segment may be empty.  Face block j stores its chunk into the neighbour's staging slot and publishes the exchange
+	// number in the neighbour's flag j; faces come first in block order, so the transfer overlaps the rest of the launch.
+	int mr;
+	unsigned int nb_top, nb_bot, nb_bulk, nb_unpack;
+	long top_lo, bot_lo;                         // first idxh of the two surface slices
+	cplx_t<T> *peer_top, *peer_bot;              // parity-0 staging slot in the neighbour's memory (null: no push)
+	unsigned long long *peer_flag_top, *peer_flag_bot;
+	long parity_stride;                          // elements between the parity-0 and parity-1 staging areas
+	unsigned long long *seq_rw;                  // device counter of completed exchanges; this launch produces *seq_rw + 1
+	unsigned int *launch_ticket;                 // non-null: the last block of the launch advances the counter
+	// consumer side: the halo slices of `in` were left in the local staging area by exchange *seq_rw (in_staged), and/or
+	// the staged halos of the exchange this launch produces are copied into `out` by the unpack blocks
+	int in_staged;
+	const cplx_t<T> *stage_lo, *stage_hi;        // local slot 0 (lower halo) / slot 1 (upper halo), parity-0 base
+	const unsigned long long *flag_lo, *flag_hi; // local per-chunk flags of slot 0 / slot 1
+	long lower_lo, upper_lo;                     // first idxh of the lower / upper halo slice
 };
 
 enum Epilogue { EPI_NONE = 0, EPI_MASS = 1, EPI_MASS_DOT = 2 };
 
 // launches on stream s the operator for output parity `par` over d3 in [d3lo, d3hi)
-// face: 0 = no push, 1 = this launch is the TOP interior slice (-> rank R, slot 0), 2 = BOTTOM (-> rank L, slot 1)
+// face: FACE_NONE   plain launch over the range
+//       FACE_TOP    the range is the TOP interior slice, pushed to rank R (slot 0)      } three-queue form
+//       FACE_BOTTOM the range is the BOTTOM interior slice, pushed to rank L (slot 1)  }
+//       FACE_BOTH   whole local interior in one segmented launch, both faces pushed
+//       FACE_BOTH_UNPACK  ... and the staged halos of this exchange copied into `out` by the last blocks of the launch
+// halo: HALO_IN_STAGED  the halo slices of `in` are in the staging area (FACE_BOTH* only)
+//       HALO_ADVANCE    the last block of the launch advances the exchange counter
+enum { FACE_NONE = 0, FACE_TOP = 1, FACE_BOTTOM = 2, FACE_BOTH = 3, FACE_BOTH_UNPACK = 4 };
+enum { HALO_EAGER = 0, HALO_OUT_STAGED = 1, HALO_IN_STAGED = 2, HALO_ADVANCE = 4 };
 template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
 									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s,
-									 int face = 0);
+									 int face = FACE_NONE, int halo = 0);
 unsigned int dslash_blocks(int d3lo, int d3hi);
 
 // full operator with halo handling (acc_Deo/acc_Doe, fermion_matrix.c:159-268); epilogue as above.
+// halo (solvers only; honoured when the peer-memory single-launch transport is active, see halo_lazy_ok()):
+//   HALO_OUT_STAGED  do not copy the received halos into `out`: the next kernel consumes them from the staging area
+//   HALO_IN_STAGED   the halos of `in` are in the staging area (left there by the previous HALO_OUT_STAGED operator)
 template <typename T>
 void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
-									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip);
-// out = (mass^2+shift) in - Deo Doe in; optionally leaves Re(in.out) (local, not yet all-reduced) in result(dot_slot)
+									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip, int halo = HALO_EAGER);
+// out = (mass^2+shift) in - Deo Doe in; optionally leaves Re(in.out) (local, not yet all-reduced) in result(dot_slot).
+// The halos of tmp are never unpacked when halo_lazy_ok(); out_staged: nor are those of `out` (CG-M consumes them staged)
 template <typename T>
 void apply_mdagm(const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, cplx_t<T> *tmp, const T *ph,
-								 double m2, int dot_slot, const int *skip);
+								 double m2, int dot_slot, const int *skip, bool out_staged = false, bool tmp_eager = false);
+void set_spin_timeout_kernels(unsigned long long ns);   // one copy of g_spin_timeout_ns per translation unit
+void set_spin_timeout_solvers(unsigned long long ns);
+bool halo_lazy_ok();                  // peer-memory transport, single-launch operator, lazy halos enabled
+HaloView make_haloview(size_t elem_bytes, bool on);
 
 // BLAS-1 (device pointers)
 enum BlasOp {

@@ -6,20 +6,19 @@
 // 3 colours of 8 neighbour spinors) is read with 128-bit (FP64) / 64-bit (FP32) loads that are
 // contiguous across the warp because idxh is the fastest index of every array.
 #include "staple_internal.cuh"
+#include <cstring>
+#include <ctime>
 
 namespace staple {
 
 // tuning knobs (scripts/tune_dslash.py sweeps them; the defaults are the measured optimum, profiles/)
-#ifndef STAPLE_DSLASH_BLOCK
-#define STAPLE_DSLASH_BLOCK 128
-#endif
 #ifndef STAPLE_DSLASH_MINBLOCKS
 #define STAPLE_DSLASH_MINBLOCKS 7       // 72 registers, 28 warps/SM: +8% over the unconstrained build (profiles/r01_tune_dslash_*.txt)
 #endif
 #ifndef STAPLE_LINK_LOAD
 #define STAPLE_LINK_LOAD 0       // 0: ld.global.cs (evict-first streaming)  1: ld.global.nc  2: ld.global.lu  3: plain
 #endif
-constexpr int kBlock = STAPLE_DSLASH_BLOCK;      // dslash CTA size
+constexpr int kBlock = kDslashBlock;      // dslash CTA size (staple_internal.cuh)
 constexpr int kBlasBlock = 256;
 
 // ------------------------------------------------------------------ small complex helpers
@@ -203,81 +202,96 @@ __device__ __forceinline__ bool grid_sum_finalize(double v[NV], double *partials
 }
 
 // ------------------------------------------------------------------ peer-memory halo channel (device side)
-// Producer: every thread has issued its peer stores; the last block to finish publishes `seq` in the
-// neighbour's flag with system-scope release semantics (fence.sys by all writers, ticket, fence.sys, store).
-__device__ __forceinline__ void face_signal(unsigned long long *peer_flag, unsigned long long seq, unsigned int *ticket,
-																						unsigned int nblocks, unsigned int *groups_done = nullptr)
+// Producer side of one chunk: every thread of the CTA has issued its peer stores; ONE system-scope fence by thread 0 after
+// the barrier makes them visible before the flag (the barrier makes the fence cumulative -- the post pattern of NCCL's simple
+// protocol; a fence.sys by every thread was measured to cost more than the transfer itself).
+__device__ __forceinline__ void chunk_signal(unsigned long long *peer_flag, unsigned long long seq)
 {
-	// ONE system-scope fence per block, by the thread that takes the ticket: the barrier orders every thread's peer
-	// stores before it (the fence is cumulative), exactly the post pattern of NCCL's simple protocol.  A fence.sys by
-	// all 128 threads of each of the ~2000 face blocks floods the memory system with membars and was measured to
-	// cost more than the transfer itself.
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(seq) : "memory");
+}
+
+// push both interior faces of a vector (3 colour arrays) into the neighbours' staging slots (standalone
+// communicate_fermion_borders; the operator's face blocks do this themselves).  grid = 2*nfb CTAs of kDslashBlock threads:
+// [0,nfb) TOP interior slice -> rank R's slot 0, [nfb,2nfb) BOTTOM interior slice -> rank L's slot 1
+template <typename C>
+__global__ void __launch_bounds__(kDslashBlock) p2p_push_kernel(const C *src, long n, long top_lo, long bot_lo, unsigned int vol3h,
+																																 unsigned int nfb, C *peer_top, C *peer_bot, long parity_stride,
+																																 unsigned long long *flag_top, unsigned long long *flag_bot,
+																																 const unsigned long long *seq_ptr)
+{
+	const unsigned long long seq = *seq_ptr + 1;
+	const bool bot = blockIdx.x >= nfb;
+	const unsigned int j = bot ? blockIdx.x - nfb : blockIdx.x, t = j * kDslashBlock + threadIdx.x;
+	C *peer = (bot ? peer_bot : peer_top) + (seq & 1ull) * parity_stride;
+	const long lo = bot ? bot_lo : top_lo;
+	if (t < vol3h) {
+		C v[3];
+#pragma unroll
+		for (int c = 0; c < 3; c++) v[c] = src[c * n + lo + t];
+#pragma unroll
+		for (int c = 0; c < 3; c++) peer[(long) c * vol3h + t] = v[c];
+	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence_system();
-		const unsigned int t = atomicAdd(ticket, 1u);
-		if (t == nblocks - 1) {
-			__threadfence_system();
-			*ticket = 0u;
-			asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(seq) : "memory");
-			if (groups_done != nullptr) atomicAdd(groups_done, 1u);   // this launch's face group no longer needs the old counter
+	if (threadIdx.x == 0) chunk_signal((bot ? flag_bot : flag_top) + j, seq);
+}
+
+// copy of staged chunks (3 colour arrays) into a halo slice: block `b` of `nb` takes chunks b, b+nb, ... four at a time --
+// threads 0..3 wait for one flag each, then every thread has 4 sites x 3 colours = 12 independent 16-byte loads in flight.
+// Not inlined in the operator: its registers must not weigh on the 72-register budget of the hops.
+template <typename C>
+__device__ __noinline__ void unpack_chunks(C *dst, long n, const C *src, const unsigned long long *flags, unsigned long long seq,
+																					 unsigned int vol3h, unsigned int nfb, unsigned int b, unsigned int nb)
+{
+	for (unsigned int j0 = b; j0 < nfb; j0 += 4 * nb) {
+		if (threadIdx.x < 4 && j0 + threadIdx.x * nb < nfb) wait_flag_sys(flags + j0 + threadIdx.x * nb, seq, 1);
+		__syncthreads();
+		C v[4][3];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const unsigned int j = j0 + k * nb, tt = j * kDslashBlock + threadIdx.x;
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				if (j < nfb && tt < vol3h) v[k][c] = __ldcg(src + (long) c * vol3h + tt);
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const unsigned int j = j0 + k * nb, tt = j * kDslashBlock + threadIdx.x;
+			if (j < nfb && tt < vol3h) {
+#pragma unroll
+				for (int c = 0; c < 3; c++) dst[c * n + tt] = v[k][c];
+			}
 		}
 	}
 }
-// Consumer: wait until the local flag has reached `seq` (written by the neighbour GPU over NVLink)
-__device__ __forceinline__ void face_wait(const unsigned long long *flag, unsigned long long seq)
-{
-	if (threadIdx.x == 0) {
-		unsigned long long v;
-		do {
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-			if (v < seq) __nanosleep(200);
-		} while (v < seq);
-	}
-	__syncthreads();
-}
 
-// push one interior slice of a vector (3 colour arrays) into a neighbour's staging slot (standalone
-// communicate_fermion_borders; the operator's face blocks do this themselves)
+// standalone unpack: copy both staging slots of exchange *seq_ptr + 1 into the halo slices once the neighbours' chunks
+// have landed; the last block to finish advances the exchange counter.  grid = 2*nb CTAs of kDslashBlock threads.
 template <typename C>
-__global__ void __launch_bounds__(256) p2p_push_kernel(const C *src, long n, long slice_lo, long vol3h, C *peer,
-																											 long parity_stride, unsigned long long *peer_flag,
-																											 const unsigned long long *seq_ptr, unsigned int *ticket)
-{
-	const unsigned long long seq = *seq_ptr + 1;
-	peer += (seq & 1ull) * parity_stride;
-	for (long t = (long) blockIdx.x * 256 + threadIdx.x; t < 3 * vol3h; t += (long) gridDim.x * 256) {
-		const long c = t / vol3h, i = t - c * vol3h;
-		peer[t] = src[c * n + slice_lo + i];
-	}
-	face_signal(peer_flag, seq, ticket, gridDim.x);
-}
-// copy both staging slots into the halo slices once the neighbours' data has landed; the last block to
-// finish advances the exchange counter
-template <typename C>
-__global__ void __launch_bounds__(256) p2p_unpack_kernel(C *dst, long n, long lower_lo, long upper_lo, long vol3h,
-																												 const C *slot0, const C *slot1, long parity_stride,
-																												 const unsigned long long *flags, unsigned long long *seq_ptr,
-																												 unsigned int *ticket, const int *skip)
+__global__ void __launch_bounds__(kDslashBlock) p2p_unpack_kernel(C *dst, long n, long lower_lo, long upper_lo, unsigned int vol3h,
+																																	 unsigned int nfb, const C *slot0, const C *slot1, long parity_stride,
+																																	 const unsigned long long *flag0, const unsigned long long *flag1,
+																																	 unsigned long long *seq_ptr, unsigned int *ticket, const int *skip)
 {
 	if (skip != nullptr && *skip != 0) return;       // the producers skipped this exchange too (same flag on every rank)
 	const unsigned long long seq = *seq_ptr + 1;
-	const int half = gridDim.x / 2;
-	const int which = blockIdx.x >= half;            // first half of the grid: lower halo, second half: upper
-	face_wait(flags + which, seq);
-	const C *src = (which ? slot1 : slot0) + (seq & 1ull) * parity_stride;
-	const long lo = which ? upper_lo : lower_lo;
-	const int b = which ? blockIdx.x - half : blockIdx.x;
-	for (long t = (long) b * 256 + threadIdx.x; t < 3 * vol3h; t += (long) half * 256) {
-		const long c = t / vol3h, i = t - c * vol3h;
-		dst[c * n + lo + i] = __ldcg(src + t);
-	}
+	const unsigned int nb = gridDim.x / 2;
+	const bool hi = blockIdx.x >= nb;                // first half of the grid: lower halo, second half: upper
+	unpack_chunks<C>(dst + (hi ? upper_lo : lower_lo), n, (hi ? slot1 : slot0) + (seq & 1ull) * parity_stride, hi ? flag1 : flag0,
+									 seq, vol3h, nfb, hi ? blockIdx.x - nb : blockIdx.x, nb);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence();
-		if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; *seq_ptr = seq; }
+		if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; __threadfence(); *seq_ptr = seq; }
 	}
 }
+
+// the exchange counter, advanced on its own (pipelined host round trip: the two face slices are separate launches)
+__global__ void seq_advance_kernel(unsigned long long *seq) { *seq = *seq + 1; }
+
+// unpack blocks per halo: at most 2 per SM (grid-stride over chunks with 12 loads in flight per thread).  Thousands of
+// 128-thread blocks only add scheduling time to the tail; 74 were measured too few to cover the HBM latency.
+static inline unsigned int unpack_blocks_for(unsigned int face_blocks) { return face_blocks < 296u ? face_blocks : 296u; }
 
 template <typename C>
 static void p2p_unpack_t(void *base, cudaStream_t s, const int *skip)
@@ -286,10 +300,10 @@ static void p2p_unpack_t(void *base, cudaStream_t s, const int *skip)
 	const Geom &g = c.g;
 	P2P &p = c.p2p;
 	const long lower_lo = (long) (g.d3_halo - 1) * g.vol3h, upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
-	long want = (3 * g.vol3h + 255) / 256;
-	const int half = (int) (want < 148 ? want : 148);
-	p2p_unpack_kernel<C><<<2 * half, 256, 0, s>>>((C *) base, g.sizeh, lower_lo, upper_lo, g.vol3h, (const C *) p.stage,
-		(const C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.flags, p.d_seq, p.tickets + 2, skip);
+	const unsigned int nb = unpack_blocks_for((unsigned int) p.nfb);
+	p2p_unpack_kernel<C><<<2 * nb, kDslashBlock, 0, s>>>((C *) base, g.sizeh, lower_lo, upper_lo, (unsigned int) g.vol3h, (unsigned int) p.nfb,
+		(const C *) p.stage, (const C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.flags, p.flags + p.nfb, p.d_seq,
+		p.tickets + 2, skip);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch();
 }
@@ -306,16 +320,12 @@ static void p2p_exchange_t(void *base, cudaStream_t s)
 	const Geom &g = c.g;
 	P2P &p = c.p2p;
 	const long top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h, bot_lo = (long) g.d3_halo * g.vol3h;
-	long want = (3 * g.vol3h + 255) / 256;
-	const int grid = (int) (want < 148 ? want : 148);
 	const long ps = (long) (2 * p.slot_bytes / sizeof(C));
 	// top interior slice -> rank R's lower halo (its slot 0); bottom interior slice -> rank L's upper halo (slot 1)
-	p2p_push_kernel<C><<<grid, 256, 0, s>>>((const C *) base, g.sizeh, top_lo, g.vol3h, (C *) p.stage_R, ps, p.flags_R + 0,
-																					p.d_seq, p.tickets + 0);
-	p2p_push_kernel<C><<<grid, 256, 0, s>>>((const C *) base, g.sizeh, bot_lo, g.vol3h, (C *) (p.stage_L + p.slot_bytes), ps,
-																					p.flags_L + 1, p.d_seq, p.tickets + 1);
+	p2p_push_kernel<C><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const C *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
+		(unsigned int) p.nfb, (C *) p.stage_R, (C *) (p.stage_L + p.slot_bytes), ps, p.flags_R, p.flags_L + p.nfb, p.d_seq);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
-	count_launch(2);
+	count_launch();
 	p2p_unpack(base, sizeof(C), s, nullptr);
 }
 void p2p_exchange_fermion(void *base, size_t elem_bytes, cudaStream_t s)
@@ -347,31 +357,29 @@ void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
 	count_launch();
 }
 
-// copy of one staged slice (3 colour arrays of nv elements) into a halo slice of `out`: grid-stride, 4 sites x 3
-// colours = 12 independent 16-byte loads in flight per thread.  Not inlined: its registers must not weigh on the
-// 72-register budget of the operator itself.
-template <typename T>
-__device__ __noinline__ void unpack_copy(cplx_t<T> *dst, long n, const cplx_t<T> *src, unsigned int nv, unsigned int first,
-																				 unsigned int stride)
+void set_spin_timeout_kernels(unsigned long long ns)
 {
-	using C = cplx_t<T>;
-	for (unsigned int t0 = first; t0 < nv; t0 += 4 * stride) {
-		C v[4][3];
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const unsigned int tt = t0 + j * stride;
-#pragma unroll
-			for (int c = 0; c < 3; c++) v[j][c] = tt < nv ? __ldcg(src + c * nv + tt) : mk<T>(0, 0);
-		}
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const unsigned int tt = t0 + j * stride;
-			if (tt < nv) {
-#pragma unroll
-				for (int c = 0; c < 3; c++) dst[c * n + tt] = v[j][c];
-			}
-		}
-	}
+	STAPLE_CUDA_CHECK(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns)));
+}
+
+bool halo_lazy_ok()
+{
+	const Ctx &c = ctx();
+	return c.nranks > 1 && c.p2p.on && c.p2p_single_launch && c.p2p_unpack_in_kernel && c.p2p_lazy;
+}
+HaloView make_haloview(size_t elem_bytes, bool on)
+{
+	const Ctx &c = ctx();
+	const Geom &g = c.g;
+	const P2P &p = c.p2p;
+	HaloView h;
+	h.on = on ? 1 : 0; h.chunk = kDslashBlock;
+	h.stage_lo = p.stage; h.stage_hi = p.stage ? p.stage + p.slot_bytes : nullptr;
+	h.flag_lo = p.flags; h.flag_hi = p.flags ? p.flags + p.nfb : nullptr;
+	h.seq = p.d_seq; h.parity_bytes = (long) (2 * p.slot_bytes);
+	h.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; h.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h; h.vol3h = g.vol3h;
+	(void) elem_bytes;
+	return h;
 }
 
 // ------------------------------------------------------------------ Dirac operator kernel
@@ -388,7 +396,47 @@ __device__ __forceinline__ void dslash_finish_dot(const DslashArgs<T> &a, double
 	}
 }
 
-template <typename T, int PAR, int EPI>
+// One hop with the spinor taken from (vin, colour stride vn, index iv) and loaded past L1 (ld.global.cg): the d3 hops,
+// whose neighbour is either the vector itself or -- on a face, with staged halos -- the staging area that a peer GPU
+// writes over NVLink (L1 is not coherent with peer writes; neighbours in d3 are vol3h sites away, so L1 had nothing to
+// offer to them anyway).
+template <typename T, bool DAG>
+__device__ __forceinline__ void hop_d3(cplx_t<T> acc[3], const cplx_t<T> *__restrict__ uk, const T *__restrict__ phk,
+																			 unsigned int im, const cplx_t<T> *vin, unsigned int iv, long n, long vn)
+{
+	using C = cplx_t<T>;
+	const T th = ld_stream(phk + im);
+	const C m00 = ld_stream(uk + im), m01 = ld_stream(uk + n + im), m02 = ld_stream(uk + 2 * n + im);
+	const C m10 = ld_stream(uk + 3 * n + im), m11 = ld_stream(uk + 4 * n + im), m12 = ld_stream(uk + 5 * n + im);
+	const C v0 = __ldcg(vin + iv), v1 = __ldcg(vin + vn + iv), v2 = __ldcg(vin + 2 * vn + iv);
+	T s, c;
+	sincos_t(th, &s, &c);
+	const C x0 = cross(m01, m12, m02, m11);
+	const C x1 = cross(m02, m10, m00, m12);
+	const C x2 = cross(m00, m11, m01, m10);
+	if (!DAG) {
+		const C p = mk<T>(c, s);
+		const C w0 = cmul(v0, p), w1 = cmul(v1, p), w2 = cmul(v2, p);
+		cfma(acc[0], m00, w0); cfma(acc[0], m01, w1); cfma(acc[0], m02, w2);
+		cfma(acc[1], m10, w0); cfma(acc[1], m11, w1); cfma(acc[1], m12, w2);
+		cfma_ca(acc[2], x0, w0); cfma_ca(acc[2], x1, w1); cfma_ca(acc[2], x2, w2);
+	} else {
+		const C p = mk<T>(-c, s);
+		const C w0 = cmul(v0, p), w1 = cmul(v1, p), w2 = cmul(v2, p);
+		cfma_ca(acc[0], m00, w0); cfma_ca(acc[0], m10, w1); cfma(acc[0], x0, w2);
+		cfma_ca(acc[1], m01, w0); cfma_ca(acc[1], m11, w1); cfma(acc[1], x1, w2);
+		cfma_ca(acc[2], m02, w0); cfma_ca(acc[2], m12, w1); cfma(acc[2], x2, w2);
+	}
+}
+
+// Hop order: the six hops in directions 0,1,2 first, the two d3 hops last.  On D3 slabs those are the only hops that can
+// need a neighbour rank's data; a face block whose input halo is staged waits for its ONE chunk flag between the two
+// groups, i.e. with three quarters of its work as slack.  (The reference adds backward 0..3 then forward 0..3,
+// fermion_matrix.c:74-89; the different summation order moves results by O(1e-16) relative, like FMA contraction does.)
+// MR = false: plain launch over [site_lo, site_lo + nsites) -- the single-GPU kernel, free of every multi-rank register.
+// MR = true : segmented launch on D3 slabs (DslashArgs).  What a block needs to know about its segment is derived from
+// blockIdx twice (before the first and before the last group of hops) instead of being carried in registers across them.
+template <typename T, int PAR, int EPI, bool MR>
 __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<T> a)
 {
 	using C = cplx_t<T>;
@@ -397,52 +445,29 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 	// only the array bases (k*9*sizeh) are 64-bit
 	unsigned int t = blockIdx.x * kBlock + threadIdx.x;
 	unsigned int lo = (unsigned int) a.site_lo, ns = (unsigned int) a.nsites;
-	C *peer = a.peer;
-	unsigned long long peer_seq = 0;
-	unsigned long long *peer_flag = a.peer_flag;
-	unsigned int *face_ticket = a.face_ticket;
-	unsigned int face_nblocks = gridDim.x;
-	if (a.fused) {            // block-uniform segment selection: top face, bottom face, bulk
-		const unsigned int fb = a.face_blocks;
-		face_nblocks = fb;
-		if (blockIdx.x < fb) { lo = (unsigned int) a.top_lo; ns = (unsigned int) a.vol3h; }
-		else if (blockIdx.x < 2 * fb) {
-			t -= fb * kBlock; lo = (unsigned int) a.bot_lo; ns = (unsigned int) a.vol3h;
-			peer = a.peer2; peer_flag = a.peer_flag2; face_ticket = a.face_ticket2;
-		}
-		else if (blockIdx.x < 2 * fb + a.bulk_blocks) { t -= 2 * fb * kBlock; peer = nullptr; }
+	if (MR) {              // block-uniform segment selection: top face, bottom face, bulk, unpack
+		const unsigned int b = blockIdx.x;
+		if (b < a.nb_top) { lo = (unsigned int) a.top_lo; ns = (unsigned int) a.vol3h; }
+		else if (b < a.nb_top + a.nb_bot) { t -= a.nb_top * kBlock; lo = (unsigned int) a.bot_lo; ns = (unsigned int) a.vol3h; }
+		else if (b < a.nb_top + a.nb_bot + a.nb_bulk) t -= (a.nb_top + a.nb_bot) * kBlock;
 		else {
-			// ---- unpack blocks (scheduled after every face and bulk block of this launch)
-			const unsigned int ub = a.unpack_blocks, b = blockIdx.x - (2 * fb + a.bulk_blocks);
-			const unsigned int which = b >= ub;                  // 0: lower halo (slot 0, from rank L), 1: upper (slot 1, from R)
+			// ---- unpack blocks (last in block order): the halos of THIS exchange, as the neighbours' face blocks deliver them
 			const unsigned long long seq = *a.seq_rw + 1;
-			face_wait(a.local_flags + which, seq);
-			const C *src = a.unpack_src + (seq & 1ull) * a.peer_parity_stride + which * a.slot_elems;
-			if (!(a.dbg & 2)) unpack_copy<T>(a.out + (which ? a.upper_lo : a.lower_lo), a.sizeh, src, (unsigned int) a.vol3h, (b - which * ub) * kBlock + threadIdx.x, ub * kBlock);
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				__threadfence();
-				if (atomicAdd(a.unpack_ticket, 1u) == 2 * ub - 1) {
-					// last unpack block: both face groups of THIS launch have read the counter once they have signalled
-					while (atomicAdd(a.unpack_ticket + 1, 0u) < 2u) __nanosleep(100);
-					a.unpack_ticket[0] = 0u; a.unpack_ticket[1] = 0u;
-					__threadfence();
-					*a.seq_rw = seq;
-				}
-			}
-			if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, 0.0);   // a zero partial, so that the ticket count stays gridDim.x
-			return;
+			const unsigned int ub = a.nb_unpack, k = b - (a.nb_top + a.nb_bot + a.nb_bulk);
+			const bool hi = k >= ub;                           // first ub blocks: lower halo (slot 0, from rank L); then upper (slot 1, from R)
+			unpack_chunks<C>(a.out + (hi ? a.upper_lo : a.lower_lo), a.sizeh, (hi ? a.stage_hi : a.stage_lo) + (seq & 1ull) * a.parity_stride,
+											 hi ? a.flag_hi : a.flag_lo, seq, (unsigned int) a.vol3h, a.nb_top, hi ? k - ub : k, ub);
+			ns = 0;                                            // no sites of its own; falls through to the common tail
 		}
 	}
-	if (peer != nullptr) {
-		peer_seq = *a.seq_ptr + 1;                       // this exchange's number (advanced by the unpack kernel)
-		peer += (peer_seq & 1ull) * a.peer_parity_stride;
-	}
-	double dot = 0.0;
-	if (t < ns) {
-		const unsigned int idx = lo + t;
-		const long n = a.sizeh;
-		const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
+	const bool active = t < ns;
+	const long n = a.sizeh;
+	const long un = 9 * n;
+	const unsigned int idx = lo + t;
+	C acc[3];
+	acc[0] = mk<T>(0, 0); acc[1] = mk<T>(0, 0); acc[2] = mk<T>(0, 0);
+	if (active) {
+		const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2;
 		const unsigned int hd0 = idx % nd0h;
 		unsigned int q = idx / nd0h;
 		const unsigned int d1 = q % nd1; q /= nd1;
@@ -450,30 +475,52 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 		const unsigned int d3 = q / nd2;
 		// d0 = 2*hd0 + rp  (fermion_matrix.c:64, :120)
 		const unsigned int rp = (d1 + d2 + d3 + PAR) & 1u;
-		const unsigned int s1 = nd0h, s2 = nd0h * nd1, s3 = (unsigned int) a.vol3h;
+		const unsigned int s1 = nd0h, s2 = nd0h * nd1;
 		const unsigned int i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
 		const unsigned int i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
 		const unsigned int i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
 		const unsigned int i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
 		const unsigned int i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
 		const unsigned int i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
-		const unsigned int i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
-		const unsigned int i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
-
-		C acc[3];
-		acc[0] = mk<T>(0, 0); acc[1] = mk<T>(0, 0); acc[2] = mk<T>(0, 0);
-		const long un = 9 * n;
 		// backward hops: link and phase of the OTHER parity at the neighbour index (:74-77, :130-133)
 		hop<T, true>(acc, a.u + (1 - PAR) * un, a.ph + (1 - PAR) * n, i0m, a.in, i0m, n);
 		hop<T, true>(acc, a.u + (3 - PAR) * un, a.ph + (3 - PAR) * n, i1m, a.in, i1m, n);
 		hop<T, true>(acc, a.u + (5 - PAR) * un, a.ph + (5 - PAR) * n, i2m, a.in, i2m, n);
-		hop<T, true>(acc, a.u + (7 - PAR) * un, a.ph + (7 - PAR) * n, i3m, a.in, i3m, n);
 		// forward hops: link and phase of this parity at the own index (:86-89, :144-147)
 		hop<T, false>(acc, a.u + (0 + PAR) * un, a.ph + (0 + PAR) * n, idx, a.in, i0p, n);
 		hop<T, false>(acc, a.u + (2 + PAR) * un, a.ph + (2 + PAR) * n, idx, a.in, i1p, n);
 		hop<T, false>(acc, a.u + (4 + PAR) * un, a.ph + (4 + PAR) * n, idx, a.in, i2p, n);
-		hop<T, false>(acc, a.u + (6 + PAR) * un, a.ph + (6 + PAR) * n, idx, a.in, i3p, n);
-
+	}
+	// ---- the two d3 hops: spinor from the vector itself, or (face block, staged input halo) from the local staging area
+	const C *v3m = a.in, *v3p = a.in;
+	long vn3m = n, vn3p = n;
+	const unsigned int s3 = (unsigned int) a.vol3h, d3 = idx / s3, nd3 = a.nd3;
+	unsigned int i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
+	unsigned int i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
+	C *peer = nullptr;                                  // this block's chunk in the neighbour's staging slot
+	unsigned long long *peer_flag = nullptr;
+	unsigned long long cur = 0;
+	if (MR) {
+		cur = *a.seq_rw;
+		const unsigned int b = blockIdx.x;
+		const unsigned long long *wait_flag = nullptr;    // the chunk of the staged input halo this block reads
+		if (b < a.nb_top) {
+			if (a.peer_top != nullptr) { peer = a.peer_top + ((cur + 1) & 1ull) * a.parity_stride; peer_flag = a.peer_flag_top + b; }
+			if (a.in_staged) { v3p = a.stage_hi + (cur & 1ull) * a.parity_stride; vn3p = a.vol3h; i3p = t; wait_flag = a.flag_hi + b; }
+		} else if (b < a.nb_top + a.nb_bot) {
+			const unsigned int j = b - a.nb_top;
+			if (a.peer_bot != nullptr) { peer = a.peer_bot + ((cur + 1) & 1ull) * a.parity_stride; peer_flag = a.peer_flag_bot + j; }
+			if (a.in_staged) { v3m = a.stage_lo + (cur & 1ull) * a.parity_stride; vn3m = a.vol3h; i3m = t; wait_flag = a.flag_lo + j; }
+		}
+		if (wait_flag != nullptr) {     // block-uniform: written by a peer GPU (exchange `cur`, produced by the previous operator)
+			if (threadIdx.x == 0) wait_flag_sys(wait_flag, cur, 1);
+			__syncthreads();
+		}
+	}
+	double dot = 0.0;
+	if (active) {
+		hop_d3<T, true>(acc, a.u + (7 - PAR) * un, a.ph + (7 - PAR) * n, MR && v3m != a.in ? idx - s3 : i3m, v3m, i3m, n, vn3m);
+		hop_d3<T, false>(acc, a.u + (6 + PAR) * un, a.ph + (6 + PAR) * n, idx, v3p, i3p, n, vn3p);
 #pragma unroll
 		for (int c = 0; c < 3; c++) {
 			C o = mk<T>(acc[c].x * (T) 0.5, acc[c].y * (T) 0.5);   // :94-96
@@ -484,17 +531,24 @@ __global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel
 				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
 			}
 			a.out[c * n + idx] = o;
-			if (EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
-			if (peer != nullptr && !(a.dbg & 1)) peer[c * a.vol3h + t] = o;   // NVLink store into the neighbour's staging slot
+			if (!MR && EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
+#ifndef STAPLE_DEBUG_NO_PEER_STORES      // timing experiments only (wrong halos): never defined in a release build
+			if (MR && peer != nullptr) peer[c * a.vol3h + t] = o;        // NVLink store into the neighbour's staging slot
+#endif
 		}
 	}
-	if (peer != nullptr) face_signal(peer_flag, peer_seq, face_ticket, face_nblocks, a.fused == 2 ? a.unpack_ticket + 1 : nullptr);
-	if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, dot);
+	if (MR) {
+		__syncthreads();              // every thread's stores are issued and its read of the exchange counter is done
+		if (threadIdx.x == 0) {
+			if (peer_flag != nullptr) chunk_signal(peer_flag, cur + 1);
+			if (a.launch_ticket != nullptr) {
+				__threadfence();
+				if (atomicAdd(a.launch_ticket, 1u) == gridDim.x - 1) { *a.launch_ticket = 0u; __threadfence(); *a.seq_rw = cur + 1; }
+			}
+		}
+	}
+	if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, dot);   // unpack blocks add a zero partial: the count stays gridDim.x
 }
-
-// unpack blocks per halo: at most 2 per SM (grid-stride copy with 12 loads in flight per thread).  Thousands of
-// 128-thread blocks only add scheduling time to the tail; 74 were measured too few to cover the HBM latency.
-static inline unsigned int unpack_blocks_for(unsigned int face_blocks) { return face_blocks < 296u ? face_blocks : 296u; }
 
 unsigned int dslash_blocks(int d3lo, int d3hi)
 {
@@ -506,39 +560,15 @@ template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
 									 unsigned int ticket_target, unsigned int partial_offset, const int *skip, cudaStream_t s,
-									 int face)
+									 int face, int halo)
 {
+	using C = cplx_t<T>;
 	const Geom &g = ctx().g;
 	if (d3hi <= d3lo) return;
 	DslashArgs<T> a;
-	a.peer = nullptr; a.peer_flag = nullptr; a.seq_ptr = nullptr; a.peer_parity_stride = 0; a.face_ticket = nullptr;
-	static const int dbg_halo = getenv("STAPLE_DEBUG_HALO") ? atoi(getenv("STAPLE_DEBUG_HALO")) : 0;   // timing experiments only: wrong halos
-	a.dbg = dbg_halo;
-	a.fused = 0; a.face_blocks = 0; a.top_lo = a.bot_lo = 0; a.peer2 = nullptr; a.peer_flag2 = nullptr; a.face_ticket2 = nullptr;
-	a.bulk_blocks = 0; a.unpack_blocks = 0; a.unpack_src = nullptr; a.slot_elems = 0; a.local_flags = nullptr; a.seq_rw = nullptr;
-	a.unpack_ticket = nullptr; a.lower_lo = a.upper_lo = 0;
-	if (face != 0) {
-		// top interior slice -> rank R's slot 0 (its lower halo); bottom interior slice -> rank L's slot 1
-		P2P &p = ctx().p2p;
-		cplx_t<T> *top = (cplx_t<T> *) p.stage_R, *bot = (cplx_t<T> *) (p.stage_L + p.slot_bytes);
-		a.seq_ptr = p.d_seq; a.peer_parity_stride = (long) (2 * p.slot_bytes / sizeof(cplx_t<T>));
-		if (face == 3 || face == 4) {       // whole local interior in one launch, both faces pushed (4: and halos unpacked)
-			a.fused = face == 4 ? 2 : 1; a.face_blocks = dslash_blocks(0, 1);
-			a.bulk_blocks = dslash_blocks(d3lo + 1, d3hi - 1);
-			if (face == 4) {
-				a.unpack_blocks = unpack_blocks_for(a.face_blocks);
-				a.unpack_src = (const cplx_t<T> *) p.stage; a.slot_elems = (long) (p.slot_bytes / sizeof(cplx_t<T>));
-				a.local_flags = p.flags; a.seq_rw = p.d_seq; a.unpack_ticket = p.tickets + 2;
-				a.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; a.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
-			}
-			a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
-			a.peer = top; a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0;
-			a.peer2 = bot; a.peer_flag2 = p.flags_L + 1; a.face_ticket2 = p.tickets + 1;
-		} else if (face == 1) { a.peer = top; a.peer_flag = p.flags_R + 0; a.face_ticket = p.tickets + 0; }
-		else { a.peer = bot; a.peer_flag = p.flags_L + 1; a.face_ticket = p.tickets + 1; }
-	}
+	memset(&a, 0, sizeof(a));
 	a.u = u; a.out = out; a.in = in; a.ph = ph; a.in0 = in0; a.m2 = m2;
-	a.out_host = (cplx_t<T> *) ctx().out_host_hook;
+	a.out_host = (C *) ctx().out_host_hook;
 	a.partials = dot_slot >= 0 ? partials(dot_slot) : nullptr;
 	a.ticket = dot_slot >= 0 ? ticket(dot_slot) : nullptr;
 	a.result = dot_slot >= 0 ? result(dot_slot) : nullptr;
@@ -546,10 +576,37 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	a.cgm = (epi == EPI_MASS_DOT) ? ctx().cgm_hook : nullptr;
 	a.cgm_red = ctx().cgm_hook_red;
 	a.site_lo = (long) d3lo * g.vol3h; a.nsites = (long) (d3hi - d3lo) * g.vol3h;
-	if (a.fused) { a.site_lo = (long) (d3lo + 1) * g.vol3h; a.nsites = (long) (d3hi - d3lo - 2) * g.vol3h; }   // bulk
 	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;
-	const unsigned int grid = a.fused ? 2 * a.face_blocks + a.bulk_blocks + 2 * a.unpack_blocks : dslash_blocks(d3lo, d3hi);
-#define STAPLE_LAUNCH(P, E) dslash_kernel<T, P, E><<<grid, kBlock, 0, s>>>(a)
+	unsigned int grid = dslash_blocks(d3lo, d3hi);
+	if (face != FACE_NONE) {
+		// top interior slice -> rank R's slot 0 (its lower halo); bottom interior slice -> rank L's slot 1
+		P2P &p = ctx().p2p;
+		const unsigned int nfb = (unsigned int) p.nfb;
+		a.mr = 1;
+		a.seq_rw = p.d_seq; a.parity_stride = (long) (2 * p.slot_bytes / sizeof(C));
+		a.peer_top = (C *) p.stage_R; a.peer_flag_top = p.flags_R;
+		a.peer_bot = (C *) (p.stage_L + p.slot_bytes); a.peer_flag_bot = p.flags_L + p.nfb;
+		a.stage_lo = (const C *) p.stage; a.stage_hi = (const C *) (p.stage + p.slot_bytes);
+		a.flag_lo = p.flags; a.flag_hi = p.flags + p.nfb;
+		a.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; a.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
+		a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
+		if (face == FACE_TOP) a.nb_top = nfb;                        // single-slice launches of the three-queue form
+		else if (face == FACE_BOTTOM) a.nb_bot = nfb;
+		else {
+			a.nb_top = a.nb_bot = nfb;
+			a.nb_bulk = dslash_blocks(d3lo + 1, d3hi - 1);
+			a.site_lo = (long) (d3lo + 1) * g.vol3h; a.nsites = (long) (d3hi - d3lo - 2) * g.vol3h;   // bulk
+			if (face == FACE_BOTH_UNPACK) a.nb_unpack = unpack_blocks_for(nfb);
+		}
+		a.in_staged = (halo & HALO_IN_STAGED) ? 1 : 0;
+		if (halo & HALO_ADVANCE) a.launch_ticket = p.tickets + 0;
+		grid = a.nb_top + a.nb_bot + a.nb_bulk + 2 * a.nb_unpack;
+	}
+	if (dot_slot >= 0 && (long) partial_offset + grid > ctx().max_partials) {
+		fprintf(stderr, "libstaple_b200: FATAL: reduction scratch too small (%u + %u partials > %ld)\n", partial_offset, grid, ctx().max_partials);
+		exit(1);
+	}
+#define STAPLE_LAUNCH(P, E) do { if (a.mr) dslash_kernel<T, P, E, true><<<grid, kBlock, 0, s>>>(a); else dslash_kernel<T, P, E, false><<<grid, kBlock, 0, s>>>(a); } while (0)
 	// the mass epilogue without the dot product runs the EPI_MASS_DOT instantiation with the reduction switched off
 	// (a.partials == nullptr): one code path less, and that instantiation fits the 72-register budget without spills
 	if (par == 0) {
@@ -567,12 +624,13 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 // acc_Deo / acc_Doe (fermion_matrix.c:159-268): operator on the local interior followed by the exchange
 // of the first/last interior slice of `out` into the neighbours' halos.
 //   single rank      : one launch over all d3
-//   async_comm       : d3p (queue 2), d3m (queue 3), bulk (queue 1) ; halo exchange after the two
+//   peer memory      : ONE segmented launch (faces, bulk, unpack), see DslashArgs
+//   async_comm (NCCL): d3p (queue 2), d3m (queue 3), bulk (queue 1) ; halo exchange after the two
 //                      surface slices, overlapped with the bulk; join (:165-183)
 //   otherwise        : one launch, then blocking exchange (:194-205)
 template <typename T>
 void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
-									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip)
+									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip, int halo)
 {
 	Ctx &c = ctx();
 	const Geom &g = c.g;
@@ -583,33 +641,49 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 	}
 	if (!c.async_comm_fermion && !c.p2p.on) {
 		launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, dslash_blocks(lo, hi), 0, skip, c.stream);
+		// dirac_times (fermion_matrix.c:196-205, :252-259): rank 0 times the blocking exchange with the wall clock and counts it
+		cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+		if (cudaStreamIsCapturing(c.stream, &cap) != cudaSuccess) cudaGetLastError();
+		const bool measure = c.myrank == 0 && cap == cudaStreamCaptureStatusNone;
+		struct timespec t0, t1;
+		if (measure) { STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.stream)); clock_gettime(CLOCK_MONOTONIC, &t0); }
 		exchange_slices(out, sizeof(cplx_t<T>), g.sizeh, 3, 1, c.stream);
+		if (measure) {
+			STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.stream)); clock_gettime(CLOCK_MONOTONIC, &t1);
+			dirac_times.totTransferTime += (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+			++dirac_times.count;
+		}
 		return;
 	}
 	const unsigned int bs = dslash_blocks(0, 1), bb = dslash_blocks(lo + 1, hi - 1);
 	const unsigned int target = 2 * bs + bb;
 	if (c.p2p.on && c.p2p_single_launch) {
-		// ONE kernel: the face blocks (scheduled first) push their slice into the neighbours' staging slots
-		// over NVLink while the bulk blocks of the same launch run; then the unpack of what the neighbours
-		// pushed.  No stream fork/join, no events.
-		if (c.p2p_unpack_in_kernel)
-			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * unpack_blocks_for(bs), 0, skip, c.stream, 4);
+		// ONE kernel: the face blocks (first in block order) push their chunks into the neighbours' staging slots over NVLink
+		// while the rest of the launch runs; the received halos are either copied into `out` by the last blocks of the same
+		// launch (the API's contract: `out` leaves with valid halos), by a separate kernel, or -- inside the solvers -- left in
+		// the staging area for the next kernel to consume.  No stream fork/join, no events, no wait on a block of this launch.
+		const bool lazy = halo_lazy_ok();
+		const int in_staged = lazy ? (halo & HALO_IN_STAGED) : 0;
+		if (lazy && (halo & HALO_OUT_STAGED))
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, FACE_BOTH, in_staged | HALO_ADVANCE);
+		else if (c.p2p_unpack_in_kernel)
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * unpack_blocks_for(bs), 0, skip, c.stream,
+											 FACE_BOTH_UNPACK, in_staged | HALO_ADVANCE);
 		else {
-			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, 3);
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, FACE_BOTH, 0);
 			p2p_unpack(out, sizeof(cplx_t<T>), c.stream, skip);
 		}
 		return;
 	}
-	// peer-memory channel: the two surface kernels store their slice into the neighbours' staging slots
-	// themselves (compute + transfer in one kernel).  A solver's `skip` flag (set in the same iteration on
-	// every rank, because the all-reduced scalars are bit-identical) silences producers and consumer alike;
-	// sequence numbers keep counting on the host, flags only ever grow.
+	// three-queue form (the reference's structure).  Peer-memory channel: the two surface kernels store their slice into the
+	// neighbours' staging slots themselves (compute + transfer in one kernel).  A solver's `skip` flag (set in the same
+	// iteration on every rank, because the all-reduced scalars are bit-identical) silences producers and consumer alike.
 	const bool p2p = c.p2p.on;
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_p, c.ev_fork, 0));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_m, c.ev_fork, 0));
-	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p, p2p ? 1 : 0);    // d3p
-	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m, p2p ? 2 : 0);   // d3m
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, hi - 1, hi, dot_slot, target, 0, skip, c.s_p, p2p ? FACE_TOP : FACE_NONE);      // d3p
+	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, lo + 1, dot_slot, target, bs, skip, c.s_m, p2p ? FACE_BOTTOM : FACE_NONE);  // d3m
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, c.s_p));
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, c.s_m));
 	launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo + 1, hi - 1, dot_slot, target, 2 * bs, skip, c.stream);   // bulk
@@ -622,29 +696,32 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 }
 
 // fermion_matrix_multiplication[_shifted] (fermion_matrix.c:723-746) with the mass term (and, for the
-// solvers, Re(in . out)) fused into the Deo epilogue.
+// solvers, Re(in . out)) fused into the Deo epilogue.  On D3 slabs over peer memory the halos of tmp = Doe in go from
+// the neighbours' face blocks to the staging area and from there straight into the d3 hops of the Deo face blocks.
 template <typename T>
 void apply_mdagm(const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, cplx_t<T> *tmp, const T *ph,
-								 double m2, int dot_slot, const int *skip)
+								 double m2, int dot_slot, const int *skip, bool out_staged, bool tmp_eager)
 {
-	apply_dslash<T>(1, EPI_NONE, u, tmp, in, ph, nullptr, 0.0, -1, skip);
-	apply_dslash<T>(0, dot_slot >= 0 ? EPI_MASS_DOT : EPI_MASS, u, out, tmp, ph, in, m2, dot_slot, skip);
+	const bool lazy = halo_lazy_ok() && !tmp_eager;
+	apply_dslash<T>(1, EPI_NONE, u, tmp, in, ph, nullptr, 0.0, -1, skip, lazy ? HALO_OUT_STAGED : HALO_EAGER);
+	apply_dslash<T>(0, dot_slot >= 0 ? EPI_MASS_DOT : EPI_MASS, u, out, tmp, ph, in, m2, dot_slot, skip,
+									(lazy ? HALO_IN_STAGED : 0) | (out_staged ? HALO_OUT_STAGED : 0));
 }
 
 template void apply_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,
-																	 const double2 *, double, int, const int *);
+																	 const double2 *, double, int, const int *, int);
 template void apply_dslash<float>(int, int, const float2 *, float2 *, const float2 *, const float *,
-																	const float2 *, double, int, const int *);
+																	const float2 *, double, int, const int *, int);
 template void apply_mdagm<double>(const double2 *, double2 *, const double2 *, double2 *, const double *,
-																	double, int, const int *);
+																	double, int, const int *, bool, bool);
 template void apply_mdagm<float>(const float2 *, float2 *, const float2 *, float2 *, const float *, double,
-																 int, const int *);
+																 int, const int *, bool, bool);
 template void launch_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,
 																		const double2 *, double, int, int, int, unsigned int, unsigned int, const int *,
-																		cudaStream_t, int);
+																		cudaStream_t, int, int);
 template void launch_dslash<float>(int, int, const float2 *, float2 *, const float2 *, const float *,
 																	 const float2 *, double, int, int, int, unsigned int, unsigned int, const int *,
-																	 cudaStream_t, int);
+																	 cudaStream_t, int, int);
 
 // ------------------------------------------------------------------ operator "with a field" (magnetic susceptibility)
 // field_times_fermion_matrix.c:77-196 with matvecmul.h:176-260: the same stencil with every link's U(1) phase multiplied by a
@@ -952,7 +1029,13 @@ using namespace staple;
 struct StreamedGraph { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs, mode; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
 static StreamedGraph g_streamed_cache[4] = {};
 static int g_streamed_next = 0;
+constexpr int kMaxChunks = 128;
+static cudaEvent_t g_ev_up[kMaxChunks], g_ev_deo[kMaxChunks];            // chunk uploaded / Deo chunk computed
+static cudaEvent_t g_tev0, g_tev_up[kMaxChunks], g_tev_deo[kMaxChunks], g_tev_dn[kMaxChunks];   // STAPLE_STREAMED_TRACE timeline
+static bool g_have_events = false, g_have_tev = false;
 namespace staple {
+// cached graphs AND the events of the chunk schedule: they belong to the device that was current when they were created
+// (staple_shutdown / a re-initialisation on another device must not leave them behind)
 void release_streamed_state()
 {
 	for (auto &e : g_streamed_cache) {
@@ -960,6 +1043,15 @@ void release_streamed_state()
 		e = StreamedGraph{};
 	}
 	g_streamed_next = 0;
+	if (g_have_events) {
+		for (int k = 0; k < kMaxChunks; k++) { cudaEventDestroy(g_ev_up[k]); cudaEventDestroy(g_ev_deo[k]); }
+		g_have_events = false;
+	}
+	if (g_have_tev) {
+		cudaEventDestroy(g_tev0);
+		for (int k = 0; k < kMaxChunks; k++) { cudaEventDestroy(g_tev_up[k]); cudaEventDestroy(g_tev_deo[k]); cudaEventDestroy(g_tev_dn[k]); }
+		g_have_tev = false;
+	}
 }
 }   // namespace staple
 
@@ -1043,7 +1135,8 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	double2 *d_in = (double2 *) dev(in_h, "in"), *d_out = DD(out_h), *d_tmp = DD(tmp);
 	const bool in_host = (const void *) d_in != (const void *) in_h, out_host = (void *) d_out != (void *) out_h;
 	const size_t vbytes = sizeof(double2) * 3 * g.sizeh;
-	if (c.nranks > 1 || !in_host || !out_host) {
+	const bool slabs = c.nranks > 1;
+	if ((slabs && !(c.p2p.on && c.p2p_single_launch)) || !in_host || !out_host) {
 		if (in_host) staple_acc_update_device(in_h, vbytes);
 		apply_dslash<double>(1, EPI_NONE, d_u, d_tmp, d_in, d_ph, nullptr, 0.0, -1, nullptr);
 		apply_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, -1, nullptr);
@@ -1051,21 +1144,20 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 		else STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 		return;
 	}
-	constexpr int kMaxChunks = 128;
-	static cudaEvent_t ev_up[kMaxChunks], ev_deo[kMaxChunks];
-	static bool have_events = false;
-	if (!have_events) {
+	cudaEvent_t *const ev_up = g_ev_up, *const ev_deo = g_ev_deo;
+	if (!g_have_events) {
 		for (int k = 0; k < kMaxChunks; k++) {
 			STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(&ev_up[k], cudaEventDisableTiming));
 			STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(&ev_deo[k], cudaEventDisableTiming));
 		}
-		have_events = true;
+		g_have_events = true;
 	}
 	// default: 16 chunks -- measured optimum on PCIe Gen5 (profiles/r01_streamed_trace.txt): smaller chunks lose copy
 	// efficiency (3 strided pieces per chunk and direction), bigger ones lengthen the 5-chunk pipeline head and tail
 	int cs = chunk_slices > 0 ? chunk_slices : (g.nd3 >= 16 ? g.nd3 / 16 : 1);
 	if (cs > g.nd3) cs = g.nd3;
-	while (g.nd3 % cs != 0 || g.nd3 / cs > kMaxChunks) cs++;   // cs = nd3 always qualifies
+	if (slabs) { while ((g.nd3 + cs - 1) / cs + 4 > kMaxChunks) cs++; }
+	else while (g.nd3 % cs != 0 || g.nd3 / cs > kMaxChunks) cs++;   // cs = nd3 always qualifies
 	const int nc = g.nd3 / cs;
 	const size_t pitch = sizeof(double2) * g.sizeh, width = sizeof(double2) * g.vol3h * cs;
 	cudaStream_t s_up = c.s_p, s_dn = c.s_m, st = c.stream;
@@ -1078,12 +1170,11 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	// STAPLE_STREAMED_TRACE=1: direct issue with timing events after every chunk upload / Deo chunk / chunk download;
 	// the timeline (ms since the call started) is printed on stderr.  Diagnostic only.
 	static const bool trace = getenv("STAPLE_STREAMED_TRACE") != nullptr;
-	static cudaEvent_t tev0, tev_up[kMaxChunks], tev_deo[kMaxChunks], tev_dn[kMaxChunks];
-	static bool have_tev = false;
-	if (trace && !have_tev) {
+	cudaEvent_t &tev0 = g_tev0, *const tev_up = g_tev_up, *const tev_deo = g_tev_deo, *const tev_dn = g_tev_dn;
+	if (trace && !g_have_tev) {
 		cudaEventCreate(&tev0);
 		for (int k = 0; k < kMaxChunks; k++) { cudaEventCreate(&tev_up[k]); cudaEventCreate(&tev_deo[k]); cudaEventCreate(&tev_dn[k]); }
-		have_tev = true;
+		g_have_tev = true;
 	}
 	auto enqueue = [&]() {
 		// the side streams may not touch `in`/`out` on the device before earlier work of the compute stream is done
@@ -1145,6 +1236,103 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_p, 0));
 		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_m, 0));
 	};
+	// ---- D3 slabs (peer-memory transport): the same pipeline per rank, boundaries first.  The local+halo box of `in` comes
+	// from the host WITH its halo slices, so Doe needs no exchange on its input and -- unlike the single-rank lattice, which is
+	// periodic in d3 -- nothing wraps around: only the two face slices couple to the neighbour ranks.
+	//   uploads   : head [0, lo+2), tail [hi-2, nd3), then the middle in chunks                       (copy stream 1)
+	//   Doe       : bottom and top face slice FIRST (they push tmp's faces to the neighbours: exchange s+1), then bulk chunks
+	//   Deo       : face slices with the halo of tmp read straight from the staging area (no unpack of tmp), pushing the
+	//               faces of `out` (exchange s+2); bulk chunks; every finished piece is downloaded       (copy stream 2)
+	//   finally   : unpack of the received halos of `out` and their download
+	// The exchange counter is device resident (advanced by one-thread kernels / the unpack kernel), so the captured graph replays.
+	auto enqueue_slabs = [&]() {
+		const int lo = g.d3_halo, hi = g.d3_halo + g.loc_n3, nd3 = g.nd3;
+		const size_t slice = (size_t) g.vol3h;
+		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, st));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_up, c.ev_fork, 0));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, c.ev_fork, 0));
+		auto copy_slices = [&](bool up, int a, int b, cudaStream_t cst) {
+			if (b <= a) return;
+			const size_t off = (size_t) a * slice, w = sizeof(double2) * slice * (size_t) (b - a);
+			if (up) STAPLE_CUDA_CHECK(cudaMemcpy2DAsync(d_in + off, pitch, (const double2 *) in_h + off, pitch, w, 3, cudaMemcpyHostToDevice, cst));
+			else STAPLE_CUDA_CHECK(cudaMemcpy2DAsync((double2 *) out_h + off, pitch, d_out + off, pitch, w, 3, cudaMemcpyDeviceToHost, cst));
+		};
+		// slices of `out` that no kernel writes (outer halo, HALO_WIDTH 2): `update host` copies the whole array, so do we
+		copy_slices(false, 0, lo - 1, s_dn); copy_slices(false, hi + 1, nd3, s_dn);
+		struct Unit { int a, b, face; bool doe, deo; };
+		Unit units[kMaxChunks]; int nu = 0;
+		units[nu++] = Unit{ lo, lo + 1, FACE_BOTTOM, false, false };
+		units[nu++] = Unit{ hi - 1, hi, FACE_TOP, false, false };
+		for (int a = lo + 1; a < hi - 1; a += cs) units[nu++] = Unit{ a, a + cs < hi - 1 ? a + cs : hi - 1, FACE_NONE, false, false };
+		int piece_of[4096]; bool doe_done[4096] = {};
+		for (int d = 0; d < nd3; d++) piece_of[d] = -1;
+		int npieces = 0, waited = -1, ndn = 0, doe_faces = 0, deo_faces = 0;
+		bool advanced = false, unpacked = false;
+		auto need_piece = [&](int a, int b) { int m = -1; for (int d = a; d < b; d++) { if (piece_of[d] < 0) return -2; if (piece_of[d] > m) m = piece_of[d]; } return m; };
+		auto download = [&](int a, int b) {
+			STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[ndn], st));
+			STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[ndn], 0));
+			ndn++;
+			copy_slices(false, a, b, s_dn);
+		};
+		auto progress = [&]() {
+			bool again = true;
+			while (again) {
+				again = false;
+				for (int k = 0; k < nu; k++) {
+					Unit &un = units[k];
+					if (!un.doe) {
+						const int m = need_piece(un.a - 1, un.b + 1);
+						if (m == -2) continue;
+						if (m > waited) { STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, ev_up[m], 0)); waited = m; }
+						launch_dslash<double>(1, EPI_NONE, d_u, d_tmp, d_in, d_ph, nullptr, 0.0, un.a, un.b, -1, 0, 0, nullptr, st, un.face, 0);
+						un.doe = true; again = true;
+						for (int d = un.a; d < un.b; d++) doe_done[d] = true;
+						if (un.face != FACE_NONE) doe_faces++;
+					}
+				}
+				if (doe_faces == 2 && !advanced) {       // both faces of tmp are on their way: exchange s+1 is what the Deo faces consume
+					seq_advance_kernel<<<1, 1, 0, st>>>(c.p2p.d_seq); count_launch(); advanced = true; again = true;
+				}
+				for (int k = 0; k < nu && advanced; k++) {
+					Unit &un = units[k];
+					if (un.deo) continue;
+					bool ok = true;                         // Doe output of the interior slices around the unit; halo slices of tmp are staged
+					for (int d = un.a - 1; d < un.b + 1; d++) if (d >= lo && d < hi && !doe_done[d]) ok = false;
+					if (!ok) continue;
+					launch_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, un.a, un.b, -1, 0, 0, nullptr, st, un.face,
+																un.face != FACE_NONE ? HALO_IN_STAGED : 0);
+					un.deo = true; again = true;
+					download(un.a, un.b);
+					if (un.face != FACE_NONE) deo_faces++;
+				}
+				if (deo_faces == 2 && !unpacked) {
+					p2p_unpack(d_out, sizeof(double2), st, nullptr);      // waits for the neighbours' chunks of exchange s+2, advances the counter
+					unpacked = true;
+					STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[ndn], st));
+					STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[ndn], 0));
+					ndn++;
+					copy_slices(false, lo - 1, lo, s_dn); copy_slices(false, hi, hi + 1, s_dn);
+				}
+			}
+		};
+		auto upload = [&](int a, int b) {
+			if (b <= a) return;
+			copy_slices(true, a, b, s_up);
+			STAPLE_CUDA_CHECK(cudaEventRecord(ev_up[npieces], s_up));
+			for (int d = a; d < b; d++) piece_of[d] = npieces;
+			npieces++;
+			progress();
+		};
+		const int head = lo + 2 < nd3 ? lo + 2 : nd3, tail = hi - 2 > head ? hi - 2 : head;
+		upload(0, head);
+		upload(tail, nd3);
+		for (int a = head; a < tail; a += cs) upload(a, a + cs < tail ? a + cs : tail);
+		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_p, s_up));
+		STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_m, s_dn));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_p, 0));
+		STAPLE_CUDA_CHECK(cudaStreamWaitEvent(st, c.ev_m, 0));
+	};
 	// The schedule is ~8 API calls per chunk: on the host that costs more than the PCIe time it hides.  It only
 	// depends on the pointers and the chunking, so it is captured ONCE into a CUDA graph (three streams, copy
 	// nodes included) and replayed with a single launch.  The legacy default stream cannot be captured: direct
@@ -1161,7 +1349,7 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 			cudaGraph_t graph = nullptr;
 			cudaGraphExec_t exec = nullptr;
 			if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-				enqueue();
+				if (slabs) enqueue_slabs(); else enqueue();
 				if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph != nullptr &&
 						cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
 					Cached &e = cache[cache_next]; cache_next = (cache_next + 1) % 4;
@@ -1176,9 +1364,10 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 		}
 	}
 	if (hit) { STAPLE_CUDA_CHECK(cudaGraphLaunch(hit->exec, st)); c.launches += hit->launches; }
+	else if (slabs) enqueue_slabs();
 	else enqueue();
 	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
-	if (trace) {
+	if (trace && !slabs) {
 		fprintf(stderr, "streamed trace: mode %d, %d chunks of %d slices\n chunk   upload_done   deo_done   download_done [ms]\n", mode, nc, cs);
 		for (int k = 0; k < nc; k++) {
 			float a = 0, b = 0, d = 0;
@@ -1194,27 +1383,27 @@ void fermion_matrix_multiplication(const su3_soa *u, vec3_soa *out, const vec3_s
 {
 	require_init("fermion_matrix_multiplication");
 	apply_mdagm<double>(CDD(u), DD(out), CDD(in), DD(temp1), (const double *) dev(pars->phases, "pars->phases"),
-											pars->ferm_mass * pars->ferm_mass, -1, nullptr);
+											pars->ferm_mass * pars->ferm_mass, -1, nullptr, false, true);
 }
 void fermion_matrix_multiplication_shifted(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *temp1,
 																					 ferm_param *pars, double shift)
 {
 	require_init("fermion_matrix_multiplication_shifted");
 	apply_mdagm<double>(CDD(u), DD(out), CDD(in), DD(temp1), (const double *) dev(pars->phases, "pars->phases"),
-											pars->ferm_mass * pars->ferm_mass + shift, -1, nullptr);
+											pars->ferm_mass * pars->ferm_mass + shift, -1, nullptr, false, true);
 }
 void fermion_matrix_multiplication_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1, ferm_param *pars)
 {
 	require_init("fermion_matrix_multiplication_f");
 	apply_mdagm<float>(CDF(u), DF(out), CDF(in), DF(temp1), (const float *) dev(pars->phases_f, "pars->phases_f"),
-										 pars->ferm_mass * pars->ferm_mass, -1, nullptr);
+										 pars->ferm_mass * pars->ferm_mass, -1, nullptr, false, true);
 }
 void fermion_matrix_multiplication_shifted_f(const su3_soa_f *u, vec3_soa_f *out, const vec3_soa_f *in, vec3_soa_f *temp1,
 																						 ferm_param *pars, float shift)
 {
 	require_init("fermion_matrix_multiplication_shifted_f");
 	apply_mdagm<float>(CDF(u), DF(out), CDF(in), DF(temp1), (const float *) dev(pars->phases_f, "pars->phases_f"),
-										 pars->ferm_mass * pars->ferm_mass + shift, -1, nullptr);
+										 pars->ferm_mass * pars->ferm_mass + shift, -1, nullptr, false, true);
 }
 
 // ---- BLAS-1

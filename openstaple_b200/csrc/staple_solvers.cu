@@ -133,11 +133,15 @@ __device__ __forceinline__ void cgm_shift_group(cplx_t<T> *out, cplx_t<T> *ps, c
 	}
 }
 
+// D3 slabs with staged halos (hv.on): the two halo slices of s = M^+M p were pushed by the neighbours' Deo face blocks into
+// the local staging area and are consumed from there -- the thread that owns a halo site waits for the flag of its chunk
+// (normally long set: the push happened at the START of the neighbours' Deo) and reads s past L1.  The site order is
+// rotated by one slice so that the halo slices come LAST in block order.
 template <typename T>
 __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_kernel(CgmCtl *c, cplx_t<T> *out, cplx_t<T> *ps, cplx_t<T> *r,
 																																const cplx_t<T> *s, long lo, long cnt, long n, long r0_lo,
 																																long r0_hi, double *partials, unsigned int *ticket,
-																																double *result, int fuse_tail, RedView red)
+																																double *result, int fuse_tail, RedView red, HaloView hv)
 {
 	if (c->done) return;
 	__shared__ double sm[32];
@@ -158,13 +162,28 @@ __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_ker
 	const long t = (long) blockIdx.x * kCgmBlock + threadIdx.x;
 	double nrm = 0.0;
 	if (t < cnt) {
-		const long i = lo + t;
+		long i = lo + t;
+		const cplx_t<T> *sp = s;
+		long sn = n, si = i;
+		bool staged = false;
+		if (hv.on) {
+			i = t + hv.vol3h < cnt ? i + hv.vol3h : i + hv.vol3h - cnt;        // interior first, then upper halo, then lower halo
+			si = i;
+			const bool lower = i >= hv.lower_lo && i < hv.lower_lo + hv.vol3h, upper = i >= hv.upper_lo && i < hv.upper_lo + hv.vol3h;
+			if (lower || upper) {
+				const unsigned long long cur = *hv.seq;
+				si = i - (lower ? hv.lower_lo : hv.upper_lo);
+				wait_flag_sys((lower ? hv.flag_lo : hv.flag_hi) + si / hv.chunk, cur, 1);
+				sp = (const cplx_t<T> *) ((lower ? hv.stage_lo : hv.stage_hi) + (cur & 1ull) * hv.parity_bytes);
+				sn = hv.vol3h; staged = true;
+			}
+		}
 		cplx_t<T> rv[3];
 #pragma unroll
 		for (int col = 0; col < 3; col++) {
 			const long j = col * n + i;
 			rv[col] = r[j];
-			const cplx_t<T> sv = s[j];
+			const cplx_t<T> sv = staged ? __ldcg(sp + col * sn + si) : sp[col * sn + si];
 			const cplx_t<T> rn = mkc<T>(rv[col].x + omega * sv.x, rv[col].y + omega * sv.y);
 			r[j] = rn;
 			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
@@ -249,6 +268,11 @@ static void ensure_ctl()
 	STAPLE_CUDA_CHECK(cudaEventCreate(&g_ev_t1));
 }
 
+void set_spin_timeout_solvers(unsigned long long ns)
+{
+	STAPLE_CUDA_CHECK(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns)));
+}
+
 void release_solver_state()        // staple_shutdown
 {
 	if (!g_d_ctl) return;
@@ -319,11 +343,15 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	// whose grid reduction feeds them (Deo -> alpha, shifted pass -> lambda): 4 launches per iteration.  With NCCL
 	// all-reduces the sum is a library call between producer and consumer: 6 launches + 2 collectives.
 	const bool fuse_tail = (c.nranks == 1 || fuse_red) && c.cgm_fuse_tail;
+	// D3 slabs over peer memory: neither h = Doe p nor s = M^+M p ever get their halo slices written -- the Deo face blocks and
+	// the halo threads of the shifted pass consume them from the staging area (no unpack, no wait inside the producing launch)
+	const bool s_staged = halo_lazy_ok();
+	const HaloView hv = make_haloview(sizeof(cplx_t<T>), s_staged);
 	auto enqueue_batch = [&]() {
 		if (fuse_tail) { c.cgm_hook = g_d_ctl; c.cgm_hook_red = red; }
 		for (int b = 0; b < batch; b++) {
 			// s = (M^+M) p, alpha = Re(p,s) fused in the Deo epilogue (:113-118)
-			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done);
+			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done, s_staged);
 			if (!fuse_tail) {
 				if (!fuse_red) allreduce_results(SLOT_ALPHA, 1, st);
 				cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA), red);
@@ -331,7 +359,7 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 			}
 			cgm_fused_kernel<T><<<grid_f, kCgmBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
 																											 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
-																											 result(SLOT_LAMBDA), fuse_tail ? 1 : 0, red);
+																											 result(SLOT_LAMBDA), fuse_tail ? 1 : 0, red, hv);
 			if (!fuse_tail) {
 				if (!fuse_red) allreduce_results(SLOT_LAMBDA, 1, st);
 				cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA), red);
