@@ -67,6 +67,16 @@ def _worker(rank, world, port, loc, mode, q):
                 getattr(lat, name)(du, out, dv, dph)
             o = out.cpu().numpy()
             errs[name] = _relerr(o[:, r1lo:r1hi], want[:, r1lo:r1hi])
+        # ---- dirac_times (fermion_matrix.c:196-205): rank 0 counts and times the BLOCKING exchanges, nothing else does
+        import ctypes as C
+
+        class _DT(C.Structure):
+            _fields_ = [("totTransferTime", C.c_double), ("count", C.c_uint)]
+        dt = _DT.in_dll(lat.L, "dirac_times")
+        if mode["async"] == 0 and mode["p2p"] == 0 and rank == 0:
+            errs["dirac_times"] = 0.0 if (dt.count == 6 and dt.totTransferTime > 0) else 1.0
+        else:
+            errs["dirac_times"] = 0.0 if dt.count == 0 else 1.0
         # ---- M^+M and reductions
         pars = lat.ferm_param(0.0507, dph)
         out, tmp = lat.new_vec(), lat.new_vec()
@@ -175,14 +185,14 @@ def _run(world, loc, mode):
         assert errs["su3_borders_rows01"] == 0.0 and errs["fermion_borders"] == 0.0, (rank, errs)
         for k in ("acc_Doe", "acc_Deo", "mdagm", "force", "stout", "stout_force"):
             assert errs[k] < 1e-13, (rank, k, errs)
-        assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0
+        assert errs["l2norm2"] < 1e-13 and errs["cgm_status"] == 0.0 and errs["dirac_times"] == 0.0, (rank, errs)
         assert errs["cgm_iters"] <= 0.02 and errs["cgm_sol"] < 1e-6, (rank, errs)
         assert errs["deo_wf"] < 1e-13 and errs["full_force"] < 1e-7, (rank, errs)      # force: iterative solves to 1e-10 inside
     print("multi-rank errors:", sorted(res)[0][1])
 
 
-@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3))],
-                         ids=["sync-nccl", "async-nccl", "p2p-one-launch", "p2p-three-queues", "p2p-launch+unpack"])
+@pytest.mark.parametrize("mode", [dict(**{"async": a, "p2p": p}) for a, p in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4))],
+                         ids=["sync-nccl", "async-nccl", "p2p-one-launch-staged-halos", "p2p-three-queues", "p2p-launch+unpack", "p2p-one-launch-eager"])
 @pytest.mark.parametrize("world,loc", [(2, (8, 8, 8, 8)), (2, (8, 4, 6, 2))])
 def test_two_gpus(world, loc, mode):
     _run(world, loc, mode)
