@@ -452,7 +452,9 @@ def solver_section(job, peak, want_fp32, want_accel, cpu_seconds, tag, fixture, 
         solf, psf = lat.new_vec(n, single=True), lat.new_vec(n, single=True)
         rf, hf, sf, pf, of = (lat.new_vec(single=True) for _ in range(5))
         srcf = src.to(torch.complex64)
-        resf = max(RESIDUE, 8e-7 * np.sqrt(lat.sizeh))            # inverter_wrappers.c:62-64
+        # inverter_wrappers.c:62-64 uses 8e-7 sqrt(sizeh) with the LOCAL sizeh (halos included), which changes with the number of
+        # ranks; here the global half-volume, so that the FP32 solve is the same problem at every N
+        resf = max(RESIDUE, 8e-7 * np.sqrt(job.interior * job.world))
         lat.multishift_invert(uf, pars, approx, solf, srcf, resf, rf, hf, sf, pf, psf, 24)
         job.barrier(); t0 = time.perf_counter()
         stf, cgf = lat.multishift_invert(uf, pars, approx, solf, srcf, resf, rf, hf, sf, pf, psf, 20000)
@@ -482,7 +484,7 @@ def solver_section(job, peak, want_fp32, want_accel, cpu_seconds, tag, fixture, 
                 res.append(float(np.sqrt(lat.l2norm2_global(h) / lat.l2norm2_global(src))))
             out["fp32_accelerated_fp64_refined"] = {"s_per_solve": walla, "total_iterations": tot, "true_rel_residual_first_last_shift": res,
                                                     "note": "FP32 CG-M + per-shift FP32-inner mixed-precision CG to the FP64 residue (singlePInvAccelMultiInv + useMixedPrecision)"}
-            parity["cg_iters"]["%s:accel" % tag] = tot
+            parity.setdefault("cg_iters_not_compared", {})["%s:accel" % tag] = tot     # its FP32 target follows the LOCAL sizeh (reference behaviour)
             if max(res) > 2 * RESIDUE:
                 parity["failures"].append("%s:accel true residuals %r" % (tag, res))
     if job.rank == 0 and job.world == 1 and cpu_seconds > 0:
@@ -496,8 +498,8 @@ def operator_section(job, peak, steps, warm):
     """device-resident Doe+Deo and M^+M timings on job's lattice"""
     lat = job.lat
     u, ph = job.u, job.ph
-    a, b = job.v.clone(), lat.new_vec()
-    ms = job.timeit(lambda: (lat.acc_Doe(u, b, a, ph), lat.acc_Deo(u, a, b, ph)), steps, warm)
+    a, b, c = job.v, lat.new_vec(), lat.new_vec()
+    ms = job.timeit(lambda: (lat.acc_Doe(u, b, a, ph), lat.acc_Deo(u, c, b, ph)), steps, warm)
     pars = lat.ferm_param(MASS, ph)
     tmp, out = lat.new_vec(), lat.new_vec()
     ms_mm = job.timeit(lambda: lat.fermion_matrix_multiplication(u, out, job.v, tmp, pars), max(10, steps // 2), 3)
@@ -568,24 +570,18 @@ def main():
         lat = job.lat
         u, v, ph = job.u, job.v, job.ph
         check_windows(job, args.lattice)
-        a, b = v.clone(), lat.new_vec()
+        a, b, c = v.clone(), lat.new_vec(), lat.new_vec()
         interior = job.interior
 
         def step():
+            # the stock test re-applies the operators to the SAME input (deo_doe_test.c:236-269); feeding the result back would
+            # grow it by up to lambda_max ~ 7 per step and overflow for large --steps
             lat.acc_Doe(u, b, a, ph)
-            lat.acc_Deo(u, a, b, ph)
-
-        def renorm():
-            # keep the ping-pong vector O(1) without touching the timed region
-            nrm = lat.l2norm2_global(a)
-            lat.multiply_fermion_x_doublefactor(a, 1.0 / np.sqrt(nrm / (3 * interior * world)))
-            if world > 1:
-                lat.communicate_fermion_borders(a)
+            lat.acc_Deo(u, c, b, ph)
 
         warm = max(3, args.warmup)
         for _ in range(warm):
             step()
-        renorm()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -604,8 +600,8 @@ def main():
         gflops = FLOP_PER_SITE * sites_per_step / (ms_step * 1e-3) / 1e9
 
         # ---- dominant kernel alone (roofline): Deo launches back to back on this stream (no exchange: acc_Deo_unsafe)
-        renorm()
-        nk = max(10, args.steps // 2)
+        del c
+        nk = max(10, min(200, args.steps // 2))
         ms_kernel = job.timeit(lambda: lat.acc_Deo_unsafe(u, b, a, ph), nk, 2)
         achieved = BYTES_PER_SITE_FP64 * interior / (ms_kernel * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "dslash_kernel<double,0,EPI_NONE> (acc_Deo_unsafe on the local slab)", "achieved": achieved,

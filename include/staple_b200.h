@@ -241,6 +241,10 @@ int staple_enable_p2p(int on);
  * (default 60; 0 = wait for ever, which is what MPI_Wait does) the waiting kernel prints what it was waiting for and
  * traps, so a dead rank surfaces as a CUDA error on the survivors instead of a hang. */
 void staple_set_spin_timeout(double seconds);
+/* The D3-slab code path on ONE GPU in one process (tests, profiling): after staple_init_geometry(..., nranks_d3 > 1, ...) this
+ * rank becomes its own L and R neighbour and its own memory stands in for the peers' mailboxes; p2p_mode as staple_enable_p2p
+ * (0: slab moves as device-to-device copies).  The lattice is the single-rank LOC lattice stored with halos.  Returns 0 on success. */
+int staple_init_loopback(int p2p_mode);
 void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
 int staple_myrank(void);
 

@@ -278,6 +278,13 @@ class Lattice:
         self.rank = rank
         self.p2p = bool(self.L.staple_enable_p2p(int(p2p))) if world > 1 else False
 
+    def init_loopback(self, p2p=1):
+        """the D3-slab code path on one GPU: this rank is its own L and R neighbour (staple_init_loopback)"""
+        if self.L.staple_init_loopback(int(p2p)) != 0:
+            raise RuntimeError("staple_init_loopback failed")
+        self.rank = 0
+        self.p2p = p2p != 0
+
     def shutdown_multidev(self):
         self.L.shutdown_multidev()
 

@@ -141,7 +141,7 @@ static Comm *load_nccl()
 void allreduce_results(int slot, int ndoubles, cudaStream_t s)
 {
 	Ctx &c = ctx();
-	if (c.nranks <= 1) return;
+	if (c.nranks <= 1 || c.loopback) return;
 	double *p = result(slot);
 	if (c.p2p.on && c.p2p.d_redq != nullptr && ndoubles <= 2) { p2p_allreduce(p, ndoubles, s); return; }
 	STAPLE_NCCL_CHECK(c.comm, c.comm->AllReduce(p, p, (size_t) ndoubles, ncclDouble, ncclSum, c.comm->comm, s));
@@ -162,6 +162,14 @@ void exchange_slices(void *base, size_t elem_bytes, long stride_elems, int narra
 	const size_t slab = (size_t) g.vol3h * thickness * elem_bytes;
 	const size_t off = (size_t) g.vol3h * g.halo_width * elem_bytes;
 	const size_t total = (size_t) g.sizeh * elem_bytes;
+	if (c.loopback) {      // this rank is its own L and R neighbour: the same four slab moves as device-to-device copies
+		for (int a = 0; a < narrays; a++) {
+			char *p = (char *) base + (size_t) a * stride_elems * elem_bytes;
+			STAPLE_CUDA_CHECK(cudaMemcpyAsync(p + total - off, p + off, slab, cudaMemcpyDeviceToDevice, s));
+			STAPLE_CUDA_CHECK(cudaMemcpyAsync(p + off - slab, p + total - off - slab, slab, cudaMemcpyDeviceToDevice, s));
+		}
+		return;
+	}
 	Comm *n = c.comm;
 	STAPLE_NCCL_CHECK(n, n->GroupStart());
 	for (int a = 0; a < narrays; a++) {
@@ -222,10 +230,39 @@ static void release_p2p()
 		STAPLE_NCCL_CHECK(c.comm, c.comm->AllReduce(p, p, 1, ncclDouble, ncclSum, c.comm->comm, c.s_comm));
 		STAPLE_CUDA_CHECK(cudaStreamSynchronize(c.s_comm));
 	}
-	for (int r = 0; r < c.nranks; r++)
+	for (int r = 0; r < c.nranks && !c.loopback; r++)
 		if (r != c.myrank && c.p2p.peer_mailbox[r]) cudaIpcCloseMemHandle(c.p2p.peer_mailbox[r]);
 	cudaFree(c.p2p.mailbox); cudaFree(c.p2p.tickets); cudaFree(c.p2p.d_seq);
 	c.p2p = P2P();
+}
+
+// local part of the peer-memory set-up: mailbox (reduction boxes, staging), tickets, counters.  Every word of the mailbox
+// starts at the resting pattern (all ones): "nothing has arrived"
+static void p2p_alloc_local()
+{
+	Ctx &c = ctx();
+	P2P &p = c.p2p;
+	const Geom &g = c.g;
+	p.vol3h = g.vol3h;
+	p.nfb = (g.vol3h + kDslashBlock - 1) / kDslashBlock;
+	p.slot_bytes = (size_t) 3 * g.vol3h * 16;
+	const size_t mb_bytes = kMailboxHeader + 4 * p.slot_bytes;
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.mailbox, mb_bytes));
+	STAPLE_CUDA_CHECK(cudaMemset(p.mailbox, 0xFF, mb_bytes));
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 4 * sizeof(unsigned int)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 4 * sizeof(unsigned int)));
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.d_seq, 2 * sizeof(unsigned long long)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.d_seq, 0, 2 * sizeof(unsigned long long)));
+	p.d_redq = p.d_seq + 1;
+	STAPLE_CUDA_CHECK(cudaDeviceSynchronize());
+}
+static void p2p_bind_neighbours()
+{
+	Ctx &c = ctx();
+	P2P &p = c.p2p;
+	p.stage = p.mailbox + kMailboxHeader;
+	p.stage_L = p.peer_mailbox[c.rank_L] + kMailboxHeader; p.stage_R = p.peer_mailbox[c.rank_R] + kMailboxHeader;
+	p.on = true;
 }
 
 }   // namespace staple
@@ -254,7 +291,7 @@ int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo
 		Geom ng;
 		fill_geom(ng, n0, n1, n2, n3, nranks_d3, halo_width);
 		if (c.inited && c.p2p.mailbox && (ng.vol3h != c.p2p.vol3h || ng.nranks != c.nranks)) release_p2p();
-		if (c.inited && c.comm && ng.nranks != c.nranks) shutdown_multidev();
+		if (c.inited && (c.comm || c.loopback) && ng.nranks != c.nranks) shutdown_multidev();
 	}
 	fill_geom(g, n0, n1, n2, n3, nranks_d3, halo_width);
 	release_streamed_state();      // cached schedules carry the previous geometry in their kernel arguments
@@ -467,7 +504,7 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 		fprintf(stderr, "MPI%02d - NRANKS_D3 = %d, nranks = %d\n", myrank, c.g.nranks, nranks);
 		exit(1);
 	}
-	if (c.comm) shutdown_multidev();                 // a second call replaces the rank layer (mailbox, communicator) instead of leaking it
+	if (c.comm || c.loopback) shutdown_multidev();   // a second call replaces the rank layer (mailbox, communicator) instead of leaking it
 	c.myrank = myrank; c.nranks = nranks;
 	c.rank_L = (myrank + (nranks - 1)) % nranks;   // multidev.c:60-61 (SALAMINO ring)
 	c.rank_R = (myrank + 1) % nranks;
@@ -505,20 +542,15 @@ int staple_enable_p2p(int on)
 	const Geom &g = c.g;
 	if (p.mailbox && p.vol3h != g.vol3h) release_p2p();  // built for another geometry (staple_init_geometry does this too)
 	if (p.stage_L) { p.on = true; return 1; }          // already mapped
+	if (c.loopback) {                                  // single process, own memory as both neighbours' memory
+		p2p_alloc_local();
+		for (int r = 0; r < kMaxRanks; r++) p.peer_mailbox[r] = p.mailbox;
+		p2p_bind_neighbours();
+		return 1;
+	}
 	if (!c.comm) { fprintf(stderr, "libstaple_b200: staple_enable_p2p before staple_init_multidev1D\n"); exit(1); }
 	if (c.nranks > kMaxRanks) { fprintf(stderr, "libstaple_b200: peer-memory channels support up to %d ranks\n", kMaxRanks); return 0; }
-	p.vol3h = g.vol3h;
-	p.nfb = (g.vol3h + kDslashBlock - 1) / kDslashBlock;
-	p.slot_bytes = (size_t) 3 * g.vol3h * 16;
-	p.stage_off = kMailboxHeader + (((size_t) 2 * p.nfb * sizeof(unsigned long long) + 1023) / 1024) * 1024;
-	const size_t mb_bytes = p.stage_off + 4 * p.slot_bytes;
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.mailbox, mb_bytes));
-	STAPLE_CUDA_CHECK(cudaMemset(p.mailbox, 0, p.stage_off));
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 4 * sizeof(unsigned int)));
-	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 4 * sizeof(unsigned int)));
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.d_seq, 2 * sizeof(unsigned long long)));
-	STAPLE_CUDA_CHECK(cudaMemset(p.d_seq, 0, 2 * sizeof(unsigned long long)));
-	p.d_redq = p.d_seq + 1;
+	p2p_alloc_local();
 	cudaIpcMemHandle_t mine;
 	STAPLE_CUDA_CHECK(cudaIpcGetMemHandle(&mine, p.mailbox));
 	cudaIpcMemHandle_t *d = nullptr, all[kMaxRanks];
@@ -555,13 +587,23 @@ int staple_enable_p2p(int on)
 			return 0;
 		}
 	}
-	p.stage = p.mailbox + p.stage_off;
-	p.flags = (unsigned long long *) (p.mailbox + kMailboxHeader);
-	p.stage_L = p.peer_mailbox[c.rank_L] + p.stage_off; p.stage_R = p.peer_mailbox[c.rank_R] + p.stage_off;
-	p.flags_L = (unsigned long long *) (p.peer_mailbox[c.rank_L] + kMailboxHeader);
-	p.flags_R = (unsigned long long *) (p.peer_mailbox[c.rank_R] + kMailboxHeader);
-	p.on = true;
+	p2p_bind_neighbours();
 	return 1;
+}
+
+// The D3-slab code path on ONE GPU, one process: the geometry must have been initialised with NRANKS_D3 > 1 (local+halo box,
+// ranges R0/R1), this rank becomes its own L and R neighbour and its own memory stands in for the peers' mailboxes.  The lattice
+// that results is the single-rank LOC_N0..3 lattice (periodic in d3 with period LOC_N3) stored with halos; every kernel, flag
+// and counter of the peer-memory transport runs exactly as on N GPUs, minus NVLink.  Used by the single-GPU parity tests and
+// for profiling the segmented operator kernel (a multi-rank run cannot be replayed by ncu).
+int staple_init_loopback(int p2p_mode)
+{
+	require_init("staple_init_loopback");
+	Ctx &c = ctx();
+	if (c.g.nranks <= 1) { fprintf(stderr, "libstaple_b200: staple_init_loopback needs a geometry with NRANKS_D3 > 1\n"); return 1; }
+	if (c.comm || c.p2p.mailbox) shutdown_multidev();
+	c.myrank = 0; c.nranks = c.g.nranks; c.rank_L = c.rank_R = 0; c.async_comm_fermion = 1; c.loopback = true;
+	return staple_enable_p2p(p2p_mode) == (p2p_mode != 0) ? 0 : 1;
 }
 
 void staple_set_spin_timeout(double seconds)
@@ -576,6 +618,7 @@ void shutdown_multidev(void)
 {
 	Ctx &c = ctx();
 	release_p2p();
+	c.loopback = false;
 	if (c.comm && c.comm->comm) {
 		cudaDeviceSynchronize();
 		c.comm->CommDestroy(c.comm->comm);

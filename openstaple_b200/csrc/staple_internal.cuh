@@ -39,33 +39,34 @@ struct CgmCtl; // CG-M control block, below
 
 // Peer-memory channels over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank owns ONE
 // shared "mailbox" allocation:
-//   header (reduction flags[2 parities][kMaxRanks] | reduction boxes[2][kMaxRanks][2 doubles]) |
-//   halo flags[2 slots][nfb] | halo staging stage[2 parities][2 slots][3 colours x vol3h x 16 B]
-// Halo slot 0 receives the data of this rank's LOWER fermion halo (written by rank L's top-face blocks),
-// slot 1 the UPPER halo (written by rank R's bottom-face blocks).  The unit of the protocol is one CTA of the
-// operator (kDslashBlock consecutive sites of a d3 slice, nfb = ceil(vol3h / kDslashBlock) of them per face):
-// the CTA that computed those sites stores them into the neighbour's staging slot and then publishes the exchange
-// number in the neighbour's flag[slot][j]; whoever consumes sites of chunk j waits for that one flag.  There is no
-// group barrier, no ticket and no wait on a block of the same launch anywhere.  Exchange number s uses staging
-// parity s&1, which makes the channel write-after-read safe without a handshake.
-// The sequence numbers live in DEVICE memory (d_seq, d_redq) and are advanced by kernels, so a captured CUDA graph
-// of solver iterations replays correctly.
+//   header (reduction boxes[2 parities][kMaxRanks][2 doubles]) | halo staging stage[2 parities][2 slots][3 colours x vol3h x 16 B]
+// Halo slot 0 receives the data of this rank's LOWER fermion halo (stored by rank L's top-face blocks), slot 1 the UPPER
+// halo (stored by rank R's bottom-face blocks).
+// THE DATA IS ITS OWN ARRIVAL FLAG.  Every 8-byte (FP32: 4-byte) word of the staging area and of the reduction boxes rests at a
+// reserved bit pattern (all ones: a NaN no arithmetic produces); a producer just stores its values into the neighbour's memory --
+// posted NVLink writes, no fence, no flag -- and a consumer spins on the very word it needs until it differs from the pattern,
+// uses it and puts the pattern back.  8-byte accesses are single-copy atomic, so a word is either old (pattern) or new (value);
+// a value that happens to equal the pattern is nudged to another NaN by the producer.  Measured motivation
+// (profiles/r02c_halo_probe_*.jsonl, r02d_*): one fence.sys after remote stores costs 7-15 us on B200/NVSwitch, whoever
+// issues it; with per-chunk flags that was 25-30 us per operator launch.  Exchange number s uses staging parity s&1: the
+// neighbour may already deliver exchange s+1 while exchange s is being consumed here, never s+2 (it needs our s+1 first).
+// The sequence numbers live in DEVICE memory (d_seq, d_redq) and are advanced by kernels, so a captured CUDA graph of
+// solver iterations replays correctly.
 constexpr int kMaxRanks = 16;
-constexpr size_t kMailboxRedFlags = 64, kMailboxRedBox = 64 + 2 * kMaxRanks * 8, kMailboxHeader = 1024;
+constexpr size_t kMailboxRedBox = 64, kMailboxHeader = 1024;
+constexpr unsigned long long kSentinel64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned int kSentinel32 = 0xFFFFFFFFu;
 struct P2P {
 	bool on = false;
 	char *mailbox = nullptr;                  // local, cudaMalloc (IPC exported)
 	char *peer_mailbox[kMaxRanks] = {};       // every rank's mailbox as mapped here ([myrank] = local)
-	char *stage = nullptr;                    // local staging = mailbox + stage_off
-	unsigned long long *flags = nullptr;      // local per-chunk flags [2 slots][nfb]
+	char *stage = nullptr;                    // local staging = mailbox + kMailboxHeader
 	char *stage_L = nullptr, *stage_R = nullptr;
-	unsigned long long *flags_L = nullptr, *flags_R = nullptr;
 	unsigned int *tickets = nullptr;          // local [4]: [0] launch ticket of the operator, [2] unpack kernel
 	unsigned long long *d_seq = nullptr;      // local: number of completed halo exchanges
 	unsigned long long *d_redq = nullptr;     // local: number of completed reductions
 	size_t slot_bytes = 0;                    // 3 * vol3h * 16
-	size_t stage_off = 0;                     // byte offset of the staging area in every mailbox
-	long nfb = 0;                             // chunks (operator CTAs) per face
+	long nfb = 0;                             // operator CTAs per face slice
 	long vol3h = 0;                           // the geometry the mailbox was built for
 };
 // by-value kernel argument of the peer-memory all-reduce
@@ -73,15 +74,12 @@ struct RedView {
 	int nranks, myrank;
 	unsigned long long *q;
 	double *box[kMaxRanks];                   // reduction boxes of every rank (parity 0 base)
-	unsigned long long *flags[kMaxRanks];
 };
-// by-value kernel argument: consumer's view of the LOCAL staging area (a vector whose halo slices were pushed by the
+// by-value kernel argument: consumer's view of the LOCAL staging area (a vector whose halo slices were stored here by the
 // neighbours but not copied into the vector: "staged" halos)
 struct HaloView {
 	int on;                                   // 0: halos are in the vector itself
-	int chunk;                                // sites per flag (operator CTA size)
-	const char *stage_lo, *stage_hi;          // parity-0 bases of slot 0 (lower halo) / slot 1 (upper halo)
-	const unsigned long long *flag_lo, *flag_hi;
+	char *stage_lo, *stage_hi;                // parity-0 bases of slot 0 (lower halo) / slot 1 (upper halo)
 	const unsigned long long *seq;            // exchange counter: the staged halos belong to exchange *seq
 	long parity_bytes;                        // bytes between the parity-0 and parity-1 staging
 	long lower_lo, upper_lo, vol3h;           // first idxh of the lower / upper fermion halo slice
@@ -103,6 +101,7 @@ struct Ctx {
 	unsigned long long launches = 0;
 	// rank layer (multidev.h:10-41)
 	int myrank = 0, nranks = 1, rank_L = 0, rank_R = 0, async_comm_fermion = 0;
+	bool loopback = false;           // staple_init_loopback: D3-slab layout and protocol with THIS rank as both neighbours
 	Comm *comm = nullptr;
 	P2P p2p;
 	bool use_graphs = true;          // CG-M iteration batches as CUDA graphs (single GPU, non-default stream)
@@ -153,18 +152,18 @@ inline RedView single_rank_redview() { RedView v; v.nranks = 1; v.myrank = 0; v.
 constexpr int kDslashBlock = STAPLE_DSLASH_BLOCK;
 
 #ifdef __CUDACC__
-// Every in-kernel wait is for a flag that a PEER GPU writes (never for a block of the same launch), so forward progress
+// Every in-kernel wait is for a word that a PEER GPU stores (never for a block of the same launch), so forward progress
 // does not depend on block scheduling order; it does depend on the peer being alive.  The spin is bounded: after
 // g_spin_timeout_ns (staple_set_spin_timeout, default 60 s; 0 = unbounded, MPI_Wait semantics) the kernel reports what it
 // was waiting for and traps, which surfaces on the host as a CUDA error instead of a hang.
 // (no relocatable device code in this build: the variable and the cold path exist once per translation unit that waits --
 // staple_kernels.cu and staple_solvers.cu -- and staple_set_spin_timeout sets both copies)
 static __device__ unsigned long long g_spin_timeout_ns = 60ull * 1000000000ull;
-static __device__ __noinline__ void spin_timeout_trap(int what, unsigned long long have, unsigned long long want)
+static __device__ __noinline__ void spin_timeout_trap(int what)
 {
-	printf("libstaple_b200: FATAL: block %u waited more than %llu s for a peer GPU (%s: have %llu, want %llu) -- is a rank dead, or "
-				 "did the ranks issue different call sequences?  (staple_set_spin_timeout changes the limit)\n",
-				 blockIdx.x, g_spin_timeout_ns / 1000000000ull, what == 1 ? "halo chunk flag" : "reduction mailbox", have, want);
+	printf("libstaple_b200: FATAL: block %u thread %u waited more than %llu s for a peer GPU (%s) -- is a rank dead, or did the "
+				 "ranks issue different call sequences?  (staple_set_spin_timeout changes the limit)\n",
+				 blockIdx.x, threadIdx.x, g_spin_timeout_ns / 1000000000ull, what == 1 ? "halo data" : "reduction mailbox");
 	__trap();
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -173,46 +172,82 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
-// what: 1 halo chunk flag, 2 reduction mailbox
-__device__ __forceinline__ void wait_flag_sys(const unsigned long long *flag, unsigned long long want, int what)
-{
-	unsigned long long v, t0 = 0;
+struct SpinGuard {
 	unsigned int spins = 0;
-	for (;;) {
-		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-		if (v >= want) return;
+	unsigned long long t0 = 0;
+	__device__ __forceinline__ void pause(int what)
+	{
 		__nanosleep(spins < 32 ? 20 : 200);
 		if ((++spins & 0x3fffu) == 0) {            // look at the clock every ~3 ms
 			const unsigned long long now = globaltimer_ns(), lim = *(volatile unsigned long long *) &g_spin_timeout_ns;
 			if (t0 == 0) t0 = now;
-			else if (lim != 0 && now - t0 > lim) spin_timeout_trap(what, v, want);
+			else if (lim != 0 && now - t0 > lim) spin_timeout_trap(what);
 		}
 	}
+};
+// consume one staged element: spin until both words have arrived, put the resting pattern back (system-scope relaxed
+// accesses: always served by L2, where the peer's NVLink writes land)
+__device__ __forceinline__ double2 take_staged(double2 *p)
+{
+	unsigned long long x, y;
+	SpinGuard g;
+	for (;;) {
+		asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+		if (x != kSentinel64 && y != kSentinel64) break;
+		g.pause(1);
+	}
+	asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(kSentinel64), "l"(kSentinel64) : "memory");
+	return make_double2(__longlong_as_double((long long) x), __longlong_as_double((long long) y));
+}
+__device__ __forceinline__ float2 take_staged(float2 *p)
+{
+	unsigned int x, y;
+	SpinGuard g;
+	for (;;) {
+		asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
+		if (x != kSentinel32 && y != kSentinel32) break;
+		g.pause(1);
+	}
+	asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(kSentinel32), "r"(kSentinel32) : "memory");
+	return make_float2(__uint_as_float(x), __uint_as_float(y));
+}
+// producer side: a value that equals the resting pattern (a NaN with all payload bits set) becomes the canonical NaN
+__device__ __forceinline__ double2 stageable(double2 v)
+{
+	if ((unsigned long long) __double_as_longlong(v.x) == kSentinel64) v.x = __longlong_as_double(0x7ff8000000000000ll);
+	if ((unsigned long long) __double_as_longlong(v.y) == kSentinel64) v.y = __longlong_as_double(0x7ff8000000000000ll);
+	return v;
+}
+__device__ __forceinline__ float2 stageable(float2 v)
+{
+	if (__float_as_uint(v.x) == kSentinel32) v.x = __uint_as_float(0x7fc00000u);
+	if (__float_as_uint(v.y) == kSentinel32) v.y = __uint_as_float(0x7fc00000u);
+	return v;
 }
 
 // One warp: every rank stores its value into every rank's box (lane = destination rank), waits for all
 // contributions to its own box and adds them in rank order -- bit-identical results everywhere, about one
 // NVLink round trip, and usable as the prologue of a kernel that consumes the sum (no separate launch).
+// Same protocol as the halos: the doubles are their own arrival flags, no fence.
 __device__ __forceinline__ void p2p_allreduce_warp(double *vals, int nd, const RedView &v)
 {
 	const int lane = threadIdx.x & 31;
 	const unsigned long long q = *v.q + 1;
 	const int par = (int) (q & 1ull);
+	double s0 = 0.0, s1 = 0.0;
 	if (lane < v.nranks) {
+		double2 mine = stageable(make_double2(vals[0], nd > 1 ? vals[1] : 0.0));
 		double *b = v.box[lane] + ((size_t) par * kMaxRanks + v.myrank) * 2;
-		b[0] = vals[0];
-		b[1] = nd > 1 ? vals[1] : 0.0;
-		__threadfence_system();
-		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(v.flags[lane] + par * kMaxRanks + v.myrank), "l"(q) : "memory");
-		wait_flag_sys(v.flags[v.myrank] + par * kMaxRanks + lane, q, 2);
+		asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(b), "d"(mine.x), "d"(mine.y) : "memory");
+		const double2 got = take_staged((double2 *) (v.box[v.myrank] + ((size_t) par * kMaxRanks + lane) * 2));
+		s0 = got.x; s1 = got.y;
 	}
-	__syncwarp();
+	// rank-ordered sum: lane r holds rank r's contribution
+	double t0 = 0.0, t1 = 0.0;
+	for (int r = 0; r < v.nranks; r++) { t0 += __shfl_sync(0xffffffffu, s0, r); t1 += __shfl_sync(0xffffffffu, s1, r); }
 	if (lane == 0) {
-		const double *mine = v.box[v.myrank] + (size_t) par * kMaxRanks * 2;
-		double s0 = 0.0, s1 = 0.0;
-		for (int r = 0; r < v.nranks; r++) { s0 += __ldcg(mine + 2 * r); s1 += __ldcg(mine + 2 * r + 1); }
-		vals[0] = s0;
-		if (nd > 1) vals[1] = s1;
+		vals[0] = t0;
+		if (nd > 1) vals[1] = t1;
 		*v.q = q;
 		__threadfence();
 	}
@@ -325,21 +360,19 @@ struct DslashArgs {
 	// ---- D3 slabs over NVLink peer memory (mr != 0): the launch is segmented by block index into
 	//   [nb_top blocks: TOP interior slice -> rank R's slot 0] [nb_bot: BOTTOM interior slice -> rank L's slot 1]
 	//   [nb_bulk: the slices in between] [2*nb_unpack: copy of the staged halos of THIS exchange into `out`]
-	// any segment may be empty.  Face block j stores its chunk into the neighbour's staging slot and publishes the exchange
-	// number in the neighbour's flag j; faces come first in block order, so the transfer overlaps the rest of the launch.
+	// any segment may be empty.  A face block stores its sites into `out` AND into the neighbour's staging slot (posted NVLink
+	// writes; the data is its own arrival flag, see P2P); faces come first in block order, so the transfer overlaps the rest.
 	int mr;
 	unsigned int nb_top, nb_bot, nb_bulk, nb_unpack;
 	long top_lo, bot_lo;                         // first idxh of the two surface slices
-	cplx_t<T> *peer_top, *peer_bot;              // parity-0 staging slot in the neighbour's memory (null: no push)
-	unsigned long long *peer_flag_top, *peer_flag_bot;
+	cplx_t<T> *peer_top, *peer_bot;              // parity-0 staging slot in the neighbour's memory
 	long parity_stride;                          // elements between the parity-0 and parity-1 staging areas
 	unsigned long long *seq_rw;                  // device counter of completed exchanges; this launch produces *seq_rw + 1
-	unsigned int *launch_ticket;                 // non-null: the last block of the launch advances the counter
+	unsigned int *launch_ticket;                 // non-null: the last face/unpack block of the launch advances the counter
 	// consumer side: the halo slices of `in` were left in the local staging area by exchange *seq_rw (in_staged), and/or
 	// the staged halos of the exchange this launch produces are copied into `out` by the unpack blocks
 	int in_staged;
-	const cplx_t<T> *stage_lo, *stage_hi;        // local slot 0 (lower halo) / slot 1 (upper halo), parity-0 base
-	const unsigned long long *flag_lo, *flag_hi; // local per-chunk flags of slot 0 / slot 1
+	cplx_t<T> *stage_lo, *stage_hi;              // local slot 0 (lower halo) / slot 1 (upper halo), parity-0 base
 	long lower_lo, upper_lo;                     // first idxh of the lower / upper halo slice
 };
 

@@ -15,6 +15,9 @@ namespace staple {
 #ifndef STAPLE_DSLASH_MINBLOCKS
 #define STAPLE_DSLASH_MINBLOCKS 7       // 72 registers, 28 warps/SM: +8% over the unconstrained build (profiles/r01_tune_dslash_*.txt)
 #endif
+#ifndef STAPLE_DSLASH_MINBLOCKS_MR
+#define STAPLE_DSLASH_MINBLOCKS_MR 6    // segmented (D3-slab) instantiations: 80 registers; at 72 the M^+M epilogue variant spills 160 B per thread
+#endif
 #ifndef STAPLE_LINK_LOAD
 #define STAPLE_LINK_LOAD 0       // 0: ld.global.cs (evict-first streaming)  1: ld.global.nc  2: ld.global.lu  3: plain
 #endif
@@ -202,22 +205,12 @@ __device__ __forceinline__ bool grid_sum_finalize(double v[NV], double *partials
 }
 
 // ------------------------------------------------------------------ peer-memory halo channel (device side)
-// Producer side of one chunk: every thread of the CTA has issued its peer stores; ONE system-scope fence by thread 0 after
-// the barrier makes them visible before the flag (the barrier makes the fence cumulative -- the post pattern of NCCL's simple
-// protocol; a fence.sys by every thread was measured to cost more than the transfer itself).
-__device__ __forceinline__ void chunk_signal(unsigned long long *peer_flag, unsigned long long seq)
-{
-	__threadfence_system();
-	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(seq) : "memory");
-}
-
 // push both interior faces of a vector (3 colour arrays) into the neighbours' staging slots (standalone
 // communicate_fermion_borders; the operator's face blocks do this themselves).  grid = 2*nfb CTAs of kDslashBlock threads:
 // [0,nfb) TOP interior slice -> rank R's slot 0, [nfb,2nfb) BOTTOM interior slice -> rank L's slot 1
 template <typename C>
 __global__ void __launch_bounds__(kDslashBlock) p2p_push_kernel(const C *src, long n, long top_lo, long bot_lo, unsigned int vol3h,
 																																 unsigned int nfb, C *peer_top, C *peer_bot, long parity_stride,
-																																 unsigned long long *flag_top, unsigned long long *flag_bot,
 																																 const unsigned long long *seq_ptr)
 {
 	const unsigned long long seq = *seq_ptr + 1;
@@ -230,34 +223,29 @@ __global__ void __launch_bounds__(kDslashBlock) p2p_push_kernel(const C *src, lo
 #pragma unroll
 		for (int c = 0; c < 3; c++) v[c] = src[c * n + lo + t];
 #pragma unroll
-		for (int c = 0; c < 3; c++) peer[(long) c * vol3h + t] = v[c];
+		for (int c = 0; c < 3; c++) peer[(long) c * vol3h + t] = stageable(v[c]);
 	}
-	__syncthreads();
-	if (threadIdx.x == 0) chunk_signal((bot ? flag_bot : flag_top) + j, seq);
 }
 
-// copy of staged chunks (3 colour arrays) into a halo slice: block `b` of `nb` takes chunks b, b+nb, ... four at a time --
-// threads 0..3 wait for one flag each, then every thread has 4 sites x 3 colours = 12 independent 16-byte loads in flight.
-// Not inlined in the operator: its registers must not weigh on the 72-register budget of the hops.
+// copy of one staged slice (3 colour arrays) into a halo slice: grid-stride, 4 sites x 3 colours = 12 independent 16-byte
+// elements in flight per thread, each taken as soon as it has arrived.  Not inlined in the operator: its registers must not
+// weigh on the register budget of the hops.
 template <typename C>
-__device__ __noinline__ void unpack_chunks(C *dst, long n, const C *src, const unsigned long long *flags, unsigned long long seq,
-																					 unsigned int vol3h, unsigned int nfb, unsigned int b, unsigned int nb)
+__device__ __noinline__ void unpack_slice(C *dst, long n, C *src, unsigned int vol3h, unsigned int first, unsigned int stride)
 {
-	for (unsigned int j0 = b; j0 < nfb; j0 += 4 * nb) {
-		if (threadIdx.x < 4 && j0 + threadIdx.x * nb < nfb) wait_flag_sys(flags + j0 + threadIdx.x * nb, seq, 1);
-		__syncthreads();
+	for (unsigned int t0 = first; t0 < vol3h; t0 += 4 * stride) {
 		C v[4][3];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const unsigned int j = j0 + k * nb, tt = j * kDslashBlock + threadIdx.x;
+			const unsigned int tt = t0 + k * stride;
 #pragma unroll
 			for (int c = 0; c < 3; c++)
-				if (j < nfb && tt < vol3h) v[k][c] = __ldcg(src + (long) c * vol3h + tt);
+				if (tt < vol3h) v[k][c] = take_staged(src + (long) c * vol3h + tt);
 		}
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const unsigned int j = j0 + k * nb, tt = j * kDslashBlock + threadIdx.x;
-			if (j < nfb && tt < vol3h) {
+			const unsigned int tt = t0 + k * stride;
+			if (tt < vol3h) {
 #pragma unroll
 				for (int c = 0; c < 3; c++) dst[c * n + tt] = v[k][c];
 			}
@@ -265,20 +253,19 @@ __device__ __noinline__ void unpack_chunks(C *dst, long n, const C *src, const u
 	}
 }
 
-// standalone unpack: copy both staging slots of exchange *seq_ptr + 1 into the halo slices once the neighbours' chunks
-// have landed; the last block to finish advances the exchange counter.  grid = 2*nb CTAs of kDslashBlock threads.
+// standalone unpack: copy both staging slots of exchange *seq_ptr + 1 into the halo slices as the neighbours' data lands;
+// the last block to finish advances the exchange counter.  grid = 2*nb CTAs of kDslashBlock threads.
 template <typename C>
 __global__ void __launch_bounds__(kDslashBlock) p2p_unpack_kernel(C *dst, long n, long lower_lo, long upper_lo, unsigned int vol3h,
-																																	 unsigned int nfb, const C *slot0, const C *slot1, long parity_stride,
-																																	 const unsigned long long *flag0, const unsigned long long *flag1,
-																																	 unsigned long long *seq_ptr, unsigned int *ticket, const int *skip)
+																																	 C *slot0, C *slot1, long parity_stride, unsigned long long *seq_ptr,
+																																	 unsigned int *ticket, const int *skip)
 {
 	if (skip != nullptr && *skip != 0) return;       // the producers skipped this exchange too (same flag on every rank)
 	const unsigned long long seq = *seq_ptr + 1;
 	const unsigned int nb = gridDim.x / 2;
 	const bool hi = blockIdx.x >= nb;                // first half of the grid: lower halo, second half: upper
-	unpack_chunks<C>(dst + (hi ? upper_lo : lower_lo), n, (hi ? slot1 : slot0) + (seq & 1ull) * parity_stride, hi ? flag1 : flag0,
-									 seq, vol3h, nfb, hi ? blockIdx.x - nb : blockIdx.x, nb);
+	unpack_slice<C>(dst + (hi ? upper_lo : lower_lo), n, (hi ? slot1 : slot0) + (seq & 1ull) * parity_stride, vol3h,
+									(hi ? blockIdx.x - nb : blockIdx.x) * kDslashBlock + threadIdx.x, nb * kDslashBlock);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence();
@@ -289,7 +276,7 @@ __global__ void __launch_bounds__(kDslashBlock) p2p_unpack_kernel(C *dst, long n
 // the exchange counter, advanced on its own (pipelined host round trip: the two face slices are separate launches)
 __global__ void seq_advance_kernel(unsigned long long *seq) { *seq = *seq + 1; }
 
-// unpack blocks per halo: at most 2 per SM (grid-stride over chunks with 12 loads in flight per thread).  Thousands of
+// unpack blocks per halo: at most 2 per SM (grid-stride copy with 12 elements in flight per thread).  Thousands of
 // 128-thread blocks only add scheduling time to the tail; 74 were measured too few to cover the HBM latency.
 static inline unsigned int unpack_blocks_for(unsigned int face_blocks) { return face_blocks < 296u ? face_blocks : 296u; }
 
@@ -301,9 +288,8 @@ static void p2p_unpack_t(void *base, cudaStream_t s, const int *skip)
 	P2P &p = c.p2p;
 	const long lower_lo = (long) (g.d3_halo - 1) * g.vol3h, upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
 	const unsigned int nb = unpack_blocks_for((unsigned int) p.nfb);
-	p2p_unpack_kernel<C><<<2 * nb, kDslashBlock, 0, s>>>((C *) base, g.sizeh, lower_lo, upper_lo, (unsigned int) g.vol3h, (unsigned int) p.nfb,
-		(const C *) p.stage, (const C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.flags, p.flags + p.nfb, p.d_seq,
-		p.tickets + 2, skip);
+	p2p_unpack_kernel<C><<<2 * nb, kDslashBlock, 0, s>>>((C *) base, g.sizeh, lower_lo, upper_lo, (unsigned int) g.vol3h,
+		(C *) p.stage, (C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.d_seq, p.tickets + 2, skip);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch();
 }
@@ -323,7 +309,7 @@ static void p2p_exchange_t(void *base, cudaStream_t s)
 	const long ps = (long) (2 * p.slot_bytes / sizeof(C));
 	// top interior slice -> rank R's lower halo (its slot 0); bottom interior slice -> rank L's upper halo (slot 1)
 	p2p_push_kernel<C><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const C *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
-		(unsigned int) p.nfb, (C *) p.stage_R, (C *) (p.stage_L + p.slot_bytes), ps, p.flags_R, p.flags_L + p.nfb, p.d_seq);
+		(unsigned int) p.nfb, (C *) p.stage_R, (C *) (p.stage_L + p.slot_bytes), ps, p.d_seq);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch();
 	p2p_unpack(base, sizeof(C), s, nullptr);
@@ -342,12 +328,9 @@ RedView make_redview()
 	Ctx &c = ctx();
 	P2P &p = c.p2p;
 	RedView v;
-	v.nranks = c.nranks; v.myrank = c.myrank; v.q = p.d_redq;
-	for (int r = 0; r < kMaxRanks; r++) { v.box[r] = nullptr; v.flags[r] = nullptr; }
-	for (int r = 0; r < c.nranks; r++) {
-		v.box[r] = (double *) (p.peer_mailbox[r] + kMailboxRedBox);
-		v.flags[r] = (unsigned long long *) (p.peer_mailbox[r] + kMailboxRedFlags);
-	}
+	v.nranks = c.loopback ? 1 : c.nranks; v.myrank = c.myrank; v.q = p.d_redq;
+	for (int r = 0; r < kMaxRanks; r++) v.box[r] = nullptr;
+	for (int r = 0; r < v.nranks; r++) v.box[r] = (double *) (p.peer_mailbox[r] + kMailboxRedBox);
 	return v;
 }
 void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s)
@@ -373,9 +356,8 @@ HaloView make_haloview(size_t elem_bytes, bool on)
 	const Geom &g = c.g;
 	const P2P &p = c.p2p;
 	HaloView h;
-	h.on = on ? 1 : 0; h.chunk = kDslashBlock;
+	h.on = on ? 1 : 0;
 	h.stage_lo = p.stage; h.stage_hi = p.stage ? p.stage + p.slot_bytes : nullptr;
-	h.flag_lo = p.flags; h.flag_hi = p.flags ? p.flags + p.nfb : nullptr;
 	h.seq = p.d_seq; h.parity_bytes = (long) (2 * p.slot_bytes);
 	h.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; h.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h; h.vol3h = g.vol3h;
 	(void) elem_bytes;
@@ -396,19 +378,20 @@ __device__ __forceinline__ void dslash_finish_dot(const DslashArgs<T> &a, double
 	}
 }
 
-// One hop with the spinor taken from (vin, colour stride vn, index iv) and loaded past L1 (ld.global.cg): the d3 hops,
-// whose neighbour is either the vector itself or -- on a face, with staged halos -- the staging area that a peer GPU
-// writes over NVLink (L1 is not coherent with peer writes; neighbours in d3 are vol3h sites away, so L1 had nothing to
-// offer to them anyway).
-template <typename T, bool DAG>
+// One d3 hop.  The spinor comes from (vin, colour stride vn, index iv), loaded past L1 (neighbours in d3 are vol3h sites away,
+// L1 has nothing to offer them) -- or, STAGED, from the local staging area that a peer GPU fills over NVLink: each element is
+// taken as soon as it has arrived (take_staged: the data is its own flag), which is the only wait of the whole exchange.
+template <typename T, bool DAG, bool MAYBE_STAGED>
 __device__ __forceinline__ void hop_d3(cplx_t<T> acc[3], const cplx_t<T> *__restrict__ uk, const T *__restrict__ phk,
-																			 unsigned int im, const cplx_t<T> *vin, unsigned int iv, long n, long vn)
+																			 unsigned int im, cplx_t<T> *vin, unsigned int iv, long n, long vn, const bool STAGED)
 {
 	using C = cplx_t<T>;
 	const T th = ld_stream(phk + im);
 	const C m00 = ld_stream(uk + im), m01 = ld_stream(uk + n + im), m02 = ld_stream(uk + 2 * n + im);
 	const C m10 = ld_stream(uk + 3 * n + im), m11 = ld_stream(uk + 4 * n + im), m12 = ld_stream(uk + 5 * n + im);
-	const C v0 = __ldcg(vin + iv), v1 = __ldcg(vin + vn + iv), v2 = __ldcg(vin + 2 * vn + iv);
+	C v0, v1, v2;
+	if (MAYBE_STAGED && STAGED) { v0 = take_staged(vin + iv); v1 = take_staged(vin + vn + iv); v2 = take_staged(vin + 2 * vn + iv); }
+	else { v0 = __ldcg(vin + iv); v1 = __ldcg(vin + vn + iv); v2 = __ldcg(vin + 2 * vn + iv); }
 	T s, c;
 	sincos_t(th, &s, &c);
 	const C x0 = cross(m01, m12, m02, m11);
@@ -430,124 +413,120 @@ __device__ __forceinline__ void hop_d3(cplx_t<T> acc[3], const cplx_t<T> *__rest
 }
 
 // Hop order: the six hops in directions 0,1,2 first, the two d3 hops last.  On D3 slabs those are the only hops that can
-// need a neighbour rank's data; a face block whose input halo is staged waits for its ONE chunk flag between the two
-// groups, i.e. with three quarters of its work as slack.  (The reference adds backward 0..3 then forward 0..3,
-// fermion_matrix.c:74-89; the different summation order moves results by O(1e-16) relative, like FMA contraction does.)
-// MR = false: plain launch over [site_lo, site_lo + nsites) -- the single-GPU kernel, free of every multi-rank register.
-// MR = true : segmented launch on D3 slabs (DslashArgs).  What a block needs to know about its segment is derived from
-// blockIdx twice (before the first and before the last group of hops) instead of being carried in registers across them.
+// need a neighbour rank's data, so a face site whose input halo is staged has three quarters of its work done before it
+// looks at the staging area.  (The reference adds backward 0..3 then forward 0..3, fermion_matrix.c:74-89; the different
+// summation order moves results by O(1e-16) relative, like FMA contraction does.)
+// FACE = false: site lo + t of a plain range -- the single-GPU kernel and the bulk blocks of a segmented launch
+// FACE = true : face site; side 1 = TOP slice (result also stored into rank R's staging slot; with staged input its FORWARD d3
+//               neighbour is staged), side 2 = BOTTOM slice (result also to rank L's slot; staged input: BACKWARD neighbour)
+// returns the site's contribution to the fused Re(in0 . out)
+template <typename T, int PAR, int EPI, bool FACE>
+__device__ __forceinline__ double dslash_site(const DslashArgs<T> &a, const unsigned int lo, const unsigned int t,
+																							cplx_t<T> *peer, cplx_t<T> *stage, const int side, const bool in_staged)
+{
+	using C = cplx_t<T>;
+	const long n = a.sizeh;
+	const long un = 9 * n;
+	const unsigned int idx = lo + t;
+	const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2, nd3 = a.nd3;
+	const unsigned int hd0 = idx % nd0h;
+	unsigned int q = idx / nd0h;
+	const unsigned int d1 = q % nd1; q /= nd1;
+	const unsigned int d2 = q % nd2;
+	const unsigned int d3 = q / nd2;
+	// d0 = 2*hd0 + rp  (fermion_matrix.c:64, :120)
+	const unsigned int rp = (d1 + d2 + d3 + PAR) & 1u;
+	const unsigned int s1 = nd0h, s2 = nd0h * nd1, s3 = (unsigned int) a.vol3h;
+	const unsigned int i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
+	const unsigned int i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
+	const unsigned int i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
+	const unsigned int i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
+	const unsigned int i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
+	const unsigned int i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
+	C acc[3];
+	acc[0] = mk<T>(0, 0); acc[1] = mk<T>(0, 0); acc[2] = mk<T>(0, 0);
+	// backward hops: link and phase of the OTHER parity at the neighbour index (:74-77, :130-133)
+	hop<T, true>(acc, a.u + (1 - PAR) * un, a.ph + (1 - PAR) * n, i0m, a.in, i0m, n);
+	hop<T, true>(acc, a.u + (3 - PAR) * un, a.ph + (3 - PAR) * n, i1m, a.in, i1m, n);
+	hop<T, true>(acc, a.u + (5 - PAR) * un, a.ph + (5 - PAR) * n, i2m, a.in, i2m, n);
+	// forward hops: link and phase of this parity at the own index (:86-89, :144-147)
+	hop<T, false>(acc, a.u + (0 + PAR) * un, a.ph + (0 + PAR) * n, idx, a.in, i0p, n);
+	hop<T, false>(acc, a.u + (2 + PAR) * un, a.ph + (2 + PAR) * n, idx, a.in, i1p, n);
+	hop<T, false>(acc, a.u + (4 + PAR) * un, a.ph + (4 + PAR) * n, idx, a.in, i2p, n);
+	const unsigned int i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
+	const unsigned int i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
+	C *const vec = const_cast<C *>(a.in);
+	const bool sm = FACE && in_staged && side == 2, sp = FACE && in_staged && side == 1;
+	hop_d3<T, true, FACE>(acc, a.u + (7 - PAR) * un, a.ph + (7 - PAR) * n, i3m, sm ? stage : vec, sm ? t : i3m, n, sm ? (long) s3 : n, sm);
+	hop_d3<T, false, FACE>(acc, a.u + (6 + PAR) * un, a.ph + (6 + PAR) * n, idx, sp ? stage : vec, sp ? t : i3p, n, sp ? (long) s3 : n, sp);
+	double dot = 0.0;
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		C o = mk<T>(acc[c].x * (T) 0.5, acc[c].y * (T) 0.5);   // :94-96
+		if (EPI != EPI_NONE) {
+			// fused combine_in1xferm_mass_minus_in2 (fermionic_utilities.c:261-272): double factor
+			const C x = ld_cached(a.in0 + c * n + idx);
+			o = mk<T>((T) ((double) x.x * a.m2 - (double) o.x), (T) ((double) x.y * a.m2 - (double) o.y));
+			if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
+		}
+		a.out[c * n + idx] = o;
+		if (!FACE && EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
+#ifndef STAPLE_DEBUG_NO_PEER_STORES      // timing experiments only (wrong halos): never defined in a release build
+		if (FACE) peer[(long) c * s3 + t] = stageable(o);     // posted NVLink store into the neighbour's staging slot
+#endif
+	}
+	return dot;
+}
+
+// MR = false: plain launch over [site_lo, site_lo + nsites) -- the single-GPU kernel.
+// MR = true : segmented launch on D3 slabs, block-uniform roles by block index (DslashArgs):
+//             [top face][bottom face][bulk][unpack]
+// No block ever waits for another block of the same launch; bulk blocks run exactly the single-GPU code and leave without
+// any tail (a per-block fence + ticket on ~16k bulk blocks was measured to cost 12 % of the launch).
 template <typename T, int PAR, int EPI, bool MR>
-__global__ void __launch_bounds__(kBlock, STAPLE_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<T> a)
+__global__ void __launch_bounds__(kBlock, MR ? STAPLE_DSLASH_MINBLOCKS_MR : STAPLE_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<T> a)
 {
 	using C = cplx_t<T>;
 	if (a.skip != nullptr && *a.skip != 0) return;
 	// sizeh < 2^31 is checked at staple_init_geometry: site indices are 32-bit (no 64-bit divisions),
 	// only the array bases (k*9*sizeh) are 64-bit
-	unsigned int t = blockIdx.x * kBlock + threadIdx.x;
-	unsigned int lo = (unsigned int) a.site_lo, ns = (unsigned int) a.nsites;
-	if (MR) {              // block-uniform segment selection: top face, bottom face, bulk, unpack
-		const unsigned int b = blockIdx.x;
-		if (b < a.nb_top) { lo = (unsigned int) a.top_lo; ns = (unsigned int) a.vol3h; }
-		else if (b < a.nb_top + a.nb_bot) { t -= a.nb_top * kBlock; lo = (unsigned int) a.bot_lo; ns = (unsigned int) a.vol3h; }
-		else if (b < a.nb_top + a.nb_bot + a.nb_bulk) t -= (a.nb_top + a.nb_bot) * kBlock;
-		else {
-			// ---- unpack blocks (last in block order): the halos of THIS exchange, as the neighbours' face blocks deliver them
-			const unsigned long long seq = *a.seq_rw + 1;
-			const unsigned int ub = a.nb_unpack, k = b - (a.nb_top + a.nb_bot + a.nb_bulk);
-			const bool hi = k >= ub;                           // first ub blocks: lower halo (slot 0, from rank L); then upper (slot 1, from R)
-			unpack_chunks<C>(a.out + (hi ? a.upper_lo : a.lower_lo), a.sizeh, (hi ? a.stage_hi : a.stage_lo) + (seq & 1ull) * a.parity_stride,
-											 hi ? a.flag_hi : a.flag_lo, seq, (unsigned int) a.vol3h, a.nb_top, hi ? k - ub : k, ub);
-			ns = 0;                                            // no sites of its own; falls through to the common tail
-		}
-	}
-	const bool active = t < ns;
-	const long n = a.sizeh;
-	const long un = 9 * n;
-	const unsigned int idx = lo + t;
-	C acc[3];
-	acc[0] = mk<T>(0, 0); acc[1] = mk<T>(0, 0); acc[2] = mk<T>(0, 0);
-	if (active) {
-		const unsigned int nd0h = a.nd0h, nd1 = a.nd1, nd2 = a.nd2;
-		const unsigned int hd0 = idx % nd0h;
-		unsigned int q = idx / nd0h;
-		const unsigned int d1 = q % nd1; q /= nd1;
-		const unsigned int d2 = q % nd2;
-		const unsigned int d3 = q / nd2;
-		// d0 = 2*hd0 + rp  (fermion_matrix.c:64, :120)
-		const unsigned int rp = (d1 + d2 + d3 + PAR) & 1u;
-		const unsigned int s1 = nd0h, s2 = nd0h * nd1;
-		const unsigned int i0m = rp ? idx : (hd0 == 0 ? idx + (nd0h - 1) : idx - 1);
-		const unsigned int i0p = rp ? (hd0 == nd0h - 1 ? idx - (nd0h - 1) : idx + 1) : idx;
-		const unsigned int i1m = d1 == 0 ? idx + s1 * (nd1 - 1) : idx - s1;
-		const unsigned int i1p = d1 == nd1 - 1 ? idx - s1 * (nd1 - 1) : idx + s1;
-		const unsigned int i2m = d2 == 0 ? idx + s2 * (nd2 - 1) : idx - s2;
-		const unsigned int i2p = d2 == nd2 - 1 ? idx - s2 * (nd2 - 1) : idx + s2;
-		// backward hops: link and phase of the OTHER parity at the neighbour index (:74-77, :130-133)
-		hop<T, true>(acc, a.u + (1 - PAR) * un, a.ph + (1 - PAR) * n, i0m, a.in, i0m, n);
-		hop<T, true>(acc, a.u + (3 - PAR) * un, a.ph + (3 - PAR) * n, i1m, a.in, i1m, n);
-		hop<T, true>(acc, a.u + (5 - PAR) * un, a.ph + (5 - PAR) * n, i2m, a.in, i2m, n);
-		// forward hops: link and phase of this parity at the own index (:86-89, :144-147)
-		hop<T, false>(acc, a.u + (0 + PAR) * un, a.ph + (0 + PAR) * n, idx, a.in, i0p, n);
-		hop<T, false>(acc, a.u + (2 + PAR) * un, a.ph + (2 + PAR) * n, idx, a.in, i1p, n);
-		hop<T, false>(acc, a.u + (4 + PAR) * un, a.ph + (4 + PAR) * n, idx, a.in, i2p, n);
-	}
-	// ---- the two d3 hops: spinor from the vector itself, or (face block, staged input halo) from the local staging area
-	const C *v3m = a.in, *v3p = a.in;
-	long vn3m = n, vn3p = n;
-	const unsigned int s3 = (unsigned int) a.vol3h, d3 = idx / s3, nd3 = a.nd3;
-	unsigned int i3m = d3 == 0 ? idx + s3 * (nd3 - 1) : idx - s3;
-	unsigned int i3p = d3 == nd3 - 1 ? idx - s3 * (nd3 - 1) : idx + s3;
-	C *peer = nullptr;                                  // this block's chunk in the neighbour's staging slot
-	unsigned long long *peer_flag = nullptr;
-	unsigned long long cur = 0;
-	if (MR) {
-		cur = *a.seq_rw;
-		const unsigned int b = blockIdx.x;
-		const unsigned long long *wait_flag = nullptr;    // the chunk of the staged input halo this block reads
-		if (b < a.nb_top) {
-			if (a.peer_top != nullptr) { peer = a.peer_top + ((cur + 1) & 1ull) * a.parity_stride; peer_flag = a.peer_flag_top + b; }
-			if (a.in_staged) { v3p = a.stage_hi + (cur & 1ull) * a.parity_stride; vn3p = a.vol3h; i3p = t; wait_flag = a.flag_hi + b; }
-		} else if (b < a.nb_top + a.nb_bot) {
-			const unsigned int j = b - a.nb_top;
-			if (a.peer_bot != nullptr) { peer = a.peer_bot + ((cur + 1) & 1ull) * a.parity_stride; peer_flag = a.peer_flag_bot + j; }
-			if (a.in_staged) { v3m = a.stage_lo + (cur & 1ull) * a.parity_stride; vn3m = a.vol3h; i3m = t; wait_flag = a.flag_lo + j; }
-		}
-		if (wait_flag != nullptr) {     // block-uniform: written by a peer GPU (exchange `cur`, produced by the previous operator)
-			if (threadIdx.x == 0) wait_flag_sys(wait_flag, cur, 1);
-			__syncthreads();
-		}
-	}
 	double dot = 0.0;
-	if (active) {
-		hop_d3<T, true>(acc, a.u + (7 - PAR) * un, a.ph + (7 - PAR) * n, MR && v3m != a.in ? idx - s3 : i3m, v3m, i3m, n, vn3m);
-		hop_d3<T, false>(acc, a.u + (6 + PAR) * un, a.ph + (6 + PAR) * n, idx, v3p, i3p, n, vn3p);
-#pragma unroll
-		for (int c = 0; c < 3; c++) {
-			C o = mk<T>(acc[c].x * (T) 0.5, acc[c].y * (T) 0.5);   // :94-96
-			if (EPI != EPI_NONE) {
-				// fused combine_in1xferm_mass_minus_in2 (fermionic_utilities.c:261-272): double factor
-				const C x = ld_cached(a.in0 + c * n + idx);
-				o = mk<T>((T) ((double) x.x * a.m2 - (double) o.x), (T) ((double) x.y * a.m2 - (double) o.y));
-				if (EPI == EPI_MASS_DOT) dot += (double) x.x * (double) o.x + (double) x.y * (double) o.y;
+	if (!MR) {
+		const unsigned int t = blockIdx.x * kBlock + threadIdx.x;
+		if (t < (unsigned int) a.nsites) dot = dslash_site<T, PAR, EPI, false>(a, (unsigned int) a.site_lo, t, nullptr, nullptr, 0, false);
+	} else {
+		const unsigned int b = blockIdx.x, b2 = a.nb_top, b3 = b2 + a.nb_bot, b4 = b3 + a.nb_bulk;
+		if (b >= b3 && b < b4) {
+			const unsigned int t = (b - b3) * kBlock + threadIdx.x;
+			if (t < (unsigned int) a.nsites) dot = dslash_site<T, PAR, EPI, false>(a, (unsigned int) a.site_lo, t, nullptr, nullptr, 0, false);
+		} else {
+			const unsigned long long cur = *a.seq_rw;       // this launch consumes exchange `cur` (staged input halos) and produces cur + 1
+			const unsigned int vol3h = (unsigned int) a.vol3h;
+			if (b < b3) {
+				// TOP face   : -> rank R's slot 0; staged input: forward neighbour slice = upper halo = local slot 1
+				// BOTTOM face: -> rank L's slot 1; staged input: backward neighbour slice = lower halo = local slot 0
+				const bool bot = b >= b2;
+				const unsigned int t = (bot ? b - b2 : b) * kBlock + threadIdx.x;
+				C *peer = (bot ? a.peer_bot : a.peer_top) + ((cur + 1) & 1ull) * a.parity_stride;
+				C *stage = (bot ? a.stage_lo : a.stage_hi) + (cur & 1ull) * a.parity_stride;
+				if (t < vol3h) dot = dslash_site<T, PAR, EPI, true>(a, (unsigned int) (bot ? a.bot_lo : a.top_lo), t, peer, stage, bot ? 2 : 1, a.in_staged != 0);
+			} else {
+				// ---- unpack blocks (last in block order): the halos of THIS exchange, element by element as they land
+				const unsigned int ub = a.nb_unpack, k = b - b4;
+				const bool hi = k >= ub;                         // first ub blocks: lower halo (slot 0, from rank L); then upper (slot 1, from R)
+				unpack_slice<C>(a.out + (hi ? a.upper_lo : a.lower_lo), a.sizeh, (hi ? a.stage_hi : a.stage_lo) + ((cur + 1) & 1ull) * a.parity_stride,
+												vol3h, (hi ? k - ub : k) * kBlock + threadIdx.x, ub * kBlock);
 			}
-			a.out[c * n + idx] = o;
-			if (!MR && EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
-#ifndef STAPLE_DEBUG_NO_PEER_STORES      // timing experiments only (wrong halos): never defined in a release build
-			if (MR && peer != nullptr) peer[c * a.vol3h + t] = o;        // NVLink store into the neighbour's staging slot
-#endif
-		}
-	}
-	if (MR) {
-		__syncthreads();              // every thread's stores are issued and its read of the exchange counter is done
-		if (threadIdx.x == 0) {
-			if (peer_flag != nullptr) chunk_signal(peer_flag, cur + 1);
 			if (a.launch_ticket != nullptr) {
-				__threadfence();
-				if (atomicAdd(a.launch_ticket, 1u) == gridDim.x - 1) { *a.launch_ticket = 0u; __threadfence(); *a.seq_rw = cur + 1; }
+				__syncthreads();          // every thread of the block has read the exchange counter
+				if (threadIdx.x == 0) {
+					__threadfence();
+					if (atomicAdd(a.launch_ticket, 1u) == a.nb_top + a.nb_bot + 2 * a.nb_unpack - 1) { *a.launch_ticket = 0u; __threadfence(); *a.seq_rw = cur + 1; }
+				}
 			}
 		}
 	}
-	if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, dot);   // unpack blocks add a zero partial: the count stays gridDim.x
+	if (EPI == EPI_MASS_DOT && a.partials != nullptr) dslash_finish_dot(a, dot);   // blocks without sites add a zero partial: the count stays gridDim.x
 }
 
 unsigned int dslash_blocks(int d3lo, int d3hi)
@@ -584,10 +563,8 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 		const unsigned int nfb = (unsigned int) p.nfb;
 		a.mr = 1;
 		a.seq_rw = p.d_seq; a.parity_stride = (long) (2 * p.slot_bytes / sizeof(C));
-		a.peer_top = (C *) p.stage_R; a.peer_flag_top = p.flags_R;
-		a.peer_bot = (C *) (p.stage_L + p.slot_bytes); a.peer_flag_bot = p.flags_L + p.nfb;
-		a.stage_lo = (const C *) p.stage; a.stage_hi = (const C *) (p.stage + p.slot_bytes);
-		a.flag_lo = p.flags; a.flag_hi = p.flags + p.nfb;
+		a.peer_top = (C *) p.stage_R; a.peer_bot = (C *) (p.stage_L + p.slot_bytes);
+		a.stage_lo = (C *) p.stage; a.stage_hi = (C *) (p.stage + p.slot_bytes);
 		a.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; a.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
 		a.top_lo = (long) (d3hi - 1) * g.vol3h; a.bot_lo = (long) d3lo * g.vol3h;
 		if (face == FACE_TOP) a.nb_top = nfb;                        // single-slice launches of the three-queue form
@@ -656,8 +633,8 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		return;
 	}
 	const unsigned int bs = dslash_blocks(0, 1), bb = dslash_blocks(lo + 1, hi - 1);
-	const unsigned int target = 2 * bs + bb;
 	if (c.p2p.on && c.p2p_single_launch) {
+		const unsigned int target = 2 * bs + bb;
 		// ONE kernel: the face blocks (first in block order) push their chunks into the neighbours' staging slots over NVLink
 		// while the rest of the launch runs; the received halos are either copied into `out` by the last blocks of the same
 		// launch (the API's contract: `out` leaves with valid halos), by a separate kernel, or -- inside the solvers -- left in
@@ -679,6 +656,7 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 	// neighbours' staging slots themselves (compute + transfer in one kernel).  A solver's `skip` flag (set in the same
 	// iteration on every rank, because the all-reduced scalars are bit-identical) silences producers and consumer alike.
 	const bool p2p = c.p2p.on;
+	const unsigned int target = 2 * bs + bb;
 	STAPLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_p, c.ev_fork, 0));
 	STAPLE_CUDA_CHECK(cudaStreamWaitEvent(c.s_m, c.ev_fork, 0));

@@ -133,9 +133,9 @@ __device__ __forceinline__ void cgm_shift_group(cplx_t<T> *out, cplx_t<T> *ps, c
 	}
 }
 
-// D3 slabs with staged halos (hv.on): the two halo slices of s = M^+M p were pushed by the neighbours' Deo face blocks into
-// the local staging area and are consumed from there -- the thread that owns a halo site waits for the flag of its chunk
-// (normally long set: the push happened at the START of the neighbours' Deo) and reads s past L1.  The site order is
+// D3 slabs with staged halos (hv.on): the two halo slices of s = M^+M p were stored by the neighbours' Deo face blocks into
+// the local staging area and are consumed from there -- the thread that owns a halo site takes its three elements as soon
+// as they have arrived (normally long before: the stores happened at the START of the neighbours' Deo).  The site order is
 // rotated by one slice so that the halo slices come LAST in block order.
 template <typename T>
 __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_kernel(CgmCtl *c, cplx_t<T> *out, cplx_t<T> *ps, cplx_t<T> *r,
@@ -163,19 +163,14 @@ __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_ker
 	double nrm = 0.0;
 	if (t < cnt) {
 		long i = lo + t;
-		const cplx_t<T> *sp = s;
-		long sn = n, si = i;
-		bool staged = false;
+		cplx_t<T> *sp = nullptr;             // staged halo site: its s lives in the staging area
+		long si = 0;
 		if (hv.on) {
 			i = t + hv.vol3h < cnt ? i + hv.vol3h : i + hv.vol3h - cnt;        // interior first, then upper halo, then lower halo
-			si = i;
 			const bool lower = i >= hv.lower_lo && i < hv.lower_lo + hv.vol3h, upper = i >= hv.upper_lo && i < hv.upper_lo + hv.vol3h;
 			if (lower || upper) {
-				const unsigned long long cur = *hv.seq;
 				si = i - (lower ? hv.lower_lo : hv.upper_lo);
-				wait_flag_sys((lower ? hv.flag_lo : hv.flag_hi) + si / hv.chunk, cur, 1);
-				sp = (const cplx_t<T> *) ((lower ? hv.stage_lo : hv.stage_hi) + (cur & 1ull) * hv.parity_bytes);
-				sn = hv.vol3h; staged = true;
+				sp = (cplx_t<T> *) ((lower ? hv.stage_lo : hv.stage_hi) + (*hv.seq & 1ull) * hv.parity_bytes);
 			}
 		}
 		cplx_t<T> rv[3];
@@ -183,7 +178,7 @@ __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_ker
 		for (int col = 0; col < 3; col++) {
 			const long j = col * n + i;
 			rv[col] = r[j];
-			const cplx_t<T> sv = staged ? __ldcg(sp + col * sn + si) : sp[col * sn + si];
+			const cplx_t<T> sv = sp != nullptr ? take_staged(sp + col * hv.vol3h + si) : s[j];
 			const cplx_t<T> rn = mkc<T>(rv[col].x + omega * sv.x, rv[col].y + omega * sv.y);
 			r[j] = rn;
 			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;

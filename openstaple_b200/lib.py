@@ -57,6 +57,8 @@ def _declare(L):
     L.staple_init_multidev1D.argtypes = [i, i, vp, i]; L.staple_init_multidev1D.restype = i
     L.staple_myrank.restype = i
     L.staple_enable_p2p.argtypes = [i]; L.staple_enable_p2p.restype = i
+    L.staple_init_loopback.argtypes = [i]; L.staple_init_loopback.restype = i
+    L.staple_set_spin_timeout.argtypes = [d]
     for s in ("", "_f"):
         for f in ("acc_Deo", "acc_Doe", "acc_Deo_unsafe", "acc_Doe_unsafe", "acc_Deo_bulk", "acc_Doe_bulk",
                   "acc_Deo_d3p", "acc_Doe_d3p", "acc_Deo_d3m", "acc_Doe_d3m"):
