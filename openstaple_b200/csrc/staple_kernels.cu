@@ -15,8 +15,14 @@ namespace staple {
 #ifndef STAPLE_DSLASH_MINBLOCKS
 #define STAPLE_DSLASH_MINBLOCKS 7       // 72 registers, 28 warps/SM: +8% over the unconstrained build (profiles/r01_tune_dslash_*.txt)
 #endif
+// segmented (D3-slab) instantiations exist twice: 6 CTAs/SM (80 registers, no spills to speak of) when the launch has bulk
+// slices, 7 CTAs/SM (72 registers, 20-150 B of spills in the face path) when it consists of face slices only -- measured on
+// 2 GPUs (profiles/r02e_halo_probe_n2_sentinel.jsonl): 64^3 x 2 per GPU 55.2 vs 57.2 us, 64^3 x 16 per GPU 328 vs 320 us
 #ifndef STAPLE_DSLASH_MINBLOCKS_MR
-#define STAPLE_DSLASH_MINBLOCKS_MR 6    // segmented (D3-slab) instantiations: 80 registers; at 72 the M^+M epilogue variant spills 160 B per thread
+#define STAPLE_DSLASH_MINBLOCKS_MR 6
+#endif
+#ifndef STAPLE_DSLASH_MINBLOCKS_FACES
+#define STAPLE_DSLASH_MINBLOCKS_FACES 7
 #endif
 #ifndef STAPLE_LINK_LOAD
 #define STAPLE_LINK_LOAD 0       // 0: ld.global.cs (evict-first streaming)  1: ld.global.nc  2: ld.global.lu  3: plain
@@ -483,8 +489,8 @@ __device__ __forceinline__ double dslash_site(const DslashArgs<T> &a, const unsi
 //             [top face][bottom face][bulk][unpack]
 // No block ever waits for another block of the same launch; bulk blocks run exactly the single-GPU code and leave without
 // any tail (a per-block fence + ticket on ~16k bulk blocks was measured to cost 12 % of the launch).
-template <typename T, int PAR, int EPI, bool MR>
-__global__ void __launch_bounds__(kBlock, MR ? STAPLE_DSLASH_MINBLOCKS_MR : STAPLE_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<T> a)
+template <typename T, int PAR, int EPI, bool MR, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T> a)
 {
 	using C = cplx_t<T>;
 	if (a.skip != nullptr && *a.skip != 0) return;
@@ -583,7 +589,10 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 		fprintf(stderr, "libstaple_b200: FATAL: reduction scratch too small (%u + %u partials > %ld)\n", partial_offset, grid, ctx().max_partials);
 		exit(1);
 	}
-#define STAPLE_LAUNCH(P, E) do { if (a.mr) dslash_kernel<T, P, E, true><<<grid, kBlock, 0, s>>>(a); else dslash_kernel<T, P, E, false><<<grid, kBlock, 0, s>>>(a); } while (0)
+#define STAPLE_LAUNCH(P, E) do { \
+		if (!a.mr) dslash_kernel<T, P, E, false, STAPLE_DSLASH_MINBLOCKS><<<grid, kBlock, 0, s>>>(a); \
+		else if (a.nb_bulk != 0) dslash_kernel<T, P, E, true, STAPLE_DSLASH_MINBLOCKS_MR><<<grid, kBlock, 0, s>>>(a); \
+		else dslash_kernel<T, P, E, true, STAPLE_DSLASH_MINBLOCKS_FACES><<<grid, kBlock, 0, s>>>(a); } while (0)
 	// the mass epilogue without the dot product runs the EPI_MASS_DOT instantiation with the reduction switched off
 	// (a.partials == nullptr): one code path less, and that instantiation fits the 72-register budget without spills
 	if (par == 0) {
