@@ -75,14 +75,14 @@ struct RedView {
 	unsigned long long *q;
 	double *box[kMaxRanks];                   // reduction boxes of every rank (parity 0 base)
 };
-// by-value kernel argument: consumer's view of the LOCAL staging area (a vector whose halo slices were stored here by the
-// neighbours but not copied into the vector: "staged" halos)
-struct HaloView {
-	int on;                                   // 0: halos are in the vector itself
-	char *stage_lo, *stage_hi;                // parity-0 bases of slot 0 (lower halo) / slot 1 (upper halo)
-	const unsigned long long *seq;            // exchange counter: the staged halos belong to exchange *seq
+// by-value kernel argument: a kernel other than the operator that produces a vector AND pushes its two interior face slices
+// into the neighbours' staging slots (CG-M: p = r + gamma p)
+struct PushView {
+	int on;
+	char *peer_top, *peer_bot;                // parity-0 staging slot in rank R's (slot 0) / rank L's (slot 1) memory
+	const unsigned long long *seq;            // exchange counter: this kernel produces exchange *seq + 1
 	long parity_bytes;                        // bytes between the parity-0 and parity-1 staging
-	long lower_lo, upper_lo, vol3h;           // first idxh of the lower / upper fermion halo slice
+	long top_lo, bot_lo, vol3h;               // first idxh of the top / bottom interior slice
 };
 
 struct Ctx {
@@ -387,7 +387,7 @@ enum Epilogue { EPI_NONE = 0, EPI_MASS = 1, EPI_MASS_DOT = 2 };
 // halo: HALO_IN_STAGED  the halo slices of `in` are in the staging area (FACE_BOTH* only)
 //       HALO_ADVANCE    the last block of the launch advances the exchange counter
 enum { FACE_NONE = 0, FACE_TOP = 1, FACE_BOTTOM = 2, FACE_BOTH = 3, FACE_BOTH_UNPACK = 4 };
-enum { HALO_EAGER = 0, HALO_OUT_STAGED = 1, HALO_IN_STAGED = 2, HALO_ADVANCE = 4 };
+enum { HALO_EAGER = 0, HALO_OUT_STAGED = 1, HALO_IN_STAGED = 2, HALO_ADVANCE = 4, HALO_NO_PUSH = 8 };
 template <typename T>
 void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									 const cplx_t<T> *in0, double m2, int d3lo, int d3hi, int dot_slot,
@@ -399,18 +399,22 @@ unsigned int dslash_blocks(int d3lo, int d3hi);
 // halo (solvers only; honoured when the peer-memory single-launch transport is active, see halo_lazy_ok()):
 //   HALO_OUT_STAGED  do not copy the received halos into `out`: the next kernel consumes them from the staging area
 //   HALO_IN_STAGED   the halos of `in` are in the staging area (left there by the previous HALO_OUT_STAGED operator)
+//   HALO_NO_PUSH     `out` is not exchanged at all (its halo slices are never read: CG-M's s = M^+M p)
 template <typename T>
 void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, const T *ph,
 									const cplx_t<T> *in0, double m2, int dot_slot, const int *skip, int halo = HALO_EAGER);
 // out = (mass^2+shift) in - Deo Doe in; optionally leaves Re(in.out) (local, not yet all-reduced) in result(dot_slot).
 // The halos of tmp are never unpacked when halo_lazy_ok(); out_staged: nor are those of `out` (CG-M consumes them staged)
+// cgm_interior: CG-M on D3 slabs with staged halos -- the halos of `in` are staged (pushed by the kernel that made it), those
+// of tmp go through the staging area, `out` is not exchanged
 template <typename T>
 void apply_mdagm(const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, cplx_t<T> *tmp, const T *ph,
-								 double m2, int dot_slot, const int *skip, bool out_staged = false, bool tmp_eager = false);
+								 double m2, int dot_slot, const int *skip, bool cgm_interior = false, bool tmp_eager = false);
 void set_spin_timeout_kernels(unsigned long long ns);   // one copy of g_spin_timeout_ns per translation unit
 void set_spin_timeout_solvers(unsigned long long ns);
 bool halo_lazy_ok();                  // peer-memory transport, single-launch operator, lazy halos enabled
-HaloView make_haloview(size_t elem_bytes, bool on);
+PushView make_pushview(bool on);
+void p2p_push_faces(const void *base, size_t elem_bytes, cudaStream_t s);   // push + advance the counter, no unpack
 
 // BLAS-1 (device pointers)
 enum BlasOp {

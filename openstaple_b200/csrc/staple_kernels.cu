@@ -356,18 +356,35 @@ bool halo_lazy_ok()
 	const Ctx &c = ctx();
 	return c.nranks > 1 && c.p2p.on && c.p2p_single_launch && c.p2p_unpack_in_kernel && c.p2p_lazy;
 }
-HaloView make_haloview(size_t elem_bytes, bool on)
+PushView make_pushview(bool on)
 {
 	const Ctx &c = ctx();
 	const Geom &g = c.g;
 	const P2P &p = c.p2p;
-	HaloView h;
-	h.on = on ? 1 : 0;
-	h.stage_lo = p.stage; h.stage_hi = p.stage ? p.stage + p.slot_bytes : nullptr;
-	h.seq = p.d_seq; h.parity_bytes = (long) (2 * p.slot_bytes);
-	h.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; h.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h; h.vol3h = g.vol3h;
-	(void) elem_bytes;
-	return h;
+	PushView v;
+	v.on = on ? 1 : 0;
+	v.peer_top = p.stage_R; v.peer_bot = p.stage_L ? p.stage_L + p.slot_bytes : nullptr;
+	v.seq = p.d_seq; v.parity_bytes = (long) (2 * p.slot_bytes);
+	v.top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h; v.bot_lo = (long) g.d3_halo * g.vol3h; v.vol3h = g.vol3h;
+	return v;
+}
+// both interior faces of a vector into the neighbours' staging slots as a new exchange, without unpacking what arrives here:
+// the next operator consumes it staged
+void p2p_push_faces(const void *base, size_t elem_bytes, cudaStream_t s)
+{
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	P2P &p = c.p2p;
+	const long top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h, bot_lo = (long) g.d3_halo * g.vol3h;
+	if (elem_bytes == 16)
+		p2p_push_kernel<double2><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const double2 *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
+			(unsigned int) p.nfb, (double2 *) p.stage_R, (double2 *) (p.stage_L + p.slot_bytes), (long) (2 * p.slot_bytes / 16), p.d_seq);
+	else
+		p2p_push_kernel<float2><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const float2 *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
+			(unsigned int) p.nfb, (float2 *) p.stage_R, (float2 *) (p.stage_L + p.slot_bytes), (long) (2 * p.slot_bytes / 8), p.d_seq);
+	seq_advance_kernel<<<1, 1, 0, s>>>(p.d_seq);
+	STAPLE_CUDA_CHECK(cudaGetLastError());
+	count_launch(2);
 }
 
 // ------------------------------------------------------------------ Dirac operator kernel
@@ -478,7 +495,7 @@ __device__ __forceinline__ double dslash_site(const DslashArgs<T> &a, const unsi
 		a.out[c * n + idx] = o;
 		if (!FACE && EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
 #ifndef STAPLE_DEBUG_NO_PEER_STORES      // timing experiments only (wrong halos): never defined in a release build
-		if (FACE) peer[(long) c * s3 + t] = stageable(o);     // posted NVLink store into the neighbour's staging slot
+		if (FACE && peer != nullptr) peer[(long) c * s3 + t] = stageable(o);     // posted NVLink store into the neighbour's staging slot
 #endif
 	}
 	return dot;
@@ -513,7 +530,7 @@ __global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T
 				// BOTTOM face: -> rank L's slot 1; staged input: backward neighbour slice = lower halo = local slot 0
 				const bool bot = b >= b2;
 				const unsigned int t = (bot ? b - b2 : b) * kBlock + threadIdx.x;
-				C *peer = (bot ? a.peer_bot : a.peer_top) + ((cur + 1) & 1ull) * a.parity_stride;
+				C *peer = a.peer_top == nullptr ? nullptr : (bot ? a.peer_bot : a.peer_top) + ((cur + 1) & 1ull) * a.parity_stride;
 				C *stage = (bot ? a.stage_lo : a.stage_hi) + (cur & 1ull) * a.parity_stride;
 				if (t < vol3h) dot = dslash_site<T, PAR, EPI, true>(a, (unsigned int) (bot ? a.bot_lo : a.top_lo), t, peer, stage, bot ? 2 : 1, a.in_staged != 0);
 			} else {
@@ -582,6 +599,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 			if (face == FACE_BOTH_UNPACK) a.nb_unpack = unpack_blocks_for(nfb);
 		}
 		a.in_staged = (halo & HALO_IN_STAGED) ? 1 : 0;
+		if (halo & HALO_NO_PUSH) a.peer_top = a.peer_bot = nullptr;
 		if (halo & HALO_ADVANCE) a.launch_ticket = p.tickets + 0;
 		grid = a.nb_top + a.nb_bot + a.nb_bulk + 2 * a.nb_unpack;
 	}
@@ -650,7 +668,9 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		// the staging area for the next kernel to consume.  No stream fork/join, no events, no wait on a block of this launch.
 		const bool lazy = halo_lazy_ok();
 		const int in_staged = lazy ? (halo & HALO_IN_STAGED) : 0;
-		if (lazy && (halo & HALO_OUT_STAGED))
+		if (lazy && (halo & HALO_NO_PUSH))
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, FACE_BOTH, in_staged | HALO_NO_PUSH);
+		else if (lazy && (halo & HALO_OUT_STAGED))
 			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, FACE_BOTH, in_staged | HALO_ADVANCE);
 		else if (c.p2p_unpack_in_kernel)
 			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * unpack_blocks_for(bs), 0, skip, c.stream,
@@ -687,12 +707,13 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 // the neighbours' face blocks to the staging area and from there straight into the d3 hops of the Deo face blocks.
 template <typename T>
 void apply_mdagm(const cplx_t<T> *u, cplx_t<T> *out, const cplx_t<T> *in, cplx_t<T> *tmp, const T *ph,
-								 double m2, int dot_slot, const int *skip, bool out_staged, bool tmp_eager)
+								 double m2, int dot_slot, const int *skip, bool cgm_interior, bool tmp_eager)
 {
 	const bool lazy = halo_lazy_ok() && !tmp_eager;
-	apply_dslash<T>(1, EPI_NONE, u, tmp, in, ph, nullptr, 0.0, -1, skip, lazy ? HALO_OUT_STAGED : HALO_EAGER);
+	const bool interior = lazy && cgm_interior;
+	apply_dslash<T>(1, EPI_NONE, u, tmp, in, ph, nullptr, 0.0, -1, skip, (lazy ? HALO_OUT_STAGED : HALO_EAGER) | (interior ? HALO_IN_STAGED : 0));
 	apply_dslash<T>(0, dot_slot >= 0 ? EPI_MASS_DOT : EPI_MASS, u, out, tmp, ph, in, m2, dot_slot, skip,
-									(lazy ? HALO_IN_STAGED : 0) | (out_staged ? HALO_OUT_STAGED : 0));
+									(lazy ? HALO_IN_STAGED : 0) | (interior ? HALO_NO_PUSH : 0));
 }
 
 template void apply_dslash<double>(int, int, const double2 *, double2 *, const double2 *, const double *,

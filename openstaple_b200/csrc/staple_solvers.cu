@@ -133,15 +133,11 @@ __device__ __forceinline__ void cgm_shift_group(cplx_t<T> *out, cplx_t<T> *ps, c
 	}
 }
 
-// D3 slabs with staged halos (hv.on): the two halo slices of s = M^+M p were stored by the neighbours' Deo face blocks into
-// the local staging area and are consumed from there -- the thread that owns a halo site takes its three elements as soon
-// as they have arrived (normally long before: the stores happened at the START of the neighbours' Deo).  The site order is
-// rotated by one slice so that the halo slices come LAST in block order.
 template <typename T>
 __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_kernel(CgmCtl *c, cplx_t<T> *out, cplx_t<T> *ps, cplx_t<T> *r,
 																																const cplx_t<T> *s, long lo, long cnt, long n, long r0_lo,
 																																long r0_hi, double *partials, unsigned int *ticket,
-																																double *result, int fuse_tail, RedView red, HaloView hv)
+																																double *result, int fuse_tail, RedView red)
 {
 	if (c->done) return;
 	__shared__ double sm[32];
@@ -162,23 +158,13 @@ __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_ker
 	const long t = (long) blockIdx.x * kCgmBlock + threadIdx.x;
 	double nrm = 0.0;
 	if (t < cnt) {
-		long i = lo + t;
-		cplx_t<T> *sp = nullptr;             // staged halo site: its s lives in the staging area
-		long si = 0;
-		if (hv.on) {
-			i = t + hv.vol3h < cnt ? i + hv.vol3h : i + hv.vol3h - cnt;        // interior first, then upper halo, then lower halo
-			const bool lower = i >= hv.lower_lo && i < hv.lower_lo + hv.vol3h, upper = i >= hv.upper_lo && i < hv.upper_lo + hv.vol3h;
-			if (lower || upper) {
-				si = i - (lower ? hv.lower_lo : hv.upper_lo);
-				sp = (cplx_t<T> *) ((lower ? hv.stage_lo : hv.stage_hi) + (*hv.seq & 1ull) * hv.parity_bytes);
-			}
-		}
+		const long i = lo + t;
 		cplx_t<T> rv[3];
 #pragma unroll
 		for (int col = 0; col < 3; col++) {
 			const long j = col * n + i;
 			rv[col] = r[j];
-			const cplx_t<T> sv = sp != nullptr ? take_staged(sp + col * hv.vol3h + si) : s[j];
+			const cplx_t<T> sv = s[j];
 			const cplx_t<T> rn = mkc<T>(rv[col].x + omega * sv.x, rv[col].y + omega * sv.y);
 			r[j] = rn;
 			if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
@@ -219,22 +205,40 @@ __global__ void __launch_bounds__(kCgmBlock, STAPLE_CGM_MINBLOCKS) cgm_fused_ker
 	}
 }
 
-// p = r + gammag p  (:147-148, combine_in1xfactor_plus_in2(loc_p, gammag, loc_r, loc_p)) with gammag on the device
+// p = r + gammag p  (:147-148, combine_in1xfactor_plus_in2(loc_p, gammag, loc_r, loc_p)) with gammag on the device.
+// D3 slabs with staged halos (pv.on): the new p of the two interior face slices is ALSO stored into the neighbours' staging
+// slots -- the exchange that the next iteration's Doe consumes; the solver's vector updates then run over the interior only
+// (the reference keeps halos consistent by updating them redundantly, fermionic_utilities.c:188: at LOC_N3 = 2 that doubles
+// the traffic of every update).
 template <typename T>
 __global__ void __launch_bounds__(kBlasBlock) cgm_pupdate_kernel(const CgmCtl *c, cplx_t<T> *p, const cplx_t<T> *r, long lo,
-																																	long cnt, long n)
+																																	long cnt, long n, PushView pv)
 {
 	if (c->done) return;
 	const double gammag = c->gammag;
 	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
 	if (t >= cnt) return;
+	const long i = lo + t;
+	cplx_t<T> *peer = nullptr;
+	long pi = 0;
+	if (pv.on) {
+		const bool top = i >= pv.top_lo && i < pv.top_lo + pv.vol3h, bot = i >= pv.bot_lo && i < pv.bot_lo + pv.vol3h;
+		if (top || bot) {
+			peer = (cplx_t<T> *) ((top ? pv.peer_top : pv.peer_bot) + ((*pv.seq + 1) & 1ull) * pv.parity_bytes);
+			pi = i - (top ? pv.top_lo : pv.bot_lo);
+		}
+	}
 #pragma unroll
 	for (int col = 0; col < 3; col++) {
-		const long j = col * n + lo + t;
-		const cplx_t<T> pv = p[j], rv = r[j];
-		p[j] = mkc<T>(pv.x * gammag + rv.x, pv.y * gammag + rv.y);
+		const long j = col * n + i;
+		const cplx_t<T> pv_ = p[j], rv = r[j];
+		const cplx_t<T> pn = mkc<T>(pv_.x * gammag + rv.x, pv_.y * gammag + rv.y);
+		p[j] = pn;
+		if (peer != nullptr) peer[col * pv.vol3h + pi] = stageable(pn);
 	}
 }
+// the exchange counter after a pushing p update (one thread; silenced by `done` like the update itself)
+__global__ void cgm_seq_advance_kernel(const CgmCtl *c, unsigned long long *seq) { if (!c->done) *seq = *seq + 1; }
 
 // ps_i = in for all i (the order assign_in_to_out calls of :89-95 in one pass)
 template <typename T>
@@ -303,7 +307,6 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	const double m2 = pars->ferm_mass * pars->ferm_mass;
 	const long n = g.sizeh, lo = g.r1_lo, cnt = g.r1_hi - g.r1_lo;
 	const unsigned int grid = (unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock);
-	const unsigned int grid_f = (unsigned int) ((cnt + kCgmBlock - 1) / kCgmBlock);
 	cudaStream_t st = c.stream;
 
 	// trial solution out = 0 (all sizeh, :67-70); r = p = in; delta = (r,r); source_norm = (in,in)
@@ -338,29 +341,35 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	// whose grid reduction feeds them (Deo -> alpha, shifted pass -> lambda): 4 launches per iteration.  With NCCL
 	// all-reduces the sum is a library call between producer and consumer: 6 launches + 2 collectives.
 	const bool fuse_tail = (c.nranks == 1 || fuse_red) && c.cgm_fuse_tail;
-	// D3 slabs over peer memory: neither h = Doe p nor s = M^+M p ever get their halo slices written -- the Deo face blocks and
-	// the halo threads of the shifted pass consume them from the staging area (no unpack, no wait inside the producing launch)
-	const bool s_staged = halo_lazy_ok();
-	const HaloView hv = make_haloview(sizeof(cplx_t<T>), s_staged);
+	// D3 slabs over peer memory: per iteration two exchanges, both consumed from the staging area by the d3 hops of the next
+	// operator's face blocks (no unpack, no wait inside the producing launch): p (pushed by the kernel that updates it) and
+	// h = Doe p.  s = M^+M p is not exchanged at all.
+	const bool interior = halo_lazy_ok();
+	const PushView pv = make_pushview(interior);
+	// vector updates: the reference's range R1 (interior + one halo slice each side) -- or, with staged halos, the interior only
+	const long ulo = interior ? g.r0_lo : lo, ucnt = interior ? g.r0_hi - g.r0_lo : cnt;
+	const unsigned int ugrid = (unsigned int) ((ucnt + kBlasBlock - 1) / kBlasBlock), ugrid_f = (unsigned int) ((ucnt + kCgmBlock - 1) / kCgmBlock);
+	if (interior) p2p_push_faces(loc_p, sizeof(cplx_t<T>), st);      // the first Doe consumes the halos of p staged, like every other
 	auto enqueue_batch = [&]() {
 		if (fuse_tail) { c.cgm_hook = g_d_ctl; c.cgm_hook_red = red; }
 		for (int b = 0; b < batch; b++) {
 			// s = (M^+M) p, alpha = Re(p,s) fused in the Deo epilogue (:113-118)
-			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done, s_staged);
+			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_ctl->done, interior);
 			if (!fuse_tail) {
 				if (!fuse_red) allreduce_results(SLOT_ALPHA, 1, st);
 				cgm_after_alpha_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_ALPHA), red);
 				count_launch();
 			}
-			cgm_fused_kernel<T><<<grid_f, kCgmBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, lo, cnt, n, g.r0_lo,
-																											 g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
-																											 result(SLOT_LAMBDA), fuse_tail ? 1 : 0, red, hv);
+			cgm_fused_kernel<T><<<ugrid_f, kCgmBlock, 0, st>>>(g_d_ctl, out, shiftferm, loc_r, loc_s, ulo, ucnt, n, g.r0_lo,
+																												g.r0_hi, partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA),
+																												result(SLOT_LAMBDA), fuse_tail ? 1 : 0, red);
 			if (!fuse_tail) {
 				if (!fuse_red) allreduce_results(SLOT_LAMBDA, 1, st);
 				cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA), red);
 				count_launch();
 			}
-			cgm_pupdate_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, lo, cnt, n);
+			cgm_pupdate_kernel<T><<<ugrid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, ulo, ucnt, n, pv);
+			if (interior) { cgm_seq_advance_kernel<<<1, 1, 0, st>>>(g_d_ctl, c.p2p.d_seq); count_launch(); }
 			count_launch(2);
 		}
 		c.cgm_hook = nullptr;
@@ -424,6 +433,9 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 		printf("Terminated multishift_invert ( target res = %1.1e,source_norm = %1.1e )\tCG count %d\n", residuo,
 					 source_norm, cg);
 
+	// interior-only updates: the solutions leave with valid halos all the same (the reference's do, through its updates over R1)
+	if (interior)
+		for (int i = 0; i < order; i++) p2p_exchange_fermion(out + (long) i * 3 * n, sizeof(cplx_t<T>), st);
 	// post-loop verification of every shifted system (:211-229)
 	int check = 1;
 	if (verbosity_lv > 2 && 0 == c.myrank) printf("Relative Res:");
