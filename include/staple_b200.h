@@ -183,6 +183,10 @@ void staple_set_use_graphs(int on);
 /* CG-M: run the scalar recurrences (ref: inverter_multishift_full.c:122-137, :143-171) in the tail of the kernel whose
  * grid reduction produces alpha / lambda (default on; 0 = one-warp kernels of their own, for A/B comparisons). */
 void staple_set_cgm_fuse_tail(int on);
+/* ker_invert_openacc / inverter_mixed_precision: iteration loop on the device (control block, recurrences in the tails of the
+ * reduction kernels, CUDA-graph batches; default on), or 0 = scalars read back by the host twice per iteration (A/B comparisons;
+ * also what runs when the sums over ranks go through NCCL instead of the peer mailboxes). */
+void staple_set_cg_device_loops(int on);
 void *staple_get_stream(void);
 void staple_synchronize(void);
 /* number of CUDA kernels launched by this library since start (bench.py "gpu_launches") */
@@ -371,6 +375,9 @@ int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalA
 int inverter_wrapper(inverter_package ip, ferm_param *pars, vec3_soa *out, const vec3_soa *in, double res,
 										 int max_cg, double shift, int convergence_importance);
 void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f);
+/* The wrapper's return value follows the reference literally, stale counter included (inverter_wrappers.c:88-95: it adds the
+ * FP32 multishift count once per shift); this is the number of refinement iterations the last accelerated call really spent. */
+int staple_last_refinement_iterations(void);
 extern vec3_soa_f *aux1_f, *ferm_shiftmulti_acc_f;   /* weak in the library: a host program's own definitions (alloc_vars.c) are used when
                                                         staple_set_sp_globals() was not called */
 

@@ -637,6 +637,9 @@ class Lattice:
         f(ip, C.addressof(pars), float(res), int(max_cg), _addr(in_e), _addr(in_o), _addr(out_e), _addr(out_o),
           _addr(phi_e), _addr(phi_o))
 
+    def last_refinement_iterations(self):
+        return int(self.L.staple_last_refinement_iterations())
+
     def set_sp_globals(self, aux1_f, ferm_shiftmulti_acc_f):
         self._keep.append((aux1_f, ferm_shiftmulti_acc_f))
         self.L.staple_set_sp_globals(_addr(aux1_f), _addr(ferm_shiftmulti_acc_f))

@@ -384,6 +384,7 @@ void staple_set_stream(void *s)
 }
 void staple_set_use_graphs(int on) { ctx().use_graphs = on != 0; }
 void staple_set_cgm_fuse_tail(int on) { ctx().cgm_fuse_tail = on != 0; }
+void staple_set_cg_device_loops(int on) { ctx().cg_device_loops = on != 0; }
 void staple_set_streamed_mode(int mode) { ctx().streamed_mode = mode; }
 void staple_use_library_stream(void)
 {

@@ -36,6 +36,7 @@ constexpr int kResultSlots = 16;        // device scalars produced by reductions
 
 struct Comm;   // NCCL state, staple_core.cu
 struct CgmCtl; // CG-M control block, below
+struct CgCtl;  // CG / mixed-precision CG control block, below
 
 // Peer-memory channels over NVLink (CUDA IPC between the one-process-per-GPU ranks).  Every rank owns ONE
 // shared "mailbox" allocation:
@@ -110,9 +111,11 @@ struct Ctx {
 	bool p2p_lazy = true;            // solvers leave intermediate halos in the staging area and consume them there
 	// set by the CG-M solver around its iteration batches: fuse the after-alpha recurrences into the Deo tail
 	CgmCtl *cgm_hook = nullptr;
+	CgCtl *cg_hook = nullptr;        // same for the single-system CG / mixed-precision CG (cg_after_alpha_warp)
 	void *out_host_hook = nullptr;   // staple_acc_Doe_Deo_streamed: the Deo chunk kernels also store their result in host memory
 	int streamed_mode = 0;           // 0: chunk downloads by the copy engine  1: stores over PCIe from the Deo kernels
 	bool cgm_fuse_tail = true;       // false: one-warp kernels of their own (staple_set_cgm_fuse_tail, A/B tests)
+	bool cg_device_loops = true;     // false: ker_invert_openacc / inverter_mixed_precision read their scalars back every iteration (A/B)
 	RedView cgm_hook_red{};
 	// last multishift statistics
 	int last_iterations = 0;
@@ -330,6 +333,56 @@ __device__ __forceinline__ void cgm_after_lambda_warp(CgmCtl *c, double *lambda_
 }
 #endif
 
+// ---- control block of the restarted CG (inverter_full.c:19-132) and of the mixed-precision CG (inverter_mixedp.c:41-181):
+// the host arrays/scalars of the reference, device resident, advanced by the kernel that completes the reduction they wait for
+struct CgCtl {
+	double alpha, delta, lambda, omega, gammag, source_norm, res;
+	double stop_factor;        // SAFETY_MARGIN: 0.95 (inverter_full.c:17) / 0.9 (inverter_mixedp.c:141)
+	double last_max_res_norm, mixed_delta;     // inverter_mixedp.c:112-114
+	int cg, cg_restarted, restarting_every, max_cg;
+	int done;                  // the iteration loop has ended: every later kernel of the batch is a no-op
+	int mixed;                 // 1: inverter_mixed_precision
+	int touch;                 // mixed: THIS iteration refreshes the residual in double precision ("magic touch")
+	int no_touch;              // = !touch: skip flag of the double-precision kernels of a mixed iteration
+	int touch_next;            // the decision for the next iteration (promoted by the p update, the last kernel of an iteration)
+	int magic_touches;
+};
+
+#ifdef __CUDACC__
+// after alpha = Re(p, s)  (inverter_full.c:82-84, inverter_mixedp.c:104-108): omega, iteration counters
+__device__ __forceinline__ void cg_after_alpha_warp(CgCtl *c, double *alpha_slot, const RedView &red)
+{
+	if (red.nranks > 1) p2p_allreduce_warp(alpha_slot, 1, red);
+	if ((threadIdx.x & 31) == 0) {
+		const double alpha = *(volatile double *) alpha_slot;
+		c->alpha = alpha; c->omega = c->delta / alpha;
+		c->cg += 1; c->cg_restarted += 1;
+	}
+}
+// after lambda = (r, r)  (inverter_full.c:92-100, inverter_mixedp.c:133-141): gammag, delta <- lambda, loop condition; mixed:
+// the "magic touch" decision of the NEXT iteration, which the reference takes at its start from the same delta (:112-114)
+__device__ __forceinline__ void cg_after_lambda_warp(CgCtl *c, double *lambda_slot, const RedView &red)
+{
+	if (red.nranks > 1) p2p_allreduce_warp(lambda_slot, 1, red);
+	if ((threadIdx.x & 31) == 0) {
+		const double lambda = *(volatile double *) lambda_slot;
+		c->lambda = lambda; c->gammag = lambda / c->delta; c->delta = lambda;
+		const bool above = sqrt(lambda / c->source_norm) > c->res * c->stop_factor;
+		const bool more = c->mixed ? c->cg < c->max_cg : c->cg_restarted < c->restarting_every;
+		const int done = (above && more) ? 0 : 1;
+		c->done = done;
+		if (c->mixed) {
+			if (c->touch) c->magic_touches += 1;
+			double lm = c->last_max_res_norm;
+			if (lm < lambda) lm = lambda;
+			const int touch = lambda < c->mixed_delta * lm ? 1 : 0;
+			if (touch) lm = 0.0;
+			c->last_max_res_norm = lm; c->touch_next = touch;
+		}
+	}
+}
+#endif
+
 // ---- precision traits -------------------------------------------------------------------
 template <typename T> struct Prec;
 template <> struct Prec<double> { using cplx = double2; };
@@ -353,6 +406,7 @@ struct DslashArgs {
 	unsigned int partial_offset;  // first partial index of this launch
 	const int *skip;          // device flag: nonzero -> kernel is a no-op (solver overrun)
 	CgmCtl *cgm;              // EPI_MASS_DOT only: the block that completes the alpha sum also advances the CG-M recurrences
+	CgCtl *cg;                // ... or those of the single-system CG
 	RedView cgm_red;
 	long site_lo, nsites;     // idxh range [site_lo, site_lo+nsites) of a plain launch / of the bulk segment
 	int nd0h, nd1, nd2, nd3;

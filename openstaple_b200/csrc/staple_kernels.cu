@@ -395,9 +395,12 @@ __device__ __forceinline__ void dslash_finish_dot(const DslashArgs<T> &a, double
 {
 	double v[1] = { dot };
 	const bool last = grid_sum_finalize<1>(v, a.partials, 0, a.ticket, a.result, a.ticket_target, a.partial_offset + blockIdx.x);
-	if (last && a.cgm != nullptr) {
+	if (last && (a.cgm != nullptr || a.cg != nullptr)) {
 		__syncthreads();
-		if (threadIdx.x < 32) cgm_after_alpha_warp(a.cgm, a.result, a.cgm_red);
+		if (threadIdx.x < 32) {
+			if (a.cgm != nullptr) cgm_after_alpha_warp(a.cgm, a.result, a.cgm_red);
+			else cg_after_alpha_warp(a.cg, a.result, a.cgm_red);
+		}
 	}
 }
 
@@ -576,6 +579,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 	a.result = dot_slot >= 0 ? result(dot_slot) : nullptr;
 	a.ticket_target = ticket_target; a.partial_offset = partial_offset; a.skip = skip;
 	a.cgm = (epi == EPI_MASS_DOT) ? ctx().cgm_hook : nullptr;
+	a.cg = (epi == EPI_MASS_DOT) ? ctx().cg_hook : nullptr;
 	a.cgm_red = ctx().cgm_hook_red;
 	a.site_lo = (long) d3lo * g.vol3h; a.nsites = (long) (d3hi - d3lo) * g.vol3h;
 	a.nd0h = g.nd0h; a.nd1 = g.nd1; a.nd2 = g.nd2; a.nd3 = g.nd3; a.vol3h = g.vol3h; a.sizeh = g.sizeh;

@@ -272,8 +272,10 @@ void set_spin_timeout_solvers(unsigned long long ns)
 	STAPLE_CUDA_CHECK(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns)));
 }
 
+void release_cg_state();
 void release_solver_state()        // staple_shutdown
 {
+	release_cg_state();
 	if (!g_d_ctl) return;
 	cudaFree(g_d_ctl); cudaFreeHost(g_h_ctl);
 	for (int i = 0; i < 2; i++) cudaEventDestroy(g_ev_snap[i]);
@@ -454,10 +456,276 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	return check == 1 ? INVERTER_SUCCESS : INVERTER_FAILURE;
 }
 
-// restarted CG (inverter_full.c:19-132).  Scalars are read back once per iteration here (two
-// reductions); the multishift solver above is the device-resident one.
+// ------------------------------------------------------------------ single-system CG, device resident
+// solution += omega p ; r -= omega s ; lambda = |r|^2 over the reduction range   (inverter_full.c:86-92; inverter_mixedp.c:110,131-133
+// with x = the FP32 accumulator `out`).  In a "touch" iteration of the mixed-precision solver r is not updated here -- it is
+// recomputed in double precision by mp_refresh_kernel, which then also owns the lambda reduction.
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) cg_update_kernel(CgCtl *c, cplx_t<T> *x, cplx_t<T> *r, const cplx_t<T> *p, const cplx_t<T> *s,
+																															 long lo, long cnt, long n, long r0_lo, long r0_hi, double *partials,
+																															 unsigned int *ticket, double *result, RedView red)
+{
+	if (c->done) return;
+	__shared__ double sm[32];
+	__shared__ bool last;
+	const double omega = c->omega;
+	const bool touch = c->touch != 0;
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	double nrm = 0.0;
+	if (t < cnt) {
+		const long i = lo + t;
+#pragma unroll
+		for (int col = 0; col < 3; col++) {
+			const long j = col * n + i;
+			const cplx_t<T> pv = p[j], xv = x[j];
+			x[j] = mkc<T>(pv.x * omega + xv.x, pv.y * omega + xv.y);
+			if (!touch) {
+				const cplx_t<T> sv = s[j], rv = r[j];
+				const cplx_t<T> rn = mkc<T>(sv.x * (-omega) + rv.x, sv.y * (-omega) + rv.y);
+				r[j] = rn;
+				if (i >= r0_lo && i < r0_hi) nrm += (double) rn.x * rn.x + (double) rn.y * rn.y;
+			}
+		}
+	}
+	if (touch) return;
+	block_sum1(nrm, sm);
+	if (threadIdx.x == 0) {
+		partials[blockIdx.x] = nrm;
+		__threadfence();
+		last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (last) {
+		__threadfence();
+		double acc = 0.0;
+		for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) acc += __ldcg(partials + k);
+		block_sum1(acc, sm);
+		if (threadIdx.x == 0) { result[0] = acc; *ticket = 0u; }
+		__syncthreads();
+		if (threadIdx.x < 32) cg_after_lambda_warp(c, result, red);
+	}
+}
+
+// p = r + gammag p  (inverter_full.c:96, inverter_mixedp.c:139)
+template <typename T>
+__global__ void __launch_bounds__(kBlasBlock) cg_pupdate_kernel(CgCtl *c, cplx_t<T> *p, const cplx_t<T> *r, long lo, long cnt, long n)
+{
+	if (c->done) return;
+	const double gammag = c->gammag;
+	// last kernel of an iteration: the magic-touch decision taken in this iteration's lambda tail becomes current (no other block
+	// of this kernel reads it; the kernels that do belong to the next iteration)
+	if (blockIdx.x == 0 && threadIdx.x == 0 && c->mixed) { const int t2 = c->touch_next; c->touch = t2; c->no_touch = t2 ? 0 : 1; }
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (t >= cnt) return;
+#pragma unroll
+	for (int col = 0; col < 3; col++) {
+		const long j = col * n + lo + t;
+		const cplx_t<T> pv = p[j], rv = r[j];
+		p[j] = mkc<T>(pv.x * gammag + rv.x, pv.y * gammag + rv.y);
+	}
+}
+
+// "magic touch", first half (inverter_mixedp.c:115-116, :126): solution += out over the update range, out = 0 everywhere
+__global__ void __launch_bounds__(kBlasBlock) mp_accumulate_kernel(const CgCtl *c, double2 *sol, float2 *out, long r1_lo, long r1_hi, long n)
+{
+	if (c->no_touch) return;
+	const long i = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	if (i >= n) return;
+#pragma unroll
+	for (int col = 0; col < 3; col++) {
+		const long j = col * n + i;
+		if (i >= r1_lo && i < r1_hi) { const float2 o = out[j]; const double2 x = sol[j]; sol[j] = make_double2(x.x + (double) o.x, x.y + (double) o.y); }
+		out[j] = make_float2(0.f, 0.f);
+	}
+}
+// second half (:118-125, :133): d_r = in - d_s ; r_f = (float) d_r ; lambda = |r_f|^2
+__global__ void __launch_bounds__(kBlasBlock) mp_refresh_kernel(CgCtl *c, const double2 *in, const double2 *d_s, double2 *d_r, float2 *r_f,
+																																long lo, long cnt, long n, long r0_lo, long r0_hi, double *partials,
+																																unsigned int *ticket, double *result, RedView red)
+{
+	if (c->no_touch) return;
+	__shared__ double sm[32];
+	__shared__ bool last;
+	const long t = (long) blockIdx.x * kBlasBlock + threadIdx.x;
+	double nrm = 0.0;
+	if (t < cnt) {
+		const long i = lo + t;
+#pragma unroll
+		for (int col = 0; col < 3; col++) {
+			const long j = col * n + i;
+			const double2 a = in[j], b = d_s[j];
+			const double2 d = make_double2(a.x - b.x, a.y - b.y);
+			d_r[j] = d;
+			const float2 f = make_float2((float) d.x, (float) d.y);
+			r_f[j] = f;
+			if (i >= r0_lo && i < r0_hi) nrm += (double) f.x * f.x + (double) f.y * f.y;
+		}
+	}
+	block_sum1(nrm, sm);
+	if (threadIdx.x == 0) {
+		partials[blockIdx.x] = nrm;
+		__threadfence();
+		last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (last) {
+		__threadfence();
+		double acc = 0.0;
+		for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) acc += __ldcg(partials + k);
+		block_sum1(acc, sm);
+		if (threadIdx.x == 0) { result[0] = acc; *ticket = 0u; }
+		__syncthreads();
+		if (threadIdx.x < 32) cg_after_lambda_warp(c, result, red);
+	}
+}
+
+static CgCtl *g_d_cg = nullptr, *g_h_cg = nullptr;     // device block; pinned: [0],[1] snapshots, [2] upload staging
+static cudaEvent_t g_ev_cgsnap[2] = { nullptr, nullptr };
+static void ensure_cg_ctl()
+{
+	if (g_d_cg) return;
+	STAPLE_CUDA_CHECK(cudaMalloc(&g_d_cg, sizeof(CgCtl)));
+	STAPLE_CUDA_CHECK(cudaHostAlloc(&g_h_cg, 3 * sizeof(CgCtl), cudaHostAllocDefault));
+	for (int i = 0; i < 2; i++) STAPLE_CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_cgsnap[i], cudaEventDisableTiming));
+}
+void release_cg_state()
+{
+	if (!g_d_cg) return;
+	cudaFree(g_d_cg); cudaFreeHost(g_h_cg);
+	for (int i = 0; i < 2; i++) cudaEventDestroy(g_ev_cgsnap[i]);
+	g_d_cg = nullptr; g_h_cg = nullptr; g_ev_cgsnap[0] = g_ev_cgsnap[1] = nullptr;
+}
+
+// device-resident iteration loops need the sums over ranks inside the kernels' tails: one rank, or the peer mailboxes
+static bool cg_device_resident()
+{
+	const Ctx &c = ctx();
+	return c.cg_device_loops && (c.nranks == 1 || c.loopback || (c.p2p.on && c.p2p.d_redq != nullptr && c.p2p_single_launch));
+}
+
+// Runs batches of `enqueue_iteration` (captured once into a CUDA graph where the stream allows it) until the device sets
+// `done`; the host looks at a pinned snapshot of the control block of the PREVIOUS batch while the next one runs, so there
+// is no host synchronisation inside the loop.  Returns the final control block.
+template <typename F>
+static CgCtl cg_run_batches(F enqueue_iteration, int max_iterations_hint)
+{
+	Ctx &c = ctx();
+	cudaStream_t st = c.stream;
+	const int batch = 8;
+	auto enqueue_batch = [&]() { for (int b = 0; b < batch; b++) enqueue_iteration(); };
+	cudaGraphExec_t gexec = nullptr;
+	const unsigned long long launches_before = c.launches;
+	unsigned long long launches_per_batch = 0;
+	if (st != nullptr && c.use_graphs) {
+		cudaGraph_t graph = nullptr;
+		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+			enqueue_batch();
+			cudaError_t e = cudaStreamEndCapture(st, &graph);
+			launches_per_batch = c.launches - launches_before;
+			c.launches = launches_before;
+			if (e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+			if (graph) cudaGraphDestroy(graph);
+		}
+		cudaGetLastError();
+	}
+	int issued = 0, snap = 0, pending[2] = { 0, 0 };
+	bool finished = false;
+	while (!finished) {
+		if (gexec) { STAPLE_CUDA_CHECK(cudaGraphLaunch(gexec, st)); c.launches += launches_per_batch; }
+		else enqueue_batch();
+		issued += batch;
+		STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_cg[snap], g_d_cg, sizeof(CgCtl), cudaMemcpyDeviceToHost, st));
+		STAPLE_CUDA_CHECK(cudaEventRecord(g_ev_cgsnap[snap], st));
+		pending[snap] = 1;
+		const int other = snap ^ 1;
+		if (pending[other]) {
+			STAPLE_CUDA_CHECK(cudaEventSynchronize(g_ev_cgsnap[other]));
+			pending[other] = 0;
+			if (g_h_cg[other].done) finished = true;
+		}
+		snap = other;
+	}
+	(void) max_iterations_hint; (void) issued;
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_cg[0], g_d_cg, sizeof(CgCtl), cudaMemcpyDeviceToHost, st));
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (gexec) cudaGraphExecDestroy(gexec);
+	return g_h_cg[0];
+}
+
+static void cg_upload_ctl(const CgCtl &h)
+{
+	g_h_cg[2] = h;
+	STAPLE_CUDA_CHECK(cudaMemcpyAsync(g_d_cg, &g_h_cg[2], sizeof(CgCtl), cudaMemcpyHostToDevice, ctx().stream));
+	STAPLE_CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+}
+
+// restarted CG (inverter_full.c:19-132).  The iteration loop (:78-101) runs on the device: per iteration Doe, Deo (mass term,
+// alpha = Re(p,s) and omega fused), ONE update kernel (solution, r, lambda, gammag, loop condition), p update -- four
+// launches, no host synchronisation; the host only sequences the restarts (:66-77) and the final check (:104-118).
+// With NCCL all-reduces (no peer mailboxes) the sums over ranks are library calls between kernels: cg_impl_hostloop.
+template <typename T>
+static int cg_impl_hostloop(const cplx_t<T> *u, ferm_param *pars, cplx_t<T> *solution, const cplx_t<T> *in, double res,
+														cplx_t<T> *loc_r, cplx_t<T> *loc_h, cplx_t<T> *loc_s, cplx_t<T> *loc_p, const int max_cg,
+														double shift, int *cg_return);
+
 template <typename T>
 static int cg_impl(const cplx_t<T> *u, ferm_param *pars, cplx_t<T> *solution, const cplx_t<T> *in, double res,
+									 cplx_t<T> *loc_r, cplx_t<T> *loc_h, cplx_t<T> *loc_s, cplx_t<T> *loc_p, const int max_cg,
+									 double shift, int *cg_return)
+{
+	if (!cg_device_resident()) return cg_impl_hostloop<T>(u, pars, solution, in, res, loc_r, loc_h, loc_s, loc_p, max_cg, shift, cg_return);
+	Ctx &c = ctx();
+	const Geom &g = c.g;
+	ensure_cg_ctl();
+	const T *ph = PhasesOf<T>::get(pars);
+	const double m2 = pars->ferm_mass * pars->ferm_mass + shift_as_seen<T>(shift);
+	const long n = g.sizeh, lo = g.r1_lo, cnt = g.r1_hi - g.r1_lo;
+	const unsigned int grid = (unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock);
+	cudaStream_t st = c.stream;
+	const bool fuse_red = c.nranks > 1 && !c.loopback;
+	const RedView red = fuse_red ? make_redview() : single_rank_redview();
+	int cg = 0;
+	double lambda = 0;
+	const double source_norm = reduce_global<T>(RED_L2NORM2, in, nullptr).re;
+	do {
+		apply_mdagm<T>(u, loc_s, solution, loc_h, ph, m2, -1, nullptr);
+		blas<T>(OP_IN1_MINUS_IN2, loc_r, in, loc_s, nullptr, 0.0);
+		blas<T>(OP_ASSIGN, loc_p, loc_r, nullptr, nullptr, 0.0);
+		const double delta = reduce_global<T>(RED_L2NORM2, loc_r, nullptr).re;
+		if (verbosity_lv > 3 && 0 == c.myrank) printf("STARTING CG:\nCG\tR\n");
+		CgCtl h;
+		memset(&h, 0, sizeof(h));
+		h.delta = delta; h.source_norm = source_norm; h.res = res; h.stop_factor = kSafetyMargin;
+		h.cg = cg; h.cg_restarted = 0; h.restarting_every = inverter_tricks.restartingEvery; h.max_cg = max_cg;
+		h.no_touch = 1;
+		cg_upload_ctl(h);
+		const CgCtl f = cg_run_batches([&]() {
+			c.cg_hook = g_d_cg; c.cgm_hook_red = red;
+			apply_mdagm<T>(u, loc_s, loc_p, loc_h, ph, m2, SLOT_ALPHA, &g_d_cg->done);
+			c.cg_hook = nullptr;
+			cg_update_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_cg, solution, loc_r, loc_p, loc_s, lo, cnt, n, g.r0_lo, g.r0_hi,
+																											 partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA), result(SLOT_LAMBDA), red);
+			cg_pupdate_kernel<T><<<grid, kBlasBlock, 0, st>>>(g_d_cg, loc_p, loc_r, lo, cnt, n);
+			count_launch(2);
+		}, max_cg);
+		cg = f.cg; lambda = f.lambda;
+	} while ((sqrt(lambda / source_norm) > res) && cg < max_cg);
+
+	apply_mdagm<T>(u, loc_s, solution, loc_h, ph, m2, -1, nullptr);
+	blas<T>(OP_IN1_MINUS_IN2, loc_h, in, loc_s, nullptr, 0.0);
+	const double current_res = reduce_global<T>(RED_L2NORM2, loc_h, nullptr).re / source_norm;
+	if (verbosity_lv > 1 && 0 == c.myrank) {
+		printf("Terminated invert after   %d    iterations", cg);
+		printf("[res/stop_res=  %e , stop_res=%e ]\n", sqrt(current_res) / res, res);
+	}
+	if (cg == max_cg && 0 == c.myrank) printf("WARNING: maximum number of iterations reached in invert\n");
+	*cg_return = cg;
+	return sqrt(current_res) <= res ? INVERTER_SUCCESS : INVERTER_FAILURE;
+}
+
+// host-driven form: scalars are read back twice per iteration
+template <typename T>
+static int cg_impl_hostloop(const cplx_t<T> *u, ferm_param *pars, cplx_t<T> *solution, const cplx_t<T> *in, double res,
 									 cplx_t<T> *loc_r, cplx_t<T> *loc_h, cplx_t<T> *loc_s, cplx_t<T> *loc_p, const int max_cg,
 									 double shift, int *cg_return)
 {
@@ -511,6 +779,7 @@ using namespace staple;
 #define CDF(p) ((const float2 *) dev(p, #p))
 
 static vec3_soa_f *g_aux1_f = nullptr, *g_ferm_shiftmulti_acc_f = nullptr;   // staple_set_sp_globals
+static int g_last_refinement_iterations = 0;
 extern "C" {
 __attribute__((weak)) vec3_soa_f *aux1_f = nullptr;                  // alloc_vars.h globals; the host program's definitions win
 __attribute__((weak)) vec3_soa_f *ferm_shiftmulti_acc_f = nullptr;
@@ -570,6 +839,61 @@ int inverter_mixed_precision(inverter_package ip, ferm_param *pars, vec3_soa *so
 	int cg = 0, magicTouchCount = 0;
 	double delta, alpha, lambda, omega, gammag, lastMaxResNorm = 0;
 	const double source_norm = reduce_global<double>(RED_L2NORM2, in, nullptr).re;
+	if (cg_device_resident()) {
+		// The iteration loop (:99-141) on the device: FP32 Doe, Deo (alpha, omega fused), one update kernel (out, r, lambda, gammag,
+		// loop condition and the magic-touch decision for the next iteration), p update; the double-precision kernels of a magic touch
+		// (solution += out, M^+M solution, r = in - s in FP64 -> FP32) are part of every iteration and return at once unless the
+		// control block says "touch".  No host synchronisation inside the loop.
+		const Geom &g = c.g;
+		ensure_cg_ctl();
+		const long lo = g.r1_lo, cnt = g.r1_hi - g.r1_lo;
+		const unsigned int grid = (unsigned int) ((cnt + kBlasBlock - 1) / kBlasBlock), grid_all = (unsigned int) ((n + kBlasBlock - 1) / kBlasBlock);
+		cudaStream_t st = c.stream;
+		const bool fuse_red = c.nranks > 1 && !c.loopback;
+		const RedView red = fuse_red ? make_redview() : single_rank_redview();
+		apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, nullptr);
+		blas<double>(OP_IN1_MINUS_IN2, d_r, in, d_s, nullptr, 0.0);
+		convert_double_to_float_vec3_soa((const vec3_soa *) d_r, (vec3_soa_f *) loc_r);
+		blas<float>(OP_ASSIGN, loc_p, loc_r, nullptr, nullptr, 0.0);
+		delta = reduce_global<float>(RED_L2NORM2, loc_r, nullptr).re;
+		blas<float>(OP_ZERO, out, nullptr, nullptr, nullptr, 0.0);
+		if (verbosity_lv > 3 && 0 == c.myrank) printf("STARTING CG:\nCG\tR - mixed precision\n");
+		CgCtl h;
+		memset(&h, 0, sizeof(h));
+		h.delta = delta; h.source_norm = source_norm; h.res = res; h.stop_factor = 0.9; h.mixed = 1;
+		h.mixed_delta = inverter_tricks.mixedPrecisionDelta; h.max_cg = max_cg; h.restarting_every = 0;
+		// the decision of the FIRST iteration (:112-114 with lastMaxResNorm = 0): lastMaxResNorm <- delta, touch iff delta < mpd * delta
+		h.last_max_res_norm = delta; h.touch = delta < h.mixed_delta * delta ? 1 : 0;
+		if (h.touch) h.last_max_res_norm = 0.0;
+		h.no_touch = h.touch ? 0 : 1;
+		cg_upload_ctl(h);
+		const CgCtl f = cg_run_batches([&]() {
+			c.cg_hook = g_d_cg; c.cgm_hook_red = red;
+			apply_mdagm<float>(u_f, loc_s, loc_p, loc_h, ph_f, m2_f, SLOT_ALPHA, &g_d_cg->done);
+			c.cg_hook = nullptr;
+			cg_update_kernel<float><<<grid, kBlasBlock, 0, st>>>(g_d_cg, out, loc_r, loc_p, loc_s, lo, cnt, n, g.r0_lo, g.r0_hi,
+																													 partials(SLOT_LAMBDA), ticket(SLOT_LAMBDA), result(SLOT_LAMBDA), red);
+			mp_accumulate_kernel<<<grid_all, kBlasBlock, 0, st>>>(g_d_cg, solution, out, g.r1_lo, g.r1_hi, n);
+			count_launch(2);
+			apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, &g_d_cg->no_touch);
+			mp_refresh_kernel<<<grid, kBlasBlock, 0, st>>>(g_d_cg, in, d_s, d_r, loc_r, lo, cnt, n, g.r0_lo, g.r0_hi, partials(SLOT_LAMBDA),
+																										 ticket(SLOT_LAMBDA), result(SLOT_LAMBDA), red);
+			cg_pupdate_kernel<float><<<grid, kBlasBlock, 0, st>>>(g_d_cg, loc_p, loc_r, lo, cnt, n);
+			count_launch(2);
+		}, max_cg);
+		cg = f.cg; magicTouchCount = f.magic_touches;
+		combine_add_in2_into_in1_mixed_precision((vec3_soa *) solution, (const vec3_soa_f *) out);
+		apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, nullptr);
+		blas<double>(OP_IN1_MINUS_IN2, d_h, in, d_s, nullptr, 0.0);
+		const double giustoono = reduce_global<double>(RED_L2NORM2, d_h, nullptr).re / source_norm;
+		if (verbosity_lv > 1 && 0 == c.myrank) {
+			printf("Terminated invert after   %d    iterations", cg);
+			printf("[res/stop_res=  %e , stop_res=%e ] (%d magic touches)\n", sqrt(giustoono) / res, res, magicTouchCount);
+		}
+		if (cg == max_cg && 0 == c.myrank) printf("WARNING: maximum number of iterations reached in invert\n");
+		*cg_return = cg;
+		return sqrt(giustoono) <= res ? INVERTER_SUCCESS : INVERTER_FAILURE;
+	}
 
 	apply_mdagm<double>(u, d_s, solution, d_h, ph, m2, -1, nullptr);
 	blas<double>(OP_IN1_MINUS_IN2, d_r, in, d_s, nullptr, 0.0);
@@ -656,6 +980,8 @@ void convergence_messages(int conv_importance, int inverter_status)
 	}
 }
 
+int staple_last_refinement_iterations(void) { return g_last_refinement_iterations; }
+
 void staple_set_sp_globals(vec3_soa_f *aux1_f, vec3_soa_f *ferm_shiftmulti_acc_f)
 {
 	g_aux1_f = aux1_f; g_ferm_shiftmulti_acc_f = ferm_shiftmulti_acc_f;
@@ -702,15 +1028,20 @@ int inverter_multishift_wrapper(inverter_package ip, ferm_param *pars, RationalA
 		convergence_messages(convergence_importance, temp_conv_check);
 		total_iterations += cg_return;
 		const size_t vbytes_f = sizeof(float2) * 3 * ctx().g.sizeh, vbytes_d = sizeof(double2) * 3 * ctx().g.sizeh;
+		g_last_refinement_iterations = 0;
 		for (int ishift = 0; ishift < approx->approx_order; ishift++) {
 			const double bshift = approx->RA_b[ishift];
-			if (verbosity_lv > 0) printf("Shift %d, %f\n", ishift, bshift);
+			printf("Shift %d, %f\n", ishift, bshift);
 			vec3_soa_f *src = (vec3_soa_f *) ((char *) sp_out + ishift * vbytes_f);
 			vec3_soa *dst = (vec3_soa *) ((char *) out + ishift * vbytes_d);
 			convert_float_to_double_vec3_soa(src, dst);
-			// the reference adds the stale cg_return here (inverter_wrappers.c:91-95); the wrapper's own
-			// return value is the meaningful count, so that is what is accumulated
-			total_iterations += inverter_wrapper(ip, pars, dst, in, res, max_cg, bshift, convergence_importance);
+			// literally the reference (inverter_wrappers.c:88-95): inverter_wrapper's return value -- an iteration count -- is what
+			// convergence_messages gets as a status, and the count that is accumulated is the multishift solve's stale cg_return;
+			// the number of refinement iterations actually spent is kept for staple_last_refinement_iterations()
+			temp_conv_check = inverter_wrapper(ip, pars, dst, in, res, max_cg, bshift, convergence_importance);
+			g_last_refinement_iterations += temp_conv_check;
+			convergence_messages(convergence_importance, temp_conv_check);
+			total_iterations += cg_return;
 		}
 	} else {
 		if (0 == ctx().myrank && verbosity_lv > 3) printf("Multishift inverter, DOUBLE precision, target res %e\n", res);

@@ -43,6 +43,7 @@ def _declare(L):
     L.staple_use_library_stream.argtypes = []
     L.staple_set_use_graphs.argtypes = [i]
     L.staple_set_cgm_fuse_tail.argtypes = [i]
+    L.staple_set_cg_device_loops.argtypes = [i]
     L.staple_set_streamed_mode.argtypes = [i]
     L.staple_kernel_launches.restype = C.c_ulonglong
     L.staple_version.restype = C.c_char_p

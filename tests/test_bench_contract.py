@@ -29,7 +29,7 @@ def test_product_line_carries_the_contract():
     assert d["vs_baseline"] is None and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
     r = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.5 < r["frac"] <= 1.05
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.5 < r["frac"] <= 1.12      # the denominator is a measured COPY bandwidth (half reads, half writes); a 95 % read stream can exceed it
     c = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("reference", "port") and c["cores"] >= 1
     e = d["e2e"]
