@@ -348,7 +348,7 @@ class Job:
             self.lat.shutdown_multidev()
 
 
-def parity_windows(job, doe_out, deo_out):
+def parity_windows(job, doe_out, deo_out, single=False):
     """Every rank: Doe(v) and Deo(Doe(v)) of its slab against the CPU oracle on three 8-slice windows of the GLOBAL lattice --
     around its lower boundary (covers the halo slice received from rank L), its middle, and its upper boundary (halo from R).
     The oracle lattice is the window itself (periodic wrap never reaches the compared slices: Doe is valid on window slices
@@ -372,6 +372,8 @@ def parity_windows(job, doe_out, deo_out):
         phw = staggered_phase_slices(np, job.gl[0], job.gl[1], job.gl[2], g3s, gl3)
         uh, vh = uw.cpu().numpy(), vw.cpu().numpy()
         del uw, vw
+        if single:          # FP32 twin: inputs rounded to float, the oracle's float restatement (phases: theta in {0, pi} rounds exactly as the float code computes it)
+            uh, vh, phw = uh.astype(np.complex64), vh.astype(np.complex64), phw.astype(np.float32)
         want_doe = S.dslash("doe", uh, vh, phw, 0, NW)
         want_deo = S.dslash("deo", uh, want_doe, phw, 0, NW)
         for k, g3 in enumerate(g3s):
@@ -697,8 +699,33 @@ def main():
         ms_kernel = job.timeit(lambda: job.lat.acc_Deo_unsafe(job.u, b, a, job.ph), 100, 5)
         o["deo_kernel"] = {"us_per_launch": ms_kernel * 1e3, "achieved_GBps": BYTES_PER_SITE_FP64 * job.interior / ms_kernel / 1e6,
                            "roofline_frac": BYTES_PER_SITE_FP64 * job.interior / ms_kernel / 1e6 / peak}
+        # single-system solvers (the per-shift refinements of the accelerated wrapper, eo_inversion): restarted CG and FP32-inner
+        # mixed-precision CG, iteration loop on the device vs read back by the host every iteration (staple_set_cg_device_loops)
+        lat = job.lat
+        phf = job.ph.to(torch.float32)
+        pars = lat.ferm_param(MASS, job.ph, phf)
+        uf = lat.new_conf(single=True); lat.convert_double_to_float_su3_soa(job.u, uf)
+        ip = osb.InverterPackage()
+        r, h, s, p = (lat.new_vec() for _ in range(4)); rf, hf, sf, pf, of = (lat.new_vec(single=True) for _ in range(5))
+        lat.setup_inverter_package_dp(ip, job.u, lat.new_vec(1), 1, r, h, s, p)
+        lat.setup_inverter_package_sp(ip, uf, lat.new_vec(1, single=True), 1, rf, hf, sf, pf, of)
+        solv = {}
+        for name, mixed in (("cg_fp64", 0), ("cg_mixed", 1)):
+            for dev_loops in (1, 0):
+                lat.L.staple_set_cg_device_loops(dev_loops)
+                lat.set_inverter_tricks(0, mixed, 0.1, 10000)
+                x = lat.new_vec()
+                lat.inverter_wrapper(ip, pars, x, job.v, 1e-2, 20000, 1e-4, osb.CONVERGENCE_NONCRITICAL)      # warm-up
+                x.zero_()
+                job.barrier(); t0 = time.perf_counter(); l0 = lat.kernel_launches()
+                its = lat.inverter_wrapper(ip, pars, x, job.v, RESIDUE, 20000, 1e-4, osb.CONVERGENCE_NONCRITICAL)
+                job.barrier(); wall = time.perf_counter() - t0
+                solv["%s_%s" % (name, "device_loop" if dev_loops else "host_loop")] = {
+                    "s_per_solve": wall, "iterations": its, "ms_per_iteration": wall * 1e3 / max(its, 1), "launches": lat.kernel_launches() - l0}
+        lat.L.staple_set_cg_device_loops(1); lat.set_inverter_tricks(0, 0, 0.1, 10000)
+        o["single_system_solvers"] = solv
         secondary["config1_32x32x32x32"] = o
-        job.close(); del job, a, b
+        job.close(); del job, a, b, uf, r, h, s, p, rf, hf, sf, pf, of
         torch.cuda.empty_cache()
     # ======================================================================== config 5: 64^3 x 16 strong scaling
     if "config5" in sections and CONFIG5[3] % (2 * world) == 0:

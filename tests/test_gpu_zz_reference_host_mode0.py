@@ -5,9 +5,7 @@ shifts for MaxCGIterations iterations (inverter_multishift_test.c:248-267).  Com
 build wrote for the same input (tests/golden/make_ref_host.py).
 
 Tolerance 1e-4: the eigenvalue comes out of a power iteration stopped by a 1e-5 relative criterion; if GPU and CPU rounding
-ever stop it one iteration apart the rescaled shifts move by that much.  Sorted last and xfail(strict=False) on purpose: added at
-the end of round 1 after the GPU budget was spent (its logic is exercised on the pure-reference binary), so the first run on
-the B200 is the driver's -- XPASS is the expected outcome."""
+ever stop it one iteration apart the rescaled shifts move by that much.  (Green on the B200 since the driver's round-1 run.)"""
 import os
 import re
 
@@ -20,7 +18,6 @@ from test_gpu_reference_host import GEOM, HOST_DIR, _exe, _read_vec3_ascii, _run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run of this test is the driver's (see the module docstring); XPASS expected")
 def test_reference_inverter_program_with_measured_spectrum(tmp_path):
     td = str(tmp_path)
     g = dict(np.load(os.path.join(HOST_DIR, "ref_host_results_%s.npz" % GEOM)))

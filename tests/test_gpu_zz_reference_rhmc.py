@@ -11,9 +11,8 @@ Tolerances: the two runs do the same arithmetic up to rounding, but MD solves st
 less in a single solve moves the force by ~1e-5 -- so plaquette / rectangle 1e-5 relative, Delta H 1e-3 absolute, iteration
 counts 2 %.
 
-Status: written at the end of round 1 after the GPU budget was spent; the pure-reference half is exercised on the CPU
-(tests/test_reference_host_cpu.py), the first B200 run of the library-linked half is the driver's.  Hence xfail(strict=False):
-XPASS is the expected outcome, an XFAIL is a finding for the next round, neither hides the other GPU tests (sorted last)."""
+Status: the single-GPU test is green on the B200 since the driver's round-1 run (a plain test now); the pure-reference half is
+exercised on the CPU (tests/test_reference_host_cpu.py)."""
 import json
 import os
 import subprocess
@@ -80,7 +79,6 @@ def compare(got, want):
         assert all(abs(a - b) <= max(2, 0.02 * b) for a, b in zip(got[k], want[k])), (k, got[k], want[k])
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run of this test is the driver's (see the module docstring)")
 def test_reference_rhmc_main_with_the_library(tmp_path):
     want = json.load(open(os.path.join(HOST_DIR, "rhmc_%s.json" % GEOM)))
     r, got = run_main("staple", str(tmp_path))
