@@ -6,7 +6,7 @@ NVLink).  The global result files are compared with the SINGLE-rank pure-referen
 the two GPU ranks saved: FP64 relative 1e-13.
 
 Written at the end of round 1 after the GPU budget was spent (the CPU half, tests/test_reference_host_multirank_cpu.py, runs the
-pure-reference two-rank program through the same launcher): xfail(strict=False) until its first run on a 2-GPU box."""
+pure-reference two-rank program through the same launcher).  First run on 2 x B200 in round 2: green (profiles/r02i_hostprograms_2gpu.log)."""
 import os
 
 import numpy as np
@@ -17,7 +17,6 @@ from test_reference_host_multirank_cpu import FILES, run_single_rank_on_saved_in
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="first multi-GPU run of this test is pending (see the module docstring); XPASS expected")
 def test_two_gpu_reference_deo_doe_program(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:

@@ -90,7 +90,6 @@ def test_reference_rhmc_main_with_the_library(tmp_path):
     compare(got, want)
 
 
-@pytest.mark.xfail(strict=False, reason="first multi-GPU run of this test is pending (see the module docstring); XPASS expected")
 def test_reference_rhmc_main_with_the_library_two_gpus(tmp_path):
     """the same program on two D3 slabs, one process per GPU under oracle/mpi_mini, against the pure-reference two-rank run"""
     import torch
