@@ -344,7 +344,8 @@ struct CgCtl {
 	int mixed;                 // 1: inverter_mixed_precision
 	int touch;                 // mixed: THIS iteration refreshes the residual in double precision ("magic touch")
 	int no_touch;              // = !touch: skip flag of the double-precision kernels of a mixed iteration
-	int touch_next;            // the decision for the next iteration (promoted by the p update, the last kernel of an iteration)
+	int touch_next;            // the decision for the next iteration (taken in the lambda tail, acted upon by cg_promote_kernel)
+	int paused;                // done was set because the next iteration is a magic touch (enqueued by the host), not because the loop ended
 	int magic_touches;
 };
 
