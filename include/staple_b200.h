@@ -200,7 +200,7 @@ int staple_posix_memalign(void **memptr, size_t alignment, size_t size);
 void staple_free(void *memptr);                                   /* ref: memory_wrapper.c:33-57 free_wrapper */
 /* The same choke point with CUDA managed memory (SURVEY 8b option i): ONE address valid on host and device, so a host
  * program built with gcc -- where every `#pragma acc update` is a no-op -- needs no other change than this allocator behind
- * posix_memalign_wrapper and staple_set_blocking(1).  oracle/host_shim.c does exactly that for the reference's own
+ * posix_memalign_wrapper and staple_set_blocking(1).  openstaple_b200/host/memory_wrapper_staple.c does exactly that for the reference's own
  * deo_doe_test / inverter_multishift_test programs (tests/test_gpu_reference_host.py). */
 int staple_posix_memalign_managed(void **memptr, size_t alignment, size_t size);
 /* on != 0: every entry point returns with its device work complete (the reference's OpenACC regions are synchronous);

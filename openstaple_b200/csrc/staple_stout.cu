@@ -28,13 +28,16 @@ template <typename T> __device__ __forceinline__ cplx_t<T> mks(T x, T y);
 template <> __device__ __forceinline__ double2 mks<double>(double x, double y) { return make_double2(x, y); }
 template <> __device__ __forceinline__ float2 mks<float>(float x, float y) { return make_float2(x, y); }
 
-struct StoutGeom { int nd0, nd1, nd2, nd3; unsigned int vol3h; long sizeh; unsigned int lo, cnt; };
+struct StoutGeom { int nd0, nd1, nd2, nd3; unsigned int vol3h; long sizeh; unsigned int lo, cnt; int tlsm; };
 static StoutGeom stout_geom()
 {
 	const Geom &g = ctx().g;
 	StoutGeom s;
 	s.nd0 = g.nd0; s.nd1 = g.nd1; s.nd2 = g.nd2; s.nd3 = g.nd3; s.vol3h = (unsigned int) g.vol3h; s.sizeh = g.sizeh;
 	s.lo = (unsigned int) (g.d3_halo * g.vol3h); s.cnt = (unsigned int) (g.loc_n3 * g.vol3h);
+	// the gauge action is a compile-time choice of the reference that also fixes HALO_WIDTH (geometry_multidev.h:6-12: 2 for
+	// ACTION_TYPE TLSM, 1 for WILSON) and C_ZERO (common_defines.h:70-85: 5/3 or 1): the run-time halo_width carries it here
+	s.tlsm = g.halo_width == 2 ? 1 : 0;
 	return s;
 }
 
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kStoutBlock, 3) stout_staples_kernel(const cpl
 	const int d2 = q % g.nd2;
 	const int d3 = q / g.nd2;
 	const int nd[4] = { g.nd0, g.nd1, g.nd2, g.nd3 };
-	const T c_zero = (T) 5.0 * (T) 0.33333333333333333333333;   // C_ZERO, ACTION_TYPE TLSM (common_defines.h:73)
+	const T c_zero = g.tlsm ? (T) 5.0 * (T) 0.33333333333333333333333 : (T) 1.0;   // C_ZERO (common_defines.h:73, :82)
 	// all eight links of this half-lattice index (both parities, four directions) in ONE thread: the 8 x 18 link
 	// reads around the two sites then hit L1/L2 while they are hot.  With the link index on grid.y instead, each
 	// of the eight sweeps re-streamed most of the configuration from HBM (ncu: 3.3 GB read for 0.4 GB of links).
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kStoutBlock) stout_rho_ta_kernel(const cplx_t<
 			acc.x += b1.x; acc.y += b1.y; acc.x += b2.x; acc.y += b2.y;
 			pr[r][c] = acc;
 		}
-	const T c_zero = (T) 5.0 * (T) 0.33333333333333333333333;
+	const T c_zero = g.tlsm ? (T) 5.0 * (T) 0.33333333333333333333333 : (T) 1.0;
 	store_ta<T, true>(ta + (long) k * 8 * n, n, idx, pr, rho / c_zero);
 }
 

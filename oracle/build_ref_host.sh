@@ -5,7 +5,7 @@
 #   oracle/_ref/<prog>_ref_<geom>     every source of the reference (its gcc recipe: OpenACC pragmas ignored, CPU)
 #   oracle/_ref/<prog>_staple_<geom>  the same main and host code, with the object files of the subsystems libstaple_b200.so
 #                                     replaces LEFT OUT and the library linked instead; the only
-#                                     source that is not the reference's is oracle/host_shim.c, which stands in for
+#                                     source that is not the reference's is openstaple_b200/host/memory_wrapper_staple.c, which stands in for
 #                                     Include/memory_wrapper.c (the allocation choke point)
 # The second binary is the drop-in claim made executable: the reference's host program, its parser, generators and file
 # writers, running its hot path on the B200 through the C ABI.  Both travel to the GPU box as binaries (oracle/_ref is
@@ -28,7 +28,7 @@ LIBDIR=$(cd "$HERE/../openstaple_b200" && pwd)
 [ -f "$LIBDIR/libstaple_b200.so" ] || { echo "build libstaple_b200.so first"; exit 1; }
 PROGLIST=${PROGS:-deo_doe_test inverter_multishift_test main}
 STAMP="$HERE/_ref/${PROGLIST##* }_staple_$GEOM"          # the program linked last
-if [ -f "$STAMP" ] && [ "$STAMP" -nt "$MPISRC" ] && [ "$STAMP" -nt "$HERE/host_shim.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
+if [ -f "$STAMP" ] && [ "$STAMP" -nt "$MPISRC" ] && [ "$STAMP" -nt "$HERE/../openstaple_b200/host/memory_wrapper_staple.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 T=8
@@ -68,7 +68,7 @@ for f in $COMMON tests_and_benchmarks/deo_doe_test tests_and_benchmarks/inverter
   gcc $CF -c "$SCR/src/$f.c" -o "$OBJ/$(echo $f | tr / _).o" & pids+=($!)
 done
 gcc -O2 -std=gnu99 -w -I"$MPIDIR" -c "$MPISRC" -o "$OBJ/mpi_single.o" & pids+=($!)
-gcc -O2 -std=gnu99 -w -I"$MPIDIR" -I"$HERE/../include" -DNRANKS_D3=$NR -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -c "$HERE/host_shim.c" -o "$OBJ/host_shim.o" & pids+=($!)
+gcc -O2 -std=gnu99 -w -I"$MPIDIR" -I"$HERE/../include" -DNRANKS_D3=$NR -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -c "$HERE/../openstaple_b200/host/memory_wrapper_staple.c" -o "$OBJ/host_shim.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 ALL=""; KEPT=""
 REPLACED=" $(echo $REPLACED) "     # one space between names, whatever the line breaks above

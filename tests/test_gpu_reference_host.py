@@ -1,7 +1,7 @@
 """The drop-in claim, executed: the reference's OWN test programs -- src/tests_and_benchmarks/deo_doe_test.c and
 inverter_multishift_test.c, unmodified, with the reference's parser, dSFMT generators, U(1) phase code and file writers --
 linked against libstaple_b200.so in place of the object files of the subsystems it replaces (oracle/build_ref_host.sh; the
-only foreign source is oracle/host_shim.c standing in for Include/memory_wrapper.c).  They run on the B200 with the input
+only foreign source is openstaple_b200/host/memory_wrapper_staple.c standing in for Include/memory_wrapper.c).  They run on the B200 with the input
 file the pure-reference CPU build was run with in the dev container (tests/golden/make_ref_host.py), and the files they
 write are compared with the files that build wrote:
 

@@ -1,6 +1,6 @@
 """Multi-GPU drop-in, executed (needs 2 GPUs; skipped otherwise): the reference's deo_doe_test built for NRANKS_D3 = 2 and
 linked against libstaple_b200.so runs as two processes, one per GPU, under oracle/mpi_mini -- the reference's own MPI code
-scatters the configuration and gathers the results through rank 0, oracle/host_shim.c hands the NCCL id around with MPI_Bcast
+scatters the configuration and gathers the results through rank 0, openstaple_b200/host/memory_wrapper_staple.c hands the NCCL id around with MPI_Bcast
 and calls staple_init_multidev1D, the operator and its halo exchange run in the library (NCCL over
 NVLink).  The global result files are compared with the SINGLE-rank pure-reference build reading the configuration and source
 the two GPU ranks saved: FP64 relative 1e-13.
