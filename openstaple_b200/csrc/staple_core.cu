@@ -219,7 +219,7 @@ static void fill_geom(Geom &g, int n0, int n1, int n2, int n3, int nranks_d3, in
 	g.r1_hi = g.sizeh - g.r1_lo;
 }
 
-// the peer-memory mailbox belongs to ONE geometry (staging slots and chunk flags are sized by vol3h): collective release
+// the peer-memory mailbox belongs to ONE geometry (staging slots are sized by vol3h): collective release
 static void release_p2p()
 {
 	Ctx &c = ctx();
@@ -232,11 +232,11 @@ static void release_p2p()
 	}
 	for (int r = 0; r < c.nranks && !c.loopback; r++)
 		if (r != c.myrank && c.p2p.peer_mailbox[r]) cudaIpcCloseMemHandle(c.p2p.peer_mailbox[r]);
-	cudaFree(c.p2p.mailbox); cudaFree(c.p2p.tickets); cudaFree(c.p2p.d_seq);
+	cudaFree(c.p2p.mailbox); cudaFree(c.p2p.d_redq);
 	c.p2p = P2P();
 }
 
-// local part of the peer-memory set-up: mailbox (reduction boxes, staging), tickets, counters.  Every word of the mailbox
+// local part of the peer-memory set-up: mailbox (reduction boxes, staging) and the reduction counter.  Every word of the mailbox
 // starts at the resting pattern (all ones): "nothing has arrived"
 static void p2p_alloc_local()
 {
@@ -249,11 +249,9 @@ static void p2p_alloc_local()
 	const size_t mb_bytes = kMailboxHeader + 4 * p.slot_bytes;
 	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.mailbox, mb_bytes));
 	STAPLE_CUDA_CHECK(cudaMemset(p.mailbox, 0xFF, mb_bytes));
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.tickets, 4 * sizeof(unsigned int)));
-	STAPLE_CUDA_CHECK(cudaMemset(p.tickets, 0, 4 * sizeof(unsigned int)));
-	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.d_seq, 2 * sizeof(unsigned long long)));
-	STAPLE_CUDA_CHECK(cudaMemset(p.d_seq, 0, 2 * sizeof(unsigned long long)));
-	p.d_redq = p.d_seq + 1;
+	STAPLE_CUDA_CHECK(cudaMalloc((void **) &p.d_redq, sizeof(unsigned long long)));
+	STAPLE_CUDA_CHECK(cudaMemset(p.d_redq, 0, sizeof(unsigned long long)));
+	p.h_seq = 0;
 	STAPLE_CUDA_CHECK(cudaDeviceSynchronize());
 }
 static void p2p_bind_neighbours()
@@ -583,7 +581,7 @@ int staple_enable_p2p(int on)
 											 "reductions stay on NCCL\n", c.myrank, cudaGetErrorString(err));
 			for (int r = 0; r < c.nranks; r++)
 				if (r != c.myrank && p.peer_mailbox[r]) cudaIpcCloseMemHandle(p.peer_mailbox[r]);
-			cudaFree(p.mailbox); cudaFree(p.tickets); cudaFree(p.d_seq);
+			cudaFree(p.mailbox); cudaFree(p.d_redq);
 			p = P2P();
 			return 0;
 		}

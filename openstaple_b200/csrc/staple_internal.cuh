@@ -51,8 +51,11 @@ struct CgCtl;  // CG / mixed-precision CG control block, below
 // (profiles/r02c_halo_probe_*.jsonl, r02d_*): one fence.sys after remote stores costs 7-15 us on B200/NVSwitch, whoever
 // issues it; with per-chunk flags that was 25-30 us per operator launch.  Exchange number s uses staging parity s&1: the
 // neighbour may already deliver exchange s+1 while exchange s is being consumed here, never s+2 (it needs our s+1 first).
-// The sequence numbers live in DEVICE memory (d_seq, d_redq) and are advanced by kernels, so a captured CUDA graph of
-// solver iterations replays correctly.
+// The exchange number is a HOST counter handed to the kernels by value (only its parity matters on the device): no device
+// counter to read, no ticket to decide who advances it, no kernel tail.  A captured CUDA graph freezes the parities of its
+// launches, which is consistent as long as it contains an EVEN number of exchanges (every solver batch does: two per
+// iteration; checked at capture) and is replayed from the parity it was captured at.  The reduction counter d_redq stays on
+// the device (one warp per reduction).
 constexpr int kMaxRanks = 16;
 constexpr size_t kMailboxRedBox = 64, kMailboxHeader = 1024;
 constexpr unsigned long long kSentinel64 = 0xFFFFFFFFFFFFFFFFull;
@@ -63,9 +66,8 @@ struct P2P {
 	char *peer_mailbox[kMaxRanks] = {};       // every rank's mailbox as mapped here ([myrank] = local)
 	char *stage = nullptr;                    // local staging = mailbox + kMailboxHeader
 	char *stage_L = nullptr, *stage_R = nullptr;
-	unsigned int *tickets = nullptr;          // local [4]: [0] launch ticket of the operator, [2] unpack kernel
-	unsigned long long *d_seq = nullptr;      // local: number of completed halo exchanges
-	unsigned long long *d_redq = nullptr;     // local: number of completed reductions
+	unsigned long long h_seq = 0;             // number of halo exchanges ENQUEUED so far (same on every rank: same call sequence)
+	unsigned long long *d_redq = nullptr;     // local, device: number of completed reductions
 	size_t slot_bytes = 0;                    // 3 * vol3h * 16
 	long nfb = 0;                             // operator CTAs per face slice
 	long vol3h = 0;                           // the geometry the mailbox was built for
@@ -81,7 +83,7 @@ struct RedView {
 struct PushView {
 	int on;
 	char *peer_top, *peer_bot;                // parity-0 staging slot in rank R's (slot 0) / rank L's (slot 1) memory
-	const unsigned long long *seq;            // exchange counter: this kernel produces exchange *seq + 1
+	unsigned long long seq;                   // the exchange this kernel produces
 	long parity_bytes;                        // bytes between the parity-0 and parity-1 staging
 	long top_lo, bot_lo, vol3h;               // first idxh of the top / bottom interior slice
 };
@@ -422,8 +424,7 @@ struct DslashArgs {
 	long top_lo, bot_lo;                         // first idxh of the two surface slices
 	cplx_t<T> *peer_top, *peer_bot;              // parity-0 staging slot in the neighbour's memory
 	long parity_stride;                          // elements between the parity-0 and parity-1 staging areas
-	unsigned long long *seq_rw;                  // device counter of completed exchanges; this launch produces *seq_rw + 1
-	unsigned int *launch_ticket;                 // non-null: the last face/unpack block of the launch advances the counter
+	unsigned long long cur;                      // exchanges enqueued before this launch: it consumes `cur` (staged input) and produces cur + 1
 	// consumer side: the halo slices of `in` were left in the local staging area by exchange *seq_rw (in_staged), and/or
 	// the staged halos of the exchange this launch produces are copied into `out` by the unpack blocks
 	int in_staged;
@@ -440,7 +441,7 @@ enum Epilogue { EPI_NONE = 0, EPI_MASS = 1, EPI_MASS_DOT = 2 };
 //       FACE_BOTH   whole local interior in one segmented launch, both faces pushed
 //       FACE_BOTH_UNPACK  ... and the staged halos of this exchange copied into `out` by the last blocks of the launch
 // halo: HALO_IN_STAGED  the halo slices of `in` are in the staging area (FACE_BOTH* only)
-//       HALO_ADVANCE    the last block of the launch advances the exchange counter
+//       HALO_ADVANCE    this launch completes an exchange (both faces pushed): the host counter advances
 enum { FACE_NONE = 0, FACE_TOP = 1, FACE_BOTTOM = 2, FACE_BOTH = 3, FACE_BOTH_UNPACK = 4 };
 enum { HALO_EAGER = 0, HALO_OUT_STAGED = 1, HALO_IN_STAGED = 2, HALO_ADVANCE = 4, HALO_NO_PUSH = 8 };
 template <typename T>

@@ -217,9 +217,8 @@ __device__ __forceinline__ bool grid_sum_finalize(double v[NV], double *partials
 template <typename C>
 __global__ void __launch_bounds__(kDslashBlock) p2p_push_kernel(const C *src, long n, long top_lo, long bot_lo, unsigned int vol3h,
 																																 unsigned int nfb, C *peer_top, C *peer_bot, long parity_stride,
-																																 const unsigned long long *seq_ptr)
+																																 const unsigned long long seq)
 {
-	const unsigned long long seq = *seq_ptr + 1;
 	const bool bot = blockIdx.x >= nfb;
 	const unsigned int j = bot ? blockIdx.x - nfb : blockIdx.x, t = j * kDslashBlock + threadIdx.x;
 	C *peer = (bot ? peer_bot : peer_top) + (seq & 1ull) * parity_stride;
@@ -259,28 +258,18 @@ __device__ __noinline__ void unpack_slice(C *dst, long n, C *src, unsigned int v
 	}
 }
 
-// standalone unpack: copy both staging slots of exchange *seq_ptr + 1 into the halo slices as the neighbours' data lands;
-// the last block to finish advances the exchange counter.  grid = 2*nb CTAs of kDslashBlock threads.
+// standalone unpack: copy both staging slots of exchange `seq` into the halo slices as the neighbours' data lands.
+// grid = 2*nb CTAs of kDslashBlock threads.
 template <typename C>
 __global__ void __launch_bounds__(kDslashBlock) p2p_unpack_kernel(C *dst, long n, long lower_lo, long upper_lo, unsigned int vol3h,
-																																	 C *slot0, C *slot1, long parity_stride, unsigned long long *seq_ptr,
-																																	 unsigned int *ticket, const int *skip)
+																																	 C *slot0, C *slot1, long parity_stride, const unsigned long long seq, const int *skip)
 {
 	if (skip != nullptr && *skip != 0) return;       // the producers skipped this exchange too (same flag on every rank)
-	const unsigned long long seq = *seq_ptr + 1;
 	const unsigned int nb = gridDim.x / 2;
 	const bool hi = blockIdx.x >= nb;                // first half of the grid: lower halo, second half: upper
 	unpack_slice<C>(dst + (hi ? upper_lo : lower_lo), n, (hi ? slot1 : slot0) + (seq & 1ull) * parity_stride, vol3h,
 									(hi ? blockIdx.x - nb : blockIdx.x) * kDslashBlock + threadIdx.x, nb * kDslashBlock);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; __threadfence(); *seq_ptr = seq; }
-	}
 }
-
-// the exchange counter, advanced on its own (pipelined host round trip: the two face slices are separate launches)
-__global__ void seq_advance_kernel(unsigned long long *seq) { *seq = *seq + 1; }
 
 // unpack blocks per halo: at most 2 per SM (grid-stride copy with 12 elements in flight per thread).  Thousands of
 // 128-thread blocks only add scheduling time to the tail; 74 were measured too few to cover the HBM latency.
@@ -295,8 +284,9 @@ static void p2p_unpack_t(void *base, cudaStream_t s, const int *skip)
 	const long lower_lo = (long) (g.d3_halo - 1) * g.vol3h, upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
 	const unsigned int nb = unpack_blocks_for((unsigned int) p.nfb);
 	p2p_unpack_kernel<C><<<2 * nb, kDslashBlock, 0, s>>>((C *) base, g.sizeh, lower_lo, upper_lo, (unsigned int) g.vol3h,
-		(C *) p.stage, (C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.d_seq, p.tickets + 2, skip);
+		(C *) p.stage, (C *) (p.stage + p.slot_bytes), (long) (2 * p.slot_bytes / sizeof(C)), p.h_seq + 1, skip);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
+	p.h_seq += 1;                                    // the exchange whose faces were pushed before this call is complete
 	count_launch();
 }
 void p2p_unpack(void *base, size_t elem_bytes, cudaStream_t s, const int *skip)
@@ -315,7 +305,7 @@ static void p2p_exchange_t(void *base, cudaStream_t s)
 	const long ps = (long) (2 * p.slot_bytes / sizeof(C));
 	// top interior slice -> rank R's lower halo (its slot 0); bottom interior slice -> rank L's upper halo (slot 1)
 	p2p_push_kernel<C><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const C *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
-		(unsigned int) p.nfb, (C *) p.stage_R, (C *) (p.stage_L + p.slot_bytes), ps, p.d_seq);
+		(unsigned int) p.nfb, (C *) p.stage_R, (C *) (p.stage_L + p.slot_bytes), ps, p.h_seq + 1);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
 	count_launch();
 	p2p_unpack(base, sizeof(C), s, nullptr);
@@ -364,7 +354,7 @@ PushView make_pushview(bool on)
 	PushView v;
 	v.on = on ? 1 : 0;
 	v.peer_top = p.stage_R; v.peer_bot = p.stage_L ? p.stage_L + p.slot_bytes : nullptr;
-	v.seq = p.d_seq; v.parity_bytes = (long) (2 * p.slot_bytes);
+	v.seq = p.h_seq + 1; v.parity_bytes = (long) (2 * p.slot_bytes);
 	v.top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h; v.bot_lo = (long) g.d3_halo * g.vol3h; v.vol3h = g.vol3h;
 	return v;
 }
@@ -378,13 +368,13 @@ void p2p_push_faces(const void *base, size_t elem_bytes, cudaStream_t s)
 	const long top_lo = (long) (g.d3_halo + g.loc_n3 - 1) * g.vol3h, bot_lo = (long) g.d3_halo * g.vol3h;
 	if (elem_bytes == 16)
 		p2p_push_kernel<double2><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const double2 *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
-			(unsigned int) p.nfb, (double2 *) p.stage_R, (double2 *) (p.stage_L + p.slot_bytes), (long) (2 * p.slot_bytes / 16), p.d_seq);
+			(unsigned int) p.nfb, (double2 *) p.stage_R, (double2 *) (p.stage_L + p.slot_bytes), (long) (2 * p.slot_bytes / 16), p.h_seq + 1);
 	else
 		p2p_push_kernel<float2><<<2 * (unsigned int) p.nfb, kDslashBlock, 0, s>>>((const float2 *) base, g.sizeh, top_lo, bot_lo, (unsigned int) g.vol3h,
-			(unsigned int) p.nfb, (float2 *) p.stage_R, (float2 *) (p.stage_L + p.slot_bytes), (long) (2 * p.slot_bytes / 8), p.d_seq);
-	seq_advance_kernel<<<1, 1, 0, s>>>(p.d_seq);
+			(unsigned int) p.nfb, (float2 *) p.stage_R, (float2 *) (p.stage_L + p.slot_bytes), (long) (2 * p.slot_bytes / 8), p.h_seq + 1);
 	STAPLE_CUDA_CHECK(cudaGetLastError());
-	count_launch(2);
+	p.h_seq += 1;
+	count_launch();
 }
 
 // ------------------------------------------------------------------ Dirac operator kernel
@@ -497,9 +487,7 @@ __device__ __forceinline__ double dslash_site(const DslashArgs<T> &a, const unsi
 		}
 		a.out[c * n + idx] = o;
 		if (!FACE && EPI == EPI_NONE && a.out_host != nullptr) a.out_host[c * n + idx] = o;   // posted PCIe writes, 512 contiguous bytes per warp
-#ifndef STAPLE_DEBUG_NO_PEER_STORES      // timing experiments only (wrong halos): never defined in a release build
 		if (FACE && peer != nullptr) peer[(long) c * s3 + t] = stageable(o);     // posted NVLink store into the neighbour's staging slot
-#endif
 	}
 	return dot;
 }
@@ -507,8 +495,9 @@ __device__ __forceinline__ double dslash_site(const DslashArgs<T> &a, const unsi
 // MR = false: plain launch over [site_lo, site_lo + nsites) -- the single-GPU kernel.
 // MR = true : segmented launch on D3 slabs, block-uniform roles by block index (DslashArgs):
 //             [top face][bottom face][bulk][unpack]
-// No block ever waits for another block of the same launch; bulk blocks run exactly the single-GPU code and leave without
-// any tail (a per-block fence + ticket on ~16k bulk blocks was measured to cost 12 % of the launch).
+// No block ever waits for another block of the same launch, and no block has a tail: the exchange number arrives by value
+// (a per-block fence + ticket to advance a device counter was measured to cost 12 % of a launch on the ~16k bulk blocks, and
+// after NVLink stores the fence waits for the remote acknowledgements).
 template <typename T, int PAR, int EPI, bool MR, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T> a)
 {
@@ -526,7 +515,7 @@ __global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T
 			const unsigned int t = (b - b3) * kBlock + threadIdx.x;
 			if (t < (unsigned int) a.nsites) dot = dslash_site<T, PAR, EPI, false>(a, (unsigned int) a.site_lo, t, nullptr, nullptr, 0, false);
 		} else {
-			const unsigned long long cur = *a.seq_rw;       // this launch consumes exchange `cur` (staged input halos) and produces cur + 1
+			const unsigned long long cur = a.cur;           // this launch consumes exchange `cur` (staged input halos) and produces cur + 1
 			const unsigned int vol3h = (unsigned int) a.vol3h;
 			if (b < b3) {
 				// TOP face   : -> rank R's slot 0; staged input: forward neighbour slice = upper halo = local slot 1
@@ -542,13 +531,6 @@ __global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T
 				const bool hi = k >= ub;                         // first ub blocks: lower halo (slot 0, from rank L); then upper (slot 1, from R)
 				unpack_slice<C>(a.out + (hi ? a.upper_lo : a.lower_lo), a.sizeh, (hi ? a.stage_hi : a.stage_lo) + ((cur + 1) & 1ull) * a.parity_stride,
 												vol3h, (hi ? k - ub : k) * kBlock + threadIdx.x, ub * kBlock);
-			}
-			if (a.launch_ticket != nullptr) {
-				__syncthreads();          // every thread of the block has read the exchange counter
-				if (threadIdx.x == 0) {
-					__threadfence();
-					if (atomicAdd(a.launch_ticket, 1u) == a.nb_top + a.nb_bot + 2 * a.nb_unpack - 1) { *a.launch_ticket = 0u; __threadfence(); *a.seq_rw = cur + 1; }
-				}
 			}
 		}
 	}
@@ -589,7 +571,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 		P2P &p = ctx().p2p;
 		const unsigned int nfb = (unsigned int) p.nfb;
 		a.mr = 1;
-		a.seq_rw = p.d_seq; a.parity_stride = (long) (2 * p.slot_bytes / sizeof(C));
+		a.cur = p.h_seq; a.parity_stride = (long) (2 * p.slot_bytes / sizeof(C));
 		a.peer_top = (C *) p.stage_R; a.peer_bot = (C *) (p.stage_L + p.slot_bytes);
 		a.stage_lo = (C *) p.stage; a.stage_hi = (C *) (p.stage + p.slot_bytes);
 		a.lower_lo = (long) (g.d3_halo - 1) * g.vol3h; a.upper_lo = (long) (g.d3_halo + g.loc_n3) * g.vol3h;
@@ -604,7 +586,7 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 		}
 		a.in_staged = (halo & HALO_IN_STAGED) ? 1 : 0;
 		if (halo & HALO_NO_PUSH) a.peer_top = a.peer_bot = nullptr;
-		if (halo & HALO_ADVANCE) a.launch_ticket = p.tickets + 0;
+		if (halo & HALO_ADVANCE) p.h_seq += 1;       // (a.cur was taken above) both faces of exchange cur + 1 are pushed by this launch
 		grid = a.nb_top + a.nb_bot + a.nb_bulk + 2 * a.nb_unpack;
 	}
 	if (dot_slot >= 0 && (long) partial_offset + grid > ctx().max_partials) {
@@ -666,7 +648,7 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 	const unsigned int bs = dslash_blocks(0, 1), bb = dslash_blocks(lo + 1, hi - 1);
 	if (c.p2p.on && c.p2p_single_launch) {
 		const unsigned int target = 2 * bs + bb;
-		// ONE kernel: the face blocks (first in block order) push their chunks into the neighbours' staging slots over NVLink
+		// ONE kernel: the face blocks (first in block order) store their sites into the neighbours' staging slots over NVLink
 		// while the rest of the launch runs; the received halos are either copied into `out` by the last blocks of the same
 		// launch (the API's contract: `out` leaves with valid halos), by a separate kernel, or -- inside the solvers -- left in
 		// the staging area for the next kernel to consume.  No stream fork/join, no events, no wait on a block of this launch.
@@ -1038,7 +1020,7 @@ using namespace staple;
 
 // captured schedules of staple_acc_Doe_Deo_streamed, keyed by buffers + chunking (geometry is baked into their kernel nodes:
 // staple_init_geometry and staple_shutdown flush them)
-struct StreamedGraph { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs, mode; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
+struct StreamedGraph { const void *u, *out, *in, *tmp, *ph, *d_in, *d_out; int cs, mode, par; long sizeh; cudaGraphExec_t exec; unsigned long long launches; };
 static StreamedGraph g_streamed_cache[4] = {};
 static int g_streamed_next = 0;
 constexpr int kMaxChunks = 128;
@@ -1304,7 +1286,7 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 					}
 				}
 				if (doe_faces == 2 && !advanced) {       // both faces of tmp are on their way: exchange s+1 is what the Deo faces consume
-					seq_advance_kernel<<<1, 1, 0, st>>>(c.p2p.d_seq); count_launch(); advanced = true; again = true;
+					c.p2p.h_seq += 1; advanced = true; again = true;
 				}
 				for (int k = 0; k < nu && advanced; k++) {
 					Unit &un = units[k];
@@ -1319,7 +1301,7 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 					if (un.face != FACE_NONE) deo_faces++;
 				}
 				if (deo_faces == 2 && !unpacked) {
-					p2p_unpack(d_out, sizeof(double2), st, nullptr);      // waits for the neighbours' chunks of exchange s+2, advances the counter
+					p2p_unpack(d_out, sizeof(double2), st, nullptr);      // takes the neighbours' data of exchange s+2 as it lands; the exchange is complete
 					unpacked = true;
 					STAPLE_CUDA_CHECK(cudaEventRecord(ev_deo[ndn], st));
 					STAPLE_CUDA_CHECK(cudaStreamWaitEvent(s_dn, ev_deo[ndn], 0));
@@ -1353,26 +1335,29 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	Cached (&cache)[4] = g_streamed_cache;
 	int &cache_next = g_streamed_next;
 	Cached *hit = nullptr;
+	const int par = slabs ? (int) (c.p2p.h_seq & 1ull) : 0;      // the staging parity the schedule starts from
 	if (st != nullptr && c.use_graphs && !trace) {
 		for (auto &e : cache)
-			if (e.exec && e.u == u && e.out == out_h && e.in == in_h && e.tmp == tmp && e.ph == backfield && e.d_in == d_in && e.d_out == d_out && e.cs == cs && e.mode == mode && e.sizeh == g.sizeh) hit = &e;
+			if (e.exec && e.u == u && e.out == out_h && e.in == in_h && e.tmp == tmp && e.ph == backfield && e.d_in == d_in && e.d_out == d_out && e.cs == cs && e.mode == mode && e.par == par && e.sizeh == g.sizeh) hit = &e;
 		if (!hit) {
-			const unsigned long long before = c.launches;
+			const unsigned long long before = c.launches, seq_before = c.p2p.h_seq;
 			cudaGraph_t graph = nullptr;
 			cudaGraphExec_t exec = nullptr;
 			if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
 				if (slabs) enqueue_slabs(); else enqueue();
-				if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph != nullptr &&
+				// (two exchanges per call on D3 slabs: the frozen staging parities replay consistently from the same starting parity)
+				if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph != nullptr && ((c.p2p.h_seq - seq_before) & 1ull) == 0 &&
 						cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
 					Cached &e = cache[cache_next]; cache_next = (cache_next + 1) % 4;
 					if (e.exec) cudaGraphExecDestroy(e.exec);
-					e = Cached{ u, out_h, in_h, tmp, backfield, d_in, d_out, cs, mode, g.sizeh, exec, c.launches - before };
+					e = Cached{ u, out_h, in_h, tmp, backfield, d_in, d_out, cs, mode, par, g.sizeh, exec, c.launches - before };
 					hit = &e;
 				}
 				if (graph) cudaGraphDestroy(graph);
 			}
 			cudaGetLastError();
 			c.launches = before;
+			c.p2p.h_seq = seq_before;      // nothing was executed
 		}
 	}
 	if (hit) { STAPLE_CUDA_CHECK(cudaGraphLaunch(hit->exec, st)); c.launches += hit->launches; }

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_pupdate_kernel(const CgmCtl *c
 	if (pv.on) {
 		const bool top = i >= pv.top_lo && i < pv.top_lo + pv.vol3h, bot = i >= pv.bot_lo && i < pv.bot_lo + pv.vol3h;
 		if (top || bot) {
-			peer = (E *) ((top ? pv.peer_top : pv.peer_bot) + ((*pv.seq + 1) & 1ull) * pv.parity_bytes);
+			peer = (E *) ((top ? pv.peer_top : pv.peer_bot) + (pv.seq & 1ull) * pv.parity_bytes);
 			pi = i - (top ? pv.top_lo : pv.bot_lo);
 		}
 	}
@@ -271,9 +271,6 @@ __global__ void __launch_bounds__(kBlasBlock) cgm_pupdate_kernel(const CgmCtl *c
 		if (peer != nullptr) peer[col * pv.vol3h + pi] = stageable_e<E>(pn);
 	}
 }
-// the exchange counter after a pushing p update (one thread; silenced by `done` like the update itself)
-__global__ void cgm_seq_advance_kernel(const CgmCtl *c, unsigned long long *seq) { if (!c->done) *seq = *seq + 1; }
-
 // ps_i = in for all i (the order assign_in_to_out calls of :89-95 in one pass)
 template <typename T>
 __global__ void __launch_bounds__(kBlasBlock) broadcast_kernel(cplx_t<T> *dst, const cplx_t<T> *src, int order, long lo,
@@ -381,15 +378,13 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	// operator's face blocks (no unpack, no wait inside the producing launch): p (pushed by the kernel that updates it) and
 	// h = Doe p.  s = M^+M p is not exchanged at all.
 	const bool interior = halo_lazy_ok();
-	const PushView pv = make_pushview(interior);
 	// vector updates: the reference's range R1 (interior + one halo slice each side) -- or, with staged halos, the interior only
 	const long ulo = interior ? g.r0_lo : lo, ucnt = interior ? g.r0_hi - g.r0_lo : cnt;
 	const unsigned int ugrid = (unsigned int) ((ucnt + kBlasBlock - 1) / kBlasBlock), ugrid_f = (unsigned int) ((ucnt + kCgmBlock - 1) / kCgmBlock);
 	if (interior) p2p_push_faces(loc_p, sizeof(cplx_t<T>), st);      // the first Doe consumes the halos of p staged, like every other
 	// FP32: two sites per thread when every range boundary is even (vol3h even: all of them are multiples of vol3h)
 	const bool pack2 = sizeof(T) == 4 && g.vol3h % 2 == 0 && ulo % 2 == 0 && ucnt % 2 == 0 && n % 2 == 0 && g.r0_lo % 2 == 0 && g.r0_hi % 2 == 0;
-	PushView pv2 = pv;
-	pv2.top_lo /= 2; pv2.bot_lo /= 2; pv2.vol3h /= 2;
+
 	auto enqueue_batch = [&]() {
 		if (fuse_tail) { c.cgm_hook = g_d_ctl; c.cgm_hook_red = red; }
 		for (int b = 0; b < batch; b++) {
@@ -413,12 +408,14 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 				cgm_after_lambda_kernel<<<1, 32, 0, st>>>(g_d_ctl, result(SLOT_LAMBDA), red);
 				count_launch();
 			}
-			if (pack2)
+			PushView pv = make_pushview(interior);         // the exchange this p update produces (its number fixes the staging parity)
+			if (pack2) {
+				pv.top_lo /= 2; pv.bot_lo /= 2; pv.vol3h /= 2;
 				cgm_pupdate_kernel<float4><<<(unsigned int) ((ucnt / 2 + kBlasBlock - 1) / kBlasBlock), kBlasBlock, 0, st>>>(
-					g_d_ctl, (float4 *) loc_p, (const float4 *) loc_r, ulo / 2, ucnt / 2, n / 2, pv2);
-			else
+					g_d_ctl, (float4 *) loc_p, (const float4 *) loc_r, ulo / 2, ucnt / 2, n / 2, pv);
+			} else
 				cgm_pupdate_kernel<cplx_t<T>><<<ugrid, kBlasBlock, 0, st>>>(g_d_ctl, loc_p, loc_r, ulo, ucnt, n, pv);
-			if (interior) { cgm_seq_advance_kernel<<<1, 1, 0, st>>>(g_d_ctl, c.p2p.d_seq); count_launch(); }
+			if (interior) c.p2p.h_seq += 1;
 			count_launch(2);
 		}
 		c.cgm_hook = nullptr;
@@ -434,14 +431,18 @@ static int multishift_impl(const cplx_t<T> *u, ferm_param *pars, RationalApprox 
 	const bool capturable = c.nranks == 1 || (c.p2p.on && c.p2p_single_launch && c.p2p.d_redq != nullptr);
 	if (capturable && st != nullptr && c.use_graphs) {
 		cudaGraph_t graph = nullptr;
+		const unsigned long long seq_before = c.p2p.h_seq;
 		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
 			enqueue_batch();
 			cudaError_t e = cudaStreamEndCapture(st, &graph);
 			launches_per_batch = c.launches - launches_before;
 			c.launches = launches_before;
-			if (e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+			// a graph freezes the staging parities of its launches: replayable only if it holds an even number of exchanges
+			const bool even = ((c.p2p.h_seq - seq_before) & 1ull) == 0;
+			if (e == cudaSuccess && graph != nullptr && even && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
 			if (graph) cudaGraphDestroy(graph);
 		}
+		c.p2p.h_seq = seq_before;      // nothing was executed
 		cudaGetLastError();
 	}
 	while (!finished) {
@@ -716,7 +717,7 @@ static bool cg_device_resident()
 struct CgBatchRunner {
 	cudaGraphExec_t gexec = nullptr;
 	unsigned long long launches_per_batch = 0;
-	int batch = 8;
+	int batch = 8, parity = 0;
 	bool lag = true;
 	template <typename F> void prepare(F enqueue_iteration)
 	{
@@ -724,16 +725,21 @@ struct CgBatchRunner {
 		cudaStream_t st = c.stream;
 		if (c.g.sizeh >= (1l << 21)) { batch = 2; lag = false; }
 		if (st == nullptr || !c.use_graphs) return;
-		const unsigned long long before = c.launches;
+		const unsigned long long before = c.launches, seq_before = c.p2p.h_seq;
 		cudaGraph_t graph = nullptr;
 		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
 			for (int b = 0; b < batch; b++) enqueue_iteration();
 			cudaError_t e = cudaStreamEndCapture(st, &graph);
 			launches_per_batch = c.launches - before;
 			c.launches = before;
-			if (e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+			// a graph freezes the staging parities of its launches: replayable only if it holds an even number of exchanges, and
+			// only from the parity it was captured at (run() checks)
+			const bool even = ((c.p2p.h_seq - seq_before) & 1ull) == 0;
+			if (e == cudaSuccess && graph != nullptr && even && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
 			if (graph) cudaGraphDestroy(graph);
 		}
+		c.p2p.h_seq = seq_before;      // nothing was executed
+		parity = (int) (seq_before & 1ull);
 		cudaGetLastError();
 	}
 	template <typename F> CgCtl run(F enqueue_iteration)
@@ -742,8 +748,9 @@ struct CgBatchRunner {
 		cudaStream_t st = c.stream;
 		int snap = 0, pending[2] = { 0, 0 };
 		bool finished = false;
+		const bool replay = gexec != nullptr && (int) (c.p2p.h_seq & 1ull) == parity;
 		while (!finished) {
-			if (gexec) { STAPLE_CUDA_CHECK(cudaGraphLaunch(gexec, st)); c.launches += launches_per_batch; }
+			if (replay) { STAPLE_CUDA_CHECK(cudaGraphLaunch(gexec, st)); c.launches += launches_per_batch; }
 			else for (int b = 0; b < batch; b++) enqueue_iteration();
 			STAPLE_CUDA_CHECK(cudaMemcpyAsync(&g_h_cg[snap], g_d_cg, sizeof(CgCtl), cudaMemcpyDeviceToHost, st));
 			STAPLE_CUDA_CHECK(cudaEventRecord(g_ev_cgsnap[snap], st));

@@ -4,7 +4,7 @@ import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 from openstaple_b200.build import build
-V = {"nopeer": ["-DSTAPLE_DEBUG_NO_PEER_STORES"], "nofence": ["-DSTAPLE_DEBUG_NO_SIGNAL_FENCE"], "mr7": ["-DSTAPLE_DSLASH_MINBLOCKS_MR=7"]}
+V = {"mr7": ["-DSTAPLE_DSLASH_MINBLOCKS_MR=7"], "faces6": ["-DSTAPLE_DSLASH_MINBLOCKS_FACES=6"]}
 for tag in (sys.argv[1:] or V):
     out = os.path.join(ROOT, "build", "lib_%s.so" % tag)
     build(force=True, extra_flags=V[tag], out=out, tag="obj_" + tag, only=["staple_kernels.cu"])
