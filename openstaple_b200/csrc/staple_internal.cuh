@@ -216,6 +216,32 @@ __device__ __forceinline__ float2 take_staged(float2 *p)
 	asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(kSentinel32), "r"(kSentinel32) : "memory");
 	return make_float2(__uint_as_float(x), __uint_as_float(y));
 }
+// the same in two steps, for consumers that want many elements in flight: peek_staged issues the load and returns at once
+// (`arrived` tells whether both words were there), take_staged(p) is the slow path for the stragglers; the caller puts the
+// resting pattern back with reset_staged once it holds the value
+__device__ __forceinline__ double2 peek_staged(double2 *p, bool *arrived)
+{
+	unsigned long long x, y;
+	asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+	*arrived = x != kSentinel64 && y != kSentinel64;
+	return make_double2(__longlong_as_double((long long) x), __longlong_as_double((long long) y));
+}
+__device__ __forceinline__ float2 peek_staged(float2 *p, bool *arrived)
+{
+	unsigned int x, y;
+	asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
+	*arrived = x != kSentinel32 && y != kSentinel32;
+	return make_float2(__uint_as_float(x), __uint_as_float(y));
+}
+__device__ __forceinline__ void reset_staged(double2 *p)
+{
+	asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(kSentinel64), "l"(kSentinel64) : "memory");
+}
+__device__ __forceinline__ void reset_staged(float2 *p)
+{
+	asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(kSentinel32), "r"(kSentinel32) : "memory");
+}
+
 // producer side: a value that equals the resting pattern (a NaN with all payload bits set) becomes the canonical NaN
 __device__ __forceinline__ double2 stageable(double2 v)
 {

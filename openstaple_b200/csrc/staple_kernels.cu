@@ -240,19 +240,29 @@ __device__ __noinline__ void unpack_slice(C *dst, long n, C *src, unsigned int v
 {
 	for (unsigned int t0 = first; t0 < vol3h; t0 += 4 * stride) {
 		C v[4][3];
+		bool ok[4][3];
+		// all twelve loads first (normally everything has landed long ago: one L2 round trip instead of twelve in a row) ...
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const unsigned int tt = t0 + k * stride;
 #pragma unroll
-			for (int c = 0; c < 3; c++)
-				if (tt < vol3h) v[k][c] = take_staged(src + (long) c * vol3h + tt);
+			for (int c = 0; c < 3; c++) {
+				ok[k][c] = true;
+				if (tt < vol3h) v[k][c] = peek_staged(src + (long) c * vol3h + tt, &ok[k][c]);
+			}
 		}
+		// ... then the stragglers one by one, the resting pattern back into the staging area, and the halo slice
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const unsigned int tt = t0 + k * stride;
 			if (tt < vol3h) {
 #pragma unroll
-				for (int c = 0; c < 3; c++) dst[c * n + tt] = v[k][c];
+				for (int c = 0; c < 3; c++) {
+					C *p = src + (long) c * vol3h + tt;
+					if (!ok[k][c]) v[k][c] = take_staged(p);
+					else reset_staged(p);
+					dst[c * n + tt] = v[k][c];
+				}
 			}
 		}
 	}
@@ -406,7 +416,12 @@ __device__ __forceinline__ void hop_d3(cplx_t<T> acc[3], const cplx_t<T> *__rest
 	const C m00 = ld_stream(uk + im), m01 = ld_stream(uk + n + im), m02 = ld_stream(uk + 2 * n + im);
 	const C m10 = ld_stream(uk + 3 * n + im), m11 = ld_stream(uk + 4 * n + im), m12 = ld_stream(uk + 5 * n + im);
 	C v0, v1, v2;
-	if (MAYBE_STAGED && STAGED) { v0 = take_staged(vin + iv); v1 = take_staged(vin + vn + iv); v2 = take_staged(vin + 2 * vn + iv); }
+	if (MAYBE_STAGED && STAGED) {
+		bool a0, a1, a2;           // three loads in flight (normally everything landed long ago); else the slow path, one by one
+		v0 = peek_staged(vin + iv, &a0); v1 = peek_staged(vin + vn + iv, &a1); v2 = peek_staged(vin + 2 * vn + iv, &a2);
+		if (a0 && a1 && a2) { reset_staged(vin + iv); reset_staged(vin + vn + iv); reset_staged(vin + 2 * vn + iv); }
+		else { v0 = take_staged(vin + iv); v1 = take_staged(vin + vn + iv); v2 = take_staged(vin + 2 * vn + iv); }
+	}
 	else { v0 = __ldcg(vin + iv); v1 = __ldcg(vin + vn + iv); v2 = __ldcg(vin + 2 * vn + iv); }
 	T s, c;
 	sincos_t(th, &s, &c);
