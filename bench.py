@@ -674,7 +674,7 @@ def main():
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread_value")}
         halo = "none"
         if world > 1:
-            halo = "nvlink peer stores from the face blocks, per-chunk flags, staged halos" if getattr(lat, "p2p", False) else "nccl send/recv"
+            halo = "nvlink peer stores from the face blocks, the data words are their own arrival flags, staged halos inside the solvers" if getattr(lat, "p2p", False) else "nccl send/recv"
         line = {"metric": "deo_doe_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
