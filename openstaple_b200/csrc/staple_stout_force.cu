@@ -237,13 +237,79 @@ __device__ __forceinline__ void acc_irho(cplx_t<T> res[3][3], const cplx_t<T> t[
 		for (int c = 0; c < 3; c++) { res[r][c].x -= rho * t[r][c].y; res[r][c].y += rho * t[r][c].x; }
 }
 
+// res += i*rho * op(a) * op(b), accumulated entry by entry (no temporary matrix)
+template <typename T, bool DA = false, bool DB = false>
+__device__ __forceinline__ void mm_acc_irho(cplx_t<T> res[3][3], const cplx_t<T> a[3][3], const cplx_t<T> b[3][3], T rho)
+{
+	using C = cplx_t<T>;
+#pragma unroll
+	for (int r = 0; r < 3; r++)
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			C acc = mkq<T>(0, 0);
+#pragma unroll
+			for (int j = 0; j < 3; j++) {
+				const C x = DA ? cj(a[j][r]) : a[r][j];
+				const C y = DB ? cj(b[c][j]) : b[j][c];
+				acc.x += x.x * y.x - x.y * y.y; acc.y += x.x * y.y + x.y * y.x;
+			}
+			res[r][c].x -= rho * acc.y; res[r][c].y += rho * acc.x;
+		}
+}
+// o -= op(a) * op(b)
+template <typename T, bool DA = false, bool DB = false>
+__device__ __forceinline__ void mm_sub(cplx_t<T> o[3][3], const cplx_t<T> a[3][3], const cplx_t<T> b[3][3])
+{
+	using C = cplx_t<T>;
+#pragma unroll
+	for (int r = 0; r < 3; r++)
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			C acc = o[r][c];
+#pragma unroll
+			for (int j = 0; j < 3; j++) {
+				const C x = DA ? cj(a[j][r]) : a[r][j];
+				const C y = DB ? cj(b[c][j]) : b[j][c];
+				acc.x -= x.x * y.x - x.y * y.y; acc.y -= x.x * y.y + x.y * y.x;
+			}
+			o[r][c] = acc;
+		}
+}
+// o += op(a) * op(b)
+template <typename T, bool DA = false, bool DB = false>
+__device__ __forceinline__ void mm_add(cplx_t<T> o[3][3], const cplx_t<T> a[3][3], const cplx_t<T> b[3][3])
+{
+	using C = cplx_t<T>;
+#pragma unroll
+	for (int r = 0; r < 3; r++)
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			C acc = o[r][c];
+#pragma unroll
+			for (int j = 0; j < 3; j++) {
+				const C x = DA ? cj(a[j][r]) : a[r][j];
+				const C y = DB ? cj(b[c][j]) : b[j][c];
+				acc.x += x.x * y.x - x.y * y.y; acc.y += x.x * y.y + x.y * y.x;
+			}
+			o[r][c] = acc;
+		}
+}
+
 // compute_sigma (stouting.c:1175-1305): Sigma = Sigma' exp(iQ) + i rho sum_{nu != mu} [ staples with one Lambda inserted ]
 //   right, A = U_nu(x+mu), B = U_mu(x+nu)^+, C = U_nu(x)^+ :  ABC (L_mu(x) - L_nu(x)) + L_nu(x+mu) ABC - A B L_mu(x+nu) C
 //   left,  A = U_nu(x+mu-nu)^+, B = U_mu(x-nu)^+, C = U_nu(x-nu) :
 //                           A B (L_nu(x-nu) - L_mu(x-nu)) C + A B C L_mu(x) - A L_nu(x+mu-nu) B C
 // TMP is left = exp(iQ) (third row rebuilt) as in the reference.
+// tuning knobs (scripts/bench_sigma.py): one thread per LINK (grid.y = 8) instead of per index looping over its eight links;
+// minimum CTAs per SM (register bound)
+#ifndef STAPLE_SIGMA_PER_LINK
+#define STAPLE_SIGMA_PER_LINK 1
+#endif
+#ifndef STAPLE_SIGMA_MINBLOCKS
+#define STAPLE_SIGMA_MINBLOCKS 1
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kSfBlock) stout_sigma_kernel(const T *lam, const cplx_t<T> *u, cplx_t<T> *sg, const T *ta, cplx_t<T> *tmp, T rho, SfGeom g)
+__global__ void __launch_bounds__(kSfBlock, STAPLE_SIGMA_MINBLOCKS) stout_sigma_kernel(const T *lam, const cplx_t<T> *u, cplx_t<T> *sg, const T *ta, cplx_t<T> *tmp, T rho, SfGeom g)
 {
 	using C = cplx_t<T>;
 	const unsigned int t = blockIdx.x * kSfBlock + threadIdx.x;
@@ -257,8 +323,13 @@ __global__ void __launch_bounds__(kSfBlock) stout_sigma_kernel(const T *lam, con
 	const int d2 = qq % g.nd2;
 	const int d3 = qq / g.nd2;
 	const int nd[4] = { g.nd0, g.nd1, g.nd2, g.nd3 };
+#if STAPLE_SIGMA_PER_LINK
+	const int k0 = blockIdx.y, k1 = blockIdx.y + 1;
+#else
+	const int k0 = 0, k1 = 8;
+#endif
 #pragma unroll 1
-	for (int k = 0; k < 8; k++) {
+	for (int k = k0; k < k1; k++) {
 		const int mu = k >> 1, p = k & 1;
 		const int x[4] = { 2 * hd0 + ((d1 + d2 + d3 + p) & 1), d1, d2, d3 };
 		auto site = [&](int dmu, int nu, int dnu) {
@@ -293,39 +364,41 @@ __global__ void __launch_bounds__(kSfBlock) stout_sigma_kernel(const T *lam, con
 		for (int it = 0; it < 3; it++) {
 			const int nu = it + (it >= mu ? 1 : 0);
 			const unsigned int ipmu = site(1, nu, 0), ipnu = site(0, nu, 1), imnu = site(0, nu, -1), ipmumnu = site(1, nu, -1);
-			C a[3][3], b[3][3], c[3][3], ab[3][3], l1[3][3], t1[3][3], t2[3][3];
-			// ---- right
-			load_su3<T>(u + (long) (2 * nu + !p) * 9 * n, n, ipmu, a);
-			load_su3<T>(u + (long) (2 * mu + !p) * 9 * n, n, ipnu, b);
-			load_su3<T>(u + (long) (2 * nu + p) * 9 * n, n, idx, c);
-			mm<T, false, true>(a, b, ab);                                     // A B,   B = U_mu(x+nu)^+
-			mm<T, false, true>(ab, c, t1);                                    // ABC,   C = U_nu(x)^+
-			load_herm<T>(lam + (long) (2 * nu + p) * 8 * n, n, idx, l1);      // E = L_nu(x)
+			C a[3][3], b[3][3], c[3][3], pm[3][3], l1[3][3], xm[3][3];
+			// ---- right: P = A B^+ ;  i rho [ P (C^+ (D - E) - G C^+) + F (P C^+) ]      (12 products per plane instead of 15)
+			load_su3<T>(u + (long) (2 * nu + !p) * 9 * n, n, ipmu, a);       // A = U_nu(x+mu)
+			load_su3<T>(u + (long) (2 * mu + !p) * 9 * n, n, ipnu, b);       // B = U_mu(x+nu)
+			mm<T, false, true>(a, b, pm);                                     // P = A B^+
+			load_su3<T>(u + (long) (2 * nu + p) * 9 * n, n, idx, c);         // C = U_nu(x)
+			load_herm<T>(lam + (long) (2 * nu + p) * 8 * n, n, idx, l1);     // E = L_nu(x)
 #pragma unroll
 			for (int r = 0; r < 3; r++)
 #pragma unroll
 				for (int cc = 0; cc < 3; cc++) l1[r][cc] = csub(lmu[r][cc], l1[r][cc]);
-			mm<T>(t1, l1, t2); acc_irho<T>(res, t2, rho);                     // + i rho ABC (D - E)
-			load_herm<T>(lam + (long) (2 * nu + !p) * 8 * n, n, ipmu, l1);    // F = L_nu(x+mu)
-			mm<T>(l1, t1, t2); acc_irho<T>(res, t2, rho);                     // + i rho F ABC
-			load_herm<T>(lam + (long) (2 * mu + !p) * 8 * n, n, ipnu, l1);    // G = L_mu(x+nu)
-			mm<T>(ab, l1, t1); mm<T, false, true>(t1, c, t2); acc_irho<T>(res, t2, -rho);   // - i rho A B G C
-			// ---- left
-			load_su3<T>(u + (long) (2 * nu + p) * 9 * n, n, ipmumnu, a);
-			load_su3<T>(u + (long) (2 * mu + !p) * 9 * n, n, imnu, b);
-			load_su3<T>(u + (long) (2 * nu + !p) * 9 * n, n, imnu, c);
-			mm<T, true, true>(a, b, ab);                                      // A B,   A = U_nu(x+mu-nu)^+, B = U_mu(x-nu)^+
-			load_herm<T>(lam + (long) (2 * nu + !p) * 8 * n, n, imnu, l1);    // G = L_nu(x-nu)
-			load_herm<T>(lam + (long) (2 * mu + !p) * 8 * n, n, imnu, t1);    // E = L_mu(x-nu)
+			mm<T, true, false>(c, l1, xm);                                    // X = C^+ (D - E)
+			load_herm<T>(lam + (long) (2 * mu + !p) * 8 * n, n, ipnu, l1);   // G = L_mu(x+nu)
+			mm_sub<T, false, true>(xm, l1, c);                                // X -= G C^+
+			mm_acc_irho<T>(res, pm, xm, rho);                                 // + i rho P X
+			mm<T, false, true>(pm, c, xm);                                    // T = P C^+
+			load_herm<T>(lam + (long) (2 * nu + !p) * 8 * n, n, ipmu, l1);   // F = L_nu(x+mu)
+			mm_acc_irho<T>(res, l1, xm, rho);                                 // + i rho F T
+			// ---- left: i rho A^+ [ B^+ ((G - E) C + C D) - F (B^+ C) ]
+			load_su3<T>(u + (long) (2 * nu + !p) * 9 * n, n, imnu, c);       // C = U_nu(x-nu)
+			load_herm<T>(lam + (long) (2 * nu + !p) * 8 * n, n, imnu, l1);   // G = L_nu(x-nu)
+			load_herm<T>(lam + (long) (2 * mu + !p) * 8 * n, n, imnu, a);    // E = L_mu(x-nu)
 #pragma unroll
 			for (int r = 0; r < 3; r++)
 #pragma unroll
-				for (int cc = 0; cc < 3; cc++) l1[r][cc] = csub(l1[r][cc], t1[r][cc]);
-			mm<T>(ab, l1, t1); mm<T>(t1, c, t2); acc_irho<T>(res, t2, rho);   // + i rho A B (G - E) C
-			mm<T>(ab, c, t1); mm<T>(t1, lmu, t2); acc_irho<T>(res, t2, rho);  // + i rho A B C D
-			load_herm<T>(lam + (long) (2 * nu + p) * 8 * n, n, ipmumnu, l1);  // F = L_nu(x+mu-nu)
-			mm<T, true, false>(a, l1, t1); mm<T, false, true>(t1, b, t2); mm<T>(t2, c, t1);
-			acc_irho<T>(res, t1, -rho);                                       // - i rho A F B C
+				for (int cc = 0; cc < 3; cc++) l1[r][cc] = csub(l1[r][cc], a[r][cc]);
+			mm<T>(l1, c, xm);                                                 // Y = (G - E) C
+			mm_add<T>(xm, c, lmu);                                            // Y += C D
+			load_su3<T>(u + (long) (2 * mu + !p) * 9 * n, n, imnu, b);       // B = U_mu(x-nu)
+			mm<T, true, false>(b, xm, pm);                                    // Z = B^+ Y
+			mm<T, true, false>(b, c, xm);                                     // W = B^+ C
+			load_herm<T>(lam + (long) (2 * nu + p) * 8 * n, n, ipmumnu, l1); // F = L_nu(x+mu-nu)
+			mm_sub<T>(pm, l1, xm);                                            // Z -= F W
+			load_su3<T>(u + (long) (2 * nu + p) * 9 * n, n, ipmumnu, a);     // A = U_nu(x+mu-nu)
+			mm_acc_irho<T, true, false>(res, a, pm, rho);                     // + i rho A^+ Z
 		}
 #pragma unroll
 		for (int w = 0; w < 9; w++) sg[((long) k * 9 + w) * n + idx] = res[w / 3][w % 3];
@@ -358,7 +431,7 @@ extern double gl_stout_rho, gl_topo_rho;
 	{                                                                                                                          \
 		require_init("compute_sigma");                                                                                           \
 		const SfGeom g = sf_geom();                                                                                              \
-		stout_sigma_kernel<T><<<(g.cnt + kSfBlock - 1) / kSfBlock, kSfBlock, 0, ctx().stream>>>(                                 \
+		stout_sigma_kernel<T><<<dim3((g.cnt + kSfBlock - 1) / kSfBlock, STAPLE_SIGMA_PER_LINK ? 8 : 1), kSfBlock, 0, ctx().stream>>>( \
 			(const T *) dev(L, "L"), CD(U), D(Sg), (const T *) dev(QA, "QA"), D(TMP), (T) (istopo ? gl_topo_rho : gl_stout_rho), g); \
 		STAPLE_CUDA_CHECK(cudaGetLastError()); count_launch();                                                                   \
 	}                                                                                                                          \

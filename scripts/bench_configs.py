@@ -49,7 +49,7 @@ def main():
     lat = osb.Lattice(loc, nranks_d3=world, device=local_rank)
     if world > 1:
         lat.init_multidev(dist, async_comm_fermion=1, p2p=args.p2p)
-    u, v = bench.make_fields(torch, lat, seed=1 + rank)
+    u, v = bench.make_fields(torch, lat, rank)
     ph_host = bench.staggered_phases(lat, rank)
     ph = lat.to_device(ph_host); phf = lat.to_device(ph_host.astype(np.float32))
     if world > 1:
