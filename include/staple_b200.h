@@ -233,15 +233,16 @@ void staple_set_streamed_mode(int mode);
 int staple_nccl_unique_id(void *id128);
 int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_comm_fermion);
 /* Optional (collective, after staple_init_multidev1D): fermion halos through NVLink peer memory instead of
- * ncclSend/Recv -- the surface kernels of acc_Deo/acc_Doe store their slice straight into the neighbour's
- * staging area (CUDA IPC) and raise a flag; returns 1 if active, 0 if it fell back to NCCL.
+ * ncclSend/Recv -- the face blocks of acc_Deo/acc_Doe store their sites straight into the neighbour's staging area (CUDA
+ * IPC; posted writes, the stored words are their own arrival flags: no fence, no flag); returns 1
+ * if active, 0 if it fell back to NCCL.
  * on = 1: acc_Deo/acc_Doe with their exchange are ONE kernel (face blocks first, bulk, unpack blocks last), and the
  *         solvers leave the halos of their intermediate vectors in the staging area, where the next kernel consumes them;
  * on = 2: the reference's three-queue structure (d3p, d3m, bulk on separate streams) with peer stores;
  * on = 3: one operator kernel + a separate unpack kernel;  on = 4: like 1 without the staged halos inside the solvers.
  * Global sums use the same mailboxes. */
 int staple_enable_p2p(int on);
-/* Every in-kernel wait of the peer-memory channels is for a flag that a PEER GPU writes; it is bounded: after `seconds`
+/* Every in-kernel wait of the peer-memory channels is for data that a PEER GPU stores; it is bounded: after `seconds`
  * (default 60; 0 = wait for ever, which is what MPI_Wait does) the waiting kernel prints what it was waiting for and
  * traps, so a dead rank surfaces as a CUDA error on the survivors instead of a hang. */
 void staple_set_spin_timeout(double seconds);

@@ -519,7 +519,7 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 }
 
 // Peer-memory channels (collective: every rank calls it after staple_init_multidev1D).  Allocates the mailbox
-// (halo staging + flags + reduction boxes), exports it with CUDA IPC, all-gathers the handles over the NCCL
+// (halo staging + reduction boxes), exports it with CUDA IPC, all-gathers the handles over the NCCL
 // communicator (no MPI needed) and maps every rank's mailbox.  Returns 1 if the channels are active.
 static void nccl_barrier(cudaStream_t st)
 {
@@ -592,7 +592,7 @@ int staple_enable_p2p(int on)
 
 // The D3-slab code path on ONE GPU, one process: the geometry must have been initialised with NRANKS_D3 > 1 (local+halo box,
 // ranges R0/R1), this rank becomes its own L and R neighbour and its own memory stands in for the peers' mailboxes.  The lattice
-// that results is the single-rank LOC_N0..3 lattice (periodic in d3 with period LOC_N3) stored with halos; every kernel, flag
+// that results is the single-rank LOC_N0..3 lattice (periodic in d3 with period LOC_N3) stored with halos; every kernel, staging slot
 // and counter of the peer-memory transport runs exactly as on N GPUs, minus NVLink.  Used by the single-GPU parity tests and
 // for profiling the segmented operator kernel (a multi-rank run cannot be replayed by ncu).
 int staple_init_loopback(int p2p_mode)

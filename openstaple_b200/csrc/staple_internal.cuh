@@ -150,7 +150,7 @@ void p2p_allreduce(double *vals, int ndoubles, cudaStream_t s);
 RedView make_redview();
 inline RedView single_rank_redview() { RedView v; v.nranks = 1; v.myrank = 0; v.q = nullptr; return v; }
 
-// operator CTA size = sites per halo chunk (scripts/tune_dslash.py sweeps it; 128 is the measured optimum)
+// operator CTA size (scripts/tune_dslash.py sweeps it; 128 is the measured optimum)
 #ifndef STAPLE_DSLASH_BLOCK
 #define STAPLE_DSLASH_BLOCK 128
 #endif
