@@ -217,8 +217,9 @@ void *staple_acc_deviceptr(const void *host);                     /* acc_devicep
  * stream, acc_Doe_d3c / acc_Deo_d3c launches as soon as the +-1 neighbour chunks they read have landed, chunk
  * downloads on a second copy stream -- PCIe runs in both directions while the operator computes.  `in` and `out`
  * are present host arrays (staple_posix_memalign), `tmp` an odd-site scratch vector; returns after `out` is valid
- * on the host.  Results are bit-identical to the unpipelined sequence.  Single rank only (with NRANKS_D3 > 1 the
- * plain sequence incl. the halo exchanges is executed). */
+ * on the host.  Results are bit-identical to the unpipelined sequence.  On D3 slabs over the peer-memory transport the same
+ * pipeline runs per rank, face slices first (`in` arrives with its halo slices, the faces of `tmp` and `out` are exchanged
+ * through the staging area); with NCCL halos the plain sequence incl. the exchanges is executed. */
 void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out, const vec3_soa *in, vec3_soa *tmp,
 																 const double_soa *backfield, int chunk_slices);
 /* how the result of the call above reaches the host: 0 (default) = chunk downloads by the copy engine, 1 = the Deo
