@@ -1145,7 +1145,7 @@ void staple_acc_Doe_Deo_streamed(const su3_soa *u, vec3_soa *out_h, const vec3_s
 	const bool in_host = (const void *) d_in != (const void *) in_h, out_host = (void *) d_out != (void *) out_h;
 	const size_t vbytes = sizeof(double2) * 3 * g.sizeh;
 	const bool slabs = c.nranks > 1;
-	if ((slabs && !(c.p2p.on && c.p2p_single_launch)) || !in_host || !out_host) {
+	if ((slabs && !(c.p2p.on && c.p2p_single_launch && g.nd3 <= 4096)) || !in_host || !out_host) {
 		if (in_host) staple_acc_update_device(in_h, vbytes);
 		apply_dslash<double>(1, EPI_NONE, d_u, d_tmp, d_in, d_ph, nullptr, 0.0, -1, nullptr);
 		apply_dslash<double>(0, EPI_NONE, d_u, d_out, d_tmp, d_ph, nullptr, 0.0, -1, nullptr);
