@@ -442,11 +442,12 @@ struct DslashArgs {
 	long vol3h, sizeh;
 	// ---- D3 slabs over NVLink peer memory (mr != 0): the launch is segmented by block index into
 	//   [nb_top blocks: TOP interior slice -> rank R's slot 0] [nb_bot: BOTTOM interior slice -> rank L's slot 1]
-	//   [nb_bulk: the slices in between] [2*nb_unpack: copy of the staged halos of THIS exchange into `out`]
+	//   [nb_bulk: the slices in between] [2*nb_unpack: copy of the staged halos of THIS exchange into `out`; before the bulk if unpack_early]
 	// any segment may be empty.  A face block stores its sites into `out` AND into the neighbour's staging slot (posted NVLink
 	// writes; the data is its own arrival flag, see P2P); faces come first in block order, so the transfer overlaps the rest.
 	int mr;
 	unsigned int nb_top, nb_bot, nb_bulk, nb_unpack;
+	int unpack_early;                            // the unpack blocks come right after the faces (bulk to hide behind) instead of last
 	long top_lo, bot_lo;                         // first idxh of the two surface slices
 	cplx_t<T> *peer_top, *peer_bot;              // parity-0 staging slot in the neighbour's memory
 	long parity_stride;                          // elements between the parity-0 and parity-1 staging areas

@@ -525,9 +525,10 @@ __global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T
 		const unsigned int t = blockIdx.x * kBlock + threadIdx.x;
 		if (t < (unsigned int) a.nsites) dot = dslash_site<T, PAR, EPI, false>(a, (unsigned int) a.site_lo, t, nullptr, nullptr, 0, false);
 	} else {
-		const unsigned int b = blockIdx.x, b2 = a.nb_top, b3 = b2 + a.nb_bot, b4 = b3 + a.nb_bulk;
-		if (b >= b3 && b < b4) {
-			const unsigned int t = (b - b3) * kBlock + threadIdx.x;
+		// block order: [top face][bottom face][unpack, if early][bulk][unpack, if late]
+		const unsigned int b = blockIdx.x, b2 = a.nb_top, b3 = b2 + a.nb_bot, bk = b3 + (a.unpack_early ? 2 * a.nb_unpack : 0), b4 = bk + a.nb_bulk;
+		if (b >= bk && b < b4) {
+			const unsigned int t = (b - bk) * kBlock + threadIdx.x;
 			if (t < (unsigned int) a.nsites) dot = dslash_site<T, PAR, EPI, false>(a, (unsigned int) a.site_lo, t, nullptr, nullptr, 0, false);
 		} else {
 			const unsigned long long cur = a.cur;           // this launch consumes exchange `cur` (staged input halos) and produces cur + 1
@@ -541,8 +542,10 @@ __global__ void __launch_bounds__(kBlock, MINB) dslash_kernel(const DslashArgs<T
 				C *stage = (bot ? a.stage_lo : a.stage_hi) + (cur & 1ull) * a.parity_stride;
 				if (t < vol3h) dot = dslash_site<T, PAR, EPI, true>(a, (unsigned int) (bot ? a.bot_lo : a.top_lo), t, peer, stage, bot ? 2 : 1, a.in_staged != 0);
 			} else {
-				// ---- unpack blocks (last in block order): the halos of THIS exchange, element by element as they land
-				const unsigned int ub = a.nb_unpack, k = b - b4;
+				// ---- unpack blocks: the halos of THIS exchange, element by element as they land.  With bulk slices to hide behind, a FEW
+				// blocks placed right after the faces (they sit out the neighbours' face computation, then copy while the bulk runs: no
+				// tail); without, many blocks at the end of the launch
+				const unsigned int ub = a.nb_unpack, k = a.unpack_early ? b - b3 : b - b4;
 				const bool hi = k >= ub;                         // first ub blocks: lower halo (slot 0, from rank L); then upper (slot 1, from R)
 				unpack_slice<C>(a.out + (hi ? a.upper_lo : a.lower_lo), a.sizeh, (hi ? a.stage_hi : a.stage_lo) + ((cur + 1) & 1ull) * a.parity_stride,
 												vol3h, (hi ? k - ub : k) * kBlock + threadIdx.x, ub * kBlock);
@@ -597,7 +600,11 @@ void launch_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const c
 			a.nb_top = a.nb_bot = nfb;
 			a.nb_bulk = dslash_blocks(d3lo + 1, d3hi - 1);
 			a.site_lo = (long) (d3lo + 1) * g.vol3h; a.nsites = (long) (d3hi - d3lo - 2) * g.vol3h;   // bulk
-			if (face == FACE_BOTH_UNPACK) a.nb_unpack = unpack_blocks_for(nfb);
+			if (face == FACE_BOTH_UNPACK) {
+				// enough bulk (>= 4 slices) to cover the neighbours' face computation and the copy: one unpack CTA per halo and two SMs
+				a.unpack_early = (d3hi - d3lo) >= 6 ? 1 : 0;
+				a.nb_unpack = a.unpack_early ? (nfb < 74u ? nfb : 74u) : unpack_blocks_for(nfb);
+			}
 		}
 		a.in_staged = (halo & HALO_IN_STAGED) ? 1 : 0;
 		if (halo & HALO_NO_PUSH) a.peer_top = a.peer_bot = nullptr;
@@ -674,7 +681,7 @@ void apply_dslash(int par, int epi, const cplx_t<T> *u, cplx_t<T> *out, const cp
 		else if (lazy && (halo & HALO_OUT_STAGED))
 			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, FACE_BOTH, in_staged | HALO_ADVANCE);
 		else if (c.p2p_unpack_in_kernel)
-			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * unpack_blocks_for(bs), 0, skip, c.stream,
+			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target + 2 * ((hi - lo) >= 6 ? (bs < 74u ? bs : 74u) : unpack_blocks_for(bs)), 0, skip, c.stream,
 											 FACE_BOTH_UNPACK, in_staged | HALO_ADVANCE);
 		else {
 			launch_dslash<T>(par, epi, u, out, in, ph, in0, m2, lo, hi, dot_slot, target, 0, skip, c.stream, FACE_BOTH, 0);
