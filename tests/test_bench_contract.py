@@ -82,3 +82,19 @@ def test_cpu_threads_do_not_disturb_one_another():
     th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
     [t.start() for t in th]; [t.join() for t in th]
     assert all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    """under torchrun (N > 1) rank 0 alone runs the reference arm; the other ranks exit 0 and print nothing"""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_workload_at_every_n():
+    import bench
+    for n in (1, 2, 4, 8):
+        c = bench.workload_config("64x64x64x128", n)
+        assert c["global_lattice"] == "64x64x64x128" and c["local_lattice"] == "64x64x64x%d" % (128 // n)
+        assert json.dumps(c) == json.dumps(bench.workload_config("64x64x64x128", n))
