@@ -610,6 +610,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "dslash_kernel<double,0,EPI_NONE> (acc_Deo_unsafe on the local slab)", "achieved": achieved,
                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "bytes_per_launch": BYTES_PER_SITE_FP64 * interior, "us_per_launch": ms_kernel * 1e3, "traffic": None,
+                    "frac_of_nominal_8TBs": achieved / 8000.0,
                     "note": "peak = measured COPY bandwidth (half reads, half writes); this kernel is a 95 % read stream and exceeds it on "
                             "the faster boxes of the pool (frac up to 1.05); ncu: DRAM bytes = 0.9993 x the algorithmic bytes (profiles/dslash_traffic.json)"}
         tf = os.path.join(ROOT, "profiles", "dslash_traffic.json")
