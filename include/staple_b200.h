@@ -252,6 +252,8 @@ void staple_set_spin_timeout(double seconds);
  * (0: slab moves as device-to-device copies).  The lattice is the single-rank LOC lattice stored with halos.  Returns 0 on success. */
 int staple_init_loopback(int p2p_mode);
 void shutdown_multidev(void);                                     /* ref: Mpi/multidev.c:110-114 */
+void staple_shutdown_multidev(void);                              /* the same under a name a host that defines shutdown_multidev itself can call */
+int staple_rank_layer_ready(void);                                /* 1 once geometry and (for NRANKS_D3 > 1) the rank layer are initialised */
 int staple_myrank(void);
 
 void communicate_fermion_borders(vec3_soa *lnh_fermion);          /* ref: Mpi/communications.c:158-167 */

@@ -272,6 +272,7 @@ extern "C" {
 
 const char *staple_version(void) { return "staple_b200 0.2 (sm_100a)"; }
 
+static void shutdown_rank_layer(void);
 int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo_width, int device)
 {
 	Ctx &c = ctx();
@@ -289,7 +290,7 @@ int staple_init_geometry(int n0, int n1, int n2, int n3, int nranks_d3, int halo
 		Geom ng;
 		fill_geom(ng, n0, n1, n2, n3, nranks_d3, halo_width);
 		if (c.inited && c.p2p.mailbox && (ng.vol3h != c.p2p.vol3h || ng.nranks != c.nranks)) release_p2p();
-		if (c.inited && (c.comm || c.loopback) && ng.nranks != c.nranks) shutdown_multidev();
+		if (c.inited && (c.comm || c.loopback) && ng.nranks != c.nranks) shutdown_rank_layer();
 	}
 	fill_geom(g, n0, n1, n2, n3, nranks_d3, halo_width);
 	release_streamed_state();      // cached schedules carry the previous geometry in their kernel arguments
@@ -347,7 +348,7 @@ void staple_shutdown(void)
 	Ctx &c = ctx();
 	if (!c.inited) return;
 	cudaDeviceSynchronize();
-	shutdown_multidev();
+	shutdown_rank_layer();
 	release_solver_state();
 	release_streamed_state();
 	cudaStream_t *streams[] = { &c.own_stream, &c.s_p, &c.s_m, &c.s_comm };
@@ -503,7 +504,7 @@ int staple_init_multidev1D(int myrank, int nranks, const void *id128, int async_
 		fprintf(stderr, "MPI%02d - NRANKS_D3 = %d, nranks = %d\n", myrank, c.g.nranks, nranks);
 		exit(1);
 	}
-	if (c.comm || c.loopback) shutdown_multidev();   // a second call replaces the rank layer (mailbox, communicator) instead of leaking it
+	if (c.comm || c.loopback) shutdown_rank_layer();   // a second call replaces the rank layer (mailbox, communicator) instead of leaking it
 	c.myrank = myrank; c.nranks = nranks;
 	c.rank_L = (myrank + (nranks - 1)) % nranks;   // multidev.c:60-61 (SALAMINO ring)
 	c.rank_R = (myrank + 1) % nranks;
@@ -600,7 +601,7 @@ int staple_init_loopback(int p2p_mode)
 	require_init("staple_init_loopback");
 	Ctx &c = ctx();
 	if (c.g.nranks <= 1) { fprintf(stderr, "libstaple_b200: staple_init_loopback needs a geometry with NRANKS_D3 > 1\n"); return 1; }
-	if (c.comm || c.p2p.mailbox) shutdown_multidev();
+	if (c.comm || c.p2p.mailbox) shutdown_rank_layer();
 	c.myrank = 0; c.nranks = c.g.nranks; c.rank_L = c.rank_R = 0; c.async_comm_fermion = 1; c.loopback = true;
 	return staple_enable_p2p(p2p_mode) == (p2p_mode != 0) ? 0 : 1;
 }
@@ -613,7 +614,9 @@ void staple_set_spin_timeout(double seconds)
 	set_spin_timeout_solvers(ns);
 }
 
-void shutdown_multidev(void)
+// internal name: a host that swaps in host/multidev_staple.c defines shutdown_multidev itself (with MPI_Finalize in it), and the
+// executable's definition would pre-empt the library's own calls to the exported symbol
+static void shutdown_rank_layer(void)
 {
 	Ctx &c = ctx();
 	release_p2p();
@@ -626,6 +629,9 @@ void shutdown_multidev(void)
 	c.comm = nullptr;
 }
 
+void shutdown_multidev(void) { shutdown_rank_layer(); }
+void staple_shutdown_multidev(void) { shutdown_rank_layer(); }   // for a host that defines shutdown_multidev itself (host/multidev_staple.c)
+int staple_rank_layer_ready(void) { return ctx().inited && (ctx().g.nranks <= 1 || ctx().comm != nullptr || ctx().loopback) ? 1 : 0; }
 int staple_myrank(void) { return ctx().myrank; }
 
 // fermion borders: 3 colour arrays, thickness FERMION_HALO = 1 (communications.c:158-167)

@@ -28,7 +28,7 @@ LIBDIR=$(cd "$HERE/../openstaple_b200" && pwd)
 [ -f "$LIBDIR/libstaple_b200.so" ] || { echo "build libstaple_b200.so first"; exit 1; }
 PROGLIST=${PROGS:-deo_doe_test inverter_multishift_test main}
 STAMP="$HERE/_ref/${PROGLIST##* }_staple_$GEOM"          # the program linked last
-if [ -f "$STAMP" ] && [ "$STAMP" -nt "$MPISRC" ] && [ "$STAMP" -nt "$HERE/../openstaple_b200/host/memory_wrapper_staple.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
+if [ -f "$STAMP" ] && [ "$STAMP" -nt "$MPISRC" ] && [ "$STAMP" -nt "$HERE/../openstaple_b200/host/memory_wrapper_staple.c" ] && [ "$STAMP" -nt "$HERE/../openstaple_b200/host/multidev_staple.c" ] && [ "$STAMP" -nt "$0" ] && [ "$STAMP" -nt "$LIBDIR/../include/staple_b200.h" ]; then echo "up to date: $STAMP"; exit 0; fi
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 T=8
@@ -69,6 +69,9 @@ for f in $COMMON tests_and_benchmarks/deo_doe_test tests_and_benchmarks/inverter
 done
 gcc -O2 -std=gnu99 -w -I"$MPIDIR" -c "$MPISRC" -o "$OBJ/mpi_single.o" & pids+=($!)
 gcc -O2 -std=gnu99 -w -I"$MPIDIR" -I"$HERE/../include" -DNRANKS_D3=$NR -DLOC_N0=$N0 -DLOC_N1=$N1 -DLOC_N2=$N2 -DLOC_N3=$N3 -c "$HERE/../openstaple_b200/host/memory_wrapper_staple.c" -o "$OBJ/host_shim.o" & pids+=($!)
+# NR > 1 only: a third build, <prog>_staplemd_<geom>, also leaves src/Mpi/multidev.c out and takes openstaple_b200/host/multidev_staple.c
+# (devinfo, pre_init_multidev1D, init_multidev1D, shutdown_multidev compiled against the host's mpi.h) in its place
+if [ "$NR" -gt 1 ]; then gcc $CF -c "$HERE/../openstaple_b200/host/multidev_staple.c" -o "$OBJ/multidev_staple.o" & pids+=($!); fi
 for p in "${pids[@]}"; do wait $p; done
 ALL=""; KEPT=""
 REPLACED=" $(echo $REPLACED) "     # one space between names, whatever the line breaks above
@@ -82,5 +85,9 @@ for prog in $PROGLIST; do      # PROGS="deo_doe_test" builds a subset
   gcc -o "$HERE/_ref/${prog}_ref_$GEOM" $mo $ALL "$OBJ/mpi_single.o" -lm
   gcc -o "$HERE/_ref/${prog}_staple_$GEOM" $mo $KEPT "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
       -L"$LIBDIR" -lstaple_b200 -Wl,-rpath,'$ORIGIN/../../openstaple_b200' -lm
+  if [ "$NR" -gt 1 ]; then
+    gcc -o "$HERE/_ref/${prog}_staplemd_$GEOM" $mo ${KEPT/$OBJ\/Mpi_multidev.o/} "$OBJ/multidev_staple.o" "$OBJ/host_shim.o" "$OBJ/mpi_single.o" \
+        -L"$LIBDIR" -lstaple_b200 -Wl,-rpath,'$ORIGIN/../../openstaple_b200' -lm
+  fi
 done
 echo "built $HERE/_ref/{${PROGS:-deo_doe_test,inverter_multishift_test,main}}_{ref,staple}_$GEOM"

@@ -17,15 +17,20 @@ from test_reference_host_multirank_cpu import FILES, run_single_rank_on_saved_in
 pytestmark = pytest.mark.gpu
 
 
-def test_two_gpu_reference_deo_doe_program(tmp_path):
+@pytest.mark.parametrize("kind", ["staple", "staplemd"])
+def test_two_gpu_reference_deo_doe_program(tmp_path, kind):
+    """kind staplemd: src/Mpi/multidev.c is left out as well and openstaple_b200/host/multidev_staple.c provides devinfo,
+    pre_init_multidev1D, init_multidev1D (which joins the library's rank layer) and shutdown_multidev"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = ":".join(x for x in (env.get("LD_LIBRARY_PATH", ""), "/usr/local/cuda/lib64") if x)
     td = str(tmp_path)
-    two = run_two_ranks("staple", td, env=env)
-    assert "hot path served by staple_b200" in open(os.path.join(td, "stderr.0")).read()
+    two = run_two_ranks(kind, td, env=env)
+    err0 = open(os.path.join(td, "stderr.0")).read()
+    assert "hot path served by staple_b200" in err0
+    assert ("joined in init_multidev1D" in err0) == (kind == "staplemd")
     one = run_single_rank_on_saved_inputs(td)
     for f in FILES:
         e = float(np.abs(two[f] - one[f]).max() / np.abs(one[f]).max())
