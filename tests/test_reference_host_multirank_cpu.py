@@ -91,3 +91,24 @@ def test_reference_two_rank_multishift_equals_its_single_rank_run(tmp_path):
     for f in MS_FILES:
         e = float(np.abs(two[f] - one[f]).max() / np.abs(one[f]).max())
         assert e < 1e-11, (f, e)
+
+
+def test_multidev_glue_build_defines_the_rank_setup_symbols():
+    """the `_staplemd_` programs (src/Mpi/multidev.c left out, openstaple_b200/host/multidev_staple.c in its place) define devinfo,
+    pre_init_multidev1D, init_multidev1D and shutdown_multidev themselves and take the teardown and the readiness query from the
+    library; the `_staple_` programs (the reference's multidev.c kept) need neither"""
+    md = os.path.join(REF, "deo_doe_test_staplemd_8x8x8x8_r2")
+    st = os.path.join(REF, "deo_doe_test_staple_8x8x8x8_r2")
+    if not (os.path.exists(md) and os.path.exists(st)):
+        pytest.skip("host programs not built")
+
+    def symbols(exe):
+        out = subprocess.run(["nm", exe], capture_output=True, text=True, check=True).stdout
+        return {l.split()[-1]: l.split()[-2] for l in out.splitlines() if len(l.split()) >= 2}
+    s = symbols(md)
+    for name in ("pre_init_multidev1D", "init_multidev1D", "shutdown_multidev"):
+        assert s.get(name) == "T", (name, s.get(name))
+    assert s.get("devinfo") in ("B", "C", "D"), s.get("devinfo")
+    assert s.get("staple_shutdown_multidev") == "U" and s.get("staple_init_multidev1D") == "U"
+    assert s.get("staple_rank_layer_ready") == "U"
+    assert "staple_shutdown_multidev" not in symbols(st)
